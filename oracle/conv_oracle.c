@@ -1,0 +1,299 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- the CPU oracle for the Conv2D hot path.
+ *
+ * A plain-C restatement of Neuro_'s reference convolution ops. Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library; the product path
+ * (neuro__b200/, include/) never links, imports or calls it.
+ *
+ * Parity status: PINNED. tests/test_oracle.py checks every function here against
+ *   (1) the five literal golden vectors of Neuro.Tests/src/TensorTests.cpp:352-425, and
+ *   (2) the reference's own TensorOpCpu / TensorOpCpuMt sources compiled unmodified
+ *       (oracle/_ref/libneuro_ref.so, built by oracle/Makefile `ref`), bit for bit, on seeded
+ *       inputs covering NCHW/NHWC, stride 1-3, pad 0-3, padX != padY, ragged (non-dividing) strides
+ *       and transposed-convolution output sizes; fixtures produced from that library are
+ *       committed under tests/golden/ so the pin also holds where /root/reference is absent.
+ *
+ * Every fp32 function accumulates in exactly the order the reference does for each output
+ * element, so it is bit-identical to the reference (compile with -ffp-contract=off). The loops
+ * are re-nested so that independent output elements can be computed by different threads:
+ * the reference's own multi-threaded variant relies on the same property
+ * (Neuro/src/Tensors/TensorOpCpuMt.cpp:173-333).
+ *
+ * Layouts (Neuro/src/Tensors/Shape.cpp:11-22, Neuro/include/Tensors/Shape.h:93-103):
+ *   fmt 0 = NCHW: x[((n*C+c)*H+h)*W+w]      fmt 1 = NHWC: x[((n*H+h)*W+w)*C+c]
+ *   kernels are KCRS in both formats: w[((k*C+c)*R+r)*S+s]
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#define API __attribute__((visibility("default")))
+
+typedef struct
+{
+    int N, C, H, W;   /* input (or input-gradient) extent */
+    int K, R, S;      /* filters */
+    int Ho, Wo;       /* output (or output-gradient) extent, supplied by the caller */
+    int stride, padX, padY;
+    int fmt;          /* 0 NCHW, 1 NHWC */
+} conv_dims;
+
+static inline size_t xi(const conv_dims* d, int n, int c, int h, int w)
+{
+    return d->fmt == 0 ? (((size_t)n * d->C + c) * d->H + h) * d->W + w
+                       : (((size_t)n * d->H + h) * d->W + w) * d->C + c;
+}
+
+static inline size_t yi(const conv_dims* d, int n, int k, int h, int w)
+{
+    return d->fmt == 0 ? (((size_t)n * d->K + k) * d->Ho + h) * d->Wo + w
+                       : (((size_t)n * d->Ho + h) * d->Wo + w) * d->K + k;
+}
+
+static inline size_t wi(const conv_dims* d, int k, int c, int r, int s)
+{
+    return (((size_t)k * d->C + c) * d->R + r) * d->S + s;
+}
+
+/* Forward. Follows TensorOpCpu::Conv2D, Neuro/src/Tensors/TensorOpCpu.cpp:1012-1052:
+ * cross-correlation, zero padding (out-of-range taps contribute 0*w, which is added like any
+ * other term), local fp32 accumulator filled in (c, r, s) order, output overwritten. */
+API void oracle_conv2d(const conv_dims* d, const float* x, const float* w, float* y)
+{
+#pragma omp parallel for collapse(2) schedule(dynamic)
+    for (int n = 0; n < d->N; ++n)
+    for (int k = 0; k < d->K; ++k)
+    for (int oh = 0; oh < d->Ho; ++oh)
+    for (int ow = 0; ow < d->Wo; ++ow)
+    {
+        const int h0 = oh * d->stride - d->padY, w0 = ow * d->stride - d->padX;
+        float val = 0;
+        for (int c = 0; c < d->C; ++c)
+        for (int r = 0; r < d->R; ++r)
+        for (int s = 0; s < d->S; ++s)
+        {
+            const int ih = h0 + r, iw = w0 + s;
+            const float xv = (ih < 0 || ih >= d->H || iw < 0 || iw >= d->W) ? 0.f : x[xi(d, n, c, ih, iw)];
+            val += xv * w[wi(d, k, c, r, s)];
+        }
+        y[yi(d, n, k, oh, ow)] = val;
+    }
+}
+
+/* Input gradient (also the forward of Conv2DTranspose, Neuro/src/Tensors/Tensor.cpp:1806-1810).
+ * Follows TensorOpCpu::Conv2DInputGradient, TensorOpCpu.cpp:1071-1126: dx zeroed, then every
+ * (n,k,oh,ow) scatters w*dy into the in-range taps. For one dx element the reference's additions
+ * arrive ordered by (k, oh, ow, r, s); the loops below keep that order per (n,c). The dx extent
+ * (H,W) is the caller's, so rows/cols the forward never read stay zero. */
+API void oracle_conv2d_input_gradient(const conv_dims* d, const float* dy, const float* w, float* dx)
+{
+    memset(dx, 0, sizeof(float) * (size_t)d->N * d->C * d->H * d->W);
+#pragma omp parallel for collapse(2) schedule(dynamic)
+    for (int n = 0; n < d->N; ++n)
+    for (int c = 0; c < d->C; ++c)
+    for (int k = 0; k < d->K; ++k)
+    for (int oh = 0; oh < d->Ho; ++oh)
+    for (int ow = 0; ow < d->Wo; ++ow)
+    {
+        const float g = dy[yi(d, n, k, oh, ow)];
+        const int h0 = oh * d->stride - d->padY, w0 = ow * d->stride - d->padX;
+        for (int r = 0; r < d->R; ++r)
+        {
+            const int ih = h0 + r;
+            if (ih < 0 || ih >= d->H) continue;
+            for (int s = 0; s < d->S; ++s)
+            {
+                const int iw = w0 + s;
+                if (iw < 0 || iw >= d->W) continue;
+                dx[xi(d, n, c, ih, iw)] += w[wi(d, k, c, r, s)] * g;
+            }
+        }
+    }
+}
+
+/* Kernel gradient. Follows TensorOpCpu::Conv2DKernelsGradient, TensorOpCpu.cpp:1129-1184: dw
+ * zeroed, then dw[k,c,r,s] += x * dy over all (n,oh,ow) with the tap in range; for one dw element
+ * the additions arrive ordered by (n, oh, ow). The filter extent (R,S) is the caller's. */
+API void oracle_conv2d_kernels_gradient(const conv_dims* d, const float* x, const float* dy, float* dw)
+{
+    memset(dw, 0, sizeof(float) * (size_t)d->K * d->C * d->R * d->S);
+#pragma omp parallel for collapse(2) schedule(dynamic)
+    for (int k = 0; k < d->K; ++k)
+    for (int c = 0; c < d->C; ++c)
+    for (int n = 0; n < d->N; ++n)
+    for (int oh = 0; oh < d->Ho; ++oh)
+    for (int ow = 0; ow < d->Wo; ++ow)
+    {
+        const float g = dy[yi(d, n, k, oh, ow)];
+        const int h0 = oh * d->stride - d->padY, w0 = ow * d->stride - d->padX;
+        for (int r = 0; r < d->R; ++r)
+        {
+            const int ih = h0 + r;
+            if (ih < 0 || ih >= d->H) continue;
+            for (int s = 0; s < d->S; ++s)
+            {
+                const int iw = w0 + s;
+                if (iw < 0 || iw >= d->W) continue;
+                dw[wi(d, k, c, r, s)] += x[xi(d, n, c, ih, iw)] * g;
+            }
+        }
+    }
+}
+
+/* Same three contractions accumulated in fp64 and rounded once: the tie-breaker when the
+ * reference's own fp32 running sums (O(len * eps) rounding on long reductions) are the larger
+ * error source. Not reference behaviour; used only to bound errors. */
+API void oracle_conv2d_f64(const conv_dims* d, const float* x, const float* w, float* y)
+{
+#pragma omp parallel for collapse(2) schedule(dynamic)
+    for (int n = 0; n < d->N; ++n)
+    for (int k = 0; k < d->K; ++k)
+    for (int oh = 0; oh < d->Ho; ++oh)
+    for (int ow = 0; ow < d->Wo; ++ow)
+    {
+        const int h0 = oh * d->stride - d->padY, w0 = ow * d->stride - d->padX;
+        double val = 0;
+        for (int c = 0; c < d->C; ++c)
+        for (int r = 0; r < d->R; ++r)
+        {
+            const int ih = h0 + r;
+            if (ih < 0 || ih >= d->H) continue;
+            for (int s = 0; s < d->S; ++s)
+            {
+                const int iw = w0 + s;
+                if (iw < 0 || iw >= d->W) continue;
+                val += (double)x[xi(d, n, c, ih, iw)] * (double)w[wi(d, k, c, r, s)];
+            }
+        }
+        y[yi(d, n, k, oh, ow)] = (float)val;
+    }
+}
+
+API void oracle_conv2d_input_gradient_f64(const conv_dims* d, const float* dy, const float* w, float* dx)
+{
+#pragma omp parallel for collapse(2) schedule(dynamic)
+    for (int n = 0; n < d->N; ++n)
+    for (int c = 0; c < d->C; ++c)
+    for (int ih = 0; ih < d->H; ++ih)
+    for (int iw = 0; iw < d->W; ++iw)
+    {
+        double val = 0;
+        for (int k = 0; k < d->K; ++k)
+        for (int r = 0; r < d->R; ++r)
+        {
+            const int th = ih + d->padY - r;
+            if (th < 0 || th % d->stride) continue;
+            const int oh = th / d->stride;
+            if (oh >= d->Ho) continue;
+            for (int s = 0; s < d->S; ++s)
+            {
+                const int tw = iw + d->padX - s;
+                if (tw < 0 || tw % d->stride) continue;
+                const int ow = tw / d->stride;
+                if (ow >= d->Wo) continue;
+                val += (double)w[wi(d, k, c, r, s)] * (double)dy[yi(d, n, k, oh, ow)];
+            }
+        }
+        dx[xi(d, n, c, ih, iw)] = (float)val;
+    }
+}
+
+API void oracle_conv2d_kernels_gradient_f64(const conv_dims* d, const float* x, const float* dy, float* dw)
+{
+#pragma omp parallel for collapse(2) schedule(dynamic)
+    for (int k = 0; k < d->K; ++k)
+    for (int c = 0; c < d->C; ++c)
+    for (int r = 0; r < d->R; ++r)
+    for (int s = 0; s < d->S; ++s)
+    {
+        double val = 0;
+        for (int n = 0; n < d->N; ++n)
+        for (int oh = 0; oh < d->Ho; ++oh)
+        {
+            const int ih = oh * d->stride - d->padY + r;
+            if (ih < 0 || ih >= d->H) continue;
+            for (int ow = 0; ow < d->Wo; ++ow)
+            {
+                const int iw = ow * d->stride - d->padX + s;
+                if (iw < 0 || iw >= d->W) continue;
+                val += (double)x[xi(d, n, c, ih, iw)] * (double)dy[yi(d, n, k, oh, ow)];
+            }
+        }
+        dw[wi(d, k, c, r, s)] = (float)val;
+    }
+}
+
+/* Activations as the reference computes them (TensorOpCpu.cpp:807-864): exp evaluated in double
+ * (the C++ overload picked for `(float)exp(-x)` with a float argument is exp(float) under
+ * <cmath>; both g++ and MSVC resolve `exp(float)` to the float overload, so expf is used). */
+static float activate(int act, float alpha, float v)
+{
+    switch (act)
+    {
+    case 1: return 1 / (1 + expf(-v));              /* _Sigmoid   :808 */
+    case 2: return v > 0.f ? v : 0.f;               /* _ReLU      :832 */
+    case 3: return 2 / (1 + expf(-2 * v)) - 1;      /* _TanH      :820 */
+    case 4: return v >= 0 ? v : alpha * (expf(v) - 1); /* _ELU    :844 */
+    case 5: return v >= 0 ? v : alpha * v;          /* _LeakyReLU :856 */
+    default: return v;                              /* _Identity */
+    }
+}
+
+/* Fused op. Follows TensorOpCpu::Conv2DBiasActivation, TensorOpCpu.cpp:1055-1062:
+ * conv (NCHW) -> broadcast add of bias[k] -> activation. act uses EActivation numbering
+ * (Neuro/include/Types.h:83-92). The reference only defines it for NCHW; fmt is honoured here
+ * so the NHWC fused path of the product can be checked too. */
+API void oracle_conv2d_bias_activation(const conv_dims* d, const float* x, const float* w, const float* bias,
+                                       int act, float alpha, float* y)
+{
+    oracle_conv2d(d, x, w, y);
+#pragma omp parallel for collapse(2)
+    for (int n = 0; n < d->N; ++n)
+    for (int k = 0; k < d->K; ++k)
+    for (int oh = 0; oh < d->Ho; ++oh)
+    for (int ow = 0; ow < d->Wo; ++ow)
+    {
+        const size_t i = yi(d, n, k, oh, ow);
+        y[i] = activate(act, alpha, y[i] + bias[k]);
+    }
+}
+
+/* Bias gradient. Follows TensorOpCpu::Conv2DBiasGradient, TensorOpCpu.cpp:1065-1068 =
+ * Sum over the W,H,N axes (SumTemplate<1,1,0,1>, :284-296): one fp32 running sum per channel,
+ * additions ordered by (n, h, w). */
+API void oracle_conv2d_bias_gradient(const conv_dims* d, const float* dy, float* db)
+{
+#pragma omp parallel for
+    for (int k = 0; k < d->K; ++k)
+    {
+        float acc = 0;
+        for (int n = 0; n < d->N; ++n)
+        for (int oh = 0; oh < d->Ho; ++oh)
+        for (int ow = 0; ow < d->Wo; ++ow)
+            acc += dy[yi(d, n, k, oh, ow)];
+        db[k] = acc;
+    }
+}
+
+/* Optimiser updates that follow the gradient exchange. Follow TensorOpCpu::AdamStep /
+ * SgdStep, TensorOpCpu.cpp:987-1009:  m = b1*m + (1-b1)*g;  v = v*b2 + (1-b2)*g*g;
+ * p = p - m / (sqrt(v) + eps) * lr   (sqrt evaluated in double, as `(float)::sqrt(x)`). */
+API void oracle_adam_step(float* p, const float* g, float* m, float* v, size_t n,
+                          float lr, float beta1, float beta2, float eps)
+{
+#pragma omp parallel for
+    for (long long i = 0; i < (long long)n; ++i)
+    {
+        m[i] = beta1 * m[i] + (1 - beta1) * 1.f * g[i];
+        v[i] = v[i] * beta2 + (1 - beta2) * 1.f * g[i] * g[i];
+        p[i] = p[i] - m[i] / ((float)sqrt((double)v[i]) + eps) * lr;
+    }
+}
+
+API void oracle_sgd_step(float* p, const float* g, size_t n, float lr)
+{
+#pragma omp parallel for
+    for (long long i = 0; i < (long long)n; ++i)
+        p[i] = 1 * p[i] + -lr * g[i];
+}

@@ -1,0 +1,213 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end to the CPU oracle.
+
+Two libraries sit behind this module:
+
+* ``oracle/_build/libconv_oracle.so``  our plain-C restatement (``oracle/conv_oracle.c``), always buildable;
+* ``oracle/_ref/libneuro_ref.so``      the reference's own TensorOpCpu / TensorOpCpuMt sources compiled
+  unmodified (``make -C oracle ref``; needs ``/root/reference`` at build time only -- the built .so
+  travels to the GPU box).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this
+module. Nothing under ``neuro__b200/`` does.
+
+Array conventions (numpy, float32, C-contiguous):
+  NCHW: x (N,C,H,W)   y (N,K,Ho,Wo)      NHWC: x (N,H,W,C)   y (N,Ho,Wo,K)      kernels: (K,C,R,S) in both.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_SO = os.path.join(_HERE, "_build", "libconv_oracle.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libneuro_ref.so")
+
+NCHW, NHWC = 0, 1
+# EActivation numbering, Neuro/include/Types.h:83-92
+IDENTITY, SIGMOID, RELU, TANH, ELU, LEAKY_RELU = 0, 1, 2, 3, 4, 5
+
+
+class ConvDims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("N", "C", "H", "W", "K", "R", "S", "Ho", "Wo", "stride", "padX", "padY", "fmt")]
+
+
+def build(ref=True):
+    """Compile the oracle (and, when /root/reference is present, the reference build)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+    if ref and os.path.isdir("/root/reference/Neuro/src/Tensors"):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_ORACLE_SO):
+            build(ref=False)
+        _lib = ctypes.CDLL(_ORACLE_SO)
+    return _lib
+
+
+def have_ref():
+    return os.path.exists(_REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _ref = ctypes.CDLL(_REF_SO)
+        _ref.neuro_ref_threads.restype = ctypes.c_int
+    return _ref
+
+
+def conv_out_size(size, f, stride, pad):
+    """Tensor::GetConvOutputShape, Neuro/src/Tensors/Tensor.cpp:2010-2029."""
+    return (size + 2 * pad - f) // stride + 1
+
+
+def conv_transpose_out_size(size, f, stride, pad):
+    """Tensor::GetConvTransposeOutputShape, Neuro/src/Tensors/Tensor.cpp:2032-2051."""
+    return (size - 1) * stride + f - 2 * pad
+
+
+def _fp(a):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _xshape(fmt, a):
+    """(N,C,H,W) extents of an activation array in either format."""
+    if fmt == NCHW:
+        n, c, h, w = a.shape
+    else:
+        n, h, w, c = a.shape
+    return n, c, h, w
+
+
+def _mk(fmt, n, c, h, w, k):
+    return (n, k, h, w) if fmt == NCHW else (n, h, w, k)
+
+
+def _dims(fmt, N, C, H, W, K, R, S, Ho, Wo, stride, padX, padY):
+    return ConvDims(N, C, H, W, K, R, S, Ho, Wo, stride, padX, padY, fmt)
+
+
+# ---------------------------------------------------------------- restatement
+
+def conv2d(x, w, stride, padX, padY=None, fmt=NCHW, f64=False):
+    padY = padX if padY is None else padY
+    N, C, H, W = _xshape(fmt, x)
+    K, C2, R, S = w.shape
+    assert C2 == C
+    Ho, Wo = conv_out_size(H, R, stride, padY), conv_out_size(W, S, stride, padX)
+    y = np.empty(_mk(fmt, N, C, Ho, Wo, K), np.float32)
+    d = _dims(fmt, N, C, H, W, K, R, S, Ho, Wo, stride, padX, padY)
+    fn = lib().oracle_conv2d_f64 if f64 else lib().oracle_conv2d
+    fn(ctypes.byref(d), _fp(x), _fp(w), _fp(y))
+    return y
+
+
+def conv2d_input_gradient(dy, w, stride, padX, padY, in_hw, fmt=NCHW, f64=False):
+    """in_hw = (H, W) of the input gradient; the caller supplies it, as in the reference."""
+    N, K, Ho, Wo = _xshape(fmt, dy)
+    K2, C, R, S = w.shape
+    assert K2 == K
+    H, W = in_hw
+    dx = np.empty(_mk(fmt, N, K, H, W, C), np.float32)
+    d = _dims(fmt, N, C, H, W, K, R, S, Ho, Wo, stride, padX, padY)
+    fn = lib().oracle_conv2d_input_gradient_f64 if f64 else lib().oracle_conv2d_input_gradient
+    fn(ctypes.byref(d), _fp(dy), _fp(w), _fp(dx))
+    return dx
+
+
+def conv2d_kernels_gradient(x, dy, stride, padX, padY, filt_rs, fmt=NCHW, f64=False):
+    """filt_rs = (R, S) of the kernel gradient; the caller supplies it, as in the reference."""
+    N, C, H, W = _xshape(fmt, x)
+    N2, K, Ho, Wo = _xshape(fmt, dy)
+    assert N2 == N
+    R, S = filt_rs
+    dw = np.empty((K, C, R, S), np.float32)
+    d = _dims(fmt, N, C, H, W, K, R, S, Ho, Wo, stride, padX, padY)
+    fn = lib().oracle_conv2d_kernels_gradient_f64 if f64 else lib().oracle_conv2d_kernels_gradient
+    fn(ctypes.byref(d), _fp(x), _fp(dy), _fp(dw))
+    return dw
+
+
+def conv2d_bias_activation(x, w, bias, stride, pad, act, alpha=0.0, fmt=NCHW):
+    N, C, H, W = _xshape(fmt, x)
+    K, _, R, S = w.shape
+    Ho, Wo = conv_out_size(H, R, stride, pad), conv_out_size(W, S, stride, pad)
+    y = np.empty(_mk(fmt, N, C, Ho, Wo, K), np.float32)
+    d = _dims(fmt, N, C, H, W, K, R, S, Ho, Wo, stride, pad, pad)
+    bias = np.ascontiguousarray(bias.reshape(-1), np.float32)
+    lib().oracle_conv2d_bias_activation(ctypes.byref(d), _fp(x), _fp(w), _fp(bias), int(act),
+                                        ctypes.c_float(alpha), _fp(y))
+    return y
+
+
+def conv2d_bias_gradient(dy, fmt=NCHW):
+    N, K, Ho, Wo = _xshape(fmt, dy)
+    db = np.empty((K,), np.float32)
+    d = _dims(fmt, N, 0, 0, 0, K, 0, 0, Ho, Wo, 1, 0, 0)
+    lib().oracle_conv2d_bias_gradient(ctypes.byref(d), _fp(dy), _fp(db))
+    return db
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps):
+    """In place on p, m, v."""
+    lib().oracle_adam_step(_fp(p), _fp(g), _fp(m), _fp(v), ctypes.c_size_t(p.size), ctypes.c_float(lr),
+                           ctypes.c_float(beta1), ctypes.c_float(beta2), ctypes.c_float(eps))
+
+
+def sgd_step(p, g, lr):
+    lib().oracle_sgd_step(_fp(p), _fp(g), ctypes.c_size_t(p.size), ctypes.c_float(lr))
+
+
+# ---------------------------------------------------------------- the reference itself
+
+def _shape4(fmt, a, kernels=False):
+    """Reference Shape(d0..d3), fastest dimension first."""
+    s = a.shape
+    return (ctypes.c_uint32 * 4)(s[3], s[2], s[1], s[0])
+
+
+def ref_threads():
+    return ref().neuro_ref_threads()
+
+
+def ref_set_threads(n=0):
+    ref().neuro_ref_set_threads(int(n))
+
+
+def ref_conv2d(x, w, stride, padX, padY=None, fmt=NCHW, mt=False):
+    padY = padX if padY is None else padY
+    N, C, H, W = _xshape(fmt, x)
+    K, _, R, S = w.shape
+    Ho, Wo = conv_out_size(H, R, stride, padY), conv_out_size(W, S, stride, padX)
+    y = np.empty(_mk(fmt, N, C, Ho, Wo, K), np.float32)
+    ref().neuro_ref_conv2d(int(mt), fmt, _fp(x), _shape4(fmt, x), _fp(w), _shape4(fmt, w), stride, padX, padY,
+                           _fp(y), _shape4(fmt, y))
+    return y
+
+
+def ref_conv2d_input_gradient(dy, w, stride, padX, padY, in_hw, fmt=NCHW, mt=False):
+    N, K, Ho, Wo = _xshape(fmt, dy)
+    C = w.shape[1]
+    dx = np.empty(_mk(fmt, N, K, in_hw[0], in_hw[1], C), np.float32)
+    ref().neuro_ref_conv2d_input_gradient(int(mt), fmt, _fp(dy), _shape4(fmt, dy), _fp(w), _shape4(fmt, w),
+                                          stride, padX, padY, _fp(dx), _shape4(fmt, dx))
+    return dx
+
+
+def ref_conv2d_kernels_gradient(x, dy, stride, padX, padY, filt_rs, fmt=NCHW, mt=False):
+    N, C, H, W = _xshape(fmt, x)
+    K = _xshape(fmt, dy)[1]
+    dw = np.empty((K, C, filt_rs[0], filt_rs[1]), np.float32)
+    ref().neuro_ref_conv2d_kernels_gradient(int(mt), fmt, _fp(x), _shape4(fmt, x), _fp(dy), _shape4(fmt, dy),
+                                            stride, padX, padY, _fp(dw), _shape4(fmt, dw))
+    return dw

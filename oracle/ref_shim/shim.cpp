@@ -1,0 +1,154 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+//
+// Host-only glue that lets the reference's own TensorOpCpu.cpp / TensorOpCpuMt.cpp / Shape.cpp
+// (compiled UNMODIFIED from /root/reference by oracle/Makefile) run their convolution loops
+// without the rest of Neuro_ (Tensor.cpp needs FreeImage/HDF5/cuDNN, Storage.cpp needs
+// windows.h). It supplies, against the reference headers, only the
+// handful of Tensor/Storage members those loops call, and a C entry point per op.
+//
+// Reference call sites this glue serves:
+//   TensorOpCpu::Conv2D                 Neuro/src/Tensors/TensorOpCpu.cpp:1012
+//   TensorOpCpu::Conv2DInputGradient    Neuro/src/Tensors/TensorOpCpu.cpp:1071
+//   TensorOpCpu::Conv2DKernelsGradient  Neuro/src/Tensors/TensorOpCpu.cpp:1129
+//   TensorOpCpuMt::{same three}         Neuro/src/Tensors/TensorOpCpuMt.cpp:173,220,278
+#include <cstdlib>
+#include <cstring>
+#include <omp.h>
+
+#include "Tensors/Tensor.h"
+#include "Tensors/TensorOpCpu.h"
+#include "Tensors/TensorOpCpuMt.h"
+
+namespace Neuro
+{
+    // ---- Storage: plain host heap, single location ----
+    Storage::Storage(int type, size_t size, const string& name)
+        : m_Type(type), m_AllocSize(size), m_Size(size), m_Name(name)
+    {
+    }
+
+    Storage::~Storage()
+    {
+        free(m_DataPtr);
+        m_DataPtr = nullptr;
+    }
+
+    void Storage::AllocateOnHost() const
+    {
+        if (!m_DataPtr)
+        {
+            Storage* self = const_cast<Storage*>(this);
+            self->m_DataPtr = (float*)calloc(m_AllocSize ? m_AllocSize : 1, sizeof(float));
+        }
+        m_DataLocation = Host;
+    }
+
+    void Storage::OverrideHost() { AllocateOnHost(); }
+    void Storage::CopyToHost(bool) const { AllocateOnHost(); }
+    const float* Storage::Data() const { AllocateOnHost(); return m_DataPtr; }
+    float* Storage::Data() { AllocateOnHost(); return m_DataPtr; }
+
+    // ---- Tensor: just enough for the conv loops ----
+    TensorOpCpu* Tensor::g_DefaultOp = nullptr;
+    TensorOpCpu* Tensor::g_ForcedOp = nullptr;
+    TensorOpCpu* Tensor::g_OpCpu = nullptr;
+    TensorOpCpu* Tensor::g_OpCpuMt = nullptr;
+    TensorOpCpu* Tensor::g_OpCpuMkl = nullptr;
+    TensorOpCpu* Tensor::g_OpGpu = nullptr;
+
+    Tensor::Tensor(const Shape& shape, const string& name, EStorageType storageType)
+        : m_Op(nullptr), m_Shape(shape), m_Storage(storageType, shape.Length, name), m_Name(name)
+    {
+    }
+
+    void Tensor::CopyToHost(bool allowAlloc) const { m_Storage.CopyToHost(allowAlloc); }
+    void Tensor::OverrideHost() { m_Storage.OverrideHost(); }
+    float* Tensor::Values() { return m_Storage.Data(); }
+    const float* Tensor::Values() const { return m_Storage.Data(); }
+
+    void Tensor::Zero()
+    {
+        memset(m_Storage.Data(), 0, sizeof(float) * m_Shape.Length);
+    }
+
+    // Same bounds semantics as the reference accessor (Tensor.cpp:2078-2084), including its
+    // one-past-the-end tolerance on the batch index, which in-range callers never hit.
+    float Tensor::TryGet(float def, int w, int h, int d, int n) const
+    {
+        const bool outside = w < 0 || w >= (int)Width() || h < 0 || h >= (int)Height() ||
+                             d < 0 || d >= (int)Depth() || n < 0 || n > (int)Batch();
+        return outside ? def : Get(w, h, d, n);
+    }
+}
+
+using namespace Neuro;
+
+namespace
+{
+    struct Dims { uint32_t d[4]; };
+
+    Shape MakeShape(const uint32_t* d) { return Shape(d[0], d[1], d[2], d[3]); }
+
+    void Load(Tensor& t, const float* src) { memcpy(t.Values(), src, sizeof(float) * t.Length()); }
+    void Store(const Tensor& t, float* dst) { memcpy(dst, t.Values(), sizeof(float) * t.Length()); }
+
+    // The op classes are stateless; their conv methods never touch `this`. Calling them
+    // non-virtually on a dummy object avoids dragging in the vtable (and through it every other op).
+    alignas(16) char g_Dummy[64];
+    const TensorOpCpu* OpSt() { return reinterpret_cast<const TensorOpCpu*>(g_Dummy); }
+    const TensorOpCpuMt* OpMt() { return reinterpret_cast<const TensorOpCpuMt*>(g_Dummy); }
+}
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+// All shapes are the reference's own Shape(d0,d1,d2,d3) = (fastest ... slowest) dimensions:
+// NCHW tensors (W,H,C,N); NHWC tensors (C,W,H,N); kernels (S,R,C,K) in both formats.
+// mt: 0 = TensorOpCpu (single thread), 1 = TensorOpCpuMt (PPL->OpenMP). fmt: 0 NCHW, 1 NHWC.
+
+REF_API int neuro_ref_threads()
+{
+    return omp_get_max_threads();
+}
+
+REF_API void neuro_ref_set_threads(int n)
+{
+    omp_set_max_active_levels(2); // PPL load-balances nested parallel_for; OpenMP needs this enabled
+    if (n > 0)
+        omp_set_num_threads(n);
+}
+
+REF_API void neuro_ref_conv2d(int mt, int fmt, const float* x, const uint32_t* xDims, const float* w, const uint32_t* wDims,
+                              uint32_t stride, uint32_t padX, uint32_t padY, float* y, const uint32_t* yDims)
+{
+    Tensor tx(MakeShape(xDims)), tw(MakeShape(wDims)), ty(MakeShape(yDims));
+    Load(tx, x); Load(tw, w);
+    if (mt)
+        OpMt()->TensorOpCpuMt::Conv2D(tx, tw, stride, padX, padY, (EDataFormat)fmt, ty);
+    else
+        OpSt()->TensorOpCpu::Conv2D(tx, tw, stride, padX, padY, (EDataFormat)fmt, ty);
+    Store(ty, y);
+}
+
+REF_API void neuro_ref_conv2d_input_gradient(int mt, int fmt, const float* dy, const uint32_t* dyDims, const float* w, const uint32_t* wDims,
+                                             uint32_t stride, uint32_t padX, uint32_t padY, float* dx, const uint32_t* dxDims)
+{
+    Tensor tdy(MakeShape(dyDims)), tw(MakeShape(wDims)), tdx(MakeShape(dxDims));
+    Load(tdy, dy); Load(tw, w);
+    if (mt)
+        OpMt()->TensorOpCpuMt::Conv2DInputGradient(tdy, tw, stride, padX, padY, (EDataFormat)fmt, tdx);
+    else
+        OpSt()->TensorOpCpu::Conv2DInputGradient(tdy, tw, stride, padX, padY, (EDataFormat)fmt, tdx);
+    Store(tdx, dx);
+}
+
+REF_API void neuro_ref_conv2d_kernels_gradient(int mt, int fmt, const float* x, const uint32_t* xDims, const float* dy, const uint32_t* dyDims,
+                                               uint32_t stride, uint32_t padX, uint32_t padY, float* dw, const uint32_t* dwDims)
+{
+    Tensor tx(MakeShape(xDims)), tdy(MakeShape(dyDims)), tdw(MakeShape(dwDims));
+    Load(tx, x); Load(tdy, dy);
+    if (mt)
+        OpMt()->TensorOpCpuMt::Conv2DKernelsGradient(tx, tdy, stride, padX, padY, (EDataFormat)fmt, tdw);
+    else
+        OpSt()->TensorOpCpu::Conv2DKernelsGradient(tx, tdy, stride, padX, padY, (EDataFormat)fmt, tdw);
+    Store(tdw, dw);
+}
