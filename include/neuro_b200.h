@@ -1,0 +1,150 @@
+/*
+ * neuro_b200.h -- C ABI of the B200-native convolution backend for Neuro_.
+ *
+ * The reference has no plugin loader or FFI: a backend is a C++ subclass of Neuro::TensorOpCpu
+ * (Neuro/include/Tensors/TensorOpCpu.h:7-78) returned by Tensor::GetOpFromMode
+ * (Neuro/src/Tensors/Tensor.cpp:2701-2716). This header is the seam we define underneath such a
+ * subclass (include/neuro_b200/TensorOpB200.h mirrors the virtual interface and unpacks Tensors
+ * into these calls; INTEGRATION.md shows the binding a Neuro_ maintainer would add).
+ *
+ * Conventions shared by every entry point
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - all tensors are dense fp32. Activation pointers (x, y, dx, dy) are DEVICE pointers unless the
+ *     function name ends in _host;
+ *   - layouts follow Neuro::Shape (Neuro/src/Tensors/Shape.cpp:11-22):
+ *       NB200_NCHW  x[((n*C+c)*H+h)*W+w]      (reference Shape(W,H,C,N))
+ *       NB200_NHWC  x[((n*H+h)*W+w)*C+c]      (reference Shape(C,W,H,N))
+ *       kernels     w[((k*C+c)*R+r)*S+s]      (reference Shape(S,R,C,K), both formats)
+ *   - outputs are OVERWRITTEN (beta = 0), like the reference CPU ops, which zero or assign them
+ *     (TensorOpCpu.cpp:1032,1076,1134); the caller owns and pre-sizes every tensor
+ *     (Tensor.cpp:1767; Conv2DOp.cpp:18,27); nothing is allocated inside except through `workspace`;
+ *   - calls are asynchronous on `stream`; no hidden device synchronisation;
+ *   - return value: 0 on success, a negative NB200_E_* code otherwise; nb200_last_error() returns a
+ *     thread-local message. (The reference's ops are void and assert in debug builds only,
+ *     Neuro/include/Types.h:9-22; its CUDA_CHECK is a no-op in release, CudaErrorCheck.h:18-22.
+ *     We always check.)
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call fails with
+ *     NB200_E_NO_DEVICE.
+ */
+#ifndef NEURO_B200_H
+#define NEURO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB200_API __attribute__((visibility("default")))
+
+/* EDataFormat, Neuro/include/Types.h:94-98 */
+enum { NB200_NCHW = 0, NB200_NHWC = 1 };
+
+/* EActivation, Neuro/include/Types.h:83-92 (same numbering; _Softmax is not an epilogue) */
+enum { NB200_ACT_IDENTITY = 0, NB200_ACT_SIGMOID = 1, NB200_ACT_RELU = 2, NB200_ACT_TANH = 3,
+       NB200_ACT_ELU = 4, NB200_ACT_LEAKY_RELU = 5 };
+
+/* Arithmetic used for the contraction (BASELINE.json north_star: TF32 <= 2e-3, 3xTF32 <= 1e-5
+ * max-normalised error against the reference CPU ops). */
+enum {
+    NB200_MATH_TF32   = 0, /* tcgen05 kind::tf32, fp32 accumulate in TMEM (default)                    */
+    NB200_MATH_3XTF32 = 1, /* split-operand TF32 (hi*hi + hi*lo + lo*hi), fp32 accumulate              */
+    NB200_MATH_FP32   = 2  /* CUDA-core fp32 FMA kernels; also what HBM-bound small-channel layers use */
+};
+
+enum {
+    NB200_OK = 0,
+    NB200_E_INVALID = -1,     /* bad descriptor / null pointer / inconsistent sizes */
+    NB200_E_NO_DEVICE = -2,   /* no CUDA device, or not an sm_100 part              */
+    NB200_E_CUDA = -3,        /* a CUDA runtime/driver call or launch failed        */
+    NB200_E_WORKSPACE = -4,   /* workspace smaller than nb200_conv2d_workspace_bytes */
+    NB200_E_UNSUPPORTED = -5
+};
+
+enum { NB200_OP_FORWARD = 0, NB200_OP_INPUT_GRADIENT = 1, NB200_OP_KERNELS_GRADIENT = 2 };
+
+/* One convolution problem. (N,C,H,W) is always the extent of the tensor on the INPUT side of the
+ * forward op (x, or dx for the input gradient); (Ho,Wo) the extent on its OUTPUT side (y, or dy).
+ * Both are supplied by the caller, exactly as the reference ops take them from the Tensor shapes:
+ * the input gradient of a strided conv, and the forward of Conv2DTranspose
+ * (Tensor.cpp:1806-1810, 2032-2051), rely on (H,W) not being derived from (Ho,Wo). */
+typedef struct nb200_conv_desc
+{
+    int32_t N, C, H, W;
+    int32_t K, R, S;
+    int32_t Ho, Wo;
+    int32_t stride;
+    int32_t padX, padY;
+    int32_t fmt;   /* NB200_NCHW | NB200_NHWC */
+    int32_t math;  /* NB200_MATH_*            */
+} nb200_conv_desc;
+
+/* Library / device introspection. */
+NB200_API const char* nb200_version(void);
+NB200_API const char* nb200_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x); fills optional outputs. */
+NB200_API int nb200_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes);
+
+/* Shape helpers = Tensor::GetPadding / GetConvOutputShape / GetConvTransposeOutputShape
+ * (Neuro/src/Tensors/Tensor.cpp:1966-1985, 2010-2029, 2032-2051). mode: 0 Valid, 1 Same, 2 Full. */
+NB200_API int32_t nb200_padding(int32_t mode, int32_t filter);
+NB200_API int32_t nb200_conv_out_size(int32_t in, int32_t filter, int32_t stride, int32_t pad);
+NB200_API int32_t nb200_conv_transpose_out_size(int32_t in, int32_t filter, int32_t stride, int32_t pad);
+
+/* Bytes of device scratch the op may use for this problem (0 is a valid answer). */
+NB200_API size_t nb200_conv2d_workspace_bytes(int32_t op, const nb200_conv_desc* d);
+
+/* Name of the kernel family the dispatcher picks for this problem ("tcgen05_fprop", "direct_fprop", ...);
+ * static storage. For reports and tests. */
+NB200_API const char* nb200_conv2d_kernel_name(int32_t op, const nb200_conv_desc* d);
+
+/* y = act(conv(x, w) + bias).
+ * Replaces TensorOpCpu::Conv2D (TensorOpCpu.h:46, TensorOpCpu.cpp:1012) when bias == NULL and
+ * act == NB200_ACT_IDENTITY, and TensorOpCpu::Conv2DBiasActivation (TensorOpCpu.h:47, .cpp:1055)
+ * otherwise. bias: K floats (reference Shape(1,1,K)). alpha: ELU / LeakyReLU coefficient. */
+NB200_API int nb200_conv2d_forward(const nb200_conv_desc* d, const float* x, const float* w,
+                                   const float* bias, int32_t act, float alpha, float* y,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* dx = conv_input_gradient(dy, w); dx has extent (N,C,H,W), dy (N,K,Ho,Wo).
+ * Replaces TensorOpCpu::Conv2DInputGradient (TensorOpCpu.h:49, TensorOpCpu.cpp:1071). Also the forward
+ * of Conv2DTranspose and the image gradient of style transfer. Elements of dx that no output tap
+ * reaches (ragged strides) are written as 0. */
+NB200_API int nb200_conv2d_input_gradient(const nb200_conv_desc* d, const float* dy, const float* w,
+                                          float* dx, void* workspace, size_t workspace_bytes, void* stream);
+
+/* dw = conv_kernels_gradient(x, dy); optionally db[k] = sum_{n,ho,wo} dy (bias gradient folded into
+ * the same pass over dy). Replaces TensorOpCpu::Conv2DKernelsGradient (TensorOpCpu.h:50,
+ * TensorOpCpu.cpp:1129); db != NULL additionally replaces Conv2DBiasGradient (TensorOpCpu.h:48). */
+NB200_API int nb200_conv2d_kernels_gradient(const nb200_conv_desc* d, const float* x, const float* dy,
+                                            float* dw, float* db, void* workspace, size_t workspace_bytes,
+                                            void* stream);
+
+/* db[k] = sum over N,Ho,Wo of dy. Replaces TensorOpCpu::Conv2DBiasGradient (TensorOpCpu.h:48,
+ * TensorOpCpu.cpp:1065 = Sum over _013Axes). Only N,K,Ho,Wo,fmt of the descriptor are read. */
+NB200_API int nb200_conv2d_bias_gradient(const nb200_conv_desc* d, const float* dy, float* db, void* stream);
+
+/* Optimiser updates that follow the gradient exchange in data-parallel Fit().
+ * Replace TensorOpCpu::AdamStep / SgdStep (TensorOpCpu.h:75-76, TensorOpCpu.cpp:987-1009), with the
+ * 1/replicas scaling of an all-reduced (summed) gradient folded in as grad_scale:
+ *   g' = grad_scale*g;  m = b1*m + (1-b1)*g';  v = b2*v + (1-b2)*g'^2;  p -= lr * m / (sqrt(v) + eps). */
+NB200_API int nb200_adam_step(float* param, const float* grad, float* m, float* v, size_t count,
+                              float grad_scale, float lr, float beta1, float beta2, float epsilon, void* stream);
+NB200_API int nb200_sgd_step(float* param, const float* grad, size_t count, float grad_scale, float lr, void* stream);
+
+/* Host-buffer variants (pageable or pinned host memory in, host memory out): stage through device
+ * buffers owned by the library on `stream`, run the op, copy the result back and wait for it. This is
+ * what a caller holding host-resident Tensors (reference residency protocol, Storage.cpp:534-604)
+ * pays per op; the TensorOpB200 C++ layer keeps intermediates device-resident instead. */
+NB200_API int nb200_conv2d_forward_host(const nb200_conv_desc* d, const float* x, const float* w,
+                                        const float* bias, int32_t act, float alpha, float* y, void* stream);
+NB200_API int nb200_conv2d_input_gradient_host(const nb200_conv_desc* d, const float* dy, const float* w,
+                                               float* dx, void* stream);
+NB200_API int nb200_conv2d_kernels_gradient_host(const nb200_conv_desc* d, const float* x, const float* dy,
+                                                 float* dw, float* db, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEURO_B200_H */

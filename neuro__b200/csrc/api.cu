@@ -1,0 +1,342 @@
+// C ABI (include/neuro_b200.h): validation, kernel-family dispatch, host-buffer staging.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace nb200
+{
+    static thread_local char g_err[512] = "";
+
+    void set_error(const char* fmt, ...)
+    {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(g_err, sizeof(g_err), fmt, ap);
+        va_end(ap);
+    }
+
+    int fail(int code, const char* fmt, ...)
+    {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(g_err, sizeof(g_err), fmt, ap);
+        va_end(ap);
+        return code;
+    }
+
+    namespace
+    {
+        // There is no CPU fallback: every compute entry point starts here.
+        int require_device()
+        {
+            int dev = -1;
+            cudaError_t e = cudaGetDevice(&dev);
+            if (e != cudaSuccess)
+            {
+                cudaGetLastError();
+                return fail(NB200_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(e));
+            }
+            static thread_local int checkedDev = -1;
+            if (checkedDev != dev)
+            {
+                int major = 0;
+                e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+                if (e != cudaSuccess)
+                    return fail(NB200_E_NO_DEVICE, "cannot query device %d: %s", dev, cudaGetErrorString(e));
+                if (major != 10)
+                    return fail(NB200_E_NO_DEVICE, "device %d has compute capability %d.x; this library is built for sm_100a only", dev, major);
+                checkedDev = dev;
+            }
+            return NB200_OK;
+        }
+
+        int validate(const nb200_conv_desc* d, int op)
+        {
+            if (!d)
+                return fail(NB200_E_INVALID, "null descriptor");
+            if (d->N < 0 || d->C < 0 || d->H < 0 || d->W < 0 || d->K < 0 || d->Ho < 0 || d->Wo < 0)
+                return fail(NB200_E_INVALID, "negative extent in descriptor");
+            if (d->R < 1 || d->S < 1 || d->stride < 1 || d->padX < 0 || d->padY < 0)
+                return fail(NB200_E_INVALID, "filter/stride/padding out of range (R=%d S=%d stride=%d padX=%d padY=%d)", d->R, d->S, d->stride, d->padX, d->padY);
+            if (d->fmt != NB200_NCHW && d->fmt != NB200_NHWC)
+                return fail(NB200_E_INVALID, "unknown data format %d", d->fmt);
+            if (d->math < NB200_MATH_TF32 || d->math > NB200_MATH_FP32)
+                return fail(NB200_E_INVALID, "unknown math mode %d", d->math);
+            const long long lim = 0xFFFFFFFFll; // Neuro::Shape::Length is uint32_t (Shape.h)
+            if ((long long)d->N * d->C * d->H * d->W > lim || (long long)d->N * d->K * d->Ho * d->Wo > lim || (long long)d->K * d->C * d->R * d->S > lim)
+                return fail(NB200_E_INVALID, "tensor exceeds 2^32-1 elements");
+            if (op == NB200_OP_FORWARD && d->N > 0 && d->K > 0)
+            {
+                // Tensor::Conv2D asserts the output shape (Tensor.cpp:1759)
+                if (d->H + 2 * d->padY < d->R || d->W + 2 * d->padX < d->S)
+                    return fail(NB200_E_INVALID, "filter larger than padded input");
+                const int ho = (d->H + 2 * d->padY - d->R) / d->stride + 1, wo = (d->W + 2 * d->padX - d->S) / d->stride + 1;
+                if (ho != d->Ho || wo != d->Wo)
+                    return fail(NB200_E_INVALID, "output extent %dx%d does not match GetConvOutputShape %dx%d", d->Ho, d->Wo, ho, wo);
+            }
+            return NB200_OK;
+        }
+
+        bool empty_out(const nb200_conv_desc& d, int op)
+        {
+            switch (op)
+            {
+            case NB200_OP_FORWARD: return (long long)d.N * d.K * d.Ho * d.Wo == 0;
+            case NB200_OP_INPUT_GRADIENT: return (long long)d.N * d.C * d.H * d.W == 0;
+            default: return (long long)d.K * d.C * d.R * d.S == 0;
+            }
+        }
+
+        enum Family { kDirect, kTc };
+
+        Family pick(int op, const nb200_conv_desc& d)
+        {
+            if (d.math == NB200_MATH_FP32)
+                return kDirect;
+            switch (op)
+            {
+            case NB200_OP_FORWARD: return tc_forward_supported(d) ? kTc : kDirect;
+            case NB200_OP_INPUT_GRADIENT: return tc_input_gradient_supported(d) ? kTc : kDirect;
+            default: return tc_kernels_gradient_supported(d) ? kTc : kDirect;
+            }
+        }
+    }
+}
+
+using namespace nb200;
+
+extern "C"
+{
+    const char* nb200_version(void) { return "neuro_b200 0.1 (sm_100a)"; }
+    const char* nb200_last_error(void) { return g_err; }
+
+    int nb200_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes)
+    {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess)
+        {
+            cudaGetLastError();
+            return fail(NB200_E_NO_DEVICE, "no usable CUDA device: %s", cudaGetErrorString(e));
+        }
+        cudaDeviceProp p;
+        NB200_CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+        if (sm_count) *sm_count = p.multiProcessorCount;
+        if (cc_major) *cc_major = p.major;
+        if (cc_minor) *cc_minor = p.minor;
+        if (hbm_bytes) *hbm_bytes = p.totalGlobalMem;
+        return p.major == 10 ? NB200_OK : fail(NB200_E_NO_DEVICE, "compute capability %d.%d is not sm_100", p.major, p.minor);
+    }
+
+    int32_t nb200_padding(int32_t mode, int32_t filter)
+    {
+        return mode == 0 ? 0 : mode == 1 ? filter / 2 : filter - 1;
+    }
+
+    int32_t nb200_conv_out_size(int32_t in, int32_t filter, int32_t stride, int32_t pad)
+    {
+        return (in + 2 * pad - filter) / stride + 1;
+    }
+
+    int32_t nb200_conv_transpose_out_size(int32_t in, int32_t filter, int32_t stride, int32_t pad)
+    {
+        return (in - 1) * stride + filter - 2 * pad;
+    }
+
+    size_t nb200_conv2d_workspace_bytes(int32_t op, const nb200_conv_desc* d)
+    {
+        if (!d || validate(d, -1) != NB200_OK)
+            return 0;
+        if (pick(op, *d) == kTc)
+            return tc_workspace_bytes(op, *d);
+        return op == NB200_OP_KERNELS_GRADIENT ? direct_kernels_gradient_workspace(*d) : 0;
+    }
+
+    const char* nb200_conv2d_kernel_name(int32_t op, const nb200_conv_desc* d)
+    {
+        if (!d || validate(d, -1) != NB200_OK)
+            return "invalid";
+        const bool tc = pick(op, *d) == kTc;
+        switch (op)
+        {
+        case NB200_OP_FORWARD: return tc ? "tcgen05_fprop" : "direct_fprop";
+        case NB200_OP_INPUT_GRADIENT: return tc ? "tcgen05_dgrad" : "direct_dgrad";
+        case NB200_OP_KERNELS_GRADIENT: return tc ? "tcgen05_wgrad" : "direct_wgrad";
+        default: return "invalid";
+        }
+    }
+
+    int nb200_conv2d_forward(const nb200_conv_desc* d, const float* x, const float* w, const float* bias, int32_t act, float alpha,
+                             float* y, void* workspace, size_t workspace_bytes, void* stream)
+    {
+        int rc = validate(d, NB200_OP_FORWARD);
+        if (rc) return rc;
+        if (act < NB200_ACT_IDENTITY || act > NB200_ACT_LEAKY_RELU)
+            return fail(NB200_E_INVALID, "activation %d is not a convolution epilogue", act);
+        if (empty_out(*d, NB200_OP_FORWARD))
+            return NB200_OK;
+        if (!y || ((!x || !w) && d->C > 0))
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        if ((rc = require_device())) return rc;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (pick(NB200_OP_FORWARD, *d) == kTc)
+            return tc_forward(*d, x, w, bias, act, alpha, y, workspace, workspace_bytes, st);
+        return direct_forward(*d, x, w, bias, act, alpha, y, st);
+    }
+
+    int nb200_conv2d_input_gradient(const nb200_conv_desc* d, const float* dy, const float* w, float* dx, void* workspace,
+                                    size_t workspace_bytes, void* stream)
+    {
+        int rc = validate(d, NB200_OP_INPUT_GRADIENT);
+        if (rc) return rc;
+        if (empty_out(*d, NB200_OP_INPUT_GRADIENT))
+            return NB200_OK;
+        if (!dx || ((!dy || !w) && (long long)d->K * d->Ho * d->Wo > 0))
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        if ((rc = require_device())) return rc;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (pick(NB200_OP_INPUT_GRADIENT, *d) == kTc)
+            return tc_input_gradient(*d, dy, w, dx, workspace, workspace_bytes, st);
+        return direct_input_gradient(*d, dy, w, dx, st);
+    }
+
+    int nb200_conv2d_kernels_gradient(const nb200_conv_desc* d, const float* x, const float* dy, float* dw, float* db,
+                                      void* workspace, size_t workspace_bytes, void* stream)
+    {
+        int rc = validate(d, NB200_OP_KERNELS_GRADIENT);
+        if (rc) return rc;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (db && d->K > 0)
+        {
+            if ((rc = nb200_conv2d_bias_gradient(d, dy, db, stream))) return rc;
+        }
+        if (empty_out(*d, NB200_OP_KERNELS_GRADIENT))
+            return NB200_OK;
+        if (!dw || ((!x || !dy) && (long long)d->N * d->Ho * d->Wo > 0))
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        if ((rc = require_device())) return rc;
+        if (pick(NB200_OP_KERNELS_GRADIENT, *d) == kTc)
+            return tc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
+        return direct_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
+    }
+
+    int nb200_conv2d_bias_gradient(const nb200_conv_desc* d, const float* dy, float* db, void* stream)
+    {
+        if (!d || d->N < 0 || d->K < 0 || d->Ho < 0 || d->Wo < 0 || (d->fmt != NB200_NCHW && d->fmt != NB200_NHWC))
+            return fail(NB200_E_INVALID, "bad descriptor");
+        if (d->K == 0)
+            return NB200_OK;
+        if (!db || (!dy && (long long)d->N * d->Ho * d->Wo > 0))
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        int rc = require_device();
+        if (rc) return rc;
+        return bias_gradient(*d, dy, db, (cudaStream_t)stream);
+    }
+
+    int nb200_adam_step(float* param, const float* grad, float* m, float* v, size_t count, float grad_scale, float lr, float beta1,
+                        float beta2, float epsilon, void* stream)
+    {
+        if (count == 0)
+            return NB200_OK;
+        if (!param || !grad || !m || !v)
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        int rc = require_device();
+        if (rc) return rc;
+        return adam_step(param, grad, m, v, count, grad_scale, lr, beta1, beta2, epsilon, (cudaStream_t)stream);
+    }
+
+    int nb200_sgd_step(float* param, const float* grad, size_t count, float grad_scale, float lr, void* stream)
+    {
+        if (count == 0)
+            return NB200_OK;
+        if (!param || !grad)
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        int rc = require_device();
+        if (rc) return rc;
+        return sgd_step(param, grad, count, grad_scale, lr, (cudaStream_t)stream);
+    }
+
+    // ---- host-buffer variants ----
+
+    namespace
+    {
+        struct DevBuf
+        {
+            void* p = nullptr;
+            cudaStream_t st;
+            explicit DevBuf(cudaStream_t s) : st(s) {}
+            ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+            cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 4, st); }
+            float* f() const { return (float*)p; }
+        };
+
+        inline size_t nx(const nb200_conv_desc& d) { return (size_t)d.N * d.C * d.H * d.W * sizeof(float); }
+        inline size_t ny(const nb200_conv_desc& d) { return (size_t)d.N * d.K * d.Ho * d.Wo * sizeof(float); }
+        inline size_t nw(const nb200_conv_desc& d) { return (size_t)d.K * d.C * d.R * d.S * sizeof(float); }
+    }
+
+    int nb200_conv2d_forward_host(const nb200_conv_desc* d, const float* x, const float* w, const float* bias, int32_t act,
+                                  float alpha, float* y, void* stream)
+    {
+        int rc = validate(d, NB200_OP_FORWARD);
+        if (rc) return rc;
+        if (empty_out(*d, NB200_OP_FORWARD)) return NB200_OK;
+        if ((rc = require_device())) return rc;
+        cudaStream_t st = (cudaStream_t)stream;
+        DevBuf dx_(st), dw_(st), db_(st), dy_(st), ws(st);
+        const size_t wsBytes = nb200_conv2d_workspace_bytes(NB200_OP_FORWARD, d);
+        NB200_CUDA_TRY(dx_.alloc(nx(*d))); NB200_CUDA_TRY(dw_.alloc(nw(*d))); NB200_CUDA_TRY(dy_.alloc(ny(*d)));
+        NB200_CUDA_TRY(ws.alloc(wsBytes));
+        NB200_CUDA_TRY(cudaMemcpyAsync(dx_.p, x, nx(*d), cudaMemcpyHostToDevice, st));
+        NB200_CUDA_TRY(cudaMemcpyAsync(dw_.p, w, nw(*d), cudaMemcpyHostToDevice, st));
+        if (bias)
+        {
+            NB200_CUDA_TRY(db_.alloc(d->K * sizeof(float)));
+            NB200_CUDA_TRY(cudaMemcpyAsync(db_.p, bias, d->K * sizeof(float), cudaMemcpyHostToDevice, st));
+        }
+        if ((rc = nb200_conv2d_forward(d, dx_.f(), dw_.f(), bias ? db_.f() : nullptr, act, alpha, dy_.f(), ws.p, wsBytes, stream))) return rc;
+        NB200_CUDA_TRY(cudaMemcpyAsync(y, dy_.p, ny(*d), cudaMemcpyDeviceToHost, st));
+        NB200_CUDA_TRY(cudaStreamSynchronize(st));
+        return NB200_OK;
+    }
+
+    int nb200_conv2d_input_gradient_host(const nb200_conv_desc* d, const float* dy, const float* w, float* dx, void* stream)
+    {
+        int rc = validate(d, NB200_OP_INPUT_GRADIENT);
+        if (rc) return rc;
+        if (empty_out(*d, NB200_OP_INPUT_GRADIENT)) return NB200_OK;
+        if ((rc = require_device())) return rc;
+        cudaStream_t st = (cudaStream_t)stream;
+        DevBuf dx_(st), dw_(st), dy_(st), ws(st);
+        const size_t wsBytes = nb200_conv2d_workspace_bytes(NB200_OP_INPUT_GRADIENT, d);
+        NB200_CUDA_TRY(dx_.alloc(nx(*d))); NB200_CUDA_TRY(dw_.alloc(nw(*d))); NB200_CUDA_TRY(dy_.alloc(ny(*d)));
+        NB200_CUDA_TRY(ws.alloc(wsBytes));
+        NB200_CUDA_TRY(cudaMemcpyAsync(dy_.p, dy, ny(*d), cudaMemcpyHostToDevice, st));
+        NB200_CUDA_TRY(cudaMemcpyAsync(dw_.p, w, nw(*d), cudaMemcpyHostToDevice, st));
+        if ((rc = nb200_conv2d_input_gradient(d, dy_.f(), dw_.f(), dx_.f(), ws.p, wsBytes, stream))) return rc;
+        NB200_CUDA_TRY(cudaMemcpyAsync(dx, dx_.p, nx(*d), cudaMemcpyDeviceToHost, st));
+        NB200_CUDA_TRY(cudaStreamSynchronize(st));
+        return NB200_OK;
+    }
+
+    int nb200_conv2d_kernels_gradient_host(const nb200_conv_desc* d, const float* x, const float* dy, float* dw, float* db, void* stream)
+    {
+        int rc = validate(d, NB200_OP_KERNELS_GRADIENT);
+        if (rc) return rc;
+        if ((rc = require_device())) return rc;
+        cudaStream_t st = (cudaStream_t)stream;
+        DevBuf dx_(st), dw_(st), db_(st), dy_(st), ws(st);
+        const size_t wsBytes = nb200_conv2d_workspace_bytes(NB200_OP_KERNELS_GRADIENT, d);
+        NB200_CUDA_TRY(dx_.alloc(nx(*d))); NB200_CUDA_TRY(dw_.alloc(nw(*d))); NB200_CUDA_TRY(dy_.alloc(ny(*d)));
+        NB200_CUDA_TRY(ws.alloc(wsBytes));
+        if (db) NB200_CUDA_TRY(db_.alloc(d->K * sizeof(float)));
+        NB200_CUDA_TRY(cudaMemcpyAsync(dx_.p, x, nx(*d), cudaMemcpyHostToDevice, st));
+        NB200_CUDA_TRY(cudaMemcpyAsync(dy_.p, dy, ny(*d), cudaMemcpyHostToDevice, st));
+        if ((rc = nb200_conv2d_kernels_gradient(d, dx_.f(), dy_.f(), dw_.f(), db ? db_.f() : nullptr, ws.p, wsBytes, stream))) return rc;
+        NB200_CUDA_TRY(cudaMemcpyAsync(dw, dw_.p, nw(*d), cudaMemcpyDeviceToHost, st));
+        if (db) NB200_CUDA_TRY(cudaMemcpyAsync(db, db_.p, d->K * sizeof(float), cudaMemcpyDeviceToHost, st));
+        NB200_CUDA_TRY(cudaStreamSynchronize(st));
+        return NB200_OK;
+    }
+}

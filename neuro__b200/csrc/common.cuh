@@ -1,0 +1,88 @@
+// Shared device/host helpers for the Conv2D kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/neuro_b200.h"
+
+namespace nb200
+{
+    // Thread-local last-error slot behind nb200_last_error().
+    void set_error(const char* fmt, ...);
+    int fail(int code, const char* fmt, ...);
+
+#define NB200_CUDA_TRY(expr)                                                                      \
+    do                                                                                            \
+    {                                                                                             \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return nb200::fail(NB200_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+    // Element strides of an activation tensor in either data format, so one kernel body serves
+    // NCHW and NHWC (Neuro::Shape semantics, Neuro/src/Tensors/Shape.cpp:11-22).
+    struct ActStrides
+    {
+        long long n, c, h, w;
+    };
+
+    __host__ __device__ inline ActStrides act_strides(int fmt, int C, int H, int W)
+    {
+        ActStrides s;
+        if (fmt == NB200_NCHW)
+        {
+            s.w = 1; s.h = W; s.c = (long long)H * W; s.n = (long long)C * H * W;
+        }
+        else
+        {
+            s.c = 1; s.w = C; s.h = (long long)W * C; s.n = (long long)H * W * C;
+        }
+        return s;
+    }
+
+    // Activations as the reference evaluates them (Neuro/src/Tensors/TensorOpCpu.cpp:807-864).
+    __device__ __forceinline__ float apply_activation(int act, float alpha, float v)
+    {
+        switch (act)
+        {
+        case NB200_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        case NB200_ACT_RELU: return v > 0.f ? v : 0.f;
+        case NB200_ACT_TANH: return 2.f / (1.f + expf(-2.f * v)) - 1.f;
+        case NB200_ACT_ELU: return v >= 0.f ? v : alpha * (expf(v) - 1.f);
+        case NB200_ACT_LEAKY_RELU: return v >= 0.f ? v : alpha * v;
+        default: return v;
+        }
+    }
+
+    inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+    // ---- kernel families (each returns an NB200_* status) ----
+
+    // CUDA-core fp32 kernels: every shape, both formats, any stride/pad. conv_direct.cu
+    int direct_forward(const nb200_conv_desc& d, const float* x, const float* w, const float* bias, int act, float alpha,
+                       float* y, cudaStream_t st);
+    int direct_input_gradient(const nb200_conv_desc& d, const float* dy, const float* w, float* dx, cudaStream_t st);
+    int direct_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes,
+                                cudaStream_t st);
+    size_t direct_kernels_gradient_workspace(const nb200_conv_desc& d);
+
+    // tcgen05/TMA implicit-GEMM kernels (NCHW). conv_tc.cu
+    bool tc_forward_supported(const nb200_conv_desc& d);
+    bool tc_input_gradient_supported(const nb200_conv_desc& d);
+    bool tc_kernels_gradient_supported(const nb200_conv_desc& d);
+    size_t tc_workspace_bytes(int op, const nb200_conv_desc& d);
+    int tc_forward(const nb200_conv_desc& d, const float* x, const float* w, const float* bias, int act, float alpha, float* y,
+                   void* ws, size_t wsBytes, cudaStream_t st);
+    int tc_input_gradient(const nb200_conv_desc& d, const float* dy, const float* w, float* dx, void* ws, size_t wsBytes,
+                          cudaStream_t st);
+    int tc_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes,
+                            cudaStream_t st);
+
+    // elementwise.cu
+    int bias_gradient(const nb200_conv_desc& d, const float* dy, float* db, cudaStream_t st);
+    int adam_step(float* p, const float* g, float* m, float* v, size_t n, float gs, float lr, float b1, float b2, float eps,
+                  cudaStream_t st);
+    int sgd_step(float* p, const float* g, size_t n, float gs, float lr, cudaStream_t st);
+}

@@ -1,0 +1,83 @@
+"""ctypes binding of the C ABI in include/neuro_b200.h (libneuro_b200.so, built in-tree by build.py).
+
+There is no fallback: if the shared library is missing, or a call fails, this raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libneuro_b200.so")
+
+NCHW, NHWC = 0, 1
+ACT_IDENTITY, ACT_SIGMOID, ACT_RELU, ACT_TANH, ACT_ELU, ACT_LEAKY_RELU = 0, 1, 2, 3, 4, 5
+MATH_TF32, MATH_3XTF32, MATH_FP32 = 0, 1, 2
+OP_FORWARD, OP_INPUT_GRADIENT, OP_KERNELS_GRADIENT = 0, 1, 2
+
+# every symbol include/neuro_b200.h declares (tests check the .so exports exactly these)
+EXPORTS = [
+    "nb200_version", "nb200_last_error", "nb200_device_info", "nb200_padding", "nb200_conv_out_size",
+    "nb200_conv_transpose_out_size", "nb200_conv2d_workspace_bytes", "nb200_conv2d_kernel_name",
+    "nb200_conv2d_forward", "nb200_conv2d_input_gradient", "nb200_conv2d_kernels_gradient",
+    "nb200_conv2d_bias_gradient", "nb200_adam_step", "nb200_sgd_step", "nb200_conv2d_forward_host",
+    "nb200_conv2d_input_gradient_host", "nb200_conv2d_kernels_gradient_host",
+]
+
+
+class ConvDesc(ctypes.Structure):
+    """struct nb200_conv_desc"""
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("N", "C", "H", "W", "K", "R", "S", "Ho", "Wo", "stride", "padX", "padY", "fmt", "math")]
+
+    def flops(self):
+        """2*N*K*Ho*Wo*C*R*S -- the dense FLOP convention shared by fwd, dgrad and wgrad."""
+        return 2.0 * self.N * self.K * self.Ho * self.Wo * self.C * self.R * self.S
+
+    def bytes(self):
+        """4*(|x|+|w|+|y|): each tensor touched once."""
+        return 4.0 * (self.N * self.C * self.H * self.W + self.K * self.C * self.R * self.S
+                      + self.N * self.K * self.Ho * self.Wo)
+
+
+class NeuroB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise NeuroB200Error(
+            "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)" % SO_PATH)
+    L = ctypes.CDLL(SO_PATH)
+    c_p, c_f, c_i, c_sz = ctypes.c_void_p, ctypes.c_float, ctypes.c_int32, ctypes.c_size_t
+    dp = ctypes.POINTER(ConvDesc)
+    L.nb200_version.restype = ctypes.c_char_p
+    L.nb200_last_error.restype = ctypes.c_char_p
+    L.nb200_device_info.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                    ctypes.POINTER(ctypes.c_int), ctypes.POINTER(c_sz)]
+    for f in (L.nb200_padding,):
+        f.argtypes = [c_i, c_i]; f.restype = c_i
+    for f in (L.nb200_conv_out_size, L.nb200_conv_transpose_out_size):
+        f.argtypes = [c_i, c_i, c_i, c_i]; f.restype = c_i
+    L.nb200_conv2d_workspace_bytes.argtypes = [c_i, dp]; L.nb200_conv2d_workspace_bytes.restype = c_sz
+    L.nb200_conv2d_kernel_name.argtypes = [c_i, dp]; L.nb200_conv2d_kernel_name.restype = ctypes.c_char_p
+    L.nb200_conv2d_forward.argtypes = [dp, c_p, c_p, c_p, c_i, c_f, c_p, c_p, c_sz, c_p]
+    L.nb200_conv2d_input_gradient.argtypes = [dp, c_p, c_p, c_p, c_p, c_sz, c_p]
+    L.nb200_conv2d_kernels_gradient.argtypes = [dp, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]
+    L.nb200_conv2d_bias_gradient.argtypes = [dp, c_p, c_p, c_p]
+    L.nb200_adam_step.argtypes = [c_p, c_p, c_p, c_p, c_sz, c_f, c_f, c_f, c_f, c_f, c_p]
+    L.nb200_sgd_step.argtypes = [c_p, c_p, c_sz, c_f, c_f, c_p]
+    L.nb200_conv2d_forward_host.argtypes = [dp, c_p, c_p, c_p, c_i, c_f, c_p, c_p]
+    L.nb200_conv2d_input_gradient_host.argtypes = [dp, c_p, c_p, c_p, c_p]
+    L.nb200_conv2d_kernels_gradient_host.argtypes = [dp, c_p, c_p, c_p, c_p, c_p]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise NeuroB200Error("nb200 call failed (%d): %s" % (rc, load().nb200_last_error().decode()))

@@ -1,0 +1,140 @@
+"""TensorOpB200 -- Python mirror of the convolution slice of Neuro::TensorOpCpu.
+
+Method names, argument order and meaning follow the reference virtuals
+(Neuro/include/Tensors/TensorOpCpu.h:46-50) and the Tensor-level wrappers that call them
+(Neuro/src/Tensors/Tensor.cpp:1757-1830), so parity tests read like the reference's own
+(Neuro.Tests/src/TensorOpGpuTests.cpp:1196-1322). Tensors are torch CUDA float32 tensors used purely as
+device memory: NCHW tensors have shape (N,C,H,W), NHWC (N,H,W,C), kernels (K,C,R,S). Outputs are pre-sized by
+the caller and overwritten, as in the reference. All compute goes through the C ABI; there is no
+torch/CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from . import lib
+from .lib import ConvDesc, NCHW, NHWC, check
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "device-resident contiguous fp32 expected"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _act_extent(fmt, t):
+    if fmt == NCHW:
+        n, c, h, w = t.shape
+    else:
+        n, h, w, c = t.shape
+    return n, c, h, w
+
+
+def get_padding(mode, kernel_size):
+    """Tensor::GetPadding (Tensor.cpp:1966-1985). mode: 'valid' | 'same' | 'full'."""
+    return lib.load().nb200_padding({"valid": 0, "same": 1, "full": 2}[mode], kernel_size)
+
+
+def get_conv_output_shape(in_shape, kernels_num, kernel_w, kernel_h, stride, padding_x, padding_y, fmt=NCHW):
+    """Tensor::GetConvOutputShape (Tensor.cpp:2010-2029); shapes are torch-order tuples."""
+    L = lib.load()
+    n, c, h, w = in_shape if fmt == NCHW else (in_shape[0], in_shape[3], in_shape[1], in_shape[2])
+    ho = L.nb200_conv_out_size(h, kernel_h, stride, padding_y)
+    wo = L.nb200_conv_out_size(w, kernel_w, stride, padding_x)
+    return (n, kernels_num, ho, wo) if fmt == NCHW else (n, ho, wo, kernels_num)
+
+
+def get_conv_transpose_output_shape(in_shape, output_depth, kernel_w, kernel_h, stride, padding_x, padding_y, fmt=NCHW):
+    """Tensor::GetConvTransposeOutputShape (Tensor.cpp:2032-2051)."""
+    L = lib.load()
+    n, c, h, w = in_shape if fmt == NCHW else (in_shape[0], in_shape[3], in_shape[1], in_shape[2])
+    ho = L.nb200_conv_transpose_out_size(h, kernel_h, stride, padding_y)
+    wo = L.nb200_conv_transpose_out_size(w, kernel_w, stride, padding_x)
+    return (n, output_depth, ho, wo) if fmt == NCHW else (n, ho, wo, output_depth)
+
+
+class TensorOpB200:
+    """Stateless apart from a grow-only device workspace per instance (reference: pooled workspace,
+    TensorOpGpu.cpp:648)."""
+
+    def __init__(self, math=lib.MATH_TF32):
+        self.math = math
+        self._ws = None
+        self._L = lib.load()
+
+    # -- helpers
+    def _desc(self, fmt, x_like, k_like, y_like, stride, padding_x, padding_y):
+        N, C, H, W = _act_extent(fmt, x_like)
+        K, C2, R, S = k_like.shape
+        N2, K2, Ho, Wo = _act_extent(fmt, y_like)
+        assert C2 == C and K2 == K and N2 == N, "tensor shapes do not describe one convolution"
+        return ConvDesc(N, C, H, W, K, R, S, Ho, Wo, stride, padding_x, padding_y, fmt, self.math)
+
+    def _workspace(self, op, d):
+        need = self._L.nb200_conv2d_workspace_bytes(op, ctypes.byref(d))
+        if need == 0:
+            return None, 0
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+        return ctypes.c_void_p(self._ws.data_ptr()), need
+
+    def kernel_name(self, op, d):
+        return self._L.nb200_conv2d_kernel_name(op, ctypes.byref(d)).decode()
+
+    # -- the op interface (TensorOpCpu.h:46-50)
+    def Conv2D(self, input, kernels, stride, paddingX, paddingY, dataFormat, output):
+        d = self._desc(dataFormat, input, kernels, output, stride, paddingX, paddingY)
+        ws, n = self._workspace(lib.OP_FORWARD, d)
+        check(self._L.nb200_conv2d_forward(ctypes.byref(d), _ptr(input), _ptr(kernels), None, lib.ACT_IDENTITY, 0.0,
+                                           _ptr(output), ws, n, _stream()))
+
+    def Conv2DBiasActivation(self, input, kernels, stride, paddingX, paddingY, bias, activation, activationAlpha, output,
+                             dataFormat=NCHW):
+        assert paddingX == paddingY  # TensorOpCpu.cpp:1057
+        d = self._desc(dataFormat, input, kernels, output, stride, paddingX, paddingY)
+        ws, n = self._workspace(lib.OP_FORWARD, d)
+        check(self._L.nb200_conv2d_forward(ctypes.byref(d), _ptr(input), _ptr(kernels), _ptr(bias), activation,
+                                           activationAlpha, _ptr(output), ws, n, _stream()))
+
+    def Conv2DBiasGradient(self, gradient, biasGradient, dataFormat=NCHW):
+        N, K, Ho, Wo = _act_extent(dataFormat, gradient)
+        d = ConvDesc(N, 0, 0, 0, K, 1, 1, Ho, Wo, 1, 0, 0, dataFormat, self.math)
+        check(self._L.nb200_conv2d_bias_gradient(ctypes.byref(d), _ptr(gradient), _ptr(biasGradient), _stream()))
+
+    def Conv2DInputGradient(self, gradient, kernels, stride, paddingX, paddingY, dataFormat, inputGradient):
+        d = self._desc(dataFormat, inputGradient, kernels, gradient, stride, paddingX, paddingY)
+        ws, n = self._workspace(lib.OP_INPUT_GRADIENT, d)
+        check(self._L.nb200_conv2d_input_gradient(ctypes.byref(d), _ptr(gradient), _ptr(kernels), _ptr(inputGradient),
+                                                  ws, n, _stream()))
+
+    def Conv2DKernelsGradient(self, input, gradient, stride, paddingX, paddingY, dataFormat, kernelsGradient,
+                              biasGradient=None):
+        d = self._desc(dataFormat, input, kernelsGradient, gradient, stride, paddingX, paddingY)
+        ws, n = self._workspace(lib.OP_KERNELS_GRADIENT, d)
+        check(self._L.nb200_conv2d_kernels_gradient(ctypes.byref(d), _ptr(input), _ptr(gradient), _ptr(kernelsGradient),
+                                                    _ptr(biasGradient), ws, n, _stream()))
+
+    # -- Tensor-level identities for transposed convolution (Tensor.cpp:1806-1830)
+    def Conv2DTransposed(self, input, kernels, stride, padding, dataFormat, result):
+        """forward of Conv2DTranspose = input gradient of the matching conv; kernels are (inDepth, outDepth, F, F)."""
+        self.Conv2DInputGradient(input, kernels, stride, padding, padding, dataFormat, result)
+
+    def Conv2DTransposedInputsGradient(self, gradient, kernels, stride, padding, dataFormat, inputsGradient):
+        self.Conv2D(gradient, kernels, stride, padding, padding, dataFormat, inputsGradient)
+
+    def Conv2DTransposedKernelsGradient(self, input, gradient, stride, padding, dataFormat, kernelsGradient):
+        """note the swapped (gradient, input) order, as in Tensor.cpp:1827-1830"""
+        self.Conv2DKernelsGradient(gradient, input, stride, padding, padding, dataFormat, kernelsGradient)
+
+    # -- optimiser tail (TensorOpCpu.h:75-76)
+    def AdamStep(self, parameter, gradient, mGrad, vGrad, lr, beta1, beta2, epsilon, gradScale=1.0):
+        check(self._L.nb200_adam_step(_ptr(parameter), _ptr(gradient), _ptr(mGrad), _ptr(vGrad), parameter.numel(),
+                                      gradScale, lr, beta1, beta2, epsilon, _stream()))
+
+    def SgdStep(self, parameter, gradient, lr, gradScale=1.0):
+        check(self._L.nb200_sgd_step(_ptr(parameter), _ptr(gradient), parameter.numel(), gradScale, lr, _stream()))

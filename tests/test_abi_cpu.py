@@ -1,0 +1,82 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports what include/neuro_b200.h declares,
+validates descriptors, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import __graft_entry__ as graft
+from neuro__b200 import lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    graft.build()
+    return lib.load()
+
+
+def test_header_and_exports_agree(L):
+    header = open(os.path.join(ROOT, "include", "neuro_b200.h")).read()
+    declared = sorted(set(re.findall(r"NB200_API[^;(]*?\b(nb200_\w+)\s*\(", header)))
+    assert declared == sorted(lib.EXPORTS)
+    out = subprocess.check_output(["nm", "-D", "--defined-only", lib.SO_PATH]).decode()
+    exported = sorted(s for s in re.findall(r" T (\w+)", out) if s.startswith("nb200_"))
+    assert exported == declared
+    for name in declared:
+        assert getattr(L, name) is not None
+
+
+def test_shape_helpers_match_reference_formulas(L):
+    # Tensor::GetPadding (Tensor.cpp:1966-1985)
+    assert [L.nb200_padding(m, 3) for m in (0, 1, 2)] == [0, 1, 2]
+    assert [L.nb200_padding(m, 4) for m in (0, 1, 2)] == [0, 2, 3]
+    # Tensor::GetConvOutputShape (:2010-2029): floor division
+    assert L.nb200_conv_out_size(6, 3, 1, 0) == 4 and L.nb200_conv_out_size(6, 3, 1, 1) == 6
+    assert L.nb200_conv_out_size(259, 4, 2, 0) == 128 and L.nb200_conv_out_size(11, 4, 2, 0) == 4
+    # Tensor::GetConvTransposeOutputShape (:2032-2051): smaller than the conv input when the stride is ragged
+    assert L.nb200_conv_transpose_out_size(4, 4, 2, 1) == 8
+    assert L.nb200_conv_transpose_out_size(4, 4, 2, 0) == 10
+
+
+def test_descriptor_validation(L):
+    d = lib.ConvDesc(1, 2, 6, 6, 1, 3, 3, 4, 4, 1, 0, 0, lib.NCHW, lib.MATH_FP32)
+    bad = lib.ConvDesc(1, 2, 6, 6, 1, 3, 3, 5, 4, 1, 0, 0, lib.NCHW, lib.MATH_FP32)
+    p = ctypes.c_void_p(16)
+    assert L.nb200_conv2d_forward(ctypes.byref(bad), p, p, None, 0, 0.0, p, None, 0, None) == -1
+    assert b"GetConvOutputShape" in L.nb200_last_error()
+    bad2 = lib.ConvDesc(1, 2, 6, 6, 1, 3, 3, 4, 4, 0, 0, 0, lib.NCHW, lib.MATH_FP32)
+    assert L.nb200_conv2d_forward(ctypes.byref(bad2), p, p, None, 0, 0.0, p, None, 0, None) == -1
+    assert L.nb200_conv2d_forward(ctypes.byref(d), None, p, None, 0, 0.0, p, None, 0, None) == -1
+    assert L.nb200_conv2d_forward(ctypes.byref(d), p, p, None, 6, 0.0, p, None, 0, None) == -1  # _Softmax is no epilogue
+    # empty batch is a no-op, not an error (and never touches the device)
+    empty = lib.ConvDesc(0, 2, 6, 6, 1, 3, 3, 4, 4, 1, 0, 0, lib.NCHW, lib.MATH_FP32)
+    assert L.nb200_conv2d_forward(ctypes.byref(empty), None, None, None, 0, 0.0, None, None, 0, None) == 0
+
+
+def test_no_cpu_fallback(L):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    d = lib.ConvDesc(1, 2, 6, 6, 1, 3, 3, 4, 4, 1, 0, 0, lib.NCHW, lib.MATH_FP32)
+    p = ctypes.c_void_p(16)
+    assert L.nb200_conv2d_forward(ctypes.byref(d), p, p, None, 0, 0.0, p, None, 0, None) == -2
+    assert L.nb200_conv2d_input_gradient(ctypes.byref(d), p, p, p, None, 0, None) == -2
+    assert L.nb200_conv2d_kernels_gradient(ctypes.byref(d), p, p, p, None, None, 0, None) == -2
+    assert L.nb200_adam_step(p, p, p, p, 4, 1.0, 0.1, 0.9, 0.999, 1e-8, None) == -2
+    with pytest.raises(lib.NeuroB200Error):
+        lib.check(-2)
+
+
+def test_product_does_not_touch_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may use oracle/."""
+    pkg = os.path.join(ROOT, "neuro__b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower().replace("# oracle-free", ""), os.path.join(dirpath, f)
+    assert "oracle" not in open(os.path.join(ROOT, "include", "neuro_b200.h")).read().lower()
