@@ -1,0 +1,215 @@
+// Thin inline-PTX wrappers for the sm_100a features the implicit-GEMM kernels use:
+// mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld / fences), UMMA descriptors.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nb200
+{
+    namespace ptx
+    {
+        __device__ __forceinline__ uint32_t smem_u32(const void* p)
+        {
+            return (uint32_t)__cvta_generic_to_shared(p);
+        }
+
+        __device__ __forceinline__ uint32_t lane_id()
+        {
+            return threadIdx.x & 31;
+        }
+
+        // ---------------- mbarrier ----------------
+        __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+        {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+        }
+
+        __device__ __forceinline__ void fence_mbar_init()
+        {
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+
+        __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+        {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        }
+
+        __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+        {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+        }
+
+        __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity)
+        {
+            uint32_t done;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(smem_u32(bar)), "r"(parity)
+                : "memory");
+            return done;
+        }
+
+        // Bounded wait: a protocol bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.
+        __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+        {
+            if (mbar_try_wait(bar, parity))
+                return;
+            const long long t0 = clock64();
+            while (!mbar_try_wait(bar, parity))
+            {
+                if (clock64() - t0 > 4000000000ll) // ~2 s at 1.9 GHz
+                {
+                    printf("nb200: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
+                    __trap();
+                }
+            }
+        }
+
+        // ---------------- TMA ----------------
+        __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m)
+        {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
+        }
+
+        __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2)
+        {
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                : "memory");
+        }
+
+        __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3)
+        {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(smem_u32(dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                : "memory");
+        }
+
+        // ---------------- tcgen05: TMEM allocation ----------------
+        // Whole warp, converged. Writes the TMEM base address (lane 0, column base) to *slot in shared memory.
+        __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t columns)
+        {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(columns) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+
+        __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t columns)
+        {
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(columns) : "memory");
+        }
+
+        __device__ __forceinline__ void tc_fence_before_sync()
+        {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+
+        __device__ __forceinline__ void tc_fence_after_sync()
+        {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+
+        // ---------------- tcgen05: MMA ----------------
+        // D[tmem] (+)= A[smem] * B[smem], TF32 inputs, fp32 accumulate. One thread issues for the CTA.
+        __device__ __forceinline__ void mma_tf32_ss(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+        {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(tmemD), "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate)
+                : "memory");
+        }
+
+        // Same with the A operand read from tensor memory (128 lanes = M rows, 8 consecutive 32-bit columns = K).
+        __device__ __forceinline__ void mma_tf32_ts(uint32_t tmemD, uint32_t tmemA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+        {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                ::"r"(tmemD), "r"(tmemA), "l"(descB), "r"(idesc), "r"(accumulate)
+                : "memory");
+        }
+
+        // Arrive on an mbarrier once every MMA issued so far by this thread has completed
+        // (implies tcgen05.fence::before_thread_sync).
+        __device__ __forceinline__ void mma_commit(uint64_t* bar)
+        {
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+        }
+
+        // ---------------- tcgen05: TMEM -> registers ----------------
+        // 32 lanes x 32 consecutive columns: thread t of the warp receives columns [col, col+32) of TMEM lane (base lane + t).
+        __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32])
+        {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+        }
+
+        // registers -> TMEM, same shape: thread t writes columns [col, col+32) of TMEM lane (base lane + t).
+        __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32])
+        {
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                  "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                  "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                  "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+                : "memory");
+        }
+
+        __device__ __forceinline__ void tmem_st_wait()
+        {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+
+        __device__ __forceinline__ void tmem_ld_wait()
+        {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+
+        // ---------------- UMMA descriptors ----------------
+        // Shared-memory matrix descriptor (sm_100 "version 1"): start address, leading / stride byte offsets
+        // (all >> 4), swizzle mode in bits [61,64). 128-byte swizzle = 2.
+        __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smemAddr, uint32_t leadingBytes, uint32_t strideBytes)
+        {
+            uint64_t d = 0;
+            d |= (uint64_t)((smemAddr >> 4) & 0x3FFF);
+            d |= (uint64_t)((leadingBytes >> 4) & 0x3FFF) << 16;
+            d |= (uint64_t)((strideBytes >> 4) & 0x3FFF) << 32;
+            d |= (uint64_t)1 << 46; // descriptor version (Blackwell)
+            d |= (uint64_t)2 << 61; // SWIZZLE_128B
+            return d;
+        }
+
+        // Instruction descriptor for kind::tf32 with fp32 accumulation.
+        // aMnMajor/bMnMajor: 1 when the operand's M (resp. N) dimension is the contiguous one in shared memory.
+        __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int aMnMajor, int bMnMajor)
+        {
+            return (1u << 4)                    // D format: F32
+                   | (2u << 7)                  // A format: TF32
+                   | (2u << 10)                 // B format: TF32
+                   | ((uint32_t)aMnMajor << 15) // A major
+                   | ((uint32_t)bMnMajor << 16) // B major
+                   | ((uint32_t)(N >> 3) << 17)
+                   | ((uint32_t)(M >> 4) << 24);
+        }
+    }
+}
