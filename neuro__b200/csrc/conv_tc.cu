@@ -3,21 +3,24 @@
 // Forward (and the stride-1 input gradient, which is a forward conv of dy with flipped, transposed filters):
 //
 //   GEMM view      D[M = pixels][N = filters] = sum over (tap, channel) A[pixel][channel@tap] * B[filter][channel@tap]
-//   CTA tile       128 pixels (4 output rows x 32 output columns of one image) x BN filters
-//   A operand      the NCHW activation tile itself: for one filter tap the 32 pixels of a row are CONTIGUOUS in W and the
-//                  channels are strided, i.e. the tile is "MN-major". One 4-D TMA box {32 w, 32 c, 4 h, 1 n} per
-//                  (tap, channel block) lands in shared memory as [h][c][w] with the 128-byte swizzle, which is exactly
-//                  the canonical MN-major SWIZZLE_128B UMMA layout (row atoms at LBO = 4 KB, 8-channel groups at 1 KB).
-//                  No im2col buffer exists anywhere: the tap shift is the TMA box origin, and zero padding is the
-//                  TMA out-of-bounds fill (negative or past-the-end coordinates read as 0).
-//   B operand      filters repacked once per call to [tap][filter][channel] (channel contiguous, rounded to TF32):
-//                  K-major, one 3-D TMA box {32 c, BN k, 1 tap} per stage.
-//   accumulator    128 lanes x BN columns of TMEM, fp32. One thread issues tcgen05.mma (M128 x BN x K8, 4 per stage).
-//   epilogue       4 warps read TMEM with tcgen05.ld (warp q owns output row q of the tile: lane = output column, so each
-//                  store instruction writes one full 128-byte line of y), fused bias + activation.
-//   pipeline       warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue; smem ring of kStages
-//                  {A 16 KB, B BN*128 B} guarded by full/empty mbarriers; tcgen05.commit releases ring slots and
-//                  signals the epilogue. Two CTAs are co-resident per SM so one tile's epilogue overlaps the other's MMAs.
+//   CTA tile       128 pixels (4 output rows x 32 output columns of one image) x BN filters, full reduction.
+//   halo tile      For each block of 32 input channels ONE 4-D TMA box {WB w, 4+R-1 h, 32 c, 1 n} brings the input
+//                  halo tile into shared memory (zero padding = TMA out-of-bounds fill). It is read once from L2 and
+//                  serves all R*S filter taps -- no im2col buffer, and no per-tap re-fetch.
+//   A operand      lives in TENSOR MEMORY. TMA box origins (and UMMA shared-memory descriptors) are 16-byte granular,
+//                  so a one-pixel tap shift along W cannot be expressed by either; instead 4 "converter" warps read the
+//                  tap-shifted window out of the halo tile (thread = pixel, conflict-free LDS), round to TF32
+//                  (cvt.rna) and tcgen05.st it as a 128-lane x 32-column K-major A tile. The MMA then runs in
+//                  TS form (A from TMEM, B from shared memory), which also halves shared-memory operand traffic.
+//   B operand      filters repacked once per call to [tap][filter][channel] (channel contiguous, TF32-rounded):
+//                  K-major SWIZZLE_128B, one 3-D TMA box {32 c, BN k, 1 tap} per (channel block, tap).
+//   accumulator    128 lanes x BN columns of TMEM, fp32; one thread issues tcgen05.mma (M128 x BN x K8, 4 per tap).
+//   epilogue       the converter warps read TMEM with tcgen05.ld (warp q owns output row q of the tile, lane = output
+//                  column, so every store instruction writes one full 128-byte line of y), fused bias + activation.
+//   pipeline       warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = converters/epilogue. Rings guarded by
+//                  mbarriers: halo (TMA -> converters), B (TMA -> MMA), A-in-TMEM (converters -> MMA);
+//                  tcgen05.commit releases B and A slots and signals the epilogue. Two CTAs are co-resident per SM
+//                  so one tile's epilogue and prologue overlap the other's MMAs.
 #include <cuda.h>
 #include <mutex>
 
@@ -28,27 +31,21 @@ namespace nb200
 {
     namespace
     {
-        constexpr int kTileW = 32;   // pixels per swizzle atom row (128 B of fp32)
-        constexpr int kTileH = 4;    // rows per CTA tile -> M = 128
-        constexpr int kBlockC = 32;  // reduction channels per pipeline stage (4 MMAs of K = 8)
+        constexpr int kTileW = 32;   // output columns per tile (= lanes of a converter warp)
+        constexpr int kTileH = 4;    // output rows per tile (= converter warps) -> M = 128
+        constexpr int kBlockC = 32;  // reduction channels per step (4 MMAs of K = 8)
         constexpr int kThreads = 192;
-        constexpr uint32_t kABytes = kTileH * kBlockC * kTileW * 4; // 16 KB
-
-        template <int BN>
-        struct FpropCfg
-        {
-            static constexpr uint32_t bBytes = BN * kBlockC * 4;
-            static constexpr uint32_t stageBytes = kABytes + bBytes;
-            // two CTAs per SM: stay under ~110 KB each
-            static constexpr int stages = (BN <= 64) ? 4 : 3;
-            static constexpr uint32_t smemBytes = stages * stageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
-        };
+        constexpr int kAStages = 4;  // A tiles in TMEM (32 columns each)
+        constexpr int kSmemBudget = 112 * 1024; // per CTA, two CTAs per SM
 
         struct FpropParams
         {
             int Cblocks;      // ceil(C / 32)
             int R, S;
             int padX, padY;
+            int wOff;         // halo tile starts at ow0 - wOff (multiple of 4 so the TMA origin is 16-byte aligned)
+            int WB, HR;       // halo tile extent
+            int xStages, bStages;
             int Ho, Wo, K;    // output extent and filter count
             int tilesW, tilesH, tilesK;
             int act;
@@ -57,9 +54,9 @@ namespace nb200
         };
 
         // ---------------------------------------------------------------- filter repack
-        // out[tap][k][c] (c padded to Cp with zeros), TF32-rounded (round to nearest, ties away: cvt.rna).
-        // mode 0 (forward):           tap = r*S+s,                 k = filter, c = channel   <- w[k][c][r][s]
-        // mode 1 (input gradient):    tap = (R-1-r)*S + (S-1-s),   "k" = channel, "c" = filter <- w[f][ch][r][s]
+        // out[tap][row][col] (col padded to outCp with zeros), TF32-rounded (cvt.rna).
+        // mode 0 (forward):           tap = r*S+s,                 row = filter,  col = channel <- w[row][col][r][s]
+        // mode 1 (input gradient):    tap = (R-1-r)*S + (S-1-s),   row = channel, col = filter  <- w[col][row][r][s]
         __global__ void repack_filters_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int C, int R, int S,
                                               int outRows, int outCp, int mode)
         {
@@ -93,15 +90,24 @@ namespace nb200
         tc_fprop_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, FpropParams p,
                         const float* __restrict__ bias, float* __restrict__ y)
         {
-            using Cfg = FpropCfg<BN>;
-            constexpr int kStages = Cfg::stages;
+            constexpr uint32_t kBBytes = BN * kBlockC * 4;
+            constexpr uint32_t kTmemCols = BN + kAStages * kBlockC <= 128 ? 128 : 256;
+            static_assert(BN + kAStages * kBlockC <= 256, "TMEM budget: two CTAs per SM x 256 columns");
 
             extern __shared__ uint8_t smemRaw[];
             uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
-            uint8_t* ring = smem;
-            uint64_t* fullBar = (uint64_t*)(smem + kStages * Cfg::stageBytes);
-            uint64_t* emptyBar = fullBar + kStages;
-            uint64_t* accBar = emptyBar + kStages;
+            const uint32_t xBytes = (uint32_t)(kBlockC * p.HR * p.WB * 4);
+            const uint32_t xBytesPad = (xBytes + 1023) & ~1023u;
+            uint8_t* bRing = smem;                                   // 1 KB aligned (128B swizzle atoms)
+            uint8_t* xRing = smem + p.bStages * kBBytes;
+            uint64_t* bars = (uint64_t*)(xRing + p.xStages * xBytesPad);
+            uint64_t* bFull = bars;            // [bStages]
+            uint64_t* bEmpty = bFull + 8;      // [bStages]
+            uint64_t* xFull = bEmpty + 8;      // [xStages]
+            uint64_t* xEmpty = xFull + 4;      // [xStages]
+            uint64_t* aFull = xEmpty + 4;      // [kAStages]
+            uint64_t* aEmpty = aFull + kAStages;
+            uint64_t* accBar = aEmpty + kAStages;
             uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
 
             const int warp = threadIdx.x >> 5;
@@ -119,44 +125,43 @@ namespace nb200
             {
                 ptx::prefetch_tensormap(&mapX);
                 ptx::prefetch_tensormap(&mapW);
-                for (int s = 0; s < kStages; ++s)
-                {
-                    ptx::mbar_init(&fullBar[s], 1);
-                    ptx::mbar_init(&emptyBar[s], 1);
-                }
+                for (int s = 0; s < p.bStages; ++s) { ptx::mbar_init(&bFull[s], 1); ptx::mbar_init(&bEmpty[s], 1); }
+                for (int s = 0; s < p.xStages; ++s) { ptx::mbar_init(&xFull[s], 1); ptx::mbar_init(&xEmpty[s], kTileH); }
+                for (int s = 0; s < kAStages; ++s) { ptx::mbar_init(&aFull[s], kTileH); ptx::mbar_init(&aEmpty[s], 1); }
                 ptx::mbar_init(accBar, 1);
                 ptx::fence_mbar_init();
             }
             if (warp == 1)
-                ptx::tmem_alloc(tmemSlot, BN);
+                ptx::tmem_alloc(tmemSlot, kTmemCols);
             ptx::tc_fence_before_sync();
             __syncthreads();
             ptx::tc_fence_after_sync();
-            const uint32_t tmemBase = *tmemSlot;
+            const uint32_t tmemAcc = *tmemSlot;
+            const uint32_t tmemA = tmemAcc + BN;
 
             const int taps = p.R * p.S;
-            const int iters = taps * p.Cblocks;
 
             if (warp == 0)
             {
                 if (lane == 0)
                 {
-                    // ===== TMA producer =====
-                    int stage = 0;
-                    uint32_t phase = 0;
-                    for (int it = 0; it < iters; ++it)
+                    // ===== TMA producer: one halo tile per channel block, one filter tile per (channel block, tap) =====
+                    int xs = 0, bs = 0;
+                    uint32_t xph = 0, bph = 0;
+                    for (int cb = 0; cb < p.Cblocks; ++cb)
                     {
-                        const int tap = it % taps, cb = it / taps;
-                        const int r = tap / p.S, s = tap % p.S;
-                        ptx::mbar_wait(&emptyBar[stage], phase ^ 1);
-                        uint8_t* a = ring + stage * Cfg::stageBytes;
-                        uint8_t* b = a + kABytes;
-                        ptx::mbar_arrive_expect_tx(&fullBar[stage], Cfg::stageBytes);
-                        // x viewed as (W, C, H, N): box {32, 32, 4, 1} at the tap-shifted origin; OOB -> 0 (= zero padding)
-                        ptx::tma_load_4d(a, &mapX, &fullBar[stage], ow0 - p.padX + s, cb * kBlockC, oh0 - p.padY + r, n);
-                        // repacked filters (Cp, K, taps): box {32, BN, 1}
-                        ptx::tma_load_3d(b, &mapW, &fullBar[stage], cb * kBlockC, k0, tap);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        ptx::mbar_wait(&xEmpty[xs], xph ^ 1);
+                        ptx::mbar_arrive_expect_tx(&xFull[xs], xBytes);
+                        // x viewed as (W, H, C, N); origin 16-byte aligned in W; out-of-bounds elements read as 0 (= zero padding)
+                        ptx::tma_load_4d(xRing + xs * xBytesPad, &mapX, &xFull[xs], ow0 - p.wOff, oh0 - p.padY, cb * kBlockC, n);
+                        if (++xs == p.xStages) { xs = 0; xph ^= 1; }
+                        for (int tap = 0; tap < taps; ++tap)
+                        {
+                            ptx::mbar_wait(&bEmpty[bs], bph ^ 1);
+                            ptx::mbar_arrive_expect_tx(&bFull[bs], kBBytes);
+                            ptx::tma_load_3d(bRing + bs * kBBytes, &mapW, &bFull[bs], cb * kBlockC, k0, tap);
+                            if (++bs == p.bStages) { bs = 0; bph ^= 1; }
+                        }
                     }
                 }
             }
@@ -164,35 +169,74 @@ namespace nb200
             {
                 if (lane == 0)
                 {
-                    // ===== MMA issuer =====
-                    constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, /*A MN-major*/ 1, /*B K-major*/ 0);
-                    int stage = 0;
-                    uint32_t phase = 0;
+                    // ===== MMA issuer: D[128 x BN] += A[tmem 128 x 32] * B[smem BN x 32]^T per tap =====
+                    constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, /*A K-major (TMEM)*/ 0, /*B K-major*/ 0);
+                    int as = 0, bs = 0;
+                    uint32_t aph = 0, bph = 0;
+                    const int iters = taps * p.Cblocks;
                     for (int it = 0; it < iters; ++it)
                     {
-                        ptx::mbar_wait(&fullBar[stage], phase);
+                        ptx::mbar_wait(&bFull[bs], bph);
+                        ptx::mbar_wait(&aFull[as], aph);
                         ptx::tc_fence_after_sync();
-                        const uint32_t a = ptx::smem_u32(ring + stage * Cfg::stageBytes);
-                        const uint32_t b = a + kABytes;
+                        const uint32_t b = ptx::smem_u32(bRing + bs * kBBytes);
 #pragma unroll
                         for (int kk = 0; kk < kBlockC / 8; ++kk)
                         {
-                            // A: MN-major SW128. Row atoms (h) 4 KB apart (LBO); this K=8 slice is the kk-th 1 KB channel group.
-                            const uint64_t da = ptx::smem_desc_sw128(a + kk * 1024, /*LBO*/ kBlockC * 128, /*SBO*/ 1024);
-                            // B: K-major SW128. 8-filter groups 1 KB apart (SBO); this K=8 slice starts 32 B into the 128 B row.
+                            // B: K-major SW128: 8-filter groups 1 KB apart (SBO); this K=8 slice starts 32 B into the 128 B row
                             const uint64_t db = ptx::smem_desc_sw128(b + kk * 32, /*LBO*/ 16, /*SBO*/ 1024);
-                            ptx::mma_tf32_ss(tmemBase, da, db, idesc, (it | kk) != 0);
+                            ptx::mma_tf32_ts(tmemAcc, tmemA + as * kBlockC + kk * 8, db, idesc, (it | kk) != 0);
                         }
-                        ptx::mma_commit(&emptyBar[stage]); // slot reusable once these MMAs have read it
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        ptx::mma_commit(&aEmpty[as]); // both slots reusable once these MMAs have consumed them
+                        ptx::mma_commit(&bEmpty[bs]);
+                        if (++as == kAStages) { as = 0; aph ^= 1; }
+                        if (++bs == p.bStages) { bs = 0; bph ^= 1; }
                     }
                     ptx::mma_commit(accBar); // accumulator complete
                 }
             }
             else
             {
-                // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 = output row of the tile =====
+                // ===== converters (then epilogue): warps 2..5; TMEM lane quadrant q = warp % 4 = output row of the tile =====
                 const int q = warp & 3;
+                const uint32_t laneSel = (uint32_t)(q * 32) << 16;
+                const int chanStride = p.HR * p.WB; // floats between channels of the halo tile
+                int xs = 0, as = 0;
+                uint32_t xph = 0, aph = 0;
+                for (int cb = 0; cb < p.Cblocks; ++cb)
+                {
+                    ptx::mbar_wait(&xFull[xs], xph);
+                    const float* xt = (const float*)(xRing + xs * xBytesPad);
+                    for (int tap = 0; tap < taps; ++tap)
+                    {
+                        const int r = tap / p.S, s = tap - r * p.S;
+                        // pixel (q, lane) of the tile, tap (r, s): halo row q + r, halo column lane + s - padX + wOff
+                        const float* src = xt + (q + r) * p.WB + (lane + s - p.padX + p.wOff);
+                        uint32_t v[kBlockC];
+#pragma unroll
+                        for (int c = 0; c < kBlockC; ++c)
+                        {
+                            const float f = src[c * chanStride];
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v[c]) : "f"(f));
+                        }
+                        ptx::mbar_wait(&aEmpty[as], aph ^ 1);
+                        ptx::tc_fence_after_sync();
+                        ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kBlockC, v);
+                        ptx::tmem_st_wait();
+                        ptx::tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0)
+                        {
+                            ptx::mbar_arrive(&aFull[as]);
+                            if (tap == taps - 1)
+                                ptx::mbar_arrive(&xEmpty[xs]); // every lane's loads of this halo tile have landed in registers
+                        }
+                        if (++as == kAStages) { as = 0; aph ^= 1; }
+                    }
+                    if (++xs == p.xStages) { xs = 0; xph ^= 1; }
+                }
+
+                // ----- epilogue -----
                 const int oh = oh0 + q, ow = ow0 + lane;
                 ptx::mbar_wait(accBar, 0);
                 ptx::tc_fence_after_sync();
@@ -204,7 +248,7 @@ namespace nb200
                     if (k0 + c0 >= p.K)
                         break; // warp-uniform
                     uint32_t v[32];
-                    ptx::tmem_ld_32x32b_x32(tmemBase + ((uint32_t)(q * 32) << 16) + c0, v);
+                    ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + c0, v);
                     ptx::tmem_ld_wait();
                     if (pixelOk)
                     {
@@ -229,7 +273,7 @@ namespace nb200
             if (warp == 1)
             {
                 ptx::tc_fence_after_sync();
-                ptx::tmem_dealloc(tmemBase, BN);
+                ptx::tmem_dealloc(tmemAcc, kTmemCols);
             }
         }
 
@@ -251,15 +295,15 @@ namespace nb200
             return fn;
         }
 
-        int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* stridesBytes, const cuuint32_t* box)
+        int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* stridesBytes, const cuuint32_t* box,
+                     CUtensorMapSwizzle swizzle)
         {
             EncodeTiledFn fn = encode_fn();
             if (!fn)
                 return fail(NB200_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
             cuuint32_t es[5] = {1, 1, 1, 1, 1};
             CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, stridesBytes, box, es,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS)
                 return fail(NB200_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
             return NB200_OK;
@@ -278,10 +322,48 @@ namespace nb200
             int N, Cin, Hin, Win, Kout, Hout, Wout, R, S, padX, padY;
         };
 
+        struct Plan
+        {
+            int BN, wOff, WB, HR, xStages, bStages;
+            size_t smemBytes;
+            bool ok;
+        };
+
+        Plan make_plan(const FwdShape& f)
+        {
+            Plan pl{};
+            pl.BN = pick_bn(f.Kout);
+            pl.wOff = round_up(f.padX, 4);
+            const int right = f.S - 1 - f.padX > 0 ? f.S - 1 - f.padX : 0;
+            pl.WB = round_up(kTileW + pl.wOff + right, 4);
+            pl.HR = kTileH + f.R - 1;
+            const size_t xBytes = ((size_t)kBlockC * pl.HR * pl.WB * 4 + 1023) & ~(size_t)1023;
+            const size_t bBytes = (size_t)pl.BN * kBlockC * 4;
+            const size_t fixed = 1024 /*alignment slack*/ + 512 /*barriers*/;
+            pl.ok = false;
+            // prefer two halo stages; give the rest to the filter ring (at least 2, at most 8)
+            for (int xs = 2; xs >= 1 && !pl.ok; --xs)
+            {
+                const long long rest = (long long)kSmemBudget - (long long)fixed - (long long)xs * (long long)xBytes;
+                int bs = (int)(rest / (long long)bBytes);
+                if (bs > 8) bs = 8;
+                if (bs >= 2)
+                {
+                    pl.xStages = xs; pl.bStages = bs; pl.ok = true;
+                    pl.smemBytes = fixed + xs * xBytes + bs * bBytes;
+                }
+            }
+            return pl;
+        }
+
         bool shape_ok(const FwdShape& f)
         {
-            return f.Win % 4 == 0 && f.Win >= kTileW && f.Hin >= 1 && f.Cin >= 8 && f.Kout >= 8 && f.padX >= 0 && f.padY >= 0 &&
-                   f.R * f.S <= 64 && f.N >= 1;
+            if (!(f.Win % 4 == 0 && f.Win >= 4 && f.Hin >= 1 && f.Cin >= 8 && f.Kout >= 8 && f.padX >= 0 && f.padY >= 0 && f.N >= 1))
+                return false;
+            if (f.R * f.S > 64 || f.padX > 16 || f.S - 1 - f.padX > 16)
+                return false;
+            const Plan pl = make_plan(f);
+            return pl.ok && pl.WB <= 256 && pl.HR <= 256;
         }
 
         size_t repack_bytes(const FwdShape& f)
@@ -290,20 +372,19 @@ namespace nb200
         }
 
         template <int BN>
-        int launch_fprop(const FwdShape& f, const CUtensorMap& mapX, const CUtensorMap& mapW, const FpropParams& p, const float* bias,
-                         float* out, cudaStream_t st)
+        int launch_fprop(const FwdShape& f, const Plan& pl, const CUtensorMap& mapX, const CUtensorMap& mapW, const FpropParams& p,
+                         const float* bias, float* out, cudaStream_t st)
         {
-            using Cfg = FpropCfg<BN>;
             static bool attrSet = false;
             if (!attrSet)
             {
-                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smemBytes));
+                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
                 attrSet = true;
             }
             const long long tiles = (long long)p.tilesK * p.tilesW * p.tilesH * f.N;
             if (tiles > 0x7FFFFFFFll)
                 return fail(NB200_E_UNSUPPORTED, "too many tiles");
-            tc_fprop_kernel<BN><<<(unsigned)tiles, kThreads, Cfg::smemBytes, st>>>(mapX, mapW, p, bias, out);
+            tc_fprop_kernel<BN><<<(unsigned)tiles, kThreads, pl.smemBytes, st>>>(mapX, mapW, p, bias, out);
             NB200_CUDA_TRY(cudaGetLastError());
             return NB200_OK;
         }
@@ -316,6 +397,9 @@ namespace nb200
                 return fail(NB200_E_WORKSPACE, "tcgen05 conv needs %zu workspace bytes, got %zu", need, wsBytes);
             if (((uintptr_t)in & 15) || ((uintptr_t)ws & 15))
                 return fail(NB200_E_INVALID, "tensor base addresses must be 16-byte aligned for TMA");
+            const Plan pl = make_plan(f);
+            if (!pl.ok)
+                return fail(NB200_E_UNSUPPORTED, "no shared-memory plan for this filter size");
 
             const int Cp = round_up(f.Cin, kBlockC);
             float* wr = (float*)ws;
@@ -328,31 +412,31 @@ namespace nb200
 
             CUtensorMap mapX, mapW;
             {
-                // activation viewed as (W, C, H, N) so that one box lands in smem as [h][c][w]
-                cuuint64_t dims[4] = {(cuuint64_t)f.Win, (cuuint64_t)f.Cin, (cuuint64_t)f.Hin, (cuuint64_t)f.N};
-                cuuint64_t strides[3] = {(cuuint64_t)f.Hin * f.Win * 4, (cuuint64_t)f.Win * 4, (cuuint64_t)f.Cin * f.Hin * f.Win * 4};
-                cuuint32_t box[4] = {kTileW, kBlockC, kTileH, 1};
-                int rc = make_map(&mapX, in, 4, dims, strides, box);
+                // activation in its natural (W, H, C, N) order; the box is the halo tile of one 32-channel block
+                cuuint64_t dims[4] = {(cuuint64_t)f.Win, (cuuint64_t)f.Hin, (cuuint64_t)f.Cin, (cuuint64_t)f.N};
+                cuuint64_t strides[3] = {(cuuint64_t)f.Win * 4, (cuuint64_t)f.Hin * f.Win * 4, (cuuint64_t)f.Cin * f.Hin * f.Win * 4};
+                cuuint32_t box[4] = {(cuuint32_t)pl.WB, (cuuint32_t)pl.HR, kBlockC, 1};
+                int rc = make_map(&mapX, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
                 if (rc) return rc;
             }
-            const int BN = pick_bn(f.Kout);
             {
                 cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)f.Kout, (cuuint64_t)(f.R * f.S)};
                 cuuint64_t strides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * f.Kout * 4};
-                cuuint32_t box[3] = {kBlockC, (cuuint32_t)BN, 1};
-                int rc = make_map(&mapW, wr, 3, dims, strides, box);
+                cuuint32_t box[3] = {kBlockC, (cuuint32_t)pl.BN, 1};
+                int rc = make_map(&mapW, wr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
                 if (rc) return rc;
             }
 
             FpropParams p;
             p.Cblocks = Cp / kBlockC;
             p.R = f.R; p.S = f.S; p.padX = f.padX; p.padY = f.padY;
+            p.wOff = pl.wOff; p.WB = pl.WB; p.HR = pl.HR; p.xStages = pl.xStages; p.bStages = pl.bStages;
             p.Ho = f.Hout; p.Wo = f.Wout; p.K = f.Kout;
-            p.tilesW = ceil_div(f.Wout, kTileW); p.tilesH = ceil_div(f.Hout, kTileH); p.tilesK = ceil_div(f.Kout, BN);
+            p.tilesW = ceil_div(f.Wout, kTileW); p.tilesH = ceil_div(f.Hout, kTileH); p.tilesK = ceil_div(f.Kout, pl.BN);
             p.act = act; p.alpha = alpha;
             p.yStrideK = (long long)f.Hout * f.Wout;
             p.yStrideN = p.yStrideK * f.Kout;
-            return BN == 64 ? launch_fprop<64>(f, mapX, mapW, p, bias, out, st) : launch_fprop<128>(f, mapX, mapW, p, bias, out, st);
+            return pl.BN == 64 ? launch_fprop<64>(f, pl, mapX, mapW, p, bias, out, st) : launch_fprop<128>(f, pl, mapX, mapW, p, bias, out, st);
         }
 
         FwdShape fwd_shape(const nb200_conv_desc& d)
