@@ -277,6 +277,250 @@ namespace nb200
             }
         }
 
+
+        // ---------------------------------------------------------------- kernel-gradient kernel
+        //   dw[k][c][r][s] = sum over pixels  dy[n][k][oh][ow] * x[n][c][oh+r-pY][ow+s-pX]           (stride 1)
+        //   GEMM view      D_s[M = 128 channels][N = BN filters] += A_s[channel][pixel] * B[filter][pixel], reduction = pixels.
+        //   CTA            one (channel tile, filter tile, filter row r) and a contiguous slice of the (n, oh) output rows
+        //                  (split-K); it keeps the S accumulators of its filter row in TMEM (S x BN columns).
+        //   step           32 consecutive output pixels of one row. TMA brings dy[BN k][32 pix] (K-major SWIZZLE_128B,
+        //                  used as-is as the B operand of all S taps) and the matching x row segment [128 c][44 w].
+        //   A operand      thread = channel: reads its 40-float row segment with 10 conflict-free LDS.128 (channel pitch
+        //                  44 floats = odd multiple of 16 B), then builds the S tap-shifted 32-pixel windows from REGISTERS,
+        //                  rounds to TF32 and tcgen05.st's them as 128-lane x 32-column K-major A tiles in TMEM.
+        //   epilogue       coalesced partials ws[split][tap][k][c]; a second kernel adds the splits in fixed order and
+        //                  transposes to KCRS (deterministic, no atomics).
+        struct WgradParams
+        {
+            int R, S, padX, padY;
+            int wOff;            // x segment starts at ow0 - wOff
+            int N, Ho, Wo;       // dy extent
+            int C, K;
+            int segs;            // ceil(Wo / 32)
+            int tilesC, tilesK, splits;
+            int rowsPerSplit;    // output rows (n, oh) per split
+            int stages;
+        };
+
+        constexpr int kWgXW = 44;                               // x segment width in floats (pitch: 176 B)
+        constexpr uint32_t kWgXBytes = 128 * kWgXW * 4;         // 22528
+        constexpr int kWgAStages = 4;
+
+        template <int BN>
+        __global__ void __launch_bounds__(kThreads, 1)
+        tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDy, WgradParams p,
+                        float* __restrict__ ws)
+        {
+            constexpr uint32_t kBBytes = BN * 32 * 4;
+            constexpr uint32_t kStageBytes = ((kWgXBytes + kBBytes) + 1023) & ~1023u;
+            constexpr uint32_t kTmemCols = 512;
+
+            extern __shared__ uint8_t smemRaw[];
+            uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+            uint64_t* bars = (uint64_t*)(smem + p.stages * kStageBytes);
+            uint64_t* full = bars;                 // [stages] TMA landed
+            uint64_t* empty = full + 8;            // [stages] 4 converter warps + 1 MMA commit
+            uint64_t* aFull = empty + 8;           // [kWgAStages]
+            uint64_t* aEmpty = aFull + kWgAStages;
+            uint64_t* accBar = aEmpty + kWgAStages;
+            uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
+
+            const int warp = threadIdx.x >> 5;
+            const int lane = threadIdx.x & 31;
+
+            int t = blockIdx.x;
+            const int split = t % p.splits; t /= p.splits;
+            const int kt = t % p.tilesK; t /= p.tilesK;
+            const int ct = t % p.tilesC; t /= p.tilesC;
+            const int r = t;
+            const int c0 = ct * 128, k0 = kt * BN;
+            const int totalRows = p.N * p.Ho;
+            const int rowBegin = split * p.rowsPerSplit;
+            const int rowEnd = min(rowBegin + p.rowsPerSplit, totalRows);
+            const int steps = max(rowEnd - rowBegin, 0) * p.segs;
+
+            if (warp == 0 && lane == 0)
+            {
+                ptx::prefetch_tensormap(&mapX);
+                ptx::prefetch_tensormap(&mapDy);
+                for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], kTileH + 1); }
+                for (int s = 0; s < kWgAStages; ++s) { ptx::mbar_init(&aFull[s], kTileH); ptx::mbar_init(&aEmpty[s], 1); }
+                ptx::mbar_init(accBar, 1);
+                ptx::fence_mbar_init();
+            }
+            if (warp == 1)
+                ptx::tmem_alloc(tmemSlot, kTmemCols);
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            ptx::tc_fence_after_sync();
+            const uint32_t tmemAcc = *tmemSlot;
+            const uint32_t tmemA = tmemAcc + kTmemCols - kWgAStages * 32;
+
+            if (warp == 0)
+            {
+                if (lane == 0)
+                {
+                    // ===== TMA producer =====
+                    int st = 0;
+                    uint32_t ph = 0;
+                    for (int row = rowBegin; row < rowEnd; ++row)
+                    {
+                        const int n = row / p.Ho, oh = row - n * p.Ho;
+                        for (int seg = 0; seg < p.segs; ++seg)
+                        {
+                            const int ow0 = seg * 32;
+                            ptx::mbar_wait(&empty[st], ph ^ 1);
+                            uint8_t* xs = smem + st * kStageBytes;
+                            uint8_t* bs = xs + kWgXBytes;
+                            ptx::mbar_arrive_expect_tx(&full[st], kWgXBytes + kBBytes);
+                            // x viewed as (W, C, H, N): box {44, 128, 1, 1}; rows above/below the image read as 0
+                            ptx::tma_load_4d(xs, &mapX, &full[st], ow0 - p.wOff, c0, oh + r - p.padY, n);
+                            // dy viewed as (Wo, K, Ho, N): box {32, BN, 1, 1} -> [k][32 pixels], 128-byte rows, swizzled
+                            ptx::tma_load_4d(bs, &mapDy, &full[st], ow0, k0, oh, n);
+                            if (++st == p.stages) { st = 0; ph ^= 1; }
+                        }
+                    }
+                }
+            }
+            else if (warp == 1)
+            {
+                if (lane == 0)
+                {
+                    // ===== MMA issuer =====
+                    constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, 0, 0);
+                    int st = 0, as = 0;
+                    uint32_t ph = 0, aph = 0;
+                    for (int it = 0; it < steps; ++it)
+                    {
+                        ptx::mbar_wait(&full[st], ph);
+                        const uint32_t b = ptx::smem_u32(smem + st * kStageBytes + kWgXBytes);
+                        for (int s = 0; s < p.S; ++s)
+                        {
+                            ptx::mbar_wait(&aFull[as], aph);
+                            ptx::tc_fence_after_sync();
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                            {
+                                const uint64_t db = ptx::smem_desc_sw128(b + kk * 32, 16, 1024);
+                                ptx::mma_tf32_ts(tmemAcc + s * BN, tmemA + as * 32 + kk * 8, db, idesc, (it | kk) != 0);
+                            }
+                            ptx::mma_commit(&aEmpty[as]);
+                            if (++as == kWgAStages) { as = 0; aph ^= 1; }
+                        }
+                        ptx::mma_commit(&empty[st]); // dy tile consumed
+                        if (++st == p.stages) { st = 0; ph ^= 1; }
+                    }
+                    ptx::mma_commit(accBar);
+                }
+            }
+            else
+            {
+                // ===== converters: thread = channel (TMEM lane) =====
+                const int q = warp & 3;
+                const uint32_t laneSel = (uint32_t)(q * 32) << 16;
+                const int cl = q * 32 + lane;
+                int st = 0, as = 0;
+                uint32_t ph = 0, aph = 0;
+                for (int it = 0; it < steps; ++it)
+                {
+                    ptx::mbar_wait(&full[st], ph);
+                    const float4* rowp = (const float4*)(smem + st * kStageBytes + cl * (kWgXW * 4));
+                    float row[40];
+#pragma unroll
+                    for (int i = 0; i < 10; ++i)
+                    {
+                        const float4 f = rowp[i];
+                        row[4 * i + 0] = f.x; row[4 * i + 1] = f.y; row[4 * i + 2] = f.z; row[4 * i + 3] = f.w;
+                    }
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(&empty[st]); // x segment is in registers
+                    for (int s = 0; s < p.S; ++s)
+                    {
+                        const int off = s - p.padX + p.wOff; // 0..8
+                        uint32_t v[32];
+#pragma unroll
+                        for (int o = 0; o <= 8; ++o)
+                            if (off == o)
+                            {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v[j]) : "f"(row[j + o]));
+                            }
+                        ptx::mbar_wait(&aEmpty[as], aph ^ 1);
+                        ptx::tc_fence_after_sync();
+                        ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * 32, v);
+                        ptx::tmem_st_wait();
+                        ptx::tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0)
+                            ptx::mbar_arrive(&aFull[as]);
+                        if (++as == kWgAStages) { as = 0; aph ^= 1; }
+                    }
+                    if (++st == p.stages) { st = 0; ph ^= 1; }
+                }
+
+                // ----- epilogue: partial[split][tap][k][c], lanes = consecutive channels -> coalesced -----
+                ptx::mbar_wait(accBar, 0);
+                ptx::tc_fence_after_sync();
+                const int c = c0 + cl;
+                const int taps = p.R * p.S;
+                for (int s = 0; s < p.S; ++s)
+                {
+                    float* dst = ws + ((long long)(split * taps + r * p.S + s) * p.K) * p.C + c;
+#pragma unroll 1
+                    for (int j0 = 0; j0 < BN; j0 += 32)
+                    {
+                        if (k0 + j0 >= p.K)
+                            break;
+                        uint32_t v[32];
+                        if (steps > 0)
+                        {
+                            ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + s * BN + j0, v);
+                            ptx::tmem_ld_wait();
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = 0u;
+                        }
+                        if (c < p.C)
+                        {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (k0 + j0 + j < p.K)
+                                    dst[(long long)(k0 + j0 + j) * p.C] = __uint_as_float(v[j]);
+                        }
+                    }
+                }
+            }
+
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            if (warp == 1)
+            {
+                ptx::tc_fence_after_sync();
+                ptx::tmem_dealloc(tmemAcc, kTmemCols);
+            }
+        }
+
+        // dw[k][c][tap] = sum over splits of partial[split][tap][k][c]
+        __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int K, int C, int taps, int splits)
+        {
+            const long long total = (long long)K * C * taps;
+            const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= total)
+                return;
+            // i enumerates (tap, k, c) with c fastest, matching the partial layout -> coalesced reads
+            const int c = (int)(i % C);
+            const int k = (int)((i / C) % K);
+            const int tap = (int)(i / ((long long)C * K));
+            float acc = 0.f;
+            for (int s = 0; s < splits; ++s)
+                acc += ws[(long long)s * total + i];
+            dw[((long long)k * C + c) * taps + tap] = acc;
+        }
+
         // ---------------------------------------------------------------- host side
         typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -449,6 +693,61 @@ namespace nb200
         {
             return FwdShape{d.N, d.K, d.Ho, d.Wo, d.C, d.H, d.W, d.R, d.S, d.S - 1 - d.padX, d.R - 1 - d.padY};
         }
+
+        // ---------------------------------------------------------------- kernel gradient, host side
+        struct WgradPlan
+        {
+            int BN, wOff, tilesC, tilesK, splits, rowsPerSplit, stages;
+            size_t smemBytes, wsBytes;
+        };
+
+        bool wgrad_shape_ok(const nb200_conv_desc& d)
+        {
+            if (d.fmt != NB200_NCHW || d.math != NB200_MATH_TF32 || d.stride != 1)
+                return false;
+            if (d.W % 4 || d.Wo % 4 || d.C < 8 || d.K < 8 || d.N < 1 || d.Ho < 1 || d.Wo < 1 || d.H < 1)
+                return false;
+            if (d.S > 6 || d.R > 16 || d.padX > 4 || d.S - 1 - d.padX > 4)
+                return false;
+            return true;
+        }
+
+        WgradPlan wgrad_plan(const nb200_conv_desc& d)
+        {
+            WgradPlan pl{};
+            pl.BN = (d.S <= 3 && d.K > 64) ? 128 : 64;
+            pl.wOff = round_up(d.padX, 4);
+            pl.tilesC = ceil_div(d.C, 128);
+            pl.tilesK = ceil_div(d.K, pl.BN);
+            const int combos = pl.tilesC * pl.tilesK * d.R;
+            const int rows = d.N * d.Ho;
+            int splits = 148 / combos;
+            if (splits < 1) splits = 1;
+            if (splits > rows) splits = rows;
+            pl.rowsPerSplit = ceil_div(rows, splits);
+            pl.splits = ceil_div(rows, pl.rowsPerSplit);
+            const size_t stage = ((size_t)kWgXBytes + (size_t)pl.BN * 128 + 1023) & ~(size_t)1023;
+            pl.stages = (int)((200 * 1024) / stage);
+            if (pl.stages > 8) pl.stages = 8;
+            pl.smemBytes = 1024 + 512 + pl.stages * stage;
+            pl.wsBytes = (size_t)pl.splits * d.R * d.S * d.K * d.C * sizeof(float);
+            return pl;
+        }
+
+        template <int BN>
+        int launch_wgrad(const WgradPlan& pl, const CUtensorMap& mapX, const CUtensorMap& mapDy, const WgradParams& p, float* ws, cudaStream_t st)
+        {
+            static bool attrSet = false;
+            if (!attrSet)
+            {
+                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                attrSet = true;
+            }
+            const long long ctas = (long long)p.splits * p.tilesK * p.tilesC * p.R;
+            tc_wgrad_kernel<BN><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapX, mapDy, p, ws);
+            NB200_CUDA_TRY(cudaGetLastError());
+            return NB200_OK;
+        }
     }
 
     bool tc_forward_supported(const nb200_conv_desc& d)
@@ -466,7 +765,7 @@ namespace nb200
         return shape_ok(dgrad_shape(d));
     }
 
-    bool tc_kernels_gradient_supported(const nb200_conv_desc&) { return false; }
+    bool tc_kernels_gradient_supported(const nb200_conv_desc& d) { return wgrad_shape_ok(d); }
 
     size_t tc_workspace_bytes(int op, const nb200_conv_desc& d)
     {
@@ -474,7 +773,7 @@ namespace nb200
         {
         case NB200_OP_FORWARD: return repack_bytes(fwd_shape(d));
         case NB200_OP_INPUT_GRADIENT: return repack_bytes(dgrad_shape(d));
-        default: return 0;
+        default: return wgrad_plan(d).wsBytes;
         }
     }
 
@@ -489,8 +788,38 @@ namespace nb200
         return run_fwd_shaped(dgrad_shape(d), 1, d.K, d.C, dy, w, nullptr, NB200_ACT_IDENTITY, 0.f, dx, ws, wsBytes, st);
     }
 
-    int tc_kernels_gradient(const nb200_conv_desc&, const float*, const float*, float*, void*, size_t, cudaStream_t)
+    int tc_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st)
     {
-        return fail(NB200_E_UNSUPPORTED, "tcgen05 kernel gradient not available");
+        const WgradPlan pl = wgrad_plan(d);
+        if (wsBytes < pl.wsBytes || !ws)
+            return fail(NB200_E_WORKSPACE, "tcgen05 kernel gradient needs %zu workspace bytes, got %zu", pl.wsBytes, wsBytes);
+        if (((uintptr_t)x & 15) || ((uintptr_t)dy & 15))
+            return fail(NB200_E_INVALID, "tensor base addresses must be 16-byte aligned for TMA");
+        CUtensorMap mapX, mapDy;
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)d.W, (cuuint64_t)d.C, (cuuint64_t)d.H, (cuuint64_t)d.N};
+            cuuint64_t strides[3] = {(cuuint64_t)d.H * d.W * 4, (cuuint64_t)d.W * 4, (cuuint64_t)d.C * d.H * d.W * 4};
+            cuuint32_t box[4] = {kWgXW, 128, 1, 1};
+            int rc = make_map(&mapX, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc) return rc;
+        }
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)d.Wo, (cuuint64_t)d.K, (cuuint64_t)d.Ho, (cuuint64_t)d.N};
+            cuuint64_t strides[3] = {(cuuint64_t)d.Ho * d.Wo * 4, (cuuint64_t)d.Wo * 4, (cuuint64_t)d.K * d.Ho * d.Wo * 4};
+            cuuint32_t box[4] = {32, (cuuint32_t)pl.BN, 1, 1};
+            int rc = make_map(&mapDy, dy, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (rc) return rc;
+        }
+        WgradParams p;
+        p.R = d.R; p.S = d.S; p.padX = d.padX; p.padY = d.padY; p.wOff = pl.wOff;
+        p.N = d.N; p.Ho = d.Ho; p.Wo = d.Wo; p.C = d.C; p.K = d.K;
+        p.segs = ceil_div(d.Wo, 32);
+        p.tilesC = pl.tilesC; p.tilesK = pl.tilesK; p.splits = pl.splits; p.rowsPerSplit = pl.rowsPerSplit; p.stages = pl.stages;
+        int rc = pl.BN == 64 ? launch_wgrad<64>(pl, mapX, mapDy, p, (float*)ws, st) : launch_wgrad<128>(pl, mapX, mapDy, p, (float*)ws, st);
+        if (rc) return rc;
+        const long long total = (long long)d.K * d.C * d.R * d.S;
+        wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)ws, dw, d.K, d.C, d.R * d.S, pl.splits);
+        NB200_CUDA_TRY(cudaGetLastError());
+        return NB200_OK;
     }
 }
