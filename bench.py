@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- the Conv2D hot path on the VGG16 shapes (BASELINE.json configs[2] / metric), on N B200s of one node.
+
+A "step" is one pass of the hot path over one batch of synthetic input: for each of VGG16's 13 conv layers at
+512x512x3 input resolution and `--batch` images per GPU
+    forward  (Conv2DBiasActivation: 3x3 s1 p1 + bias + ReLU)      -> nb200_conv2d_forward
+    input gradient  (Conv2DInputGradient)                        -> nb200_conv2d_input_gradient
+    kernel gradient (Conv2DKernelsGradient)                      -> nb200_conv2d_kernels_gradient
+followed by the data-parallel tail of ModelBase::Fit: sum-all-reduce of the 14.7 M kernel gradients over NCCL
+(N > 1) and one fused Adam update (grad scale 1/N). Batch sharding = weak scaling: every rank holds `--batch` images.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for the meaning of every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# (C, K, H=W) of the 13 conv layers of VGG16 at 512x512 input: Neuro/src/Applications/VGG16.cpp:73-91
+VGG16 = [(3, 64, 512), (64, 64, 512), (64, 128, 256), (128, 128, 256), (128, 256, 128), (256, 256, 128), (256, 256, 128),
+         (256, 512, 64), (512, 512, 64), (512, 512, 64), (512, 512, 32), (512, 512, 32), (512, 512, 32)]
+F, STRIDE, PAD = 3, 1, 1
+
+
+def layer_flops(C, K, HW, batch=1):
+    return 2.0 * batch * K * HW * HW * C * F * F
+
+
+SAMPLE_FLOPS_PER_OP = sum(layer_flops(*l) for l in VGG16)   # 160.4 GFLOP per image for fwd (= dgrad = wgrad)
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_burst": p["bf16_tflops"], "bf16_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([v.strip() for v in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        smax = int(float(self.rows[0][1])) if self.rows else None
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+
+def cpu_reference_run(steps, warmup, res):
+    """Times the reference's own CPU implementation (oracle/_ref = TensorOpCpuMt compiled from the reference sources;
+    else the oracle port) on a bounded sample: the same 13-layer stack, batch 1, at `res` x `res` input."""
+    import numpy as np
+    from neuro__b200 import synth
+    from oracle import oracle as O
+
+    use_ref = O.have_ref()
+    if use_ref:
+        O.ref_set_threads(0)
+        cores = O.ref_threads()
+    else:
+        O.build(ref=False)
+        cores = os.cpu_count()
+    scale = 512 // res
+    layers = [(C, K, HW // scale) for (C, K, HW) in VGG16]
+    frac = sum(layer_flops(*l) for l in layers) / SAMPLE_FLOPS_PER_OP
+    data = []
+    for i, (C, K, HW) in enumerate(layers):
+        x = synth.uniform(synth.SEED_X + i, (1, C, HW, HW))
+        w = synth.glorot_uniform(synth.SEED_W + i, K, C, F, F)
+        dy = synth.uniform(synth.SEED_DY + i, (1, K, HW, HW))
+        data.append((x, w, dy, HW))
+
+    def step():
+        for (x, w, dy, HW) in data:
+            if use_ref:
+                O.ref_conv2d(x, w, STRIDE, PAD, PAD, mt=True)
+                O.ref_conv2d_input_gradient(dy, w, STRIDE, PAD, PAD, (HW, HW), mt=True)
+                O.ref_conv2d_kernels_gradient(x, dy, STRIDE, PAD, PAD, (F, F), mt=True)
+            else:
+                O.conv2d(x, w, STRIDE, PAD, PAD)
+                O.conv2d_input_gradient(dy, w, STRIDE, PAD, PAD, (HW, HW))
+                O.conv2d_kernels_gradient(x, dy, STRIDE, PAD, PAD, (F, F))
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = frac / dt    # equivalent full-resolution samples per second (FLOP-linear extrapolation of the sample)
+    sample = ("VGG16 13-layer fwd+dgrad+wgrad, batch 1, %dx%dx3 input (%.5f of the 481.2 GFLOP per 512x512 sample), "
+              "samples/s extrapolated linearly in FLOPs; %s" % (res, res, frac,
+              "reference TensorOpCpuMt (PPL->OpenMP; dgrad parallel over N only, wgrad over K only)" if use_ref else "oracle port (OpenMP)"))
+    return {"value": value, "unit": "samples/s", "cores": cores, "kind": "reference" if use_ref else "port", "sample": sample,
+            "seconds_per_step": dt, "gflops": 3 * frac * SAMPLE_FLOPS_PER_OP / dt / 1e9}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = 32 if (args.steps + args.warmup) > 6 else 64
+    cb = cpu_reference_run(args.steps, args.warmup, res)
+    line = {
+        "impl": "reference", "metric": "vgg16_conv_fwd_dgrad_wgrad_samples_per_s", "value": cb["value"], "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.batch, args.gpus),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch, gpus):
+    return {"workload": "VGG16 conv stack @512x512x3 (13 layers 3x3 s1 p1): fwd(bias+ReLU) + input-gradient + kernel-gradient "
+                        "+ gradient all-reduce + Adam",
+            "per_gpu_batch": batch, "global_batch": batch * gpus, "parallelism": "dp%d (batch sharded)" % gpus,
+            "math": "tf32 tensor cores, fp32 accumulate (first layer C=3: fp32 CUDA cores)",
+            "l2": "inputs larger than L2: each step streams every layer's tensors once (>1 GB per step at batch 4)"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from neuro__b200 import lib, synth
+    from neuro__b200.tensor_op import TensorOpB200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = lib.load()
+    op = TensorOpB200(lib.MATH_TF32)
+    B = args.batch
+    dev = torch.device("cuda", local)
+    gen = torch.Generator(device=dev); gen.manual_seed(synth.SEED_MODEL)   # same weights on every rank (replicas)
+    dgen = torch.Generator(device=dev); dgen.manual_seed(1000 + rank)       # different data shard per rank
+
+    # flat parameter / gradient / Adam-moment buckets with per-layer views (one all-reduce bucket per layer)
+    sizes = [K * C * F * F for (C, K, HW) in VGG16]
+    total = sum(sizes)
+    params = torch.empty(total, device=dev); grads = torch.zeros(total, device=dev)
+    m = torch.zeros(total, device=dev); v = torch.zeros(total, device=dev)
+    layers = []
+    off = 0
+    for (C, K, HW), sz in zip(VGG16, sizes):
+        limit = (6.0 / (C * F * F + K * F * F)) ** 0.5                       # GlorotUniform (VarianceScaling.cpp:59-65)
+        w = params[off:off + sz].view(K, C, F, F)
+        w.copy_((torch.rand(K, C, F, F, device=dev, generator=gen) * 2 - 1) * limit)
+        dw = grads[off:off + sz].view(K, C, F, F)
+        off += sz
+        x = torch.rand(B, C, HW, HW, device=dev, generator=dgen) * 2 - 1   # U(-1,1) (Tensor::FillWithRand default)
+        dy = torch.rand(B, K, HW, HW, device=dev, generator=dgen) * 2 - 1
+        y = torch.empty(B, K, HW, HW, device=dev); dx = torch.empty(B, C, HW, HW, device=dev)
+        bias = torch.zeros(K, device=dev)                                    # Conv2D bias init = zeros (Conv2D.h:46)
+        desc = lib.ConvDesc(B, C, HW, HW, K, F, F, HW, HW, STRIDE, PAD, PAD, lib.NCHW, lib.MATH_TF32)
+        layers.append(dict(x=x, w=w, dw=dw, dy=dy, y=y, dx=dx, bias=bias, desc=desc))
+    names = [[op.kernel_name(o, l["desc"]) for o in (0, 1, 2)] for l in layers]
+
+    lr, b1, b2, eps = 1e-5, 0.9, 0.999, 1e-8
+
+    def step(events=None):
+        def timed(tag, fn):
+            if events is None:
+                fn(); return
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); events.append((tag, e0, e1))
+        for i, l in enumerate(layers):
+            timed((0, i), lambda l=l: op.Conv2DBiasActivation(l["x"], l["w"], STRIDE, PAD, PAD, l["bias"], lib.ACT_RELU, 0.0, l["y"]))
+        works = []
+        for i in reversed(range(len(layers))):
+            l = layers[i]
+            timed((1, i), lambda l=l: op.Conv2DInputGradient(l["dy"], l["w"], STRIDE, PAD, PAD, lib.NCHW, l["dx"]))
+            timed((2, i), lambda l=l: op.Conv2DKernelsGradient(l["x"], l["dy"], STRIDE, PAD, PAD, lib.NCHW, l["dw"]))
+            if world > 1:   # exchange step: overlaps with the remaining layers' dgrad/wgrad
+                works.append(dist.all_reduce(l["dw"], op=dist.ReduceOp.SUM, async_op=True))
+        for wk in works:
+            wk.wait()
+        timed((3, 0), lambda: op.AdamStep(params, grads, m, v, lr, b1, b2, eps, gradScale=1.0 / world))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region (device-resident inputs) ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = L.nb200_kernel_launches()
+    events = []
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for _ in range(args.steps):
+        step(events)
+    t1.record()
+    barrier()
+    launches = L.nb200_kernel_launches() - launches0
+    if sampler:
+        sampler.stop_flag = True
+    ms = t0.elapsed_time(t1) / args.steps
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev); dist.all_reduce(tmax, op=dist.ReduceOp.MAX); ms = float(tmax.item())
+    fam_ms = {0: 0.0, 1: 0.0, 2: 0.0, 3: 0.0}
+    tc_ms = {0: 0.0, 1: 0.0, 2: 0.0}; tc_fl = {0: 0.0, 1: 0.0, 2: 0.0}
+    for (fam, i), e0, e1 in events:
+        dt = e0.elapsed_time(e1)
+        fam_ms[fam] += dt
+        if fam < 3 and names[i][fam].startswith("tcgen05"):
+            tc_ms[fam] += dt; tc_fl[fam] += layers[i]["desc"].flops()
+
+    # ---- e2e: the same step through the public API with HOST input and HOST result, copies inside the timed region ----
+    img_host = torch.from_numpy(synth.uniform(synth.SEED_X, (B, 3, 512, 512))).pin_memory()
+    grad_host = torch.empty((B, 3, 512, 512), dtype=torch.float32).pin_memory()
+    def e2e_step():
+        layers[0]["x"].copy_(img_host, non_blocking=True)     # H2D of this step's input batch
+        step()
+        grad_host.copy_(layers[0]["dx"], non_blocking=True)   # D2H of the step's result (image gradient, as style transfer reads)
+    e2e_step(); barrier()
+    s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    s0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    s1.record()
+    barrier()
+    e2e_ms = s0.elapsed_time(s1) / e2e_steps
+    if world > 1:
+        tmax = torch.tensor([e2e_ms], device=dev); dist.all_reduce(tmax, op=dist.ReduceOp.MAX); e2e_ms = float(tmax.item())
+
+    if rank == 0:
+        peaks = read_peaks()
+        tf32_peak = peaks["bf16_sustained"] / 2.0       # TF32 dense = half the bf16 rate; sustained: kernels timed inside a long step
+        dom = max((0, 1, 2), key=lambda f: fam_ms[f])
+        fam_names = {0: "tc_fprop_kernel (forward)", 1: "tc_fprop_kernel (input gradient)", 2: "tc_wgrad_kernel (kernel gradient)"}
+        achieved = tc_fl[dom] / (tc_ms[dom] * 1e-3) / 1e12 if tc_ms[dom] > 0 else 0.0
+        per_op = {n: {"ms_per_step": fam_ms[f] / args.steps,
+                      "tflops": (B * SAMPLE_FLOPS_PER_OP) / (fam_ms[f] / args.steps * 1e-3) / 1e12,
+                      "tensor_core_tflops": (tc_fl[f] / (tc_ms[f] * 1e-3) / 1e12) if tc_ms[f] > 0 else None,
+                      "frac_of_tf32_peak": ((tc_fl[f] / (tc_ms[f] * 1e-3) / 1e12) / tf32_peak) if tc_ms[f] > 0 else None}
+                  for f, n in ((0, "forward"), (1, "input_gradient"), (2, "kernels_gradient"))}
+        line = {
+            "metric": "vgg16_conv_fwd_dgrad_wgrad_samples_per_s", "value": B * world / (ms * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": workload_config(B, world),
+            "tflops_total": 3 * B * world * SAMPLE_FLOPS_PER_OP / (ms * 1e-3) / 1e12,
+            "per_op": per_op, "adam_ms_per_step": fam_ms[3] / args.steps,
+            "roofline": {"bound": "tensor", "kernel": fam_names[dom], "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tf32_peak if tf32_peak else None, "traffic": None,
+                         "peak_source": "%s bf16_tflops_sustained / 2 (MEASURED_PEAKS.json has no TF32 entry; TF32 dense = 1/2 bf16)" % peaks["source"],
+                         "share_of_step": fam_ms[dom] / sum(fam_ms.values()) if sum(fam_ms.values()) else None},
+            "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": img_host.numel() * 4,
+                    "d2h_bytes_per_step": grad_host.numel() * 4, "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary() if sampler else None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_run(1, 0, 64)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4, help="images per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,8 @@ typedef struct nb200_conv_desc
 /* Library / device introspection. */
 NB200_API const char* nb200_version(void);
 NB200_API const char* nb200_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (for benchmark bookkeeping). */
+NB200_API unsigned long long nb200_kernel_launches(void);
 /* 0 if the current device can run the kernels (compute capability 10.x); fills optional outputs. */
 NB200_API int nb200_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes);
 

@@ -7,6 +7,9 @@
 namespace nb200
 {
     static thread_local char g_err[512] = "";
+    static unsigned long long g_launches = 0;
+
+    void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
     void set_error(const char* fmt, ...)
     {
@@ -110,6 +113,7 @@ extern "C"
 {
     const char* nb200_version(void) { return "neuro_b200 0.1 (sm_100a)"; }
     const char* nb200_last_error(void) { return g_err; }
+    unsigned long long nb200_kernel_launches(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
     int nb200_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes)
     {

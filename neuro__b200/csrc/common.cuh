@@ -11,6 +11,7 @@ namespace nb200
 {
     // Thread-local last-error slot behind nb200_last_error().
     void set_error(const char* fmt, ...);
+    void count_launch(int n = 1); // feeds nb200_kernel_launches()
     int fail(int code, const char* fmt, ...);
 
 #define NB200_CUDA_TRY(expr)                                                                      \

@@ -258,6 +258,7 @@ namespace nb200
         dim3 grid(ceil_div(pixels, kPixelsPerBlock), ceil_div(d.K, kFiltersPerThread));
         direct_fprop_kernel<<<grid, kPixelsPerBlock, 0, st>>>(g, x, w, bias, act, alpha, y);
         NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
         return NB200_OK;
     }
 
@@ -270,6 +271,7 @@ namespace nb200
         dim3 grid(ceil_div(pixels, kPixelsPerBlock), ceil_div(d.C, kFiltersPerThread));
         direct_dgrad_kernel<<<grid, kPixelsPerBlock, 0, st>>>(g, dy, w, dx);
         NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
         return NB200_OK;
     }
 
@@ -300,10 +302,12 @@ namespace nb200
         dim3 grid(d.K, d.C, slices);
         direct_wgrad_kernel<<<grid, kWgradThreads, 0, st>>>(g, x, dy, out, slices);
         NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
         if (slices > 1)
         {
             reduce_slices_kernel<<<ceil_div(count, 256), 256, 0, st>>>((const float*)ws, dw, count, slices);
             NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
         }
         return NB200_OK;
     }

@@ -630,6 +630,7 @@ namespace nb200
                 return fail(NB200_E_UNSUPPORTED, "too many tiles");
             tc_fprop_kernel<BN><<<(unsigned)tiles, kThreads, pl.smemBytes, st>>>(mapX, mapW, p, bias, out);
             NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
             return NB200_OK;
         }
 
@@ -652,6 +653,7 @@ namespace nb200
                 const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
                 repack_filters_kernel<<<blocks, 256, 0, st>>>(w, wr, wK, wC, f.R, f.S, f.Kout, Cp, repackMode);
                 NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
             }
 
             CUtensorMap mapX, mapW;
@@ -746,6 +748,7 @@ namespace nb200
             const long long ctas = (long long)p.splits * p.tilesK * p.tilesC * p.R;
             tc_wgrad_kernel<BN><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapX, mapDy, p, ws);
             NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
             return NB200_OK;
         }
     }
@@ -820,6 +823,7 @@ namespace nb200
         const long long total = (long long)d.K * d.C * d.R * d.S;
         wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)ws, dw, d.K, d.C, d.R * d.S, pl.splits);
         NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
         return NB200_OK;
     }
 }

@@ -80,6 +80,7 @@ namespace nb200
         const ActStrides ys = act_strides(d.fmt, d.K, d.Ho, d.Wo);
         bias_gradient_kernel<<<d.K, kReduceThreads, 0, st>>>(dy, db, d.N, d.K, d.Ho * d.Wo, ys, d.fmt == NB200_NCHW);
         NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
         return NB200_OK;
     }
 
@@ -90,6 +91,7 @@ namespace nb200
             return NB200_OK;
         adam_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, gs, lr, b1, b2, eps);
         NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
         return NB200_OK;
     }
 
@@ -99,6 +101,7 @@ namespace nb200
             return NB200_OK;
         sgd_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, n, gs, lr);
         NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
         return NB200_OK;
     }
 }

@@ -15,7 +15,7 @@ OP_FORWARD, OP_INPUT_GRADIENT, OP_KERNELS_GRADIENT = 0, 1, 2
 
 # every symbol include/neuro_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = [
-    "nb200_version", "nb200_last_error", "nb200_device_info", "nb200_padding", "nb200_conv_out_size",
+    "nb200_version", "nb200_last_error", "nb200_kernel_launches", "nb200_device_info", "nb200_padding", "nb200_conv_out_size",
     "nb200_conv_transpose_out_size", "nb200_conv2d_workspace_bytes", "nb200_conv2d_kernel_name",
     "nb200_conv2d_forward", "nb200_conv2d_input_gradient", "nb200_conv2d_kernels_gradient",
     "nb200_conv2d_bias_gradient", "nb200_adam_step", "nb200_sgd_step", "nb200_conv2d_forward_host",
@@ -57,6 +57,7 @@ def load():
     dp = ctypes.POINTER(ConvDesc)
     L.nb200_version.restype = ctypes.c_char_p
     L.nb200_last_error.restype = ctypes.c_char_p
+    L.nb200_kernel_launches.restype = ctypes.c_ulonglong
     L.nb200_device_info.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                     ctypes.POINTER(ctypes.c_int), ctypes.POINTER(c_sz)]
     for f in (L.nb200_padding,):

@@ -35,6 +35,9 @@ namespace Neuro
 
     void Storage::AllocateOnHost() const
     {
+        // read-only fast path: the conv loops call this once per element access from every thread
+        if (m_DataPtr && m_DataLocation == Host)
+            return;
         if (!m_DataPtr)
         {
             Storage* self = const_cast<Storage*>(this);
