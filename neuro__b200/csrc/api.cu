@@ -91,10 +91,12 @@ namespace nb200
             }
         }
 
-        enum Family { kDirect, kTc };
+        enum Family { kDirect, kTc, kSmallC };
 
         Family pick(int op, const nb200_conv_desc& d)
         {
+            if (smallc_supported(d))
+                return kSmallC; // fp32 CUDA cores, HBM-bound: serves every math mode
             if (d.math == NB200_MATH_FP32)
                 return kDirect;
             switch (op)
@@ -152,8 +154,11 @@ extern "C"
     {
         if (!d || validate(d, -1) != NB200_OK)
             return 0;
-        if (pick(op, *d) == kTc)
+        const Family f = pick(op, *d);
+        if (f == kTc)
             return tc_workspace_bytes(op, *d);
+        if (f == kSmallC)
+            return op == NB200_OP_KERNELS_GRADIENT ? smallc_wgrad_workspace(*d) : 0;
         return op == NB200_OP_KERNELS_GRADIENT ? direct_kernels_gradient_workspace(*d) : 0;
     }
 
@@ -161,12 +166,12 @@ extern "C"
     {
         if (!d || validate(d, -1) != NB200_OK)
             return "invalid";
-        const bool tc = pick(op, *d) == kTc;
+        const Family f = pick(op, *d);
         switch (op)
         {
-        case NB200_OP_FORWARD: return tc ? "tcgen05_fprop" : "direct_fprop";
-        case NB200_OP_INPUT_GRADIENT: return tc ? "tcgen05_dgrad" : "direct_dgrad";
-        case NB200_OP_KERNELS_GRADIENT: return tc ? "tcgen05_wgrad" : "direct_wgrad";
+        case NB200_OP_FORWARD: return f == kTc ? "tcgen05_fprop" : f == kSmallC ? "smallc_fprop" : "direct_fprop";
+        case NB200_OP_INPUT_GRADIENT: return f == kTc ? "tcgen05_dgrad" : f == kSmallC ? "smallc_dgrad" : "direct_dgrad";
+        case NB200_OP_KERNELS_GRADIENT: return f == kTc ? "tcgen05_wgrad" : f == kSmallC ? "smallc_wgrad" : "direct_wgrad";
         default: return "invalid";
         }
     }
@@ -184,8 +189,11 @@ extern "C"
             return fail(NB200_E_INVALID, "null tensor pointer");
         if ((rc = require_device())) return rc;
         cudaStream_t st = (cudaStream_t)stream;
-        if (pick(NB200_OP_FORWARD, *d) == kTc)
+        const Family f = pick(NB200_OP_FORWARD, *d);
+        if (f == kTc)
             return tc_forward(*d, x, w, bias, act, alpha, y, workspace, workspace_bytes, st);
+        if (f == kSmallC)
+            return smallc_forward(*d, x, w, bias, act, alpha, y, st);
         return direct_forward(*d, x, w, bias, act, alpha, y, st);
     }
 
@@ -200,8 +208,11 @@ extern "C"
             return fail(NB200_E_INVALID, "null tensor pointer");
         if ((rc = require_device())) return rc;
         cudaStream_t st = (cudaStream_t)stream;
-        if (pick(NB200_OP_INPUT_GRADIENT, *d) == kTc)
+        const Family f = pick(NB200_OP_INPUT_GRADIENT, *d);
+        if (f == kTc)
             return tc_input_gradient(*d, dy, w, dx, workspace, workspace_bytes, st);
+        if (f == kSmallC)
+            return smallc_input_gradient(*d, dy, w, dx, st);
         return direct_input_gradient(*d, dy, w, dx, st);
     }
 
@@ -220,8 +231,11 @@ extern "C"
         if (!dw || ((!x || !dy) && (long long)d->N * d->Ho * d->Wo > 0))
             return fail(NB200_E_INVALID, "null tensor pointer");
         if ((rc = require_device())) return rc;
-        if (pick(NB200_OP_KERNELS_GRADIENT, *d) == kTc)
+        const Family f = pick(NB200_OP_KERNELS_GRADIENT, *d);
+        if (f == kTc)
             return tc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
+        if (f == kSmallC)
+            return smallc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         return direct_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
     }
 

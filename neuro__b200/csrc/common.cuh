@@ -69,6 +69,15 @@ namespace nb200
                                 cudaStream_t st);
     size_t direct_kernels_gradient_workspace(const nb200_conv_desc& d);
 
+    // HBM-bound 3x3 stride-1 kernels for C <= 4 input channels (first layers). conv_smallc.cu
+    bool smallc_supported(const nb200_conv_desc& d);
+    size_t smallc_wgrad_workspace(const nb200_conv_desc& d);
+    int smallc_forward(const nb200_conv_desc& d, const float* x, const float* w, const float* bias, int act, float alpha, float* y,
+                       cudaStream_t st);
+    int smallc_input_gradient(const nb200_conv_desc& d, const float* dy, const float* w, float* dx, cudaStream_t st);
+    int smallc_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes,
+                                cudaStream_t st);
+
     // tcgen05/TMA implicit-GEMM kernels (NCHW). conv_tc.cu
     bool tc_forward_supported(const nb200_conv_desc& d);
     bool tc_input_gradient_supported(const nb200_conv_desc& d);

@@ -1,0 +1,426 @@
+// HBM-bound first-layer kernels: 3x3, stride 1, NCHW, C <= 4 input channels (VGG block1_conv1: 3 -> 64 at 512x512,
+// 12.9 FLOP/B). Tensor cores have nothing to add at this arithmetic intensity, so these are
+// CUDA-core fp32 kernels organised around the only thing that matters here: touch the K-channel tensor (y or dy)
+// exactly once with full 128-byte lines, and keep the tiny x / filter tensors in registers, L1 or shared memory.
+//
+//   forward          thread = 4 consecutive output pixels; the 3x3xC input window (C*18 floats) lives in registers and is
+//                    reused for every filter; filters come from shared memory as broadcast LDS.128; y is written with
+//                    coalesced 16-byte stores (one 512-byte run per warp and filter).
+//   input gradient   thread = 4 consecutive dx pixels x C channels; streams dy once (aligned float4 + two edge scalars per
+//                    row), flipped filters from shared memory.
+//   kernel gradient  warp = one filter k, lanes = pixels: streams dy[k] once with coalesced float4 loads, x windows come
+//                    from L1 (shared by the 8 warps of the block), 9*C running sums per lane, one shuffle reduction at the
+//                    end; deterministic split over output rows + fixed-order second pass.
+#include "common.cuh"
+
+namespace nb200
+{
+    namespace
+    {
+        constexpr int kSmallThreads = 256;
+
+        struct SmallGeo
+        {
+            int N, H, W, K, Ho, Wo, pad;
+            int aligned; // every tensor base is 16-byte aligned (vector paths allowed)
+        };
+
+        // ------------------------------------------------------------ forward
+        template <int C>
+        __global__ void __launch_bounds__(kSmallThreads)
+        smallc_fprop_kernel(SmallGeo g, const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                            int act, float alpha, float* __restrict__ y)
+        {
+            constexpr int T = C * 9;              // taps per filter
+            constexpr int TP = (T + 3) & ~3;      // padded to a multiple of 4 for LDS.128
+            extern __shared__ float sw[];         // [K][TP]
+            for (int i = threadIdx.x; i < g.K * TP; i += kSmallThreads)
+            {
+                const int k = i / TP, t = i - k * TP;
+                sw[i] = t < T ? w[k * T + t] : 0.f;
+            }
+            __syncthreads();
+
+            const int quadsPerRow = (g.Wo + 3) >> 2;
+            const long long quads = (long long)g.N * g.Ho * quadsPerRow;
+            const long long q = (long long)blockIdx.x * kSmallThreads + threadIdx.x;
+            if (q >= quads)
+                return;
+            const int qw = (int)(q % quadsPerRow);
+            const int oh = (int)((q / quadsPerRow) % g.Ho);
+            const int n = (int)(q / ((long long)quadsPerRow * g.Ho));
+            const int ow0 = qw * 4;
+
+            // input window: C x 3 rows x 6 columns (ow0-pad .. ow0-pad+5), zero padded
+            float xin[C][3][6];
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                {
+                    const int ih = oh - g.pad + r;
+                    const float* row = x + (((long long)n * C + c) * g.H + ih) * g.W;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j)
+                    {
+                        const int iw = ow0 - g.pad + j;
+                        xin[c][r][j] = (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) ? __ldg(row + iw) : 0.f;
+                    }
+                }
+
+            const long long plane = (long long)g.Ho * g.Wo;
+            float* yp = y + (long long)n * g.K * plane + (long long)oh * g.Wo + ow0;
+            const bool vec = g.aligned && (g.Wo & 3) == 0; // then every quad is complete and 16-byte aligned
+            for (int k = 0; k < g.K; ++k)
+            {
+                float wk[TP];
+                const float4* wp = (const float4*)(sw + k * TP);
+#pragma unroll
+                for (int i = 0; i < TP / 4; ++i)
+                {
+                    const float4 f = wp[i];
+                    wk[4 * i] = f.x; wk[4 * i + 1] = f.y; wk[4 * i + 2] = f.z; wk[4 * i + 3] = f.w;
+                }
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int s = 0; s < 3; ++s)
+                        {
+                            const float wv = wk[(c * 3 + r) * 3 + s];
+                            a0 = fmaf(xin[c][r][s], wv, a0);
+                            a1 = fmaf(xin[c][r][s + 1], wv, a1);
+                            a2 = fmaf(xin[c][r][s + 2], wv, a2);
+                            a3 = fmaf(xin[c][r][s + 3], wv, a3);
+                        }
+                const float b = bias ? __ldg(bias + k) : 0.f;
+                a0 = apply_activation(act, alpha, a0 + b); a1 = apply_activation(act, alpha, a1 + b);
+                a2 = apply_activation(act, alpha, a2 + b); a3 = apply_activation(act, alpha, a3 + b);
+                float* dst = yp + k * plane;
+                if (vec)
+                    __stcs((float4*)dst, make_float4(a0, a1, a2, a3)); // streaming store: y is not re-read by this kernel
+                else
+                {
+                    if (ow0 < g.Wo) dst[0] = a0;
+                    if (ow0 + 1 < g.Wo) dst[1] = a1;
+                    if (ow0 + 2 < g.Wo) dst[2] = a2;
+                    if (ow0 + 3 < g.Wo) dst[3] = a3;
+                }
+            }
+        }
+
+        // ------------------------------------------------------------ input gradient
+        // dx[n][c][h][w] = sum_k sum_{r,s} dy[n][k][h+pad-r][w+pad-s] * w[k][c][r][s]
+        template <int C>
+        __global__ void __launch_bounds__(kSmallThreads)
+        smallc_dgrad_kernel(SmallGeo g, const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx)
+        {
+            constexpr int T = C * 9;
+            constexpr int TP = (T + 3) & ~3;
+            extern __shared__ float sw[];         // [K][TP], taps flipped: sw[k][(c*3+a)*3+b] = w[k][c][2-a][2-b]
+            for (int i = threadIdx.x; i < g.K * TP; i += kSmallThreads)
+            {
+                const int k = i / TP, t = i - k * TP;
+                float v = 0.f;
+                if (t < T)
+                {
+                    const int c = t / 9, a = (t % 9) / 3, b = t % 3;
+                    v = w[(k * C + c) * 9 + (2 - a) * 3 + (2 - b)];
+                }
+                sw[i] = v;
+            }
+            __syncthreads();
+
+            const int quadsPerRow = (g.W + 3) >> 2;
+            const long long quads = (long long)g.N * g.H * quadsPerRow;
+            const long long q = (long long)blockIdx.x * kSmallThreads + threadIdx.x;
+            if (q >= quads)
+                return;
+            const int qw = (int)(q % quadsPerRow);
+            const int h = (int)((q / quadsPerRow) % g.H);
+            const int n = (int)(q / ((long long)quadsPerRow * g.H));
+            const int w0 = qw * 4;
+            // with flipped taps this is a forward conv of dy with pad' = 2 - pad: window rows h-pad'+a, cols w0-pad'+j
+            const int pp = 2 - g.pad;
+
+            float acc[C][4];
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    acc[c][j] = 0.f;
+
+            const long long plane = (long long)g.Ho * g.Wo;
+            const float* dyn = dy + (long long)n * g.K * plane;
+            const bool fast = g.aligned && pp == 1 && (g.Wo & 3) == 0 && w0 + 4 <= g.Wo; // aligned float4 centre + 2 edge scalars
+            for (int k = 0; k < g.K; ++k)
+            {
+                float win[3][6];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                {
+                    const int oh = h - pp + a;
+                    const bool rowOk = oh >= 0 && oh < g.Ho;
+                    const float* row = dyn + k * plane + (long long)oh * g.Wo;
+                    if (fast)
+                    {
+                        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float l = 0.f, rr = 0.f;
+                        if (rowOk)
+                        {
+                            f = __ldcs((const float4*)(row + w0));
+                            if (w0 > 0) l = __ldg(row + w0 - 1);
+                            if (w0 + 4 < g.Wo) rr = __ldg(row + w0 + 4);
+                        }
+                        win[a][0] = l; win[a][1] = f.x; win[a][2] = f.y; win[a][3] = f.z; win[a][4] = f.w; win[a][5] = rr;
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j)
+                        {
+                            const int ow = w0 - pp + j;
+                            win[a][j] = (rowOk && ow >= 0 && ow < g.Wo) ? __ldg(row + ow) : 0.f;
+                        }
+                    }
+                }
+                float wk[TP];
+                const float4* wp = (const float4*)(sw + k * TP);
+#pragma unroll
+                for (int i = 0; i < TP / 4; ++i)
+                {
+                    const float4 f = wp[i];
+                    wk[4 * i] = f.x; wk[4 * i + 1] = f.y; wk[4 * i + 2] = f.z; wk[4 * i + 3] = f.w;
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b)
+                        {
+                            const float wv = wk[(c * 3 + a) * 3 + b];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                acc[c][j] = fmaf(win[a][b + j], wv, acc[c][j]);
+                        }
+            }
+
+            const bool vec = g.aligned && (g.W & 3) == 0;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+            {
+                float* dst = dx + (((long long)n * C + c) * g.H + h) * g.W + w0;
+                if (vec)
+                    *(float4*)dst = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (w0 + j < g.W) dst[j] = acc[c][j];
+                }
+            }
+        }
+
+        // ------------------------------------------------------------ kernel gradient
+        // dw[k][c][r][s] = sum_{n,oh,ow} dy[n][k][oh][ow] * x[n][c][oh+r-pad][ow+s-pad]
+        // grid (ceil(K/8), slices): warp wIdx of the block owns filter k = blockIdx.x*8 + wIdx and the slice's output rows.
+        template <int C>
+        __global__ void __launch_bounds__(kSmallThreads)
+        smallc_wgrad_kernel(SmallGeo g, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part,
+                            int rowsPerSlice)
+        {
+            constexpr int T = C * 9;
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            const int k = blockIdx.x * 8 + warp;
+            const int slice = blockIdx.y;
+            const int rows = g.N * g.Ho;
+            const int rowBegin = slice * rowsPerSlice;
+            const int rowEnd = min(rowBegin + rowsPerSlice, rows);
+
+            float acc[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+                acc[t] = 0.f;
+
+            if (k < g.K)
+            {
+                const long long plane = (long long)g.Ho * g.Wo;
+                const bool vec = g.aligned && (g.Wo & 3) == 0;
+                const bool xfast = g.aligned && g.pad == 1 && (g.W & 3) == 0;
+                for (int row = rowBegin; row < rowEnd; ++row)
+                {
+                    const int n = row / g.Ho, oh = row - n * g.Ho;
+                    const float* drow = dy + ((long long)n * g.K + k) * plane + (long long)oh * g.Wo;
+                    for (int ow0 = lane * 4; ow0 < g.Wo; ow0 += 128)
+                    {
+                        float d[4];
+                        if (vec)
+                        {
+                            const float4 f = __ldcs((const float4*)(drow + ow0));
+                            d[0] = f.x; d[1] = f.y; d[2] = f.z; d[3] = f.w;
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                d[j] = ow0 + j < g.Wo ? __ldg(drow + ow0 + j) : 0.f;
+                        }
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+#pragma unroll
+                            for (int r = 0; r < 3; ++r)
+                            {
+                                const int ih = oh - g.pad + r;
+                                if (ih < 0 || ih >= g.H)
+                                    continue; // warp-uniform
+                                const float* xr = x + (((long long)n * C + c) * g.H + ih) * g.W;
+                                float xv[6];
+                                if (xfast && ow0 + 4 <= g.W)
+                                {
+                                    const float4 f = __ldg((const float4*)(xr + ow0));
+                                    xv[0] = ow0 > 0 ? __ldg(xr + ow0 - 1) : 0.f;
+                                    xv[1] = f.x; xv[2] = f.y; xv[3] = f.z; xv[4] = f.w;
+                                    xv[5] = ow0 + 4 < g.W ? __ldg(xr + ow0 + 4) : 0.f;
+                                }
+                                else
+                                {
+#pragma unroll
+                                    for (int j = 0; j < 6; ++j)
+                                    {
+                                        const int iw = ow0 - g.pad + j;
+                                        xv[j] = (iw >= 0 && iw < g.W) ? __ldg(xr + iw) : 0.f;
+                                    }
+                                }
+#pragma unroll
+                                for (int s = 0; s < 3; ++s)
+                                {
+                                    float a = acc[(c * 3 + r) * 3 + s];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        a = fmaf(d[j], xv[s + j], a);
+                                    acc[(c * 3 + r) * 3 + s] = a;
+                                }
+                            }
+                    }
+                }
+            }
+
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+            {
+                float v = acc[t];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && k < g.K)
+                    part[((long long)slice * g.K + k) * T + t] = v;
+            }
+        }
+
+        __global__ void smallc_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int count, int slices)
+        {
+            const int i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= count)
+                return;
+            float v = 0.f;
+            for (int s = 0; s < slices; ++s)
+                v += part[(long long)s * count + i];
+            out[i] = v;
+        }
+
+        SmallGeo small_geo(const nb200_conv_desc& d, const void* a, const void* b, const void* c)
+        {
+            const int aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
+            return SmallGeo{d.N, d.H, d.W, d.K, d.Ho, d.Wo, d.padX, aligned};
+        }
+
+        int wgrad_slices(const nb200_conv_desc& d)
+        {
+            const int rows = d.N * d.Ho;
+            const int kBlocks = ceil_div(d.K, 8);
+            int want = ceil_div(148 * 6, kBlocks);
+            if (want > rows) want = rows;
+            if (want < 1) want = 1;
+            return want;
+        }
+    }
+
+    bool smallc_supported(const nb200_conv_desc& d)
+    {
+        return d.fmt == NB200_NCHW && d.C >= 1 && d.C <= 4 && d.R == 3 && d.S == 3 && d.stride == 1 && d.padX == d.padY && d.padX <= 2 &&
+               d.K >= 1 && d.K * ((d.C * 9 + 3) & ~3) * 4 <= 96 * 1024 &&
+               d.Ho == d.H + 2 * d.padY - 2 && d.Wo == d.W + 2 * d.padX - 2 && d.N >= 1 && d.Ho >= 1 && d.Wo >= 1;
+    }
+
+    size_t smallc_wgrad_workspace(const nb200_conv_desc& d)
+    {
+        return (size_t)wgrad_slices(d) * d.K * d.C * 9 * sizeof(float);
+    }
+
+#define SMALLC_DISPATCH(CALL)          \
+    switch (d.C)                       \
+    {                                  \
+    case 1: { CALL(1); break; }        \
+    case 2: { CALL(2); break; }        \
+    case 3: { CALL(3); break; }        \
+    default: { CALL(4); break; }       \
+    }
+
+    int smallc_forward(const nb200_conv_desc& d, const float* x, const float* w, const float* bias, int act, float alpha, float* y,
+                       cudaStream_t st)
+    {
+        const SmallGeo g = small_geo(d, x, y, nullptr);
+        const long long quads = (long long)d.N * d.Ho * ((d.Wo + 3) / 4);
+        const size_t smem = (size_t)d.K * ((d.C * 9 + 3) & ~3) * 4;
+#define CALL(CC)                                                                                                              \
+        if (smem > 48 * 1024)                                                                                                  \
+            NB200_CUDA_TRY(cudaFuncSetAttribute(smallc_fprop_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        smallc_fprop_kernel<CC><<<ceil_div(quads, kSmallThreads), kSmallThreads, smem, st>>>(g, x, w, bias, act, alpha, y);
+        SMALLC_DISPATCH(CALL)
+#undef CALL
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        return NB200_OK;
+    }
+
+    int smallc_input_gradient(const nb200_conv_desc& d, const float* dy, const float* w, float* dx, cudaStream_t st)
+    {
+        const SmallGeo g = small_geo(d, dy, dx, nullptr);
+        const long long quads = (long long)d.N * d.H * ((d.W + 3) / 4);
+        const size_t smem = (size_t)d.K * ((d.C * 9 + 3) & ~3) * 4;
+#define CALL(CC)                                                                                                              \
+        if (smem > 48 * 1024)                                                                                                  \
+            NB200_CUDA_TRY(cudaFuncSetAttribute(smallc_dgrad_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        smallc_dgrad_kernel<CC><<<ceil_div(quads, kSmallThreads), kSmallThreads, smem, st>>>(g, dy, w, dx);
+        SMALLC_DISPATCH(CALL)
+#undef CALL
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        return NB200_OK;
+    }
+
+    int smallc_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes,
+                                cudaStream_t st)
+    {
+        const SmallGeo g = small_geo(d, x, dy, nullptr);
+        const int slices = wgrad_slices(d);
+        const size_t need = smallc_wgrad_workspace(d);
+        if (wsBytes < need || !ws)
+            return fail(NB200_E_WORKSPACE, "small-channel kernel gradient needs %zu workspace bytes, got %zu", need, wsBytes);
+        const int rowsPerSlice = ceil_div(d.N * d.Ho, slices);
+        dim3 grid(ceil_div(d.K, 8), slices);
+#define CALL(CC) smallc_wgrad_kernel<CC><<<grid, kSmallThreads, 0, st>>>(g, x, dy, (float*)ws, rowsPerSlice);
+        SMALLC_DISPATCH(CALL)
+#undef CALL
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        const int count = d.K * d.C * 9;
+        smallc_reduce_kernel<<<ceil_div(count, 256), 256, 0, st>>>((const float*)ws, dw, count, slices);
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        return NB200_OK;
+    }
+}
