@@ -34,9 +34,13 @@ namespace nb200
         constexpr int kTileW = 32;   // output columns per tile (= lanes of a converter warp)
         constexpr int kTileH = 4;    // output rows per tile (= converter warps) -> M = 128
         constexpr int kBlockC = 32;  // reduction channels per step (4 MMAs of K = 8)
-        constexpr int kThreads = 192;
+        constexpr int kThreads = 192;        // kernel gradient: producer + MMA + 4 converter warps
+        constexpr int kFpropThreads = 352;   // forward: filter producer + MMA + halo producer + 2 groups of 4 converter warps
+        constexpr int kFirstConvWarp = 3;
+        constexpr int kConvGroups = 2;
         constexpr int kAStages = 4;  // A tiles in TMEM (32 columns each)
-        constexpr int kSmemBudget = 112 * 1024; // per CTA, two CTAs per SM
+        constexpr int kSmemBudget2 = 112 * 1024; // per CTA when two CTAs share an SM (BN <= 128)
+        constexpr int kSmemBudget1 = 220 * 1024; // one CTA per SM (BN = 256)
 
         struct FpropParams
         {
@@ -86,13 +90,14 @@ namespace nb200
 
         // ---------------------------------------------------------------- forward kernel
         template <int BN>
-        __global__ void __launch_bounds__(kThreads, 2)
+        __global__ void __launch_bounds__(kFpropThreads, (BN > 128 ? 1 : 2))
         tc_fprop_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, FpropParams p,
                         const float* __restrict__ bias, float* __restrict__ y)
         {
             constexpr uint32_t kBBytes = BN * kBlockC * 4;
-            constexpr uint32_t kTmemCols = BN + kAStages * kBlockC <= 128 ? 128 : 256;
-            static_assert(BN + kAStages * kBlockC <= 256, "TMEM budget: two CTAs per SM x 256 columns");
+            // BN <= 128: two CTAs per SM x 256 columns; BN = 256: one CTA per SM x 512 columns
+            constexpr uint32_t kTmemCols = BN > 128 ? 512 : 256;
+            static_assert(BN + kAStages * kBlockC <= kTmemCols, "TMEM budget");
 
             extern __shared__ uint8_t smemRaw[];
             uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
@@ -126,7 +131,7 @@ namespace nb200
                 ptx::prefetch_tensormap(&mapX);
                 ptx::prefetch_tensormap(&mapW);
                 for (int s = 0; s < p.bStages; ++s) { ptx::mbar_init(&bFull[s], 1); ptx::mbar_init(&bEmpty[s], 1); }
-                for (int s = 0; s < p.xStages; ++s) { ptx::mbar_init(&xFull[s], 1); ptx::mbar_init(&xEmpty[s], kTileH); }
+                for (int s = 0; s < p.xStages; ++s) { ptx::mbar_init(&xFull[s], 1); ptx::mbar_init(&xEmpty[s], kTileH * kConvGroups); }
                 for (int s = 0; s < kAStages; ++s) { ptx::mbar_init(&aFull[s], kTileH); ptx::mbar_init(&aEmpty[s], 1); }
                 ptx::mbar_init(accBar, 1);
                 ptx::fence_mbar_init();
@@ -145,16 +150,10 @@ namespace nb200
             {
                 if (lane == 0)
                 {
-                    // ===== TMA producer: one halo tile per channel block, one filter tile per (channel block, tap) =====
-                    int xs = 0, bs = 0;
-                    uint32_t xph = 0, bph = 0;
+                    // ===== TMA producer (filters): one tile per (channel block, tap) =====
+                    int bs = 0;
+                    uint32_t bph = 0;
                     for (int cb = 0; cb < p.Cblocks; ++cb)
-                    {
-                        ptx::mbar_wait(&xEmpty[xs], xph ^ 1);
-                        ptx::mbar_arrive_expect_tx(&xFull[xs], xBytes);
-                        // x viewed as (W, H, C, N); origin 16-byte aligned in W; out-of-bounds elements read as 0 (= zero padding)
-                        ptx::tma_load_4d(xRing + xs * xBytesPad, &mapX, &xFull[xs], ow0 - p.wOff, oh0 - p.padY, cb * kBlockC, n);
-                        if (++xs == p.xStages) { xs = 0; xph ^= 1; }
                         for (int tap = 0; tap < taps; ++tap)
                         {
                             ptx::mbar_wait(&bEmpty[bs], bph ^ 1);
@@ -162,6 +161,22 @@ namespace nb200
                             ptx::tma_load_3d(bRing + bs * kBBytes, &mapW, &bFull[bs], cb * kBlockC, k0, tap);
                             if (++bs == p.bStages) { bs = 0; bph ^= 1; }
                         }
+                }
+            }
+            else if (warp == 2)
+            {
+                if (lane == 0)
+                {
+                    // ===== TMA producer (activations): one halo tile per channel block, independent of the filter ring =====
+                    int xs = 0;
+                    uint32_t xph = 0;
+                    for (int cb = 0; cb < p.Cblocks; ++cb)
+                    {
+                        ptx::mbar_wait(&xEmpty[xs], xph ^ 1);
+                        ptx::mbar_arrive_expect_tx(&xFull[xs], xBytes);
+                        // x viewed as (W, H, C, N); origin 16-byte aligned in W; out-of-bounds elements read as 0 (= zero padding)
+                        ptx::tma_load_4d(xRing + xs * xBytesPad, &mapX, &xFull[xs], ow0 - p.wOff, oh0 - p.padY, cb * kBlockC, n);
+                        if (++xs == p.xStages) { xs = 0; xph ^= 1; }
                     }
                 }
             }
@@ -197,18 +212,25 @@ namespace nb200
             }
             else
             {
-                // ===== converters (then epilogue): warps 2..5; TMEM lane quadrant q = warp % 4 = output row of the tile =====
+                // ===== converters (then epilogue): warps 3..10 in two groups that alternate taps =====
+                // TMEM lane quadrant q = warp % 4 = output row of the tile; group g handles iterations it = g (mod 2),
+                // i.e. A stages {g, g+2}. Each warp overlaps the TMEM store of one tap with the loads of its next tap.
                 const int q = warp & 3;
+                const int g = (warp - kFirstConvWarp) >> 2;
                 const uint32_t laneSel = (uint32_t)(q * 32) << 16;
                 const int chanStride = p.HR * p.WB; // floats between channels of the halo tile
-                int xs = 0, as = 0;
-                uint32_t xph = 0, aph = 0;
+                bool pending = false;
+                int pendStage = 0;
                 for (int cb = 0; cb < p.Cblocks; ++cb)
                 {
-                    ptx::mbar_wait(&xFull[xs], xph);
+                    const int xs = cb % p.xStages;
+                    ptx::mbar_wait(&xFull[xs], (uint32_t)(cb / p.xStages) & 1);
                     const float* xt = (const float*)(xRing + xs * xBytesPad);
                     for (int tap = 0; tap < taps; ++tap)
                     {
+                        const int it = cb * taps + tap;
+                        if ((it & 1) != g)
+                            continue;
                         const int r = tap / p.S, s = tap - r * p.S;
                         // pixel (q, lane) of the tile, tap (r, s): halo row q + r, halo column lane + s - padX + wOff
                         const float* src = xt + (q + r) * p.WB + (lane + s - p.padX + p.wOff);
@@ -219,31 +241,44 @@ namespace nb200
                             const float f = src[c * chanStride];
                             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v[c]) : "f"(f));
                         }
-                        ptx::mbar_wait(&aEmpty[as], aph ^ 1);
+                        if (pending)
+                        {
+                            // the previous tap's store has had the whole load phase to land
+                            ptx::tmem_st_wait();
+                            ptx::tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0)
+                                ptx::mbar_arrive(&aFull[pendStage]);
+                        }
+                        const int as = it & (kAStages - 1);
+                        ptx::mbar_wait(&aEmpty[as], ((uint32_t)(it / kAStages) & 1) ^ 1);
                         ptx::tc_fence_after_sync();
                         ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kBlockC, v);
-                        ptx::tmem_st_wait();
-                        ptx::tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0)
-                        {
-                            ptx::mbar_arrive(&aFull[as]);
-                            if (tap == taps - 1)
-                                ptx::mbar_arrive(&xEmpty[xs]); // every lane's loads of this halo tile have landed in registers
-                        }
-                        if (++as == kAStages) { as = 0; aph ^= 1; }
+                        pending = true;
+                        pendStage = as;
                     }
-                    if (++xs == p.xStages) { xs = 0; xph ^= 1; }
+                    // every load of this halo tile has been consumed into registers (the stores above read them)
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(&xEmpty[xs]);
+                }
+                if (pending)
+                {
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(&aFull[pendStage]);
                 }
 
-                // ----- epilogue -----
+                // ----- epilogue: the two warps of a quadrant split the filter columns -----
                 const int oh = oh0 + q, ow = ow0 + lane;
                 ptx::mbar_wait(accBar, 0);
                 ptx::tc_fence_after_sync();
                 const bool pixelOk = oh < p.Ho && ow < p.Wo;
                 float* yp = y + n * p.yStrideN + (long long)oh * p.Wo + ow;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32)
+                for (int c0 = g * 32; c0 < BN; c0 += 32 * kConvGroups)
                 {
                     if (k0 + c0 >= p.K)
                         break; // warp-uniform
@@ -557,7 +592,9 @@ namespace nb200
 
         int pick_bn(int K)
         {
-            return K <= 64 ? 64 : 128;
+            // Shared-memory traffic per MMA cycle falls with the tile's N (the converted A tile is reused across more
+            // filters), so take the widest accumulator the filter count fills.
+            return K <= 64 ? 64 : K <= 128 ? 128 : 256;
         }
 
         // Forward-shaped problem: act tensor `in` (N, Cin, Hin, Win) -> out (N, Kout, Hout, Wout), filters repacked by `mode`.
@@ -584,11 +621,12 @@ namespace nb200
             const size_t xBytes = ((size_t)kBlockC * pl.HR * pl.WB * 4 + 1023) & ~(size_t)1023;
             const size_t bBytes = (size_t)pl.BN * kBlockC * 4;
             const size_t fixed = 1024 /*alignment slack*/ + 512 /*barriers*/;
+            const long long budget = pl.BN > 128 ? kSmemBudget1 : kSmemBudget2;
             pl.ok = false;
-            // prefer two halo stages; give the rest to the filter ring (at least 2, at most 8)
-            for (int xs = 2; xs >= 1 && !pl.ok; --xs)
+            // prefer two (three when alone on the SM) halo stages; give the rest to the filter ring (at least 2, at most 8)
+            for (int xs = pl.BN > 128 ? 3 : 2; xs >= 1 && !pl.ok; --xs)
             {
-                const long long rest = (long long)kSmemBudget - (long long)fixed - (long long)xs * (long long)xBytes;
+                const long long rest = budget - (long long)fixed - (long long)xs * (long long)xBytes;
                 int bs = (int)(rest / (long long)bBytes);
                 if (bs > 8) bs = 8;
                 if (bs >= 2)
@@ -622,13 +660,13 @@ namespace nb200
             static bool attrSet = false;
             if (!attrSet)
             {
-                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, BN > 128 ? kSmemBudget1 : kSmemBudget2));
                 attrSet = true;
             }
             const long long tiles = (long long)p.tilesK * p.tilesW * p.tilesH * f.N;
             if (tiles > 0x7FFFFFFFll)
                 return fail(NB200_E_UNSUPPORTED, "too many tiles");
-            tc_fprop_kernel<BN><<<(unsigned)tiles, kThreads, pl.smemBytes, st>>>(mapX, mapW, p, bias, out);
+            tc_fprop_kernel<BN><<<(unsigned)tiles, kFpropThreads, pl.smemBytes, st>>>(mapX, mapW, p, bias, out);
             NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
             return NB200_OK;
@@ -682,7 +720,9 @@ namespace nb200
             p.act = act; p.alpha = alpha;
             p.yStrideK = (long long)f.Hout * f.Wout;
             p.yStrideN = p.yStrideK * f.Kout;
-            return pl.BN == 64 ? launch_fprop<64>(f, pl, mapX, mapW, p, bias, out, st) : launch_fprop<128>(f, pl, mapX, mapW, p, bias, out, st);
+            return pl.BN == 64 ? launch_fprop<64>(f, pl, mapX, mapW, p, bias, out, st)
+                 : pl.BN == 128 ? launch_fprop<128>(f, pl, mapX, mapW, p, bias, out, st)
+                                : launch_fprop<256>(f, pl, mapX, mapW, p, bias, out, st);
         }
 
         FwdShape fwd_shape(const nb200_conv_desc& d)
