@@ -23,6 +23,8 @@
 //                  so one tile's epilogue and prologue overlap the other's MMAs.
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
+#include <vector>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -34,13 +36,52 @@ namespace nb200
         constexpr int kTileW = 32;   // output columns per tile (= lanes of a converter warp)
         constexpr int kTileH = 4;    // output rows per tile (= converter warps) -> M = 128
         constexpr int kBlockC = 32;  // reduction channels per step (4 MMAs of K = 8)
-        constexpr int kThreads = 192;        // kernel gradient: producer + MMA + 4 converter warps
+        constexpr int kThreads = 320;        // kernel gradient: producer + MMA + 2 groups of 4 converter warps
         constexpr int kFpropThreads = 352;   // forward: filter producer + MMA + halo producer + 2 groups of 4 converter warps
         constexpr int kFirstConvWarp = 3;
         constexpr int kConvGroups = 2;
-        constexpr int kAStages = 4;  // A tiles in TMEM (32 columns each)
+        constexpr int kAStagesMax = 8;
+        // A tiles in TMEM (32 columns each): BN = 256 owns all 512 columns (256 accumulator + 8 A tiles); BN <= 128 shares the
+        // SM with a second CTA (256 columns: accumulator + 4 A tiles).
+        __host__ __device__ constexpr int a_stages(int BN) { return BN > 128 ? 8 : 4; }
         constexpr int kSmemBudget2 = 112 * 1024; // per CTA when two CTAs share an SM (BN <= 128)
         constexpr int kSmemBudget1 = 220 * 1024; // one CTA per SM (BN = 256)
+
+        // Optional wait-time instrumentation (NB200_DEBUG_WAITS=1): each role accumulates the cycles it spends blocked on
+        // each barrier class into dbg[cta][slot]. Null pointer = disabled (one uniform branch per wait).
+        enum { kDbgBFull = 0, kDbgAFull, kDbgBEmpty, kDbgXEmpty, kDbgXFull, kDbgAEmpty, kDbgAcc, kDbgTotal, kDbgSlots = 8 };
+
+        struct WaitAcc
+        {
+            long long v[kDbgSlots];
+            long long* sink; // global row to flush into, or nullptr (instrumentation off)
+            __device__ __forceinline__ explicit WaitAcc(long long* s) : sink(s)
+            {
+#pragma unroll
+                for (int i = 0; i < kDbgSlots; ++i) v[i] = 0;
+            }
+            __device__ __forceinline__ void flush()
+            {
+                if (sink)
+                {
+#pragma unroll
+                    for (int i = 0; i < kDbgSlots; ++i)
+                        if (v[i]) sink[i] = v[i];
+                }
+            }
+        };
+
+        __device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, WaitAcc& acc, int slot)
+        {
+            if (acc.sink == nullptr)
+            {
+                ptx::mbar_wait(bar, parity);
+                return;
+            }
+            const long long t0 = clock64();
+            ptx::mbar_wait(bar, parity);
+            acc.v[slot] += clock64() - t0;
+        }
 
         struct FpropParams
         {
@@ -55,6 +96,7 @@ namespace nb200
             int act;
             float alpha;
             long long yStrideN, yStrideK; // elements
+            long long* dbg;               // wait-time instrumentation sink or nullptr
         };
 
         // ---------------------------------------------------------------- filter repack
@@ -95,6 +137,7 @@ namespace nb200
                         const float* __restrict__ bias, float* __restrict__ y)
         {
             constexpr uint32_t kBBytes = BN * kBlockC * 4;
+            constexpr int kAStages = a_stages(BN);
             // BN <= 128: two CTAs per SM x 256 columns; BN = 256: one CTA per SM x 512 columns
             constexpr uint32_t kTmemCols = BN > 128 ? 512 : 256;
             static_assert(BN + kAStages * kBlockC <= kTmemCols, "TMEM budget");
@@ -111,8 +154,8 @@ namespace nb200
             uint64_t* xFull = bEmpty + 8;      // [xStages]
             uint64_t* xEmpty = xFull + 4;      // [xStages]
             uint64_t* aFull = xEmpty + 4;      // [kAStages]
-            uint64_t* aEmpty = aFull + kAStages;
-            uint64_t* accBar = aEmpty + kAStages;
+            uint64_t* aEmpty = aFull + kAStagesMax;
+            uint64_t* accBar = aEmpty + kAStagesMax;
             uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
 
             const int warp = threadIdx.x >> 5;
@@ -145,6 +188,13 @@ namespace nb200
             const uint32_t tmemA = tmemAcc + BN;
 
             const int taps = p.R * p.S;
+            // per-CTA debug rows: [0] filter producer, [1] MMA issuer, [2] halo producer, [3] converter warp 3 lane 0
+            long long* dbgBase = p.dbg ? p.dbg + (long long)blockIdx.x * 4 * kDbgSlots : nullptr;
+            WaitAcc dbgP((dbgBase && lane == 0) ? dbgBase : nullptr);
+            WaitAcc dbgM((dbgBase && lane == 0) ? dbgBase + kDbgSlots : nullptr);
+            WaitAcc dbgX((dbgBase && lane == 0) ? dbgBase + 2 * kDbgSlots : nullptr);
+            WaitAcc dbgC((dbgBase && warp == kFirstConvWarp && lane == 0) ? dbgBase + 3 * kDbgSlots : nullptr);
+            const long long tStart = clock64();
 
             if (warp == 0)
             {
@@ -156,7 +206,7 @@ namespace nb200
                     for (int cb = 0; cb < p.Cblocks; ++cb)
                         for (int tap = 0; tap < taps; ++tap)
                         {
-                            ptx::mbar_wait(&bEmpty[bs], bph ^ 1);
+                            timed_wait(&bEmpty[bs], bph ^ 1, dbgP, kDbgBEmpty);
                             ptx::mbar_arrive_expect_tx(&bFull[bs], kBBytes);
                             ptx::tma_load_3d(bRing + bs * kBBytes, &mapW, &bFull[bs], cb * kBlockC, k0, tap);
                             if (++bs == p.bStages) { bs = 0; bph ^= 1; }
@@ -172,7 +222,7 @@ namespace nb200
                     uint32_t xph = 0;
                     for (int cb = 0; cb < p.Cblocks; ++cb)
                     {
-                        ptx::mbar_wait(&xEmpty[xs], xph ^ 1);
+                        timed_wait(&xEmpty[xs], xph ^ 1, dbgX, kDbgXEmpty);
                         ptx::mbar_arrive_expect_tx(&xFull[xs], xBytes);
                         // x viewed as (W, H, C, N); origin 16-byte aligned in W; out-of-bounds elements read as 0 (= zero padding)
                         ptx::tma_load_4d(xRing + xs * xBytesPad, &mapX, &xFull[xs], ow0 - p.wOff, oh0 - p.padY, cb * kBlockC, n);
@@ -182,33 +232,40 @@ namespace nb200
             }
             else if (warp == 1)
             {
-                if (lane == 0)
+                // ===== MMA issuer: D[128 x BN] += A[tmem 128 x 32] * B[smem BN x 32]^T per tap =====
+                // The whole warp runs the (warp-uniform) loop; one elected lane issues the tcgen05 instructions.
+                constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, /*A K-major (TMEM)*/ 0, /*B K-major*/ 0);
+                // B: K-major SW128: 8-filter groups 1 KB apart (SBO); a K=8 slice starts kk*32 B into the 128 B row
+                const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(bRing), /*LBO*/ 16, /*SBO*/ 1024);
+                int as = 0, bs = 0;
+                uint32_t aph = 0, bph = 0;
+                const int iters = taps * p.Cblocks;
+                const long long tLoop = dbgM.sink ? clock64() : 0;
+                for (int it = 0; it < iters; ++it)
                 {
-                    // ===== MMA issuer: D[128 x BN] += A[tmem 128 x 32] * B[smem BN x 32]^T per tap =====
-                    constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, /*A K-major (TMEM)*/ 0, /*B K-major*/ 0);
-                    int as = 0, bs = 0;
-                    uint32_t aph = 0, bph = 0;
-                    const int iters = taps * p.Cblocks;
-                    for (int it = 0; it < iters; ++it)
+                    timed_wait(&bFull[bs], bph, dbgM, kDbgBFull);
+                    timed_wait(&aFull[as], aph, dbgM, kDbgAFull);
+                    const long long tIssue = dbgM.sink ? clock64() : 0;
+                    ptx::tc_fence_after_sync();
+                    if (ptx::elect_one())
                     {
-                        ptx::mbar_wait(&bFull[bs], bph);
-                        ptx::mbar_wait(&aFull[as], aph);
-                        ptx::tc_fence_after_sync();
-                        const uint32_t b = ptx::smem_u32(bRing + bs * kBBytes);
+                        const uint64_t db = descB0 + (uint64_t)((bs * kBBytes) >> 4);
+                        const uint32_t ta = tmemA + as * kBlockC;
 #pragma unroll
                         for (int kk = 0; kk < kBlockC / 8; ++kk)
-                        {
-                            // B: K-major SW128: 8-filter groups 1 KB apart (SBO); this K=8 slice starts 32 B into the 128 B row
-                            const uint64_t db = ptx::smem_desc_sw128(b + kk * 32, /*LBO*/ 16, /*SBO*/ 1024);
-                            ptx::mma_tf32_ts(tmemAcc, tmemA + as * kBlockC + kk * 8, db, idesc, (it | kk) != 0);
-                        }
+                            ptx::mma_tf32_ts(tmemAcc, ta + kk * 8, db + kk * 2, idesc, (it | kk) != 0);
                         ptx::mma_commit(&aEmpty[as]); // both slots reusable once these MMAs have consumed them
                         ptx::mma_commit(&bEmpty[bs]);
-                        if (++as == kAStages) { as = 0; aph ^= 1; }
-                        if (++bs == p.bStages) { bs = 0; bph ^= 1; }
                     }
-                    ptx::mma_commit(accBar); // accumulator complete
+                    __syncwarp();
+                    if (dbgM.sink) dbgM.v[kDbgAcc] += clock64() - tIssue;
+                    if (++as == kAStages) { as = 0; aph ^= 1; }
+                    if (++bs == p.bStages) { bs = 0; bph ^= 1; }
                 }
+                if (dbgM.sink) dbgM.v[kDbgTotal] = clock64() - tLoop;
+                if (ptx::elect_one())
+                    ptx::mma_commit(accBar); // accumulator complete
+                __syncwarp();
             }
             else
             {
@@ -218,28 +275,35 @@ namespace nb200
                 const int q = warp & 3;
                 const int g = (warp - kFirstConvWarp) >> 2;
                 const uint32_t laneSel = (uint32_t)(q * 32) << 16;
-                const int chanStride = p.HR * p.WB; // floats between channels of the halo tile
+                const uint32_t chanStrideB = (uint32_t)(p.HR * p.WB * 4); // bytes between channels of the halo tile
+                const uint32_t xRing32 = ptx::smem_u32(xRing);
                 bool pending = false;
                 int pendStage = 0;
                 for (int cb = 0; cb < p.Cblocks; ++cb)
                 {
                     const int xs = cb % p.xStages;
-                    ptx::mbar_wait(&xFull[xs], (uint32_t)(cb / p.xStages) & 1);
-                    const float* xt = (const float*)(xRing + xs * xBytesPad);
-                    for (int tap = 0; tap < taps; ++tap)
+                    timed_wait(&xFull[xs], (uint32_t)(cb / p.xStages) & 1, dbgC, kDbgXFull);
+                    const uint32_t xt = xRing32 + xs * xBytesPad;
+                    int r = 0, s = 0;
+                    for (int tap = 0; tap < taps; ++tap, (++s == p.S ? (s = 0, ++r) : 0))
                     {
                         const int it = cb * taps + tap;
                         if ((it & 1) != g)
                             continue;
-                        const int r = tap / p.S, s = tap - r * p.S;
                         // pixel (q, lane) of the tile, tap (r, s): halo row q + r, halo column lane + s - padX + wOff
-                        const float* src = xt + (q + r) * p.WB + (lane + s - p.padX + p.wOff);
+                        const uint32_t src = xt + (uint32_t)(((q + r) * p.WB + (lane + s - p.padX + p.wOff)) << 2);
                         uint32_t v[kBlockC];
-#pragma unroll
-                        for (int c = 0; c < kBlockC; ++c)
+                        if (chanStrideB == 960u) // 3x3 filters: compile-time channel pitch -> LDS with immediate offsets
                         {
-                            const float f = src[c * chanStride];
-                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v[c]) : "f"(f));
+#pragma unroll
+                            for (int c = 0; c < kBlockC; ++c)
+                                v[c] = ptx::tf32_round_bits(ptx::lds_b32(src + c * 960u));
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int c = 0; c < kBlockC; ++c)
+                                v[c] = ptx::tf32_round_bits(ptx::lds_b32(src + c * chanStrideB));
                         }
                         if (pending)
                         {
@@ -251,7 +315,7 @@ namespace nb200
                                 ptx::mbar_arrive(&aFull[pendStage]);
                         }
                         const int as = it & (kAStages - 1);
-                        ptx::mbar_wait(&aEmpty[as], ((uint32_t)(it / kAStages) & 1) ^ 1);
+                        timed_wait(&aEmpty[as], ((uint32_t)(it / kAStages) & 1) ^ 1, dbgC, kDbgAEmpty);
                         ptx::tc_fence_after_sync();
                         ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kBlockC, v);
                         pending = true;
@@ -273,7 +337,7 @@ namespace nb200
 
                 // ----- epilogue: the two warps of a quadrant split the filter columns -----
                 const int oh = oh0 + q, ow = ow0 + lane;
-                ptx::mbar_wait(accBar, 0);
+                timed_wait(accBar, 0, dbgC, kDbgAcc);
                 ptx::tc_fence_after_sync();
                 const bool pixelOk = oh < p.Ho && ow < p.Wo;
                 float* yp = y + n * p.yStrideN + (long long)oh * p.Wo + ow;
@@ -312,6 +376,263 @@ namespace nb200
             }
         }
 
+
+
+        // ---------------------------------------------------------------- forward kernel, CTA-pair form (cta_group::2)
+        // Same algorithm, but two CTAs of a cluster (one TPC = two SMs) cooperate on a 256-pixel x BN-filter tile:
+        //   - each CTA converts the A tile of ITS 128 pixels (4 of the pair's 8 output rows) into its own TMEM;
+        //   - each CTA loads only HALF of every filter tile (BN/2 filters); the pair leader issues
+        //     tcgen05.mma.cta_group::2 (M = 256), which reads B halves from both shared memories;
+        //   - accumulator rows 0-127 / 128-255 stay in the leader's / peer's TMEM, so each CTA runs its own epilogue.
+        // Per MMA cycle this halves the filter bytes written by TMA and read by the tensor core in every SM, which is
+        // what bounds the single-CTA kernel (ncu: tensor pipe ~30 %, shared-memory pipes saturated).
+        // Cross-CTA signalling: filter TMA loads of both CTAs complete_tx on the LEADER's bFull barrier; converter warps
+        // of both CTAs arrive on the LEADER's aFull barrier (remote arrive through mapa); the leader's
+        // tcgen05.commit multicasts to the bEmpty / aEmpty / accBar barriers of BOTH CTAs.
+        template <int BN>
+        __global__ void __launch_bounds__(kFpropThreads, (BN > 128 ? 1 : 2))
+        tc_fprop2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, FpropParams p,
+                         const float* __restrict__ bias, float* __restrict__ y)
+        {
+            constexpr int BNH = BN / 2;
+            constexpr int kAStages = a_stages(BN);
+            constexpr uint32_t kBBytes = BNH * kBlockC * 4;
+            constexpr uint32_t kTmemCols = BN > 128 ? 512 : 256;
+            static_assert(BN + kAStages * kBlockC <= kTmemCols, "TMEM budget");
+
+            extern __shared__ uint8_t smemRaw[];
+            uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+            const uint32_t xBytes = (uint32_t)(kBlockC * p.HR * p.WB * 4);
+            const uint32_t xBytesPad = (xBytes + 1023) & ~1023u;
+            uint8_t* bRing = smem;
+            uint8_t* xRing = smem + p.bStages * kBBytes;
+            uint64_t* bars = (uint64_t*)(xRing + p.xStages * xBytesPad);
+            uint64_t* bFull = bars;            // [bStages]   (leader's copy is the live one)
+            uint64_t* bEmpty = bFull + 8;      // [bStages]
+            uint64_t* xFull = bEmpty + 8;      // [xStages]   local
+            uint64_t* xEmpty = xFull + 4;      // [xStages]   local
+            uint64_t* aFull = xEmpty + 4;      // [kAStages]  (leader's copy is the live one)
+            uint64_t* aEmpty = aFull + kAStagesMax;
+            uint64_t* accBar = aEmpty + kAStagesMax;
+            uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
+
+            const int warp = threadIdx.x >> 5;
+            const int lane = threadIdx.x & 31;
+            const uint32_t rank = ptx::cluster_ctarank();
+            const bool leader = rank == 0;
+
+            int t = blockIdx.x >> 1; // pair index; filter tile fastest (L2 reuse of the activation tile)
+            const int kt = t % p.tilesK; t /= p.tilesK;
+            const int tw = t % p.tilesW; t /= p.tilesW;
+            const int th = t % p.tilesH; t /= p.tilesH;
+            const int n = t;
+            const int ow0 = tw * kTileW, oh0 = th * (2 * kTileH) + (int)rank * kTileH, k0 = kt * BN;
+
+            if (warp == 0 && lane == 0)
+            {
+                ptx::prefetch_tensormap(&mapX);
+                ptx::prefetch_tensormap(&mapW);
+                for (int s = 0; s < p.bStages; ++s) { ptx::mbar_init(&bFull[s], 1); ptx::mbar_init(&bEmpty[s], 1); }
+                for (int s = 0; s < p.xStages; ++s) { ptx::mbar_init(&xFull[s], 1); ptx::mbar_init(&xEmpty[s], kTileH * kConvGroups); }
+                for (int s = 0; s < kAStages; ++s) { ptx::mbar_init(&aFull[s], 2 * kTileH); ptx::mbar_init(&aEmpty[s], 1); }
+                ptx::mbar_init(accBar, 1);
+                ptx::fence_mbar_init();
+            }
+            if (warp == 1)
+                ptx::tmem_alloc_2sm(tmemSlot, kTmemCols);
+            ptx::tc_fence_before_sync();
+            ptx::cluster_sync(); // both CTAs' barriers are initialised before any remote arrive / TMA signal
+            ptx::tc_fence_after_sync();
+            const uint32_t tmemAcc = *tmemSlot;
+            const uint32_t tmemA = tmemAcc + BN;
+
+            const int taps = p.R * p.S;
+            // per-CTA debug rows: [0] filter producer, [1] MMA issuer, [2] halo producer, [3] converter warp 3 lane 0
+            long long* dbgBase = p.dbg ? p.dbg + (long long)blockIdx.x * 4 * kDbgSlots : nullptr;
+            WaitAcc dbgP((dbgBase && lane == 0) ? dbgBase : nullptr);
+            WaitAcc dbgM((dbgBase && lane == 0) ? dbgBase + kDbgSlots : nullptr);
+            WaitAcc dbgX((dbgBase && lane == 0) ? dbgBase + 2 * kDbgSlots : nullptr);
+            WaitAcc dbgC((dbgBase && warp == kFirstConvWarp && lane == 0) ? dbgBase + 3 * kDbgSlots : nullptr);
+            const long long tStart = clock64();
+
+            if (warp == 0)
+            {
+                if (lane == 0)
+                {
+                    // ===== TMA producer (filters): this CTA's half of each tile; bytes are counted on the leader's barrier =====
+                    int bs = 0;
+                    uint32_t bph = 0;
+                    for (int cb = 0; cb < p.Cblocks; ++cb)
+                        for (int tap = 0; tap < taps; ++tap)
+                        {
+                            timed_wait(&bEmpty[bs], bph ^ 1, dbgP, kDbgBEmpty);
+                            if (leader)
+                                ptx::mbar_arrive_expect_tx(&bFull[bs], 2 * kBBytes);
+                            ptx::tma_load_3d_2sm(bRing + bs * kBBytes, &mapW, ptx::mapa_u32(&bFull[bs], 0), cb * kBlockC, k0 + (int)rank * BNH, tap);
+                            if (++bs == p.bStages) { bs = 0; bph ^= 1; }
+                        }
+                }
+            }
+            else if (warp == 2)
+            {
+                if (lane == 0)
+                {
+                    // ===== TMA producer (activations): this CTA's halo tile per channel block =====
+                    int xs = 0;
+                    uint32_t xph = 0;
+                    for (int cb = 0; cb < p.Cblocks; ++cb)
+                    {
+                        timed_wait(&xEmpty[xs], xph ^ 1, dbgX, kDbgXEmpty);
+                        ptx::mbar_arrive_expect_tx(&xFull[xs], xBytes);
+                        ptx::tma_load_4d(xRing + xs * xBytesPad, &mapX, &xFull[xs], ow0 - p.wOff, oh0 - p.padY, cb * kBlockC, n);
+                        if (++xs == p.xStages) { xs = 0; xph ^= 1; }
+                    }
+                }
+            }
+            else if (warp == 1)
+            {
+                if (leader)
+                {
+                    // ===== MMA issuer (pair leader): D[256 x BN] += A[tmem of both CTAs] * B[halves in both smem]^T =====
+                    constexpr uint32_t idesc = ptx::idesc_tf32(256, BN, 0, 0);
+                    const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(bRing), /*LBO*/ 16, /*SBO*/ 1024);
+                    int as = 0, bs = 0;
+                    uint32_t aph = 0, bph = 0;
+                    const int iters = taps * p.Cblocks;
+                    for (int it = 0; it < iters; ++it)
+                    {
+                        timed_wait(&bFull[bs], bph, dbgM, kDbgBFull);
+                        timed_wait(&aFull[as], aph, dbgM, kDbgAFull);
+                        ptx::tc_fence_after_sync();
+                        if (ptx::elect_one())
+                        {
+                            const uint64_t db = descB0 + (uint64_t)((bs * kBBytes) >> 4);
+                            const uint32_t ta = tmemA + as * kBlockC;
+#pragma unroll
+                            for (int kk = 0; kk < kBlockC / 8; ++kk)
+                                ptx::mma_tf32_ts_2sm(tmemAcc, ta + kk * 8, db + kk * 2, idesc, (it | kk) != 0);
+                            ptx::mma_commit_2sm(&aEmpty[as], 3);
+                            ptx::mma_commit_2sm(&bEmpty[bs], 3);
+                        }
+                        __syncwarp();
+                        if (++as == kAStages) { as = 0; aph ^= 1; }
+                        if (++bs == p.bStages) { bs = 0; bph ^= 1; }
+                    }
+                    if (ptx::elect_one())
+                        ptx::mma_commit_2sm(accBar, 3);
+                    __syncwarp();
+                }
+            }
+            else
+            {
+                // ===== converters (then epilogue), as in the single-CTA kernel; aFull lives in the leader =====
+                const int q = warp & 3;
+                const int g = (warp - kFirstConvWarp) >> 2;
+                const uint32_t laneSel = (uint32_t)(q * 32) << 16;
+                const uint32_t chanStrideB = (uint32_t)(p.HR * p.WB * 4);
+                const uint32_t xRing32 = ptx::smem_u32(xRing);
+                bool pending = false;
+                int pendStage = 0;
+                for (int cb = 0; cb < p.Cblocks; ++cb)
+                {
+                    const int xs = cb % p.xStages;
+                    timed_wait(&xFull[xs], (uint32_t)(cb / p.xStages) & 1, dbgC, kDbgXFull);
+                    const uint32_t xt = xRing32 + xs * xBytesPad;
+                    int r = 0, s = 0;
+                    for (int tap = 0; tap < taps; ++tap, (++s == p.S ? (s = 0, ++r) : 0))
+                    {
+                        const int it = cb * taps + tap;
+                        if ((it & 1) != g)
+                            continue;
+                        const uint32_t src = xt + (uint32_t)(((q + r) * p.WB + (lane + s - p.padX + p.wOff)) << 2);
+                        uint32_t v[kBlockC];
+                        if (chanStrideB == 960u) // 3x3 filters: compile-time channel pitch -> LDS with immediate offsets
+                        {
+#pragma unroll
+                            for (int c = 0; c < kBlockC; ++c)
+                                v[c] = ptx::tf32_round_bits(ptx::lds_b32(src + c * 960u));
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int c = 0; c < kBlockC; ++c)
+                                v[c] = ptx::tf32_round_bits(ptx::lds_b32(src + c * chanStrideB));
+                        }
+                        if (pending)
+                        {
+                            ptx::tmem_st_wait();
+                            ptx::tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0)
+                                ptx::mbar_arrive_cluster(ptx::mapa_u32(&aFull[pendStage], 0));
+                        }
+                        const int as = it & (kAStages - 1);
+                        timed_wait(&aEmpty[as], ((uint32_t)(it / kAStages) & 1) ^ 1, dbgC, kDbgAEmpty);
+                        ptx::tc_fence_after_sync();
+                        ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kBlockC, v);
+                        pending = true;
+                        pendStage = as;
+                    }
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(&xEmpty[xs]);
+                }
+                if (pending)
+                {
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive_cluster(ptx::mapa_u32(&aFull[pendStage], 0));
+                }
+
+                // ----- epilogue: this CTA's 128 accumulator rows -----
+                const int oh = oh0 + q, ow = ow0 + lane;
+                timed_wait(accBar, 0, dbgC, kDbgAcc);
+                ptx::tc_fence_after_sync();
+                const bool pixelOk = oh < p.Ho && ow < p.Wo;
+                float* yp = y + n * p.yStrideN + (long long)oh * p.Wo + ow;
+#pragma unroll 1
+                for (int c0 = g * 32; c0 < BN; c0 += 32 * kConvGroups)
+                {
+                    if (k0 + c0 >= p.K)
+                        break; // warp-uniform
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + c0, v);
+                    ptx::tmem_ld_wait();
+                    if (pixelOk)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                        {
+                            const int k = k0 + c0 + j;
+                            if (k < p.K)
+                            {
+                                float f = __uint_as_float(v[j]);
+                                if (bias)
+                                    f += __ldg(bias + k);
+                                yp[k * p.yStrideK] = apply_activation(p.act, p.alpha, f);
+                            }
+                        }
+                    }
+                }
+            }
+
+            if (warp == 0) dbgP.flush();
+            if (warp == 1) dbgM.flush();
+            if (warp == 2) dbgX.flush();
+            if (warp == kFirstConvWarp) dbgC.flush();
+            if (dbgBase && threadIdx.x == 0)
+                dbgBase[kDbgTotal] = clock64() - tStart;
+            // neither CTA may exit (or free TMEM) while the other can still signal its barriers or read its filter halves
+            ptx::tc_fence_before_sync();
+            ptx::cluster_sync();
+            if (warp == 1)
+            {
+                ptx::tc_fence_after_sync();
+                ptx::tmem_dealloc_2sm(tmemAcc, kTmemCols);
+            }
+        }
 
         // ---------------------------------------------------------------- kernel-gradient kernel
         //   dw[k][c][r][s] = sum over pixels  dy[n][k][oh][ow] * x[n][c][oh+r-pY][ow+s-pX]           (stride 1)
@@ -419,57 +740,57 @@ namespace nb200
             }
             else if (warp == 1)
             {
-                if (lane == 0)
-                {
-                    // ===== MMA issuer =====
-                    constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, 0, 0);
-                    int st = 0, as = 0;
-                    uint32_t ph = 0, aph = 0;
-                    for (int it = 0; it < steps; ++it)
-                    {
-                        ptx::mbar_wait(&full[st], ph);
-                        const uint32_t b = ptx::smem_u32(smem + st * kStageBytes + kWgXBytes);
-                        for (int s = 0; s < p.S; ++s)
-                        {
-                            ptx::mbar_wait(&aFull[as], aph);
-                            ptx::tc_fence_after_sync();
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                            {
-                                const uint64_t db = ptx::smem_desc_sw128(b + kk * 32, 16, 1024);
-                                ptx::mma_tf32_ts(tmemAcc + s * BN, tmemA + as * 32 + kk * 8, db, idesc, (it | kk) != 0);
-                            }
-                            ptx::mma_commit(&aEmpty[as]);
-                            if (++as == kWgAStages) { as = 0; aph ^= 1; }
-                        }
-                        ptx::mma_commit(&empty[st]); // dy tile consumed
-                        if (++st == p.stages) { st = 0; ph ^= 1; }
-                    }
-                    ptx::mma_commit(accBar);
-                }
-            }
-            else
-            {
-                // ===== converters: thread = channel (TMEM lane) =====
-                const int q = warp & 3;
-                const uint32_t laneSel = (uint32_t)(q * 32) << 16;
-                const int cl = q * 32 + lane;
+                // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
+                constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, 0, 0);
+                const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(smem + kWgXBytes), 16, 1024);
                 int st = 0, as = 0;
                 uint32_t ph = 0, aph = 0;
                 for (int it = 0; it < steps; ++it)
                 {
                     ptx::mbar_wait(&full[st], ph);
-                    const float4* rowp = (const float4*)(smem + st * kStageBytes + cl * (kWgXW * 4));
-                    float row[40];
+                    const uint64_t db = descB0 + (uint64_t)((st * kStageBytes) >> 4);
+                    for (int s = 0; s < p.S; ++s)
+                    {
+                        ptx::mbar_wait(&aFull[as], aph);
+                        ptx::tc_fence_after_sync();
+                        if (ptx::elect_one())
+                        {
+                            const uint32_t ta = tmemA + as * 32;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                ptx::mma_tf32_ts(tmemAcc + s * BN, ta + kk * 8, db + kk * 2, idesc, (it | kk) != 0);
+                            ptx::mma_commit(&aEmpty[as]);
+                            if (s == p.S - 1)
+                                ptx::mma_commit(&empty[st]); // dy tile consumed
+                        }
+                        __syncwarp();
+                        if (++as == kWgAStages) { as = 0; aph ^= 1; }
+                    }
+                    if (++st == p.stages) { st = 0; ph ^= 1; }
+                }
+                if (ptx::elect_one())
+                    ptx::mma_commit(accBar);
+                __syncwarp();
+            }
+            else
+            {
+                // ===== converters: thread = channel (TMEM lane); two groups of 4 warps alternate steps =====
+                const int q = warp & 3;
+                const int g = (warp - 2) >> 2;
+                const uint32_t laneSel = (uint32_t)(q * 32) << 16;
+                const int cl = q * 32 + lane;
+                const uint32_t smem32 = ptx::smem_u32(smem);
+                bool pending = false;
+                int pendStage = 0;
+                for (int it = g; it < steps; it += 2)
+                {
+                    const int st = it % p.stages;
+                    ptx::mbar_wait(&full[st], (uint32_t)(it / p.stages) & 1);
+                    const uint32_t rowp = smem32 + st * kStageBytes + cl * (kWgXW * 4);
+                    uint32_t row[40];
 #pragma unroll
                     for (int i = 0; i < 10; ++i)
-                    {
-                        const float4 f = rowp[i];
-                        row[4 * i + 0] = f.x; row[4 * i + 1] = f.y; row[4 * i + 2] = f.z; row[4 * i + 3] = f.w;
-                    }
-                    __syncwarp();
-                    if (lane == 0)
-                        ptx::mbar_arrive(&empty[st]); // x segment is in registers
+                        ptx::lds_v4(rowp + i * 16, row[4 * i + 0], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
                     for (int s = 0; s < p.S; ++s)
                     {
                         const int off = s - p.padX + p.wOff; // 0..8
@@ -480,19 +801,35 @@ namespace nb200
                             {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j)
-                                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v[j]) : "f"(row[j + o]));
+                                    v[j] = ptx::tf32_round_bits(row[j + o]);
                             }
-                        ptx::mbar_wait(&aEmpty[as], aph ^ 1);
+                        if (pending)
+                        {
+                            ptx::tmem_st_wait();
+                            ptx::tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0)
+                                ptx::mbar_arrive(&aFull[pendStage]);
+                        }
+                        const int j = it * p.S + s; // global tap sequence number = MMA consumption order
+                        const int as = j & (kWgAStages - 1);
+                        ptx::mbar_wait(&aEmpty[as], ((uint32_t)(j / kWgAStages) & 1) ^ 1);
                         ptx::tc_fence_after_sync();
                         ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * 32, v);
-                        ptx::tmem_st_wait();
-                        ptx::tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0)
-                            ptx::mbar_arrive(&aFull[as]);
-                        if (++as == kWgAStages) { as = 0; aph ^= 1; }
+                        pending = true;
+                        pendStage = as;
                     }
-                    if (++st == p.stages) { st = 0; ph ^= 1; }
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(&empty[st]); // x segment fully consumed into registers / TMEM stores issued
+                }
+                if (pending)
+                {
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(&aFull[pendStage]);
                 }
 
                 // ----- epilogue: partial[split][tap][k][c], lanes = consecutive channels -> coalesced -----
@@ -504,7 +841,7 @@ namespace nb200
                 {
                     float* dst = ws + ((long long)(split * taps + r * p.S + s) * p.K) * p.C + c;
 #pragma unroll 1
-                    for (int j0 = 0; j0 < BN; j0 += 32)
+                    for (int j0 = g * 32; j0 < BN; j0 += 64)
                     {
                         if (k0 + j0 >= p.K)
                             break;
@@ -606,6 +943,7 @@ namespace nb200
         struct Plan
         {
             int BN, wOff, WB, HR, xStages, bStages;
+            bool pair; // CTA-pair (cta_group::2) kernel
             size_t smemBytes;
             bool ok;
         };
@@ -613,18 +951,22 @@ namespace nb200
         Plan make_plan(const FwdShape& f)
         {
             Plan pl{};
+            // The CTA-pair (cta_group::2) kernel is correct but, as measured on B200 (profiles/), slower than the
+            // single-CTA kernel for every VGG/DCGAN shape, so it is opt-in (NB200_FPROP_PAIR=1) until that is understood.
+            static const bool usePair = getenv("NB200_FPROP_PAIR") != nullptr;
+            pl.pair = usePair;
             pl.BN = pick_bn(f.Kout);
             pl.wOff = round_up(f.padX, 4);
             const int right = f.S - 1 - f.padX > 0 ? f.S - 1 - f.padX : 0;
             pl.WB = round_up(kTileW + pl.wOff + right, 4);
             pl.HR = kTileH + f.R - 1;
             const size_t xBytes = ((size_t)kBlockC * pl.HR * pl.WB * 4 + 1023) & ~(size_t)1023;
-            const size_t bBytes = (size_t)pl.BN * kBlockC * 4;
+            const size_t bBytes = (size_t)(pl.pair ? pl.BN / 2 : pl.BN) * kBlockC * 4;
             const size_t fixed = 1024 /*alignment slack*/ + 512 /*barriers*/;
             const long long budget = pl.BN > 128 ? kSmemBudget1 : kSmemBudget2;
             pl.ok = false;
             // prefer two (three when alone on the SM) halo stages; give the rest to the filter ring (at least 2, at most 8)
-            for (int xs = pl.BN > 128 ? 3 : 2; xs >= 1 && !pl.ok; --xs)
+            for (int xs = 2; xs >= 1 && !pl.ok; --xs)
             {
                 const long long rest = budget - (long long)fixed - (long long)xs * (long long)xBytes;
                 int bs = (int)(rest / (long long)bBytes);
@@ -664,11 +1006,57 @@ namespace nb200
                 attrSet = true;
             }
             const long long tiles = (long long)p.tilesK * p.tilesW * p.tilesH * f.N;
-            if (tiles > 0x7FFFFFFFll)
+            if (tiles > 0x3FFFFFFFll)
                 return fail(NB200_E_UNSUPPORTED, "too many tiles");
-            tc_fprop_kernel<BN><<<(unsigned)tiles, kFpropThreads, pl.smemBytes, st>>>(mapX, mapW, p, bias, out);
+            static const bool debugWaits = getenv("NB200_DEBUG_WAITS") != nullptr;
+            const long long ctas = pl.pair ? 2 * tiles : tiles;
+            FpropParams pd = p;
+            long long* dbgDev = nullptr;
+            if (debugWaits)
+            {
+                NB200_CUDA_TRY(cudaMalloc(&dbgDev, ctas * 4 * kDbgSlots * sizeof(long long)));
+                NB200_CUDA_TRY(cudaMemset(dbgDev, 0, ctas * 4 * kDbgSlots * sizeof(long long)));
+                pd.dbg = dbgDev;
+            }
+            if (pl.pair)
+            {
+                static bool attrSet2 = false;
+                if (!attrSet2)
+                {
+                    NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, BN > 128 ? kSmemBudget1 : kSmemBudget2));
+                    attrSet2 = true;
+                }
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3((unsigned)(2 * tiles));
+                cfg.blockDim = dim3(kFpropThreads);
+                cfg.dynamicSmemBytes = pl.smemBytes;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                NB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_fprop2_kernel<BN>, mapX, mapW, pd, bias, out));
+            }
+            else
+                tc_fprop_kernel<BN><<<(unsigned)tiles, kFpropThreads, pl.smemBytes, st>>>(mapX, mapW, pd, bias, out);
             NB200_CUDA_TRY(cudaGetLastError());
-        count_launch();
+            count_launch();
+            if (debugWaits)
+            {
+                NB200_CUDA_TRY(cudaStreamSynchronize(st));
+                std::vector<long long> h((size_t)ctas * 4 * kDbgSlots);
+                NB200_CUDA_TRY(cudaMemcpy(h.data(), dbgDev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                cudaFree(dbgDev);
+                double sum[4][kDbgSlots] = {};
+                for (long long c = 0; c < ctas; ++c)
+                    for (int r = 0; r < 4; ++r)
+                        for (int k = 0; k < kDbgSlots; ++k)
+                            sum[r][k] += (double)h[((size_t)c * 4 + r) * kDbgSlots + k];
+                const double inv = 1.0 / (double)ctas;
+                fprintf(stderr, "[nb200 waits] BN=%d pair=%d ctas=%lld iters=%d | total %.0f cyc/CTA | filterTMA: bEmpty %.0f | MMA: loop %.0f issue %.0f bFull %.0f aFull %.0f | haloTMA: xEmpty %.0f | conv(w3): xFull %.0f aEmpty %.0f acc %.0f\n",
+                        BN, (int)pl.pair, ctas, p.Cblocks * p.R * p.S, sum[0][kDbgTotal] * inv, sum[0][kDbgBEmpty] * inv, sum[1][kDbgTotal] * inv, sum[1][kDbgAcc] * inv, sum[1][kDbgBFull] * inv,
+                        sum[1][kDbgAFull] * inv, sum[2][kDbgXEmpty] * inv, sum[3][kDbgXFull] * inv, sum[3][kDbgAEmpty] * inv, sum[3][kDbgAcc] * inv);
+            }
             return NB200_OK;
         }
 
@@ -706,7 +1094,7 @@ namespace nb200
             {
                 cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)f.Kout, (cuuint64_t)(f.R * f.S)};
                 cuuint64_t strides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * f.Kout * 4};
-                cuuint32_t box[3] = {kBlockC, (cuuint32_t)pl.BN, 1};
+                cuuint32_t box[3] = {kBlockC, (cuuint32_t)(pl.pair ? pl.BN / 2 : pl.BN), 1};
                 int rc = make_map(&mapW, wr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
                 if (rc) return rc;
             }
@@ -716,8 +1104,8 @@ namespace nb200
             p.R = f.R; p.S = f.S; p.padX = f.padX; p.padY = f.padY;
             p.wOff = pl.wOff; p.WB = pl.WB; p.HR = pl.HR; p.xStages = pl.xStages; p.bStages = pl.bStages;
             p.Ho = f.Hout; p.Wo = f.Wout; p.K = f.Kout;
-            p.tilesW = ceil_div(f.Wout, kTileW); p.tilesH = ceil_div(f.Hout, kTileH); p.tilesK = ceil_div(f.Kout, pl.BN);
-            p.act = act; p.alpha = alpha;
+            p.tilesW = ceil_div(f.Wout, kTileW); p.tilesH = ceil_div(f.Hout, pl.pair ? 2 * kTileH : kTileH); p.tilesK = ceil_div(f.Kout, pl.BN);
+            p.act = act; p.alpha = alpha; p.dbg = nullptr;
             p.yStrideK = (long long)f.Hout * f.Wout;
             p.yStrideN = p.yStrideK * f.Kout;
             return pl.BN == 64 ? launch_fprop<64>(f, pl, mapX, mapW, p, bias, out, st)
