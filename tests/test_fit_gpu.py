@@ -1,0 +1,42 @@
+"""Loss curves of the CUDA path track the reference over N training steps (BASELINE.json north_star), single GPU:
+the same ConvStackTrainer is run once with the oracle-backed op on CPU and once with TensorOpB200 on cuda:0."""
+import numpy as np
+import pytest
+import torch
+
+from neuro__b200 import lib, synth
+from neuro__b200.fit import ConvLayerSpec, ConvStackTrainer
+from neuro__b200.tensor_op import TensorOpB200
+from tests.oracle_op import OracleOp
+
+pytestmark = pytest.mark.gpu
+
+LAYERS = [ConvLayerSpec(16, 3, 1, 1, lib.ACT_RELU), ConvLayerSpec(16, 3, 1, 1, lib.ACT_LEAKY_RELU, 0.2), ConvLayerSpec(8, 3, 1, 1, lib.ACT_TANH)]
+IN_SHAPE = (8, 32, 32)
+N, BATCH, EPOCHS = 8, 4, 5
+
+
+def _run(op, device, optimizer):
+    tr = ConvStackTrainer(op, IN_SHAPE, LAYERS, device, optimizer=optimizer, lr=0.01)
+    x = torch.from_numpy(synth.uniform(synth.SEED_X, (N,) + IN_SHAPE))
+    t = torch.from_numpy(synth.uniform(synth.SEED_DY, (N,) + tr.out_shape, -0.5, 0.5))
+    return tr.fit(x, t, BATCH, epochs=EPOCHS), tr.params.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("optimizer", ["adam", "sgd"])
+@pytest.mark.parametrize("math,tol", [(lib.MATH_TF32, 5e-3), (lib.MATH_FP32, 1e-4)], ids=["tf32", "fp32"])
+def test_loss_curve_tracks_reference(math, tol, optimizer):
+    ref_losses, ref_params = _run(OracleOp(), torch.device("cpu"), optimizer)
+    op = TensorOpB200(math)
+    d = lib.ConvDesc(BATCH, 8, 32, 32, 16, 3, 3, 32, 32, 1, 1, 1, lib.NCHW, math)
+    if math == lib.MATH_TF32:
+        assert op.kernel_name(lib.OP_FORWARD, d) == "tcgen05_fprop" and op.kernel_name(lib.OP_KERNELS_GRADIENT, d) == "tcgen05_wgrad"
+    losses, params = _run(op, torch.device("cuda", 0), optimizer)
+    assert len(losses) == len(ref_losses) == (N // BATCH) * EPOCHS
+    rel = np.abs(np.array(losses) - np.array(ref_losses)) / np.abs(np.array(ref_losses))
+    assert rel.max() <= tol, (losses, ref_losses)
+    assert ref_losses[-1] < ref_losses[0]
+    # Adam divides by sqrt(v): where the gradient is ~0 a TF32-sized perturbation can flip the sign of an lr-sized step,
+    # so parameters are compared loosely there; SGD parameters track tightly.
+    ptol = {("adam", lib.MATH_TF32): 5e-2, ("adam", lib.MATH_FP32): 1e-3, ("sgd", lib.MATH_TF32): 5e-3, ("sgd", lib.MATH_FP32): 1e-5}
+    assert np.abs(params - ref_params).max() <= ptol[(optimizer, math)]
