@@ -1,0 +1,235 @@
+// C++ parity tests for the host layer (include/neuro_b200/*.hpp), written the way the reference writes its own:
+//   Neuro.Tests/src/TensorTests.cpp:352-425       known-answer Conv2D vectors
+//   Neuro.Tests/src/TensorOpGpuTests.cpp:1196-1322  "SetForcedOpMode(CPU) ... SetForcedOpMode(GPU) ... r.Equals(r2)"
+// The CPU side is the oracle (oracle/conv_oracle.c) registered as EOpMode::CPU; the device side is TensorOpB200.
+// Test infrastructure: links liboracle; built and run by tests/test_cpp_host.py (-m gpu).
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "neuro_b200/tensor_op_b200.hpp"
+
+using namespace NeuroB200;
+
+extern "C"
+{
+    struct conv_dims { int N, C, H, W, K, R, S, Ho, Wo, stride, padX, padY, fmt; };
+    void oracle_conv2d(const conv_dims*, const float*, const float*, float*);
+    void oracle_conv2d_input_gradient(const conv_dims*, const float*, const float*, float*);
+    void oracle_conv2d_kernels_gradient(const conv_dims*, const float*, const float*, float*);
+    void oracle_conv2d_bias_activation(const conv_dims*, const float*, const float*, const float*, int, float, float*);
+    void oracle_conv2d_bias_gradient(const conv_dims*, const float*, float*);
+    void oracle_adam_step(float*, const float*, float*, float*, size_t, float, float, float, float);
+    void oracle_sgd_step(float*, const float*, size_t, float);
+}
+
+// EOpMode::CPU for the tests = the oracle behind the same virtual interface
+class TensorOpOracle : public TensorOp
+{
+    static conv_dims Dims(const Tensor& x, const Tensor& k, const Tensor& y, uint32_t stride, uint32_t px, uint32_t py, EDataFormat fmt)
+    {
+        conv_dims d{};
+        if (fmt == NCHW) { d.W = x.Len(0); d.H = x.Len(1); d.C = x.Len(2); d.N = x.Len(3); d.Wo = y.Len(0); d.Ho = y.Len(1); }
+        else { d.C = x.Len(0); d.W = x.Len(1); d.H = x.Len(2); d.N = x.Len(3); d.Wo = y.Len(1); d.Ho = y.Len(2); }
+        d.S = k.Len(0); d.R = k.Len(1); d.K = k.Len(3); d.stride = stride; d.padX = px; d.padY = py; d.fmt = fmt;
+        return d;
+    }
+public:
+    EOpMode OpMode() const override { return CPU; }
+    bool IsDeviceBackend() const override { return false; }
+    void Conv2D(const Tensor& x, const Tensor& k, uint32_t s, uint32_t px, uint32_t py, EDataFormat f, Tensor& y) const override
+    { const conv_dims d = Dims(x, k, y, s, px, py, f); y.OverrideHost(); oracle_conv2d(&d, x.Values(), k.Values(), y.Values()); }
+    void Conv2DBiasActivation(const Tensor& x, const Tensor& k, uint32_t s, uint32_t px, uint32_t py, const Tensor& b, EActivation a, float alpha, Tensor& y) override
+    { const conv_dims d = Dims(x, k, y, s, px, py, NCHW); y.OverrideHost(); oracle_conv2d_bias_activation(&d, x.Values(), k.Values(), b.Values(), (int)a, alpha, y.Values()); }
+    void Conv2DBiasGradient(const Tensor& g, Tensor& db) override
+    { conv_dims d{}; d.N = g.Batch(); d.K = g.Depth(); d.Ho = g.Height(); d.Wo = g.Width(); db.OverrideHost(); oracle_conv2d_bias_gradient(&d, g.Values(), db.Values()); }
+    void Conv2DInputGradient(const Tensor& g, const Tensor& k, uint32_t s, uint32_t px, uint32_t py, EDataFormat f, Tensor& dx) const override
+    { const conv_dims d = Dims(dx, k, g, s, px, py, f); dx.OverrideHost(); oracle_conv2d_input_gradient(&d, g.Values(), k.Values(), dx.Values()); }
+    void Conv2DKernelsGradient(const Tensor& x, const Tensor& g, uint32_t s, uint32_t px, uint32_t py, EDataFormat f, Tensor& dw) const override
+    { const conv_dims d = Dims(x, dw, g, s, px, py, f); dw.OverrideHost(); oracle_conv2d_kernels_gradient(&d, x.Values(), g.Values(), dw.Values()); }
+    void AdamStep(Tensor& p, const Tensor& g, Tensor& m, Tensor& v, float lr, float b1, float b2, float eps) const override
+    { oracle_adam_step(p.Values(), g.Values(), m.Values(), v.Values(), p.Length(), lr, b1, b2, eps); }
+    void SgdStep(Tensor& p, const Tensor& g, float lr) const override { oracle_sgd_step(p.Values(), g.Values(), p.Length(), lr); }
+};
+
+static int g_Failed = 0, g_Run = 0;
+#define TEST_METHOD(name) static void name(); static struct name##_reg { name##_reg() { Registry().push_back({#name, name}); } } name##_inst; static void name()
+struct TestEntry { const char* name; void (*fn)(); };
+static std::vector<TestEntry>& Registry() { static std::vector<TestEntry> r; return r; }
+#define IsTrue(cond) do { if (!(cond)) { printf("    FAILED: %s (%s:%d)\n", #cond, __FILE__, __LINE__); ++g_Failed; } } while (0)
+
+static float g_Tol = 1e-5f; // reference default Equals epsilon; TF32 mode uses the max-normalised 2e-3 bound instead
+static bool g_Tf32 = false;
+static bool Close(const Tensor& got, const Tensor& ref, float absEps = 1e-5f)
+{
+    return g_Tf32 ? got.MaxNormalisedError(ref) <= 2e-3f : got.Equals(ref, absEps);
+}
+
+// ---- TensorTests.cpp:352-425: literal vectors, run on the device backend ----
+TEST_METHOD(Conv2D_Valid_1Kernel_1Batch)
+{
+    Tensor::SetDefaultOpMode(B200);
+    Tensor t1(Shape(6, 6, 2)); t1.FillWithRange(0);
+    Tensor t2(Shape(3, 3, 2)); t2.FillWithRange(0);
+    Tensor r = t1.Conv2D(t2, 1, 0, NCHW);
+    Tensor correct({ 5511, 5664, 5817, 5970, 6429, 6582, 6735, 6888, 7347, 7500, 7653, 7806, 8265, 8418, 8571, 8724 }, Shape(4, 4, 1));
+    IsTrue(r.Equals(correct));
+}
+
+TEST_METHOD(Conv2D_Same_1Kernel_1Batch)
+{
+    Tensor::SetDefaultOpMode(B200);
+    Tensor t1(Shape(6, 6, 2)); t1.FillWithRange(0);
+    Tensor t2(Shape(3, 3, 2)); t2.FillWithRange(0);
+    Tensor r = t1.Conv2D(t2, 1, Tensor::GetPadding(Same, 3), NCHW);
+    Tensor correct({ 2492, 3674, 3794, 3914, 4034, 2624, 3765, 5511, 5664, 5817, 5970, 3855, 4413, 6429, 6582, 6735, 6888, 4431, 5061, 7347, 7500, 7653, 7806, 5007, 5709, 8265, 8418, 8571, 8724, 5583, 3416, 4898, 4982, 5066, 5150, 3260 }, Shape(6, 6, 1));
+    IsTrue(r.Equals(correct));
+}
+
+// ---- TensorOpGpuTests.cpp:1196-1322, same shapes, CPU vs device ----
+TEST_METHOD(Conv2D_Valid_CompareWithCpuResult)
+{
+    Tensor t(Shape(26, 26, 3, 3)); t.FillWithRand(11);
+    Tensor kernals(Shape(3, 3, 3, 2)); kernals.FillWithRand(12);
+    Tensor::SetForcedOpMode(CPU);
+    Tensor r = t.Conv2D(kernals, 1, 0, NCHW);
+    Tensor::SetForcedOpMode(B200);
+    Tensor r2 = t.Conv2D(kernals, 1, 0, NCHW);
+    IsTrue(r2.IsOnDevice());
+    IsTrue(Close(r2, r));
+}
+
+TEST_METHOD(Conv2D_Same_CompareWithCpuResult)
+{
+    Tensor t(Shape(26, 26, 3, 3)); t.FillWithRand(11);
+    Tensor kernals(Shape(3, 3, 3, 2)); kernals.FillWithRand(12);
+    Tensor::SetForcedOpMode(CPU);
+    Tensor r = t.Conv2D(kernals, 1, 1, NCHW);
+    Tensor::SetForcedOpMode(B200);
+    Tensor r2 = t.Conv2D(kernals, 1, 1, NCHW);
+    IsTrue(Close(r2, r));
+}
+
+TEST_METHOD(Conv2D_NHWC_CompareWithCpuResult) // commented out in the reference's GPU tests; supported here
+{
+    Tensor t(Shape(3, 26, 26, 3)); t.FillWithRand(11);
+    Tensor kernals(Shape(3, 3, 3, 2)); kernals.FillWithRand(12);
+    Tensor::SetForcedOpMode(CPU);
+    Tensor r = t.Conv2D(kernals, 1, 0, NHWC);
+    Tensor::SetForcedOpMode(B200);
+    Tensor r2 = t.Conv2D(kernals, 1, 0, NHWC);
+    IsTrue(Close(r2, r));
+}
+
+TEST_METHOD(Conv2DBiasActivation_Valid_CompareWithCpuResult)
+{
+    Tensor t(Shape(26, 26, 3, 3)); t.FillWithRand(11);
+    Tensor kernals(Shape(3, 3, 3, 2)); kernals.FillWithRand(12);
+    Tensor bias(Shape(1, 1, 2, 1)); bias.FillWithRand(14);
+    Tensor::SetForcedOpMode(CPU);
+    Tensor r = t.Conv2DBiasActivation(kernals, 1, 0, bias, _ReLU, 1);
+    Tensor::SetForcedOpMode(B200);
+    Tensor r2 = t.Conv2DBiasActivation(kernals, 1, 0, bias, _ReLU, 1);
+    IsTrue(Close(r2, r));
+}
+
+TEST_METHOD(Conv2DBiasGradient_CompareWithCpuResult)
+{
+    uint32_t features = 5;
+    Tensor gradient(Shape(24, 24, features, 3)); gradient.FillWithRand(13);
+    Tensor::SetForcedOpMode(CPU);
+    Tensor biasGradient(Shape(1, 1, features, 1));
+    gradient.Conv2DBiasGradient(gradient, biasGradient);
+    Tensor::SetForcedOpMode(B200);
+    Tensor biasGradient2(Shape(1, 1, features, 1));
+    gradient.Conv2DBiasGradient(gradient, biasGradient2);
+    IsTrue(biasGradient.Equals(biasGradient2, 0.0001f));
+}
+
+TEST_METHOD(Conv2DInputGradient_CompareWithCpuResult)
+{
+    Tensor input(Shape(26, 26, 3, 3));
+    Tensor kernels(Shape(3, 3, 3, 2)); kernels.FillWithRand(12);
+    Tensor gradient(Shape(24, 24, 2, 3)); gradient.FillWithRand(13);
+    Tensor::SetForcedOpMode(CPU);
+    Tensor inputGradient(input.GetShape());
+    gradient.Conv2DInputsGradient(gradient, kernels, 1, 0, NCHW, inputGradient);
+    Tensor::SetForcedOpMode(B200);
+    Tensor inputGradient2(input.GetShape());
+    gradient.Conv2DInputsGradient(gradient, kernels, 1, 0, NCHW, inputGradient2);
+    IsTrue(Close(inputGradient2, inputGradient));
+}
+
+TEST_METHOD(Conv2DKernelsGradient_CompareWithCpuResult)
+{
+    Tensor input(Shape(26, 26, 3, 3)); input.FillWithRand(11);
+    Tensor kernels(Shape(3, 3, 3, 2));
+    Tensor gradient(Shape(24, 24, 2, 3)); gradient.FillWithRand(13);
+    Tensor::SetForcedOpMode(CPU);
+    Tensor kernelsGradient(kernels.GetShape());
+    input.Conv2DKernelsGradient(input, gradient, 1, 0, NCHW, kernelsGradient);
+    Tensor::SetForcedOpMode(B200);
+    Tensor kernelsGradient2(kernels.GetShape());
+    input.Conv2DKernelsGradient(input, gradient, 1, 0, NCHW, kernelsGradient2);
+    IsTrue(Close(kernelsGradient2, kernelsGradient, 0.0001f)); // the reference allows 1e-4 here (TensorOpGpuTests.cpp:1320)
+}
+
+// ---- tensor-core sized layer + residency: intermediates stay on the device between ops ----
+TEST_METHOD(ConvChain_StaysOnDevice_VggLikeBlock)
+{
+    Tensor x(Shape(64, 64, 64, 2)); x.FillWithRand(11);
+    Tensor k1(Shape(3, 3, 64, 64)); k1.FillWithRand(12, -0.05f, 0.05f);
+    Tensor k2(Shape(3, 3, 64, 128)); k2.FillWithRand(15, -0.05f, 0.05f);
+    Tensor b1(Shape(1, 1, 64)); b1.FillWithRand(14, -0.1f, 0.1f);
+    Tensor b2(Shape(1, 1, 128)); b2.FillWithRand(16, -0.1f, 0.1f);
+    Tensor::SetForcedOpMode(CPU);
+    Tensor y1 = x.Conv2DBiasActivation(k1, 1, 1, b1, _ReLU, 0);
+    Tensor y2 = y1.Conv2DBiasActivation(k2, 1, 1, b2, _ReLU, 0);
+    Tensor::SetForcedOpMode(B200);
+    Tensor z1 = x.Conv2DBiasActivation(k1, 1, 1, b1, _ReLU, 0);
+    IsTrue(z1.IsOnDevice());
+    Tensor z2(y2.GetShape());
+    z1.Conv2DBiasActivation(k2, 1, 1, b2, _ReLU, 0, z2);
+    IsTrue(z1.IsOnDevice() && z2.IsOnDevice());      // no host round trip between the two layers
+    IsTrue(z2.MaxNormalisedError(y2) <= (g_Tf32 ? 2e-3f : 1e-5f));
+    // transposed-convolution identity: forward of Conv2DTranspose = input gradient (Tensor.cpp:1806-1810)
+    Tensor kt(Shape(4, 4, 32, 128)); kt.FillWithRand(17, -0.05f, 0.05f); // (F,F,outDepth,inDepth)
+    Tensor::SetForcedOpMode(CPU);
+    Tensor up = y2.Conv2DTransposed(kt, 32, 2, 1, NCHW);
+    Tensor::SetForcedOpMode(B200);
+    Tensor up2 = z2.Conv2DTransposed(kt, 32, 2, 1, NCHW);
+    IsTrue(up2.GetShape() == Shape(128, 128, 32, 2));
+    IsTrue(up2.MaxNormalisedError(up) <= (g_Tf32 ? 2e-3f : 1e-5f));
+}
+
+TEST_METHOD(AdamAndSgdStep_CompareWithCpuResult)
+{
+    Tensor p(Shape(1000)), g(Shape(1000)), m(Shape(1000)), v(Shape(1000));
+    p.FillWithRand(1); g.FillWithRand(2); m.FillWithRand(3, 0, 0.1f); v.FillWithRand(4, 0, 0.1f);
+    Tensor p2(p), m2(m), v2(v);
+    Tensor::GetOpFromMode(CPU)->AdamStep(p, g, m, v, 0.01f, 0.9f, 0.999f, 1e-8f);
+    Tensor::GetOpFromMode(B200)->AdamStep(p2, g, m2, v2, 0.01f, 0.9f, 0.999f, 1e-8f);
+    IsTrue(p.Equals(p2, 1e-6f) && m.Equals(m2, 1e-6f) && v.Equals(v2, 1e-6f));
+    Tensor::GetOpFromMode(CPU)->SgdStep(p, g, 0.05f);
+    Tensor::GetOpFromMode(B200)->SgdStep(p2, g, 0.05f);
+    IsTrue(p.Equals(p2, 1e-6f));
+}
+
+int main(int argc, char** argv)
+{
+    const std::string mode = argc > 1 ? argv[1] : "fp32";
+    g_Tf32 = mode == "tf32";
+    Tensor::RegisterOp(CPU, new TensorOpOracle());
+    Tensor::RegisterOp(B200, new TensorOpB200(g_Tf32 ? NB200_MATH_TF32 : NB200_MATH_FP32));
+    for (const TestEntry& t : Registry())
+    {
+        const int before = g_Failed;
+        ++g_Run;
+        try { t.fn(); }
+        catch (const std::exception& e) { printf("    EXCEPTION: %s\n", e.what()); ++g_Failed; }
+        printf("[%s] %s (%s)\n", g_Failed == before ? " OK " : "FAIL", t.name, mode.c_str());
+        Tensor::ClearForcedOpMode();
+    }
+    printf("%d tests, %d failed\n", g_Run, g_Failed);
+    return g_Failed ? 1 : 0;
+}
