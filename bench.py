@@ -47,25 +47,32 @@ def read_peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe): one looping nvidia-smi
+    process (-lms 50) started before and terminated after the region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([v.strip() for v in out.split(",")])
-            except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        self.rows = []
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill(); out = ""
+        self.rows = [[v.strip() for v in line.split(",")] for line in out.splitlines() if line.strip()]
 
     def summary(self):
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
@@ -236,6 +243,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.15)   # let the first samples land inside the region
     launches0 = L.nb200_kernel_launches()
     events = []
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -247,7 +255,7 @@ def run_ours(args):
     barrier()
     launches = L.nb200_kernel_launches() - launches0
     if sampler:
-        sampler.stop_flag = True
+        sampler.stop()
     ms = t0.elapsed_time(t1) / args.steps
     if world > 1:
         tmax = torch.tensor([ms], device=dev); dist.all_reduce(tmax, op=dist.ReduceOp.MAX); ms = float(tmax.item())
@@ -316,7 +324,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4, help="images per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -656,13 +656,16 @@ namespace nb200
             int tilesC, tilesK, splits;
             int rowsPerSplit;    // output rows (n, oh) per split
             int stages;
+            int pack;            // C <= 64: two filter taps share one A tile (lanes 0-63 tap 2g, lanes 64-127 tap 2g+1)
+            int groups;          // accumulators per CTA: S, or ceil(S/2) when packed
+            uint32_t xBytes;     // bytes of the x box (128 or 64 channel rows)
         };
 
         constexpr int kWgXW = 44;                               // x segment width in floats (pitch: 176 B)
         constexpr uint32_t kWgXBytes = 128 * kWgXW * 4;         // 22528
         constexpr int kWgAStages = 4;
 
-        template <int BN>
+        template <int BN, bool PACK>
         __global__ void __launch_bounds__(kThreads, 1)
         tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDy, WgradParams p,
                         float* __restrict__ ws)
@@ -728,7 +731,7 @@ namespace nb200
                             ptx::mbar_wait(&empty[st], ph ^ 1);
                             uint8_t* xs = smem + st * kStageBytes;
                             uint8_t* bs = xs + kWgXBytes;
-                            ptx::mbar_arrive_expect_tx(&full[st], kWgXBytes + kBBytes);
+                            ptx::mbar_arrive_expect_tx(&full[st], p.xBytes + kBBytes);
                             // x viewed as (W, C, H, N): box {44, 128, 1, 1}; rows above/below the image read as 0
                             ptx::tma_load_4d(xs, &mapX, &full[st], ow0 - p.wOff, c0, oh + r - p.padY, n);
                             // dy viewed as (Wo, K, Ho, N): box {32, BN, 1, 1} -> [k][32 pixels], 128-byte rows, swizzled
@@ -749,7 +752,7 @@ namespace nb200
                 {
                     ptx::mbar_wait(&full[st], ph);
                     const uint64_t db = descB0 + (uint64_t)((st * kStageBytes) >> 4);
-                    for (int s = 0; s < p.S; ++s)
+                    for (int s = 0; s < p.groups; ++s)
                     {
                         ptx::mbar_wait(&aFull[as], aph);
                         ptx::tc_fence_after_sync();
@@ -760,7 +763,7 @@ namespace nb200
                             for (int kk = 0; kk < 4; ++kk)
                                 ptx::mma_tf32_ts(tmemAcc + s * BN, ta + kk * 8, db + kk * 2, idesc, (it | kk) != 0);
                             ptx::mma_commit(&aEmpty[as]);
-                            if (s == p.S - 1)
+                            if (s == p.groups - 1)
                                 ptx::mma_commit(&empty[st]); // dy tile consumed
                         }
                         __syncwarp();
@@ -786,18 +789,26 @@ namespace nb200
                 {
                     const int st = it % p.stages;
                     ptx::mbar_wait(&full[st], (uint32_t)(it / p.stages) & 1);
-                    const uint32_t rowp = smem32 + st * kStageBytes + cl * (kWgXW * 4);
+                    const uint32_t rowp = smem32 + st * kStageBytes + (PACK ? (cl & 63) : cl) * (kWgXW * 4);
                     uint32_t row[40];
 #pragma unroll
                     for (int i = 0; i < 10; ++i)
                         ptx::lds_v4(rowp + i * 16, row[4 * i + 0], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
-                    for (int s = 0; s < p.S; ++s)
+                    for (int grp = 0; grp < p.groups; ++grp)
                     {
-                        const int off = s - p.padX + p.wOff; // 0..8
+                        // tap column handled by this lane in this group (packed: the two lane halves take adjacent taps)
+                        const int s = PACK ? 2 * grp + (cl >> 6) : grp;
+                        const int off = s - p.padX + p.wOff; // 0..8 for a real tap
                         uint32_t v[32];
+                        if (PACK)
+                        {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                v[j] = 0u; // lanes whose tap does not exist (odd S, upper half of the last group) feed zeros
+                        }
 #pragma unroll
                         for (int o = 0; o <= 8; ++o)
-                            if (off == o)
+                            if ((!PACK || s < p.S) && off == o)
                             {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j)
@@ -811,7 +822,7 @@ namespace nb200
                             if (lane == 0)
                                 ptx::mbar_arrive(&aFull[pendStage]);
                         }
-                        const int j = it * p.S + s; // global tap sequence number = MMA consumption order
+                        const int j = it * p.groups + grp; // global A-tile sequence number = MMA consumption order
                         const int as = j & (kWgAStages - 1);
                         ptx::mbar_wait(&aEmpty[as], ((uint32_t)(j / kWgAStages) & 1) ^ 1);
                         ptx::tc_fence_after_sync();
@@ -835,11 +846,13 @@ namespace nb200
                 // ----- epilogue: partial[split][tap][k][c], lanes = consecutive channels -> coalesced -----
                 ptx::mbar_wait(accBar, 0);
                 ptx::tc_fence_after_sync();
-                const int c = c0 + cl;
+                const int c = c0 + (PACK ? (cl & 63) : cl);
                 const int taps = p.R * p.S;
-                for (int s = 0; s < p.S; ++s)
+                for (int grp = 0; grp < p.groups; ++grp)
                 {
-                    float* dst = ws + ((long long)(split * taps + r * p.S + s) * p.K) * p.C + c;
+                    const int s = PACK ? 2 * grp + (cl >> 6) : grp;
+                    const bool tapOk = s < p.S;
+                    float* dst = ws + ((long long)(split * taps + r * p.S + (tapOk ? s : 0)) * p.K) * p.C + c;
 #pragma unroll 1
                     for (int j0 = g * 32; j0 < BN; j0 += 64)
                     {
@@ -848,7 +861,7 @@ namespace nb200
                         uint32_t v[32];
                         if (steps > 0)
                         {
-                            ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + s * BN + j0, v);
+                            ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + grp * BN + j0, v);
                             ptx::tmem_ld_wait();
                         }
                         else
@@ -856,7 +869,7 @@ namespace nb200
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = 0u;
                         }
-                        if (c < p.C)
+                        if (tapOk && c < p.C)
                         {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
@@ -956,6 +969,13 @@ namespace nb200
             static const bool usePair = getenv("NB200_FPROP_PAIR") != nullptr;
             pl.pair = usePair;
             pl.BN = pick_bn(f.Kout);
+            {
+                // A 256-wide tile runs one CTA per SM; if that leaves most SMs idle (small feature maps), halve the tile
+                // width to double the number of CTAs instead.
+                const long long spatial = (long long)f.N * ceil_div(f.Hout, kTileH) * ceil_div(f.Wout, kTileW);
+                if (pl.BN == 256 && spatial * ceil_div(f.Kout, 256) <= 96)
+                    pl.BN = 128;
+            }
             pl.wOff = round_up(f.padX, 4);
             const int right = f.S - 1 - f.padX > 0 ? f.S - 1 - f.padX : 0;
             pl.WB = round_up(kTileW + pl.wOff + right, 4);
@@ -1127,7 +1147,7 @@ namespace nb200
         // ---------------------------------------------------------------- kernel gradient, host side
         struct WgradPlan
         {
-            int BN, wOff, tilesC, tilesK, splits, rowsPerSplit, stages;
+            int BN, wOff, tilesC, tilesK, splits, rowsPerSplit, stages, pack, groups;
             size_t smemBytes, wsBytes;
         };
 
@@ -1145,7 +1165,9 @@ namespace nb200
         WgradPlan wgrad_plan(const nb200_conv_desc& d)
         {
             WgradPlan pl{};
-            pl.BN = (d.S <= 3 && d.K > 64) ? 128 : 64;
+            pl.pack = d.C <= 64;
+            pl.groups = pl.pack ? (d.S + 1) / 2 : d.S;
+            pl.BN = (pl.groups <= 3 && d.K > 64) ? 128 : 64;
             pl.wOff = round_up(d.padX, 4);
             pl.tilesC = ceil_div(d.C, 128);
             pl.tilesK = ceil_div(d.K, pl.BN);
@@ -1164,17 +1186,17 @@ namespace nb200
             return pl;
         }
 
-        template <int BN>
+        template <int BN, bool PACK>
         int launch_wgrad(const WgradPlan& pl, const CUtensorMap& mapX, const CUtensorMap& mapDy, const WgradParams& p, float* ws, cudaStream_t st)
         {
             static bool attrSet = false;
             if (!attrSet)
             {
-                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<BN, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
                 attrSet = true;
             }
             const long long ctas = (long long)p.splits * p.tilesK * p.tilesC * p.R;
-            tc_wgrad_kernel<BN><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapX, mapDy, p, ws);
+            tc_wgrad_kernel<BN, PACK><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapX, mapDy, p, ws);
             NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
             return NB200_OK;
@@ -1230,7 +1252,7 @@ namespace nb200
         {
             cuuint64_t dims[4] = {(cuuint64_t)d.W, (cuuint64_t)d.C, (cuuint64_t)d.H, (cuuint64_t)d.N};
             cuuint64_t strides[3] = {(cuuint64_t)d.H * d.W * 4, (cuuint64_t)d.W * 4, (cuuint64_t)d.C * d.H * d.W * 4};
-            cuuint32_t box[4] = {kWgXW, 128, 1, 1};
+            cuuint32_t box[4] = {kWgXW, (cuuint32_t)(pl.pack ? 64 : 128), 1, 1};
             int rc = make_map(&mapX, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
             if (rc) return rc;
         }
@@ -1246,7 +1268,9 @@ namespace nb200
         p.N = d.N; p.Ho = d.Ho; p.Wo = d.Wo; p.C = d.C; p.K = d.K;
         p.segs = ceil_div(d.Wo, 32);
         p.tilesC = pl.tilesC; p.tilesK = pl.tilesK; p.splits = pl.splits; p.rowsPerSplit = pl.rowsPerSplit; p.stages = pl.stages;
-        int rc = pl.BN == 64 ? launch_wgrad<64>(pl, mapX, mapDy, p, (float*)ws, st) : launch_wgrad<128>(pl, mapX, mapDy, p, (float*)ws, st);
+        p.pack = pl.pack; p.groups = pl.groups; p.xBytes = (uint32_t)((pl.pack ? 64 : 128) * kWgXW * 4);
+        int rc = pl.pack ? (pl.BN == 64 ? launch_wgrad<64, true>(pl, mapX, mapDy, p, (float*)ws, st) : launch_wgrad<128, true>(pl, mapX, mapDy, p, (float*)ws, st))
+                         : (pl.BN == 64 ? launch_wgrad<64, false>(pl, mapX, mapDy, p, (float*)ws, st) : launch_wgrad<128, false>(pl, mapX, mapDy, p, (float*)ws, st));
         if (rc) return rc;
         const long long total = (long long)d.K * d.C * d.R * d.S;
         wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)ws, dw, d.K, d.C, d.R * d.S, pl.splits);
