@@ -103,8 +103,9 @@ namespace nb200
         // out[tap][row][col] (col padded to outCp with zeros), TF32-rounded (cvt.rna).
         // mode 0 (forward):           tap = r*S+s,                 row = filter,  col = channel <- w[row][col][r][s]
         // mode 1 (input gradient):    tap = (R-1-r)*S + (S-1-s),   row = channel, col = filter  <- w[col][row][r][s]
+        // x3 != 0: out holds two such tensors back to back, hi = tf32(v) then lo = tf32(v - hi) (3xTF32 operand split).
         __global__ void repack_filters_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int C, int R, int S,
-                                              int outRows, int outCp, int mode)
+                                              int outRows, int outCp, int mode, int x3)
         {
             const long long total = (long long)R * S * outRows * outCp;
             for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
@@ -127,20 +128,32 @@ namespace nb200
                 uint32_t t;
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
                 out[i] = __uint_as_float(t);
+                if (x3)
+                {
+                    uint32_t tl;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tl) : "f"(v - __uint_as_float(t)));
+                    out[total + i] = __uint_as_float(tl);
+                }
             }
         }
 
         // ---------------------------------------------------------------- forward kernel
-        template <int BN>
-        __global__ void __launch_bounds__(kFpropThreads, (BN > 128 ? 1 : 2))
+        // X3 = 3xTF32: every operand is split into hi = tf32(v) and lo = tf32(v - hi); the product is accumulated as
+        // hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-22 relative), which recovers fp32-class accuracy
+        // (<= 1e-5 max-normalised against the reference) at a third of the TF32 rate. A tiles carry [hi | lo] (64 columns),
+        // filter stages carry a hi and a lo tile (the repack writes both).
+        template <int BN, bool X3>
+        __global__ void __launch_bounds__(kFpropThreads, ((BN > 128 || X3) ? 1 : 2))
         tc_fprop_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, FpropParams p,
                         const float* __restrict__ bias, float* __restrict__ y)
         {
-            constexpr uint32_t kBBytes = BN * kBlockC * 4;
-            constexpr int kAStages = a_stages(BN);
-            // BN <= 128: two CTAs per SM x 256 columns; BN = 256: one CTA per SM x 512 columns
-            constexpr uint32_t kTmemCols = BN > 128 ? 512 : 256;
-            static_assert(BN + kAStages * kBlockC <= kTmemCols, "TMEM budget");
+            constexpr uint32_t kBTile = BN * kBlockC * 4;             // one filter tile
+            constexpr uint32_t kBBytes = kBTile * (X3 ? 2 : 1);       // a filter stage: hi tile (+ lo tile)
+            constexpr int kAStages = X3 ? 4 : a_stages(BN);
+            constexpr int kACols = X3 ? 2 * kBlockC : kBlockC;        // TMEM columns per A stage
+            // BN <= 128: two CTAs per SM x 256 columns; BN = 256 or 3xTF32: one CTA per SM x 512 columns
+            constexpr uint32_t kTmemCols = (BN > 128 || X3) ? 512 : 256;
+            static_assert(BN + kAStages * kACols <= kTmemCols, "TMEM budget");
 
             extern __shared__ uint8_t smemRaw[];
             uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
@@ -156,7 +169,8 @@ namespace nb200
             uint64_t* aFull = xEmpty + 4;      // [kAStages]
             uint64_t* aEmpty = aFull + kAStagesMax;
             uint64_t* accBar = aEmpty + kAStagesMax;
-            uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
+            uint64_t* accFree = accBar + 1;    // 3xTF32 only: the accumulator has been drained into registers
+            uint32_t* tmemSlot = (uint32_t*)(accFree + 1);
 
             const int warp = threadIdx.x >> 5;
             const int lane = threadIdx.x & 31;
@@ -177,6 +191,7 @@ namespace nb200
                 for (int s = 0; s < p.xStages; ++s) { ptx::mbar_init(&xFull[s], 1); ptx::mbar_init(&xEmpty[s], kTileH * kConvGroups); }
                 for (int s = 0; s < kAStages; ++s) { ptx::mbar_init(&aFull[s], kTileH); ptx::mbar_init(&aEmpty[s], 1); }
                 ptx::mbar_init(accBar, 1);
+                ptx::mbar_init(accFree, kTileH * kConvGroups);
                 ptx::fence_mbar_init();
             }
             if (warp == 1)
@@ -209,6 +224,8 @@ namespace nb200
                             timed_wait(&bEmpty[bs], bph ^ 1, dbgP, kDbgBEmpty);
                             ptx::mbar_arrive_expect_tx(&bFull[bs], kBBytes);
                             ptx::tma_load_3d(bRing + bs * kBBytes, &mapW, &bFull[bs], cb * kBlockC, k0, tap);
+                            if (X3) // lo parts live behind the hi parts in the repacked tensor (tap index + taps)
+                                ptx::tma_load_3d(bRing + bs * kBBytes + kBTile, &mapW, &bFull[bs], cb * kBlockC, k0, taps + tap);
                             if (++bs == p.bStages) { bs = 0; bph ^= 1; }
                         }
                 }
@@ -241,29 +258,42 @@ namespace nb200
                 uint32_t aph = 0, bph = 0;
                 const int iters = taps * p.Cblocks;
                 const long long tLoop = dbgM.sink ? clock64() : 0;
+                int tapc = 0, cbc = 0; // position inside the current channel block (3xTF32 drains the accumulator per block)
                 for (int it = 0; it < iters; ++it)
                 {
                     timed_wait(&bFull[bs], bph, dbgM, kDbgBFull);
                     timed_wait(&aFull[as], aph, dbgM, kDbgAFull);
+                    if (X3 && tapc == 0 && cbc > 0)
+                        ptx::mbar_wait(accFree, (uint32_t)(cbc - 1) & 1); // previous block's partial sums are in registers
                     const long long tIssue = dbgM.sink ? clock64() : 0;
                     ptx::tc_fence_after_sync();
                     if (ptx::elect_one())
                     {
                         const uint64_t db = descB0 + (uint64_t)((bs * kBBytes) >> 4);
-                        const uint32_t ta = tmemA + as * kBlockC;
+                        const uint32_t ta = tmemA + as * kACols;
 #pragma unroll
                         for (int kk = 0; kk < kBlockC / 8; ++kk)
-                            ptx::mma_tf32_ts(tmemAcc, ta + kk * 8, db + kk * 2, idesc, (it | kk) != 0);
+                        {
+                            ptx::mma_tf32_ts(tmemAcc, ta + kk * 8, db + kk * 2, idesc, ((X3 ? tapc : it) | kk) != 0);        // hi * hi
+                            if (X3)
+                            {
+                                ptx::mma_tf32_ts(tmemAcc, ta + kk * 8, db + (kBTile >> 4) + kk * 2, idesc, 1);            // hi * lo
+                                ptx::mma_tf32_ts(tmemAcc, ta + kBlockC + kk * 8, db + kk * 2, idesc, 1);                  // lo * hi
+                            }
+                        }
                         ptx::mma_commit(&aEmpty[as]); // both slots reusable once these MMAs have consumed them
                         ptx::mma_commit(&bEmpty[bs]);
+                        if (X3 && tapc == taps - 1)
+                            ptx::mma_commit(accBar); // this channel block's partial accumulator is complete
                     }
                     __syncwarp();
+                    if (++tapc == taps) { tapc = 0; ++cbc; }
                     if (dbgM.sink) dbgM.v[kDbgAcc] += clock64() - tIssue;
                     if (++as == kAStages) { as = 0; aph ^= 1; }
                     if (++bs == p.bStages) { bs = 0; bph ^= 1; }
                 }
                 if (dbgM.sink) dbgM.v[kDbgTotal] = clock64() - tLoop;
-                if (ptx::elect_one())
+                if (!X3 && ptx::elect_one())
                     ptx::mma_commit(accBar); // accumulator complete
                 __syncwarp();
             }
@@ -279,6 +309,19 @@ namespace nb200
                 const uint32_t xRing32 = ptx::smem_u32(xRing);
                 bool pending = false;
                 int pendStage = 0;
+                // 3xTF32: the tensor core's fp32 accumulator truncates on every add, a bias that grows with the length of
+                // the accumulation chain (measured 3.8e-5 max-normalised at C = 512). So the chain is cut per channel block:
+                // each block's partial sums are drained from TMEM and added, round-to-nearest, into registers.
+                constexpr int kOwnChunks = X3 ? (BN / (32 * kConvGroups)) : 1;
+                float racc[kOwnChunks][32];
+                if (X3)
+                {
+#pragma unroll
+                    for (int ch = 0; ch < kOwnChunks; ++ch)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            racc[ch][j] = 0.f;
+                }
                 for (int cb = 0; cb < p.Cblocks; ++cb)
                 {
                     const int xs = cb % p.xStages;
@@ -305,6 +348,18 @@ namespace nb200
                             for (int c = 0; c < kBlockC; ++c)
                                 v[c] = ptx::tf32_round_bits(ptx::lds_b32(src + c * chanStrideB));
                         }
+                        uint32_t vlo[kBlockC]; // only live in the 3xTF32 instantiation
+                        if (X3)
+                        {
+#pragma unroll
+                            for (int c = 0; c < kBlockC; ++c)
+                            {
+                                const float full = __uint_as_float(v[c] - 0x1000u);           // undo the rounding add: the raw fp32 value
+                                const uint32_t hi = v[c] & 0xFFFFE000u;                         // exactly what the tensor core will read
+                                vlo[c] = ptx::tf32_round_bits(__float_as_uint(full - __uint_as_float(hi)));
+                                v[c] = hi;
+                            }
+                        }
                         if (pending)
                         {
                             // the previous tap's store has had the whole load phase to land
@@ -317,7 +372,9 @@ namespace nb200
                         const int as = it & (kAStages - 1);
                         timed_wait(&aEmpty[as], ((uint32_t)(it / kAStages) & 1) ^ 1, dbgC, kDbgAEmpty);
                         ptx::tc_fence_after_sync();
-                        ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kBlockC, v);
+                        ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kACols, v);
+                        if (X3)
+                            ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kACols + kBlockC, vlo);
                         pending = true;
                         pendStage = as;
                     }
@@ -325,6 +382,34 @@ namespace nb200
                     __syncwarp();
                     if (lane == 0)
                         ptx::mbar_arrive(&xEmpty[xs]);
+                    if (X3)
+                    {
+                        if (pending) // the MMAs of this block cannot finish before its last A tile is published
+                        {
+                            ptx::tmem_st_wait();
+                            ptx::tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0)
+                                ptx::mbar_arrive(&aFull[pendStage]);
+                            pending = false;
+                        }
+                        ptx::mbar_wait(accBar, (uint32_t)cb & 1);
+                        ptx::tc_fence_after_sync();
+#pragma unroll
+                        for (int ch = 0; ch < kOwnChunks; ++ch)
+                        {
+                            uint32_t pv[32];
+                            ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + (g + ch * kConvGroups) * 32, pv);
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                racc[ch][j] += __uint_as_float(pv[j]);
+                        }
+                        ptx::tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0)
+                            ptx::mbar_arrive(accFree);
+                    }
                 }
                 if (pending)
                 {
@@ -337,18 +422,15 @@ namespace nb200
 
                 // ----- epilogue: the two warps of a quadrant split the filter columns -----
                 const int oh = oh0 + q, ow = ow0 + lane;
-                timed_wait(accBar, 0, dbgC, kDbgAcc);
-                ptx::tc_fence_after_sync();
+                if (!X3)
+                {
+                    timed_wait(accBar, 0, dbgC, kDbgAcc);
+                    ptx::tc_fence_after_sync();
+                }
                 const bool pixelOk = oh < p.Ho && ow < p.Wo;
                 float* yp = y + n * p.yStrideN + (long long)oh * p.Wo + ow;
-#pragma unroll 1
-                for (int c0 = g * 32; c0 < BN; c0 += 32 * kConvGroups)
-                {
-                    if (k0 + c0 >= p.K)
-                        break; // warp-uniform
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + c0, v);
-                    ptx::tmem_ld_wait();
+                // bias + activation + one full 128-byte line per store instruction (lanes = 32 consecutive output columns)
+                auto store_chunk = [&](int c0, const uint32_t (&v)[32]) {
                     if (pixelOk)
                     {
 #pragma unroll
@@ -363,6 +445,35 @@ namespace nb200
                                 yp[k * p.yStrideK] = apply_activation(p.act, p.alpha, f);
                             }
                         }
+                    }
+                };
+                if (X3)
+                {
+#pragma unroll
+                    for (int ch = 0; ch < kOwnChunks; ++ch)
+                    {
+                        const int c0 = (g + ch * kConvGroups) * 32;
+                        if (k0 + c0 < p.K)
+                        {
+                            uint32_t v[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                v[j] = __float_as_uint(racc[ch][j]);
+                            store_chunk(c0, v);
+                        }
+                    }
+                }
+                else
+                {
+#pragma unroll 1
+                    for (int c0 = g * 32; c0 < BN; c0 += 32 * kConvGroups)
+                    {
+                        if (k0 + c0 >= p.K)
+                            break; // warp-uniform
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + c0, v);
+                        ptx::tmem_ld_wait();
+                        store_chunk(c0, v);
                     }
                 }
             }
@@ -951,6 +1062,7 @@ namespace nb200
         struct FwdShape
         {
             int N, Cin, Hin, Win, Kout, Hout, Wout, R, S, padX, padY;
+            int x3; // 3xTF32 operand split
         };
 
         struct Plan
@@ -967,8 +1079,10 @@ namespace nb200
             // The CTA-pair (cta_group::2) kernel is correct but, as measured on B200 (profiles/), slower than the
             // single-CTA kernel for every VGG/DCGAN shape, so it is opt-in (NB200_FPROP_PAIR=1) until that is understood.
             static const bool usePair = getenv("NB200_FPROP_PAIR") != nullptr;
-            pl.pair = usePair;
+            pl.pair = usePair && !f.x3;
             pl.BN = pick_bn(f.Kout);
+            if (f.x3 && pl.BN > 128)
+                pl.BN = 128; // hi+lo filter stages are twice as large; keep the ring deep enough
             {
                 // A 256-wide tile runs one CTA per SM; if that leaves most SMs idle (small feature maps), halve the tile
                 // width to double the number of CTAs instead.
@@ -981,9 +1095,9 @@ namespace nb200
             pl.WB = round_up(kTileW + pl.wOff + right, 4);
             pl.HR = kTileH + f.R - 1;
             const size_t xBytes = ((size_t)kBlockC * pl.HR * pl.WB * 4 + 1023) & ~(size_t)1023;
-            const size_t bBytes = (size_t)(pl.pair ? pl.BN / 2 : pl.BN) * kBlockC * 4;
+            const size_t bBytes = (size_t)(pl.pair ? pl.BN / 2 : pl.BN) * kBlockC * 4 * (f.x3 ? 2 : 1);
             const size_t fixed = 1024 /*alignment slack*/ + 512 /*barriers*/;
-            const long long budget = pl.BN > 128 ? kSmemBudget1 : kSmemBudget2;
+            const long long budget = (pl.BN > 128 || f.x3) ? kSmemBudget1 : kSmemBudget2;
             pl.ok = false;
             // prefer two (three when alone on the SM) halo stages; give the rest to the filter ring (at least 2, at most 8)
             for (int xs = 2; xs >= 1 && !pl.ok; --xs)
@@ -1012,17 +1126,17 @@ namespace nb200
 
         size_t repack_bytes(const FwdShape& f)
         {
-            return (size_t)f.R * f.S * f.Kout * round_up(f.Cin, kBlockC) * sizeof(float);
+            return (size_t)f.R * f.S * f.Kout * round_up(f.Cin, kBlockC) * sizeof(float) * (f.x3 ? 2 : 1);
         }
 
-        template <int BN>
+        template <int BN, bool X3>
         int launch_fprop(const FwdShape& f, const Plan& pl, const CUtensorMap& mapX, const CUtensorMap& mapW, const FpropParams& p,
                          const float* bias, float* out, cudaStream_t st)
         {
             static bool attrSet = false;
             if (!attrSet)
             {
-                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, BN > 128 ? kSmemBudget1 : kSmemBudget2));
+                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (BN > 128 || X3) ? kSmemBudget1 : kSmemBudget2));
                 attrSet = true;
             }
             const long long tiles = (long long)p.tilesK * p.tilesW * p.tilesH * f.N;
@@ -1038,7 +1152,7 @@ namespace nb200
                 NB200_CUDA_TRY(cudaMemset(dbgDev, 0, ctas * 4 * kDbgSlots * sizeof(long long)));
                 pd.dbg = dbgDev;
             }
-            if (pl.pair)
+            if (pl.pair && !X3)
             {
                 static bool attrSet2 = false;
                 if (!attrSet2)
@@ -1058,7 +1172,7 @@ namespace nb200
                 NB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_fprop2_kernel<BN>, mapX, mapW, pd, bias, out));
             }
             else
-                tc_fprop_kernel<BN><<<(unsigned)tiles, kFpropThreads, pl.smemBytes, st>>>(mapX, mapW, pd, bias, out);
+                tc_fprop_kernel<BN, X3><<<(unsigned)tiles, kFpropThreads, pl.smemBytes, st>>>(mapX, mapW, pd, bias, out);
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             if (debugWaits)
@@ -1097,7 +1211,7 @@ namespace nb200
             {
                 const long long total = (long long)f.R * f.S * f.Kout * Cp;
                 const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-                repack_filters_kernel<<<blocks, 256, 0, st>>>(w, wr, wK, wC, f.R, f.S, f.Kout, Cp, repackMode);
+                repack_filters_kernel<<<blocks, 256, 0, st>>>(w, wr, wK, wC, f.R, f.S, f.Kout, Cp, repackMode, f.x3);
                 NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
             }
@@ -1112,7 +1226,7 @@ namespace nb200
                 if (rc) return rc;
             }
             {
-                cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)f.Kout, (cuuint64_t)(f.R * f.S)};
+                cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)f.Kout, (cuuint64_t)(f.R * f.S * (f.x3 ? 2 : 1))};
                 cuuint64_t strides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * f.Kout * 4};
                 cuuint32_t box[3] = {kBlockC, (cuuint32_t)(pl.pair ? pl.BN / 2 : pl.BN), 1};
                 int rc = make_map(&mapW, wr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -1128,20 +1242,22 @@ namespace nb200
             p.act = act; p.alpha = alpha; p.dbg = nullptr;
             p.yStrideK = (long long)f.Hout * f.Wout;
             p.yStrideN = p.yStrideK * f.Kout;
-            return pl.BN == 64 ? launch_fprop<64>(f, pl, mapX, mapW, p, bias, out, st)
-                 : pl.BN == 128 ? launch_fprop<128>(f, pl, mapX, mapW, p, bias, out, st)
-                                : launch_fprop<256>(f, pl, mapX, mapW, p, bias, out, st);
+            if (f.x3)
+                return pl.BN == 64 ? launch_fprop<64, true>(f, pl, mapX, mapW, p, bias, out, st) : launch_fprop<128, true>(f, pl, mapX, mapW, p, bias, out, st);
+            return pl.BN == 64 ? launch_fprop<64, false>(f, pl, mapX, mapW, p, bias, out, st)
+                 : pl.BN == 128 ? launch_fprop<128, false>(f, pl, mapX, mapW, p, bias, out, st)
+                                : launch_fprop<256, false>(f, pl, mapX, mapW, p, bias, out, st);
         }
 
         FwdShape fwd_shape(const nb200_conv_desc& d)
         {
-            return FwdShape{d.N, d.C, d.H, d.W, d.K, d.Ho, d.Wo, d.R, d.S, d.padX, d.padY};
+            return FwdShape{d.N, d.C, d.H, d.W, d.K, d.Ho, d.Wo, d.R, d.S, d.padX, d.padY, d.math == NB200_MATH_3XTF32};
         }
 
         // stride-1 input gradient as a forward conv of dy: pad' = F-1-pad, flipped taps, filter/channel roles swapped
         FwdShape dgrad_shape(const nb200_conv_desc& d)
         {
-            return FwdShape{d.N, d.K, d.Ho, d.Wo, d.C, d.H, d.W, d.R, d.S, d.S - 1 - d.padX, d.R - 1 - d.padY};
+            return FwdShape{d.N, d.K, d.Ho, d.Wo, d.C, d.H, d.W, d.R, d.S, d.S - 1 - d.padX, d.R - 1 - d.padY, d.math == NB200_MATH_3XTF32};
         }
 
         // ---------------------------------------------------------------- kernel gradient, host side
@@ -1205,12 +1321,12 @@ namespace nb200
 
     bool tc_forward_supported(const nb200_conv_desc& d)
     {
-        return d.fmt == NB200_NCHW && d.math == NB200_MATH_TF32 && d.stride == 1 && shape_ok(fwd_shape(d));
+        return d.fmt == NB200_NCHW && (d.math == NB200_MATH_TF32 || d.math == NB200_MATH_3XTF32) && d.stride == 1 && shape_ok(fwd_shape(d));
     }
 
     bool tc_input_gradient_supported(const nb200_conv_desc& d)
     {
-        if (d.fmt != NB200_NCHW || d.math != NB200_MATH_TF32 || d.stride != 1)
+        if (d.fmt != NB200_NCHW || (d.math != NB200_MATH_TF32 && d.math != NB200_MATH_3XTF32) || d.stride != 1)
             return false;
         // the gather needs dx extent == what a forward conv of dy with pad' = F-1-pad produces
         if (d.H != d.Ho + d.R - 1 - 2 * d.padY || d.W != d.Wo + d.S - 1 - 2 * d.padX)

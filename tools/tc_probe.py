@@ -29,12 +29,13 @@ CASES = [
 if len(sys.argv) > 1:
     CASES = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
 
-op = TensorOpB200(lib.MATH_TF32)
+import os
+op = TensorOpB200(int(os.environ.get("NB200_MATH", lib.MATH_TF32)))
 for cfg in CASES:
     N, C, H, W, K, R, S, st, px, py = cfg
     x, w, dy = make_inputs(lib.NCHW, N, C, H, W, K, R, S, st, px, py, glorot=True)
     Ho, Wo = dy.shape[2], dy.shape[3]
-    d = lib.ConvDesc(N, C, H, W, K, R, S, Ho, Wo, st, px, py, lib.NCHW, lib.MATH_TF32)
+    d = lib.ConvDesc(N, C, H, W, K, R, S, Ho, Wo, st, px, py, lib.NCHW, op.math)
     names = [op.kernel_name(o, d) for o in (0, 1, 2)]
     xd, wd, dyd = dev(x), dev(w), dev(dy)
     y = torch.zeros(dy.shape, device="cuda"); dx = torch.zeros(x.shape, device="cuda"); dw = torch.zeros(w.shape, device="cuda")
