@@ -91,7 +91,7 @@ namespace nb200
             }
         }
 
-        enum Family { kDirect, kTc, kSmallC };
+        enum Family { kDirect, kTc, kSmallC, kGather };
 
         Family pick(int op, const nb200_conv_desc& d)
         {
@@ -99,10 +99,18 @@ namespace nb200
                 return kSmallC; // fp32 CUDA cores, HBM-bound: serves every math mode
             if (d.math == NB200_MATH_FP32)
                 return kDirect;
+            // The halo-tile kernels tile 32 output columns per row; on narrower maps (or where they do not apply at all:
+            // strides, odd widths) the gathered-A kernel keeps the tensor cores busy instead.
             switch (op)
             {
-            case NB200_OP_FORWARD: return tc_forward_supported(d) ? kTc : kDirect;
-            case NB200_OP_INPUT_GRADIENT: return tc_input_gradient_supported(d) ? kTc : kDirect;
+            case NB200_OP_FORWARD:
+                if (tc_forward_supported(d) && d.Wo >= 24) return kTc;
+                if (tc_gather_forward_supported(d)) return kGather;
+                return tc_forward_supported(d) ? kTc : kDirect;
+            case NB200_OP_INPUT_GRADIENT:
+                if (tc_input_gradient_supported(d) && d.W >= 24) return kTc;
+                if (tc_gather_input_gradient_supported(d)) return kGather;
+                return tc_input_gradient_supported(d) ? kTc : kDirect;
             default: return tc_kernels_gradient_supported(d) ? kTc : kDirect;
             }
         }
@@ -159,6 +167,8 @@ extern "C"
             return tc_workspace_bytes(op, *d);
         if (f == kSmallC)
             return op == NB200_OP_KERNELS_GRADIENT ? smallc_wgrad_workspace(*d) : 0;
+        if (f == kGather)
+            return tc_gather_workspace_bytes(op, *d);
         return op == NB200_OP_KERNELS_GRADIENT ? direct_kernels_gradient_workspace(*d) : 0;
     }
 
@@ -169,8 +179,8 @@ extern "C"
         const Family f = pick(op, *d);
         switch (op)
         {
-        case NB200_OP_FORWARD: return f == kTc ? "tcgen05_fprop" : f == kSmallC ? "smallc_fprop" : "direct_fprop";
-        case NB200_OP_INPUT_GRADIENT: return f == kTc ? "tcgen05_dgrad" : f == kSmallC ? "smallc_dgrad" : "direct_dgrad";
+        case NB200_OP_FORWARD: return f == kTc ? "tcgen05_fprop" : f == kGather ? "tcgen05_gather_fprop" : f == kSmallC ? "smallc_fprop" : "direct_fprop";
+        case NB200_OP_INPUT_GRADIENT: return f == kTc ? "tcgen05_dgrad" : f == kGather ? "tcgen05_gather_dgrad" : f == kSmallC ? "smallc_dgrad" : "direct_dgrad";
         case NB200_OP_KERNELS_GRADIENT: return f == kTc ? "tcgen05_wgrad" : f == kSmallC ? "smallc_wgrad" : "direct_wgrad";
         default: return "invalid";
         }
@@ -194,6 +204,8 @@ extern "C"
             return tc_forward(*d, x, w, bias, act, alpha, y, workspace, workspace_bytes, st);
         if (f == kSmallC)
             return smallc_forward(*d, x, w, bias, act, alpha, y, st);
+        if (f == kGather)
+            return tc_gather_forward(*d, x, w, bias, act, alpha, y, workspace, workspace_bytes, st);
         return direct_forward(*d, x, w, bias, act, alpha, y, st);
     }
 
@@ -213,6 +225,8 @@ extern "C"
             return tc_input_gradient(*d, dy, w, dx, workspace, workspace_bytes, st);
         if (f == kSmallC)
             return smallc_input_gradient(*d, dy, w, dx, st);
+        if (f == kGather)
+            return tc_gather_input_gradient(*d, dy, w, dx, workspace, workspace_bytes, st);
         return direct_input_gradient(*d, dy, w, dx, st);
     }
 

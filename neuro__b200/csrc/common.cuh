@@ -90,6 +90,15 @@ namespace nb200
     int tc_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes,
                             cudaStream_t st);
 
+    // gathered-A tensor-core kernel: any stride / padding / map size, forward and input gradient. conv_tc.cu
+    bool tc_gather_forward_supported(const nb200_conv_desc& d);
+    bool tc_gather_input_gradient_supported(const nb200_conv_desc& d);
+    size_t tc_gather_workspace_bytes(int op, const nb200_conv_desc& d);
+    int tc_gather_forward(const nb200_conv_desc& d, const float* x, const float* w, const float* bias, int act, float alpha, float* y,
+                          void* ws, size_t wsBytes, cudaStream_t st);
+    int tc_gather_input_gradient(const nb200_conv_desc& d, const float* dy, const float* w, float* dx, void* ws, size_t wsBytes,
+                                 cudaStream_t st);
+
     // elementwise.cu
     int bias_gradient(const nb200_conv_desc& d, const float* dy, float* db, cudaStream_t st);
     int adam_step(float* p, const float* g, float* m, float* v, size_t n, float gs, float lr, float b1, float b2, float eps,

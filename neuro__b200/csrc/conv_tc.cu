@@ -119,11 +119,16 @@ namespace nb200
                     if (col < C)
                         v = w[((long long)row * C + col) * R * S + tap];
                 }
-                else
+                else if (mode == 1)
                 {
                     const int r = R - 1 - tap / S, s = S - 1 - tap % S;
                     if (col < K)
                         v = w[(((long long)col * C + row) * R + r) * S + s];
+                }
+                else // mode 2 (gathered input gradient): tap = r*S+s unflipped, row = channel, col = filter
+                {
+                    if (col < K)
+                        v = w[((long long)col * C + row) * R * S + tap];
                 }
                 uint32_t t;
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
@@ -745,6 +750,238 @@ namespace nb200
             }
         }
 
+
+        // ---------------------------------------------------------------- gather kernel (any stride / padding / map size)
+        // Same MMA pipeline as tc_fprop_kernel (filters by TMA, A operand converted into tensor memory, TS-form
+        // tcgen05.mma, fused epilogue) but the A tile is GATHERED: the 128 rows of a tile are 128 consecutive entries of a
+        // flattened pixel list (n, a, b), and for every filter tap each converter thread computes its own input address
+        //      iy = a * iyMul + iyAdd[tap],   ix = b * ixMul + ixAdd[tap]        (out of range -> 0)
+        // and loads straight from global memory / L1 (coalesced along b). This covers what the halo-tile kernel cannot:
+        // strided forward convolutions, feature maps narrower than a 32-pixel row tile (the batch folds into M), widths
+        // that are not multiples of 4, and -- through one launch per stride-parity class of output pixels -- the input
+        // gradient of strided convolutions (= the forward of Conv2DTranspose), where each class sees only its own taps.
+        struct GatherParams
+        {
+            int Cblocks, ntaps;
+            int C, H, W;                    // gathered tensor: channels, rows, cols
+            int K, Ho, Wo;                  // produced tensor: channels, rows, cols
+            int PH, PW;                     // pixel list extent per image
+            int oyMul, oyAdd, oxMul, oxAdd; // produced pixel of list entry (a, b)
+            int iyMul, ixMul;
+            long long totalPix;             // N * PH * PW
+            int tilesK, bStages;
+            int act;
+            float alpha;
+            short iyAdd[32], ixAdd[32], wtap[32];
+        };
+
+        template <int BN>
+        __global__ void __launch_bounds__(kFpropThreads, (BN > 128 ? 1 : 2))
+        tc_gather_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ GatherParams p, const float* __restrict__ in,
+                         const float* __restrict__ bias, float* __restrict__ out)
+        {
+            constexpr uint32_t kBBytes = BN * kBlockC * 4;
+            constexpr int kAStages = a_stages(BN);
+            constexpr uint32_t kTmemCols = BN > 128 ? 512 : 256;
+
+            extern __shared__ uint8_t smemRaw[];
+            uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+            uint8_t* bRing = smem;
+            uint64_t* bars = (uint64_t*)(smem + p.bStages * kBBytes);
+            uint64_t* bFull = bars;
+            uint64_t* bEmpty = bFull + 8;
+            uint64_t* aFull = bEmpty + 8;
+            uint64_t* aEmpty = aFull + kAStagesMax;
+            uint64_t* accBar = aEmpty + kAStagesMax;
+            uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
+
+            const int warp = threadIdx.x >> 5;
+            const int lane = threadIdx.x & 31;
+            const int kt = blockIdx.x % p.tilesK;
+            const long long tile = blockIdx.x / p.tilesK;
+            const int k0 = kt * BN;
+
+            if (warp == 0 && lane == 0)
+            {
+                ptx::prefetch_tensormap(&mapW);
+                for (int s = 0; s < p.bStages; ++s) { ptx::mbar_init(&bFull[s], 1); ptx::mbar_init(&bEmpty[s], 1); }
+                for (int s = 0; s < kAStages; ++s) { ptx::mbar_init(&aFull[s], kTileH); ptx::mbar_init(&aEmpty[s], 1); }
+                ptx::mbar_init(accBar, 1);
+                ptx::fence_mbar_init();
+            }
+            if (warp == 1)
+                ptx::tmem_alloc(tmemSlot, kTmemCols);
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            ptx::tc_fence_after_sync();
+            const uint32_t tmemAcc = *tmemSlot;
+            const uint32_t tmemA = tmemAcc + BN;
+            const int iters = p.ntaps * p.Cblocks;
+
+            if (warp == 0)
+            {
+                if (lane == 0)
+                {
+                    int bs = 0;
+                    uint32_t bph = 0;
+                    for (int cb = 0; cb < p.Cblocks; ++cb)
+                        for (int t = 0; t < p.ntaps; ++t)
+                        {
+                            ptx::mbar_wait(&bEmpty[bs], bph ^ 1);
+                            ptx::mbar_arrive_expect_tx(&bFull[bs], kBBytes);
+                            ptx::tma_load_3d(bRing + bs * kBBytes, &mapW, &bFull[bs], cb * kBlockC, k0, p.wtap[t]);
+                            if (++bs == p.bStages) { bs = 0; bph ^= 1; }
+                        }
+                }
+            }
+            else if (warp == 1)
+            {
+                constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, 0, 0);
+                const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(bRing), 16, 1024);
+                int as = 0, bs = 0;
+                uint32_t aph = 0, bph = 0;
+                for (int it = 0; it < iters; ++it)
+                {
+                    ptx::mbar_wait(&bFull[bs], bph);
+                    ptx::mbar_wait(&aFull[as], aph);
+                    ptx::tc_fence_after_sync();
+                    if (ptx::elect_one())
+                    {
+                        const uint64_t db = descB0 + (uint64_t)((bs * kBBytes) >> 4);
+                        const uint32_t ta = tmemA + as * kBlockC;
+#pragma unroll
+                        for (int kk = 0; kk < kBlockC / 8; ++kk)
+                            ptx::mma_tf32_ts(tmemAcc, ta + kk * 8, db + kk * 2, idesc, (it | kk) != 0);
+                        ptx::mma_commit(&aEmpty[as]);
+                        ptx::mma_commit(&bEmpty[bs]);
+                    }
+                    __syncwarp();
+                    if (++as == kAStages) { as = 0; aph ^= 1; }
+                    if (++bs == p.bStages) { bs = 0; bph ^= 1; }
+                }
+                if (ptx::elect_one())
+                    ptx::mma_commit(accBar);
+                __syncwarp();
+            }
+            else if (warp >= kFirstConvWarp)
+            {
+                const int q = warp & 3;
+                const int g = (warp - kFirstConvWarp) >> 2;
+                const uint32_t laneSel = (uint32_t)(q * 32) << 16;
+                // this thread's entry of the pixel list
+                const long long pix = tile * 128 + q * 32 + lane;
+                const bool pixOk = pix < p.totalPix;
+                const int b = (int)(pix % p.PW);
+                const int a = (int)((pix / p.PW) % p.PH);
+                const long long n = pix / ((long long)p.PW * p.PH);
+                const long long plane = (long long)p.H * p.W;
+                const float* inN = in + n * p.C * plane;
+
+                bool pending = false;
+                int pendStage = 0;
+                for (int it = g; it < iters; it += kConvGroups)
+                {
+                    const int cb = it / p.ntaps, t = it - cb * p.ntaps;
+                    const int iy = a * p.iyMul + p.iyAdd[t], ix = b * p.ixMul + p.ixAdd[t];
+                    const bool ok = pixOk && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                    const int cbase = cb * kBlockC;
+                    uint32_t v[kBlockC];
+                    if (ok)
+                    {
+                        const float* src = inN + cbase * plane + (long long)iy * p.W + ix;
+                        if (cbase + kBlockC <= p.C)
+                        {
+#pragma unroll
+                            for (int c = 0; c < kBlockC; ++c)
+                                v[c] = ptx::tf32_round_bits(__float_as_uint(__ldg(src + c * plane)));
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int c = 0; c < kBlockC; ++c)
+                                v[c] = cbase + c < p.C ? ptx::tf32_round_bits(__float_as_uint(__ldg(src + c * plane))) : 0u;
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int c = 0; c < kBlockC; ++c)
+                            v[c] = 0u;
+                    }
+                    if (pending)
+                    {
+                        ptx::tmem_st_wait();
+                        ptx::tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0)
+                            ptx::mbar_arrive(&aFull[pendStage]);
+                    }
+                    const int as = it & (kAStages - 1);
+                    ptx::mbar_wait(&aEmpty[as], ((uint32_t)(it / kAStages) & 1) ^ 1);
+                    ptx::tc_fence_after_sync();
+                    ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kBlockC, v);
+                    pending = true;
+                    pendStage = as;
+                }
+                if (pending)
+                {
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(&aFull[pendStage]);
+                }
+
+                // ----- epilogue -----
+                const int oy = a * p.oyMul + p.oyAdd, ox = b * p.oxMul + p.oxAdd;
+                const bool outOk = pixOk && oy < p.Ho && ox < p.Wo;
+                const long long oplane = (long long)p.Ho * p.Wo;
+                float* op = out + n * p.K * oplane + (long long)oy * p.Wo + ox;
+                ptx::mbar_wait(accBar, 0);
+                ptx::tc_fence_after_sync();
+#pragma unroll 1
+                for (int c0 = g * 32; c0 < BN; c0 += 32 * kConvGroups)
+                {
+                    if (k0 + c0 >= p.K)
+                        break;
+                    uint32_t v[32];
+                    if (iters > 0)
+                    {
+                        ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + c0, v);
+                        ptx::tmem_ld_wait();
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0u; // a pixel class no tap reaches (e.g. 1x1 filters, stride 2)
+                    }
+                    if (outOk)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                        {
+                            const int k = k0 + c0 + j;
+                            if (k < p.K)
+                            {
+                                float f = __uint_as_float(v[j]);
+                                if (bias)
+                                    f += __ldg(bias + k);
+                                op[k * oplane] = apply_activation(p.act, p.alpha, f);
+                            }
+                        }
+                    }
+                }
+            }
+
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            if (warp == 1)
+            {
+                ptx::tc_fence_after_sync();
+                ptx::tmem_dealloc(tmemAcc, kTmemCols);
+            }
+        }
+
         // ---------------------------------------------------------------- kernel-gradient kernel
         //   dw[k][c][r][s] = sum over pixels  dy[n][k][oh][ow] * x[n][c][oh+r-pY][ow+s-pX]           (stride 1)
         //   GEMM view      D_s[M = 128 channels][N = BN filters] += A_s[channel][pixel] * B[filter][pixel], reduction = pixels.
@@ -1249,6 +1486,70 @@ namespace nb200
                                 : launch_fprop<256, false>(f, pl, mapX, mapW, p, bias, out, st);
         }
 
+
+        // ---------------------------------------------------------------- gather kernel, host side
+        template <int BN>
+        int launch_gather(const CUtensorMap& mapW, const GatherParams& p, int bStages, const float* in, const float* bias, float* out, cudaStream_t st)
+        {
+            static bool attrSet = false;
+            if (!attrSet)
+            {
+                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_gather_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, BN > 128 ? kSmemBudget1 : kSmemBudget2));
+                attrSet = true;
+            }
+            const long long tiles = (p.totalPix + 127) / 128 * p.tilesK;
+            if (tiles > 0x7FFFFFFFll)
+                return fail(NB200_E_UNSUPPORTED, "too many tiles");
+            const size_t smemBytes = 1024 + 512 + (size_t)bStages * BN * kBlockC * 4;
+            tc_gather_kernel<BN><<<(unsigned)tiles, kFpropThreads, smemBytes, st>>>(mapW, p, in, bias, out);
+            NB200_CUDA_TRY(cudaGetLastError());
+            count_launch();
+            return NB200_OK;
+        }
+
+        // Repack filters and build the filter tensor map; returns BN.
+        int gather_prepare(int Kout, int Cin, int R, int S, int repackMode, int wK, int wC, const float* w, void* ws, size_t wsBytes, cudaStream_t st,
+                           CUtensorMap* mapW, int* BN, int* bStages, int* Cblocks)
+        {
+            const int Cp = round_up(Cin, kBlockC);
+            const size_t need = (size_t)R * S * Kout * Cp * sizeof(float);
+            if (wsBytes < need || !ws)
+                return fail(NB200_E_WORKSPACE, "tcgen05 gather conv needs %zu workspace bytes, got %zu", need, wsBytes);
+            if ((uintptr_t)ws & 15)
+                return fail(NB200_E_INVALID, "workspace must be 16-byte aligned for TMA");
+            const long long total = (long long)R * S * Kout * Cp;
+            const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+            repack_filters_kernel<<<blocks, 256, 0, st>>>(w, (float*)ws, wK, wC, R, S, Kout, Cp, repackMode, 0);
+            NB200_CUDA_TRY(cudaGetLastError());
+            count_launch();
+            *BN = pick_bn(Kout);
+            cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)Kout, (cuuint64_t)(R * S)};
+            cuuint64_t strides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * Kout * 4};
+            cuuint32_t box[3] = {kBlockC, (cuuint32_t)*BN, 1};
+            int rc = make_map(mapW, ws, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (rc) return rc;
+            const long long budget = (*BN > 128 ? kSmemBudget1 : kSmemBudget2) - 1536;
+            int bs = (int)(budget / ((long long)*BN * kBlockC * 4));
+            *bStages = bs > 8 ? 8 : bs;
+            *Cblocks = Cp / kBlockC;
+            return NB200_OK;
+        }
+
+        bool gather_ok(const nb200_conv_desc& d)
+        {
+            // C or K below 8 (first / last layers of the GAN configs) run with zero-padded operand tiles: wasteful for the
+            // tensor core, irrelevant in time (these layers are bound by the gather), and far faster than CUDA-core loops.
+            return d.fmt == NB200_NCHW && d.math == NB200_MATH_TF32 && d.C >= 1 && d.K >= 1 && d.R * d.S <= 32 && d.N >= 1 &&
+                   d.H >= 1 && d.W >= 1 && d.Ho >= 1 && d.Wo >= 1 && d.R <= 127 && d.S <= 127 && d.padX <= 127 && d.padY <= 127;
+        }
+
+        int dispatch_gather(int BN, const CUtensorMap& mapW, const GatherParams& p, int bStages, const float* in, const float* bias, float* out, cudaStream_t st)
+        {
+            return BN == 64 ? launch_gather<64>(mapW, p, bStages, in, bias, out, st)
+                 : BN == 128 ? launch_gather<128>(mapW, p, bStages, in, bias, out, st)
+                             : launch_gather<256>(mapW, p, bStages, in, bias, out, st);
+        }
+
         FwdShape fwd_shape(const nb200_conv_desc& d)
         {
             return FwdShape{d.N, d.C, d.H, d.W, d.K, d.Ho, d.Wo, d.R, d.S, d.padX, d.padY, d.math == NB200_MATH_3XTF32};
@@ -1317,6 +1618,84 @@ namespace nb200
         count_launch();
             return NB200_OK;
         }
+    }
+
+
+    // ---- gather kernel entry points ----
+    bool tc_gather_forward_supported(const nb200_conv_desc& d) { return gather_ok(d); }
+    bool tc_gather_input_gradient_supported(const nb200_conv_desc& d) { return gather_ok(d); }
+
+    size_t tc_gather_workspace_bytes(int op, const nb200_conv_desc& d)
+    {
+        if (op == NB200_OP_FORWARD)
+            return (size_t)d.R * d.S * d.K * round_up(d.C, kBlockC) * sizeof(float);
+        return (size_t)d.R * d.S * d.C * round_up(d.K, kBlockC) * sizeof(float);
+    }
+
+    int tc_gather_forward(const nb200_conv_desc& d, const float* x, const float* w, const float* bias, int act, float alpha, float* y, void* ws,
+                          size_t wsBytes, cudaStream_t st)
+    {
+        CUtensorMap mapW;
+        int BN, bStages, Cblocks;
+        int rc = gather_prepare(d.K, d.C, d.R, d.S, 0, d.K, d.C, w, ws, wsBytes, st, &mapW, &BN, &bStages, &Cblocks);
+        if (rc) return rc;
+        GatherParams p{};
+        p.Cblocks = Cblocks; p.ntaps = d.R * d.S;
+        p.C = d.C; p.H = d.H; p.W = d.W; p.K = d.K; p.Ho = d.Ho; p.Wo = d.Wo;
+        p.PH = d.Ho; p.PW = d.Wo; p.oyMul = 1; p.oyAdd = 0; p.oxMul = 1; p.oxAdd = 0; p.iyMul = d.stride; p.ixMul = d.stride;
+        p.totalPix = (long long)d.N * d.Ho * d.Wo;
+        p.tilesK = ceil_div(d.K, BN); p.bStages = bStages; p.act = act; p.alpha = alpha;
+        for (int r = 0; r < d.R; ++r)
+            for (int s2 = 0; s2 < d.S; ++s2)
+            {
+                const int t = r * d.S + s2;
+                p.iyAdd[t] = (short)(r - d.padY); p.ixAdd[t] = (short)(s2 - d.padX); p.wtap[t] = (short)t;
+            }
+        return dispatch_gather(BN, mapW, p, bStages, x, bias, y, st);
+    }
+
+    int tc_gather_input_gradient(const nb200_conv_desc& d, const float* dy, const float* w, float* dx, void* ws, size_t wsBytes, cudaStream_t st)
+    {
+        // produced tensor = dx (C channels, H x W); gathered tensor = dy (K channels, Ho x Wo); filters [tap][c][k]
+        CUtensorMap mapW;
+        int BN, bStages, Cblocks;
+        int rc = gather_prepare(d.C, d.K, d.R, d.S, 2, d.K, d.C, w, ws, wsBytes, st, &mapW, &BN, &bStages, &Cblocks);
+        if (rc) return rc;
+        const int st2 = d.stride;
+        for (int ph = 0; ph < st2; ++ph)
+            for (int pw = 0; pw < st2; ++pw)
+            {
+                if (ph >= d.H || pw >= d.W)
+                    continue;
+                GatherParams p{};
+                p.Cblocks = Cblocks;
+                p.C = d.K; p.H = d.Ho; p.W = d.Wo; p.K = d.C; p.Ho = d.H; p.Wo = d.W;
+                p.PH = (d.H - ph + st2 - 1) / st2; p.PW = (d.W - pw + st2 - 1) / st2;
+                p.oyMul = st2; p.oyAdd = ph; p.oxMul = st2; p.oxAdd = pw; p.iyMul = 1; p.ixMul = 1;
+                p.totalPix = (long long)d.N * p.PH * p.PW;
+                p.tilesK = ceil_div(d.C, BN); p.bStages = bStages; p.act = NB200_ACT_IDENTITY; p.alpha = 0.f;
+                int nt = 0;
+                // taps that reach this parity class: (ph + padY - r) divisible by the stride (and likewise in x)
+                for (int r = 0; r < d.R; ++r)
+                {
+                    const int ty = ph + d.padY - r;
+                    if (((ty % st2) + st2) % st2 != 0) continue;
+                    for (int s2 = 0; s2 < d.S; ++s2)
+                    {
+                        const int tx = pw + d.padX - s2;
+                        if (((tx % st2) + st2) % st2 != 0) continue;
+                        // exact division (ty, tx may be negative)
+                        p.iyAdd[nt] = (short)(ty >= 0 ? ty / st2 : -((-ty) / st2));
+                        p.ixAdd[nt] = (short)(tx >= 0 ? tx / st2 : -((-tx) / st2));
+                        p.wtap[nt] = (short)(r * d.S + s2);
+                        ++nt;
+                    }
+                }
+                p.ntaps = nt;
+                rc = dispatch_gather(BN, mapW, p, bStages, dy, nullptr, dx, st);
+                if (rc) return rc;
+            }
+        return NB200_OK;
     }
 
     bool tc_forward_supported(const nb200_conv_desc& d)

@@ -67,6 +67,14 @@ TC_CASES = [
     (0, 2, 3, 30, 27, 10, 3, 3, 1, 1, 1),      # small-channel, ragged width (scalar paths)
     (0, 2, 4, 20, 24, 12, 3, 3, 1, 2, 2),      # small-channel, full padding
     (0, 2, 2, 20, 24, 12, 3, 3, 1, 0, 0),      # small-channel, valid padding
+    # gathered-A tensor-core kernel: strides, tiny maps (batch folds into M), odd widths, tap-less parity classes
+    (0, 8, 128, 8, 8, 128, 3, 3, 2, 1, 1),     # DCGAN D conv3: 8x8 -> 4x4
+    (0, 8, 128, 4, 4, 256, 3, 3, 1, 1, 1),     # DCGAN D conv4: 4x4 maps
+    (0, 8, 128, 8, 8, 256, 4, 4, 2, 1, 1),     # DCGAN G deconv1 geometry (dgrad = 4x4 -> 8x8 transposed conv)
+    (0, 2, 16, 11, 11, 16, 4, 4, 2, 0, 0),     # ragged stride: last input row/col unreachable
+    (0, 1, 16, 35, 35, 32, 4, 4, 2, 0, 0),     # PatchGAN-like odd width
+    (0, 2, 16, 9, 9, 24, 1, 1, 2, 0, 0),       # 1x1 stride 2: three of the four dx parity classes have no tap
+    (0, 2, 24, 13, 10, 40, 3, 3, 3, 1, 1),     # stride 3
 ]
 
 
