@@ -111,7 +111,10 @@ namespace nb200
                 if (tc_input_gradient_supported(d) && d.W >= 24) return kTc;
                 if (tc_gather_input_gradient_supported(d)) return kGather;
                 return tc_input_gradient_supported(d) ? kTc : kDirect;
-            default: return tc_kernels_gradient_supported(d) ? kTc : kDirect;
+            default:
+                if (tc_kernels_gradient_supported(d) && d.Wo >= 24) return kTc;
+                if (tc_gather_kernels_gradient_supported(d)) return kGather;
+                return tc_kernels_gradient_supported(d) ? kTc : kDirect;
             }
         }
     }
@@ -168,7 +171,7 @@ extern "C"
         if (f == kSmallC)
             return op == NB200_OP_KERNELS_GRADIENT ? smallc_wgrad_workspace(*d) : 0;
         if (f == kGather)
-            return tc_gather_workspace_bytes(op, *d);
+            return op == NB200_OP_KERNELS_GRADIENT ? tc_gather_kernels_gradient_workspace(*d) : tc_gather_workspace_bytes(op, *d);
         return op == NB200_OP_KERNELS_GRADIENT ? direct_kernels_gradient_workspace(*d) : 0;
     }
 
@@ -181,7 +184,7 @@ extern "C"
         {
         case NB200_OP_FORWARD: return f == kTc ? "tcgen05_fprop" : f == kGather ? "tcgen05_gather_fprop" : f == kSmallC ? "smallc_fprop" : "direct_fprop";
         case NB200_OP_INPUT_GRADIENT: return f == kTc ? "tcgen05_dgrad" : f == kGather ? "tcgen05_gather_dgrad" : f == kSmallC ? "smallc_dgrad" : "direct_dgrad";
-        case NB200_OP_KERNELS_GRADIENT: return f == kTc ? "tcgen05_wgrad" : f == kSmallC ? "smallc_wgrad" : "direct_wgrad";
+        case NB200_OP_KERNELS_GRADIENT: return f == kTc ? "tcgen05_wgrad" : f == kGather ? "tcgen05_gather_wgrad" : f == kSmallC ? "smallc_wgrad" : "direct_wgrad";
         default: return "invalid";
         }
     }
@@ -250,6 +253,8 @@ extern "C"
             return tc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         if (f == kSmallC)
             return smallc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
+        if (f == kGather)
+            return tc_gather_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         return direct_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
     }
 

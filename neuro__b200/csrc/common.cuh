@@ -99,6 +99,11 @@ namespace nb200
     int tc_gather_input_gradient(const nb200_conv_desc& d, const float* dy, const float* w, float* dx, void* ws, size_t wsBytes,
                                  cudaStream_t st);
 
+    bool tc_gather_kernels_gradient_supported(const nb200_conv_desc& d);
+    size_t tc_gather_kernels_gradient_workspace(const nb200_conv_desc& d);
+    int tc_gather_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes,
+                                   cudaStream_t st);
+
     // elementwise.cu
     int bias_gradient(const nb200_conv_desc& d, const float* dy, float* db, cudaStream_t st);
     int adam_step(float* p, const float* g, float* m, float* v, size_t n, float gs, float lr, float b1, float b2, float eps,

@@ -1237,6 +1237,243 @@ namespace nb200
             }
         }
 
+
+        // ---------------------------------------------------------------- gathered kernel gradient (any stride / map size)
+        //   dw[k][c][r][s] = sum over (n, oh, ow)  dy[n][k][oh][ow] * x[n][c][oh*st-pY+r][ow*st-pX+s]
+        // Same GEMM view as tc_wgrad_kernel (M = 128 channels, N = BN filters, reduction = pixels, one accumulator per tap
+        // of the CTA's tap group, split-K over pixel chunks, deterministic two-pass reduction), but built for the shapes
+        // the row-segment kernel cannot take: strides, and maps so small that a 32-pixel reduction chunk spans whole
+        // images. A chunk is 32 consecutive entries of the flattened (n, oh*Wo+ow) list: PXI = min(32, Ho*Wo) pixels from
+        // each of 32/PXI images. dy arrives by one 3-D TMA box {PXI, BN, 32/PXI} as 32/PXI K-major sub-tiles (128-, 64- or
+        // 32-byte rows, matching swizzle). x is gathered with lanes = pixels (coalesced), then each warp transposes its
+        // 32 channels x 32 pixels block through a private padded shared-memory scratch so that thread = channel holds
+        // the 32 pixels the TMEM A tile wants.
+        struct WgatherParams
+        {
+            int C, H, W, K, Ho, Wo, N;
+            int S, stride, padX, padY;
+            int PXI;              // pixels per image per chunk
+            int chunksPerImg;     // Ho*Wo / PXI
+            long long chunks;     // total 32-pixel chunks
+            int tilesC, tilesK, groups, tapsPerGroup, ntaps, splits;
+            long long chunksPerSplit;
+            int stages;
+            uint32_t rowBytes, layoutType;
+        };
+
+        constexpr int kWgScratchFloats = 32 * 33;
+
+        template <int BN>
+        __global__ void __launch_bounds__(kThreads, 1)
+        tc_wgrad_gather_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ WgatherParams p, const float* __restrict__ x,
+                               float* __restrict__ ws)
+        {
+            constexpr uint32_t kBBytes = BN * 32 * 4;
+            constexpr uint32_t kTmemCols = 512;
+
+            extern __shared__ uint8_t smemRaw[];
+            uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+            float* scratch = (float*)(smem + p.stages * kBBytes);              // [8 warps][32][33]
+            uint64_t* bars = (uint64_t*)(scratch + 8 * kWgScratchFloats);
+            uint64_t* full = bars;
+            uint64_t* empty = full + 8;
+            uint64_t* aFull = empty + 8;
+            uint64_t* aEmpty = aFull + kWgAStages;
+            uint64_t* accBar = aEmpty + kWgAStages;
+            uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
+
+            const int warp = threadIdx.x >> 5;
+            const int lane = threadIdx.x & 31;
+
+            int t = blockIdx.x;
+            const int split = t % p.splits; t /= p.splits;
+            const int kt = t % p.tilesK; t /= p.tilesK;
+            const int ct = t % p.tilesC; t /= p.tilesC;
+            const int grp = t;
+            const int c0 = ct * 128, k0 = kt * BN;
+            const int tap0 = grp * p.tapsPerGroup;
+            const int ntap = min(p.tapsPerGroup, p.ntaps - tap0);
+            const long long chunkBegin = split * p.chunksPerSplit;
+            const long long chunkEnd = min(chunkBegin + p.chunksPerSplit, p.chunks);
+            const int steps = (int)max(chunkEnd - chunkBegin, 0ll);
+            const int imgsPerChunk = 32 / p.PXI;
+
+            if (warp == 0 && lane == 0)
+            {
+                ptx::prefetch_tensormap(&mapDy);
+                for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+                for (int s = 0; s < kWgAStages; ++s) { ptx::mbar_init(&aFull[s], kTileH); ptx::mbar_init(&aEmpty[s], 1); }
+                ptx::mbar_init(accBar, 1);
+                ptx::fence_mbar_init();
+            }
+            if (warp == 1)
+                ptx::tmem_alloc(tmemSlot, kTmemCols);
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            ptx::tc_fence_after_sync();
+            const uint32_t tmemAcc = *tmemSlot;
+            const uint32_t tmemA = tmemAcc + kTmemCols - kWgAStages * 32;
+
+            if (warp == 0)
+            {
+                if (lane == 0)
+                {
+                    int st = 0;
+                    uint32_t ph = 0;
+                    for (long long ch = chunkBegin; ch < chunkEnd; ++ch)
+                    {
+                        const long long img0 = ch / p.chunksPerImg * imgsPerChunk; // first image of the chunk
+                        const int hw0 = (int)(ch % p.chunksPerImg) * p.PXI;
+                        ptx::mbar_wait(&empty[st], ph ^ 1);
+                        ptx::mbar_arrive_expect_tx(&full[st], kBBytes);
+                        // dy viewed as (Ho*Wo, K, N): box {PXI, BN, 32/PXI}; images / filters past the end read as 0
+                        ptx::tma_load_3d(smem + st * kBBytes, &mapDy, &full[st], hw0, k0, (int)img0);
+                        if (++st == p.stages) { st = 0; ph ^= 1; }
+                    }
+                }
+            }
+            else if (warp == 1)
+            {
+                constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, 0, 0);
+                const uint64_t descB0 = ptx::smem_desc_kmajor(ptx::smem_u32(smem), 8 * p.rowBytes, p.layoutType);
+                const uint32_t subTile = BN * p.rowBytes;   // bytes of one image's sub-tile
+                int st = 0, as = 0;
+                uint32_t ph = 0, aph = 0;
+                for (int it = 0; it < steps; ++it)
+                {
+                    ptx::mbar_wait(&full[st], ph);
+                    const uint32_t stageOff = st * kBBytes;
+                    for (int tp = 0; tp < ntap; ++tp)
+                    {
+                        ptx::mbar_wait(&aFull[as], aph);
+                        ptx::tc_fence_after_sync();
+                        if (ptx::elect_one())
+                        {
+                            const uint32_t ta = tmemA + as * 32;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                            {
+                                // reduction elements kk*8 .. kk*8+7: sub-tile (kk*8)/PXI, byte offset ((kk*8)%PXI)*4 inside the row
+                                const uint32_t off = stageOff + ((kk * 8) / p.PXI) * subTile + (((kk * 8) % p.PXI) << 2);
+                                ptx::mma_tf32_ts(tmemAcc + tp * BN, ta + kk * 8, descB0 + (uint64_t)(off >> 4), idesc, (it | kk) != 0);
+                            }
+                            ptx::mma_commit(&aEmpty[as]);
+                            if (tp == ntap - 1)
+                                ptx::mma_commit(&empty[st]);
+                        }
+                        __syncwarp();
+                        if (++as == kWgAStages) { as = 0; aph ^= 1; }
+                    }
+                    if (++st == p.stages) { st = 0; ph ^= 1; }
+                }
+                if (ptx::elect_one())
+                    ptx::mma_commit(accBar);
+                __syncwarp();
+            }
+            else
+            {
+                const int q = warp & 3;
+                const int g = (warp - 2) >> 2;
+                const uint32_t laneSel = (uint32_t)(q * 32) << 16;
+                float* myScratch = scratch + (warp - 2) * kWgScratchFloats;
+                const long long plane = (long long)p.H * p.W;
+                const int cw0 = c0 + q * 32;   // this warp's 32 channels
+                const int hwTotal = p.Ho * p.Wo;
+                bool pending = false;
+                int pendStage = 0;
+                const long long nTiles = (long long)steps * ntap;
+                for (long long j = g; j < nTiles; j += 2)
+                {
+                    const int it = (int)(j / ntap), tp = (int)(j - (long long)it * ntap);
+                    const int tap = tap0 + tp;
+                    const int r = tap / p.S, s = tap - r * p.S;
+                    // lane = pixel of the chunk
+                    const long long ch = chunkBegin + it;
+                    const long long img = ch / p.chunksPerImg * imgsPerChunk + lane / p.PXI;
+                    const int hw = (int)(ch % p.chunksPerImg) * p.PXI + lane % p.PXI;
+                    const int oh = hw / p.Wo, ow = hw - oh * p.Wo;
+                    const int iy = oh * p.stride - p.padY + r, ix = ow * p.stride - p.padX + s;
+                    const bool ok = img < p.N && hw < hwTotal && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                    const float* src = x + (img * p.C + cw0) * plane + (long long)iy * p.W + ix;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                    {
+                        const float f = (ok && cw0 + c < p.C) ? __ldg(src + c * plane) : 0.f;
+                        myScratch[c * 33 + lane] = f;              // row = channel, column = pixel
+                    }
+                    __syncwarp();
+                    uint32_t v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        v[i] = ptx::tf32_round_bits(__float_as_uint(myScratch[lane * 33 + i])); // lane = channel, i = pixel
+                    __syncwarp();
+                    if (pending)
+                    {
+                        ptx::tmem_st_wait();
+                        ptx::tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0)
+                            ptx::mbar_arrive(&aFull[pendStage]);
+                    }
+                    const int as = (int)(j & (kWgAStages - 1));
+                    ptx::mbar_wait(&aEmpty[as], ((uint32_t)(j / kWgAStages) & 1) ^ 1);
+                    ptx::tc_fence_after_sync();
+                    ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * 32, v);
+                    pending = true;
+                    pendStage = as;
+                }
+                if (pending)
+                {
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(&aFull[pendStage]);
+                }
+
+                // ----- epilogue: partial[split][tap][k][c] -----
+                ptx::mbar_wait(accBar, 0);
+                ptx::tc_fence_after_sync();
+                const int c = c0 + q * 32 + lane;
+                for (int tp = 0; tp < ntap; ++tp)
+                {
+                    float* dst = ws + ((long long)(split * p.ntaps + tap0 + tp) * p.K) * p.C + c;
+#pragma unroll 1
+                    for (int j0 = g * 32; j0 < BN; j0 += 64)
+                    {
+                        if (k0 + j0 >= p.K)
+                            break;
+                        uint32_t v[32];
+                        if (steps > 0)
+                        {
+                            ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + tp * BN + j0, v);
+                            ptx::tmem_ld_wait();
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = 0u;
+                        }
+                        if (c < p.C)
+                        {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (k0 + j0 + j < p.K)
+                                    dst[(long long)(k0 + j0 + j) * p.C] = __uint_as_float(v[j]);
+                        }
+                    }
+                }
+            }
+
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            if (warp == 1)
+            {
+                ptx::tc_fence_after_sync();
+                ptx::tmem_dealloc(tmemAcc, kTmemCols);
+            }
+        }
+
         // dw[k][c][tap] = sum over splits of partial[split][tap][k][c]
         __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int K, int C, int taps, int splits)
         {
@@ -1695,6 +1932,105 @@ namespace nb200
                 rc = dispatch_gather(BN, mapW, p, bStages, dy, nullptr, dx, st);
                 if (rc) return rc;
             }
+        return NB200_OK;
+    }
+
+
+    // ---- gathered kernel gradient ----
+    namespace
+    {
+        struct WgatherPlan
+        {
+            int BN, PXI, tapsPerGroup, groups, tilesC, tilesK, splits, stages;
+            long long chunks, chunksPerSplit;
+            size_t wsBytes, smemBytes;
+            bool ok;
+        };
+
+        WgatherPlan wgather_plan(const nb200_conv_desc& d)
+        {
+            WgatherPlan pl{};
+            const int hw = d.Ho * d.Wo;
+            pl.PXI = hw >= 32 ? 32 : hw;
+            // maps of >= 32 pixels: 32-pixel chunks inside one image, the last one padded by the TMA zero fill (needs the
+            // 16-byte stride rule: Ho*Wo % 4 == 0); smaller maps: 16 or 8 pixels from each of 2 or 4 images
+            pl.ok = d.fmt == NB200_NCHW && d.math == NB200_MATH_TF32 && (pl.PXI == 32 ? hw % 4 == 0 : (pl.PXI == 16 || pl.PXI == 8)) &&
+                    d.R * d.S <= 32 && d.C >= 1 && d.K >= 1 && d.N >= 1 && d.H >= 1 && d.W >= 1;
+            if (!pl.ok)
+                return pl;
+            pl.BN = d.K > 64 ? 128 : 64;
+            const int ntaps = d.R * d.S;
+            pl.tapsPerGroup = 384 / pl.BN; // accumulator columns (512 - 128 for the A ring) / BN
+            if (pl.tapsPerGroup > ntaps) pl.tapsPerGroup = ntaps;
+            pl.groups = ceil_div(ntaps, pl.tapsPerGroup);
+            pl.tilesC = ceil_div(d.C, 128);
+            pl.tilesK = ceil_div(d.K, pl.BN);
+            const long long imgGroups = ((long long)d.N + 32 / pl.PXI - 1) / (32 / pl.PXI);
+            pl.chunks = imgGroups * ceil_div(hw, pl.PXI);
+            const int combos = pl.tilesC * pl.tilesK * pl.groups;
+            long long splits = 148 / combos;
+            if (splits < 1) splits = 1;
+            if (splits > pl.chunks) splits = pl.chunks;
+            pl.chunksPerSplit = (pl.chunks + splits - 1) / splits;
+            pl.splits = (int)((pl.chunks + pl.chunksPerSplit - 1) / pl.chunksPerSplit);
+            pl.stages = 6;
+            pl.smemBytes = 1024 + 512 + (size_t)pl.stages * pl.BN * 128 + 8 * kWgScratchFloats * sizeof(float);
+            pl.wsBytes = (size_t)pl.splits * ntaps * d.K * d.C * sizeof(float);
+            return pl;
+        }
+
+        template <int BN>
+        int launch_wgather(const WgatherPlan& pl, const CUtensorMap& mapDy, const WgatherParams& p, const float* x, float* ws, cudaStream_t st)
+        {
+            static bool attrSet = false;
+            if (!attrSet)
+            {
+                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_gather_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                attrSet = true;
+            }
+            const long long ctas = (long long)p.splits * p.tilesK * p.tilesC * p.groups;
+            tc_wgrad_gather_kernel<BN><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapDy, p, x, ws);
+            NB200_CUDA_TRY(cudaGetLastError());
+            count_launch();
+            return NB200_OK;
+        }
+    }
+
+    bool tc_gather_kernels_gradient_supported(const nb200_conv_desc& d) { return wgather_plan(d).ok; }
+    size_t tc_gather_kernels_gradient_workspace(const nb200_conv_desc& d) { return wgather_plan(d).wsBytes; }
+
+    int tc_gather_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st)
+    {
+        const WgatherPlan pl = wgather_plan(d);
+        if (!pl.ok)
+            return fail(NB200_E_UNSUPPORTED, "gathered kernel gradient does not take this shape");
+        if (wsBytes < pl.wsBytes || !ws)
+            return fail(NB200_E_WORKSPACE, "tcgen05 kernel gradient needs %zu workspace bytes, got %zu", pl.wsBytes, wsBytes);
+        if ((uintptr_t)dy & 15)
+            return fail(NB200_E_INVALID, "tensor base addresses must be 16-byte aligned for TMA");
+        const int hw = d.Ho * d.Wo;
+        CUtensorMap mapDy;
+        {
+            cuuint64_t dims[3] = {(cuuint64_t)hw, (cuuint64_t)d.K, (cuuint64_t)d.N};
+            cuuint64_t strides[2] = {(cuuint64_t)hw * 4, (cuuint64_t)d.K * hw * 4};
+            cuuint32_t box[3] = {(cuuint32_t)pl.PXI, (cuuint32_t)pl.BN, (cuuint32_t)(32 / pl.PXI)};
+            const CUtensorMapSwizzle sw = pl.PXI == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : pl.PXI == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+            int rc = make_map(&mapDy, dy, 3, dims, strides, box, sw);
+            if (rc) return rc;
+        }
+        WgatherParams p{};
+        p.C = d.C; p.H = d.H; p.W = d.W; p.K = d.K; p.Ho = d.Ho; p.Wo = d.Wo; p.N = d.N;
+        p.S = d.S; p.stride = d.stride; p.padX = d.padX; p.padY = d.padY;
+        p.PXI = pl.PXI; p.chunksPerImg = ceil_div(hw, pl.PXI); p.chunks = pl.chunks;
+        p.tilesC = pl.tilesC; p.tilesK = pl.tilesK; p.groups = pl.groups; p.tapsPerGroup = pl.tapsPerGroup; p.ntaps = d.R * d.S;
+        p.splits = pl.splits; p.chunksPerSplit = pl.chunksPerSplit; p.stages = pl.stages;
+        p.rowBytes = (uint32_t)pl.PXI * 4; p.layoutType = pl.PXI == 32 ? 2u : pl.PXI == 16 ? 4u : 6u;
+        int rc = pl.BN == 64 ? launch_wgather<64>(pl, mapDy, p, x, (float*)ws, st) : launch_wgather<128>(pl, mapDy, p, x, (float*)ws, st);
+        if (rc) return rc;
+        const long long total = (long long)d.K * d.C * d.R * d.S;
+        wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)ws, dw, d.K, d.C, d.R * d.S, pl.splits);
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
         return NB200_OK;
     }
 

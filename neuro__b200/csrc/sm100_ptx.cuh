@@ -306,6 +306,18 @@ namespace nb200
             return d;
         }
 
+        // Same for the narrower K-major swizzle modes (rows of 64 / 32 bytes): layout type 4 = SWIZZLE_64B, 6 = SWIZZLE_32B.
+        __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t smemAddr, uint32_t strideBytes, uint32_t layoutType)
+        {
+            uint64_t d = 0;
+            d |= (uint64_t)((smemAddr >> 4) & 0x3FFF);
+            d |= (uint64_t)1 << 16;
+            d |= (uint64_t)((strideBytes >> 4) & 0x3FFF) << 32;
+            d |= (uint64_t)1 << 46;
+            d |= (uint64_t)layoutType << 61;
+            return d;
+        }
+
         // Instruction descriptor for kind::tf32 with fp32 accumulation.
         // aMnMajor/bMnMajor: 1 when the operand's M (resp. N) dimension is the contiguous one in shared memory.
         __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int aMnMajor, int bMnMajor)

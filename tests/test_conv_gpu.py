@@ -75,6 +75,9 @@ TC_CASES = [
     (0, 1, 16, 35, 35, 32, 4, 4, 2, 0, 0),     # PatchGAN-like odd width
     (0, 2, 16, 9, 9, 24, 1, 1, 2, 0, 0),       # 1x1 stride 2: three of the four dx parity classes have no tap
     (0, 2, 24, 13, 10, 40, 3, 3, 3, 1, 1),     # stride 3
+    (0, 4, 16, 4, 8, 16, 3, 3, 2, 1, 1),       # 2x4 output maps: 8-pixel reduction sub-tiles (SWIZZLE_32B rows)
+    (0, 6, 200, 16, 16, 72, 4, 4, 2, 1, 1),    # two channel tiles, ragged filter tile, 16 taps in tap groups
+    (0, 3, 16, 12, 12, 16, 3, 3, 2, 1, 1),     # 6x6 = 36-pixel output maps: last reduction chunk is partial
 ]
 
 
