@@ -62,7 +62,7 @@ namespace nb200
             }
             __device__ __forceinline__ void flush()
             {
-                if (sink)
+                if (sink && (threadIdx.x & 31) == 0) // every lane of the role's warp keeps the (identical) timers
                 {
 #pragma unroll
                     for (int i = 0; i < kDbgSlots; ++i)
@@ -72,6 +72,18 @@ namespace nb200
         };
 
         __device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, WaitAcc& acc, int slot)
+        {
+            if (acc.sink == nullptr)
+            {
+                ptx::mbar_wait(bar, parity);
+                return;
+            }
+            const long long t0 = clock64();
+            ptx::mbar_wait(bar, parity);
+            acc.v[slot] += clock64() - t0;
+        }
+
+        __device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, WaitAcc& acc, int slot)
         {
             if (acc.sink == nullptr)
             {
@@ -147,6 +159,42 @@ namespace nb200
         // hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-22 relative), which recovers fp32-class accuracy
         // (<= 1e-5 max-normalised against the reference) at a third of the TF32 rate. A tiles carry [hi | lo] (64 columns),
         // filter stages carry a hi and a lo tile (the repack writes both).
+        // Bias + activation + store of one 32-filter chunk of this thread's pixel (lanes = 32 consecutive output columns, so
+        // every store instruction writes one full 128-byte line). The activation is a template parameter: the per-element
+        // switch and the exp paths stay out of the identity / ReLU / leaky-ReLU instantiations (the epilogue used to cost
+        // as many issue slots as the whole main loop of a 64-filter tile). Lane j carries bias[kBase + j]; shuffles broadcast it.
+        template <int ACT>
+        __device__ __forceinline__ void store_chunk_t(float* yp, long long strideK, int kBase, int K, float biasLane, int act, float alpha,
+                                                      bool pixelOk, const uint32_t (&v)[32])
+        {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+            {
+                const float b = __shfl_sync(0xffffffffu, biasLane, j);
+                if (pixelOk && kBase + j < K)
+                {
+                    float f = __uint_as_float(v[j]) + b;
+                    if constexpr (ACT == NB200_ACT_RELU) f = f > 0.f ? f : 0.f;
+                    else if constexpr (ACT == NB200_ACT_LEAKY_RELU) f = f >= 0.f ? f : alpha * f;
+                    else if constexpr (ACT != NB200_ACT_IDENTITY) f = apply_activation(act, alpha, f);
+                    yp[(long long)(kBase + j) * strideK] = f;
+                }
+            }
+        }
+
+        __device__ __forceinline__ void store_chunk(float* yp, long long strideK, int kBase, int K, const float* __restrict__ bias, int lane,
+                                                    int act, float alpha, bool pixelOk, const uint32_t (&v)[32])
+        {
+            const float bl = (bias && kBase + lane < K) ? __ldg(bias + kBase + lane) : 0.f;
+            switch (act)
+            {
+            case NB200_ACT_IDENTITY: store_chunk_t<NB200_ACT_IDENTITY>(yp, strideK, kBase, K, bl, act, alpha, pixelOk, v); break;
+            case NB200_ACT_RELU: store_chunk_t<NB200_ACT_RELU>(yp, strideK, kBase, K, bl, act, alpha, pixelOk, v); break;
+            case NB200_ACT_LEAKY_RELU: store_chunk_t<NB200_ACT_LEAKY_RELU>(yp, strideK, kBase, K, bl, act, alpha, pixelOk, v); break;
+            default: store_chunk_t<-1>(yp, strideK, kBase, K, bl, act, alpha, pixelOk, v); break;
+            }
+        }
+
         template <int BN, bool X3>
         __global__ void __launch_bounds__(kFpropThreads, ((BN > 128 || X3) ? 1 : 2))
         tc_fprop_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, FpropParams p,
@@ -206,14 +254,18 @@ namespace nb200
             ptx::tc_fence_after_sync();
             const uint32_t tmemAcc = *tmemSlot;
             const uint32_t tmemA = tmemAcc + BN;
+            // 32-bit shared addresses of the barrier arrays, computed once (see sm100_ptx.cuh)
+            const uint32_t bFull32 = ptx::smem_u32(bFull), bEmpty32 = ptx::smem_u32(bEmpty), xFull32 = ptx::smem_u32(xFull),
+                           xEmpty32 = ptx::smem_u32(xEmpty), aFull32 = ptx::smem_u32(aFull), aEmpty32 = ptx::smem_u32(aEmpty),
+                           accBar32 = ptx::smem_u32(accBar), accFree32 = ptx::smem_u32(accFree);
 
             const int taps = p.R * p.S;
             // per-CTA debug rows: [0] filter producer, [1] MMA issuer, [2] halo producer, [3] converter warp 3 lane 0
             long long* dbgBase = p.dbg ? p.dbg + (long long)blockIdx.x * 4 * kDbgSlots : nullptr;
-            WaitAcc dbgP((dbgBase && lane == 0) ? dbgBase : nullptr);
-            WaitAcc dbgM((dbgBase && lane == 0) ? dbgBase + kDbgSlots : nullptr);
-            WaitAcc dbgX((dbgBase && lane == 0) ? dbgBase + 2 * kDbgSlots : nullptr);
-            WaitAcc dbgC((dbgBase && warp == kFirstConvWarp && lane == 0) ? dbgBase + 3 * kDbgSlots : nullptr);
+            WaitAcc dbgP(dbgBase ? dbgBase : nullptr);
+            WaitAcc dbgM(dbgBase ? dbgBase + kDbgSlots : nullptr);
+            WaitAcc dbgX(dbgBase ? dbgBase + 2 * kDbgSlots : nullptr);
+            WaitAcc dbgC((dbgBase && warp == kFirstConvWarp) ? dbgBase + 3 * kDbgSlots : nullptr);
             const long long tStart = clock64();
 
             if (warp == 0)
@@ -266,10 +318,10 @@ namespace nb200
                 int tapc = 0, cbc = 0; // position inside the current channel block (3xTF32 drains the accumulator per block)
                 for (int it = 0; it < iters; ++it)
                 {
-                    timed_wait(&bFull[bs], bph, dbgM, kDbgBFull);
-                    timed_wait(&aFull[as], aph, dbgM, kDbgAFull);
+                    timed_wait(bFull32 + 8u * bs, bph, dbgM, kDbgBFull);
+                    timed_wait(aFull32 + 8u * as, aph, dbgM, kDbgAFull);
                     if (X3 && tapc == 0 && cbc > 0)
-                        ptx::mbar_wait(accFree, (uint32_t)(cbc - 1) & 1); // previous block's partial sums are in registers
+                        ptx::mbar_wait(accFree32, (uint32_t)(cbc - 1) & 1); // previous block's partial sums are in registers
                     const long long tIssue = dbgM.sink ? clock64() : 0;
                     ptx::tc_fence_after_sync();
                     if (ptx::elect_one())
@@ -286,10 +338,10 @@ namespace nb200
                                 ptx::mma_tf32_ts(tmemAcc, ta + kBlockC + kk * 8, db + kk * 2, idesc, 1);                  // lo * hi
                             }
                         }
-                        ptx::mma_commit(&aEmpty[as]); // both slots reusable once these MMAs have consumed them
-                        ptx::mma_commit(&bEmpty[bs]);
+                        ptx::mma_commit(aEmpty32 + 8u * as); // both slots reusable once these MMAs have consumed them
+                        ptx::mma_commit(bEmpty32 + 8u * bs);
                         if (X3 && tapc == taps - 1)
-                            ptx::mma_commit(accBar); // this channel block's partial accumulator is complete
+                            ptx::mma_commit(accBar32); // this channel block's partial accumulator is complete
                     }
                     __syncwarp();
                     if (++tapc == taps) { tapc = 0; ++cbc; }
@@ -299,7 +351,7 @@ namespace nb200
                 }
                 if (dbgM.sink) dbgM.v[kDbgTotal] = clock64() - tLoop;
                 if (!X3 && ptx::elect_one())
-                    ptx::mma_commit(accBar); // accumulator complete
+                    ptx::mma_commit(accBar32); // accumulator complete
                 __syncwarp();
             }
             else
@@ -314,6 +366,7 @@ namespace nb200
                 const uint32_t xRing32 = ptx::smem_u32(xRing);
                 bool pending = false;
                 int pendStage = 0;
+                const long long tConv = dbgC.sink ? clock64() : 0;
                 // 3xTF32: the tensor core's fp32 accumulator truncates on every add, a bias that grows with the length of
                 // the accumulation chain (measured 3.8e-5 max-normalised at C = 512). So the chain is cut per channel block:
                 // each block's partial sums are drained from TMEM and added, round-to-nearest, into registers.
@@ -330,7 +383,7 @@ namespace nb200
                 for (int cb = 0; cb < p.Cblocks; ++cb)
                 {
                     const int xs = cb % p.xStages;
-                    timed_wait(&xFull[xs], (uint32_t)(cb / p.xStages) & 1, dbgC, kDbgXFull);
+                    timed_wait(xFull32 + 8u * xs, (uint32_t)(cb / p.xStages) & 1, dbgC, kDbgXFull);
                     const uint32_t xt = xRing32 + xs * xBytesPad;
                     int r = 0, s = 0;
                     for (int tap = 0; tap < taps; ++tap, (++s == p.S ? (s = 0, ++r) : 0))
@@ -341,6 +394,7 @@ namespace nb200
                         // pixel (q, lane) of the tile, tap (r, s): halo row q + r, halo column lane + s - padX + wOff
                         const uint32_t src = xt + (uint32_t)(((q + r) * p.WB + (lane + s - p.padX + p.wOff)) << 2);
                         uint32_t v[kBlockC];
+                        const long long tA = dbgC.sink ? clock64() : 0;
                         if (chanStrideB == 960u) // 3x3 filters: compile-time channel pitch -> LDS with immediate offsets
                         {
 #pragma unroll
@@ -368,25 +422,48 @@ namespace nb200
                         if (pending)
                         {
                             // the previous tap's store has had the whole load phase to land
-                            ptx::tmem_st_wait();
-                            ptx::tc_fence_before_sync();
-                            __syncwarp();
-                            if (lane == 0)
-                                ptx::mbar_arrive(&aFull[pendStage]);
+                            if (dbgC.sink)
+                            {
+                                // v[] is consumed here so the clock read sits after the loads have landed
+                                uint32_t x = 0;
+#pragma unroll
+                                for (int c = 0; c < kBlockC; ++c) x ^= v[c];
+                                const long long t0 = clock64() + (x == 0x12345u ? 1 : 0);
+                                dbgC.v[kDbgAFull] += t0 - tA;        // converter row: slot AFull = load + round phase
+                                ptx::tmem_st_wait();
+                                const long long t1 = clock64();
+                                dbgC.v[kDbgBFull] += t1 - t0;        // slot BFull = tcgen05.st completion wait
+                                ptx::tc_fence_before_sync();
+                                __syncwarp();
+                                if (lane == 0)
+                                    ptx::mbar_arrive(aFull32 + 8u * pendStage);
+                                __syncwarp();
+                                dbgC.v[kDbgXEmpty] += clock64() - t1; // slot XEmpty = fence + arrive
+                            }
+                            else
+                            {
+                                ptx::tmem_st_wait();
+                                ptx::tc_fence_before_sync();
+                                __syncwarp();
+                                if (lane == 0)
+                                    ptx::mbar_arrive(aFull32 + 8u * pendStage);
+                            }
                         }
                         const int as = it & (kAStages - 1);
-                        timed_wait(&aEmpty[as], ((uint32_t)(it / kAStages) & 1) ^ 1, dbgC, kDbgAEmpty);
+                        timed_wait(aEmpty32 + 8u * as, ((uint32_t)(it / kAStages) & 1) ^ 1, dbgC, kDbgAEmpty);
+                        const long long tS = dbgC.sink ? clock64() : 0;
                         ptx::tc_fence_after_sync();
                         ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kACols, v);
                         if (X3)
                             ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kACols + kBlockC, vlo);
+                        if (dbgC.sink) dbgC.v[kDbgBEmpty] += clock64() - tS; // slot BEmpty = tcgen05.st issue
                         pending = true;
                         pendStage = as;
                     }
                     // every load of this halo tile has been consumed into registers (the stores above read them)
                     __syncwarp();
                     if (lane == 0)
-                        ptx::mbar_arrive(&xEmpty[xs]);
+                        ptx::mbar_arrive(xEmpty32 + 8u * xs);
                     if (X3)
                     {
                         if (pending) // the MMAs of this block cannot finish before its last A tile is published
@@ -395,10 +472,10 @@ namespace nb200
                             ptx::tc_fence_before_sync();
                             __syncwarp();
                             if (lane == 0)
-                                ptx::mbar_arrive(&aFull[pendStage]);
+                                ptx::mbar_arrive(aFull32 + 8u * pendStage);
                             pending = false;
                         }
-                        ptx::mbar_wait(accBar, (uint32_t)cb & 1);
+                        ptx::mbar_wait(accBar32, (uint32_t)cb & 1);
                         ptx::tc_fence_after_sync();
 #pragma unroll
                         for (int ch = 0; ch < kOwnChunks; ++ch)
@@ -413,7 +490,7 @@ namespace nb200
                         ptx::tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0)
-                            ptx::mbar_arrive(accFree);
+                            ptx::mbar_arrive(accFree32);
                     }
                 }
                 if (pending)
@@ -422,35 +499,21 @@ namespace nb200
                     ptx::tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0)
-                        ptx::mbar_arrive(&aFull[pendStage]);
+                        ptx::mbar_arrive(aFull32 + 8u * pendStage);
                 }
 
                 // ----- epilogue: the two warps of a quadrant split the filter columns -----
                 const int oh = oh0 + q, ow = ow0 + lane;
                 if (!X3)
                 {
-                    timed_wait(accBar, 0, dbgC, kDbgAcc);
+                    timed_wait(accBar32, 0, dbgC, kDbgAcc);
                     ptx::tc_fence_after_sync();
                 }
                 const bool pixelOk = oh < p.Ho && ow < p.Wo;
                 float* yp = y + n * p.yStrideN + (long long)oh * p.Wo + ow;
                 // bias + activation + one full 128-byte line per store instruction (lanes = 32 consecutive output columns)
                 auto store_chunk = [&](int c0, const uint32_t (&v)[32]) {
-                    if (pixelOk)
-                    {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                        {
-                            const int k = k0 + c0 + j;
-                            if (k < p.K)
-                            {
-                                float f = __uint_as_float(v[j]);
-                                if (bias)
-                                    f += __ldg(bias + k);
-                                yp[k * p.yStrideK] = apply_activation(p.act, p.alpha, f);
-                            }
-                        }
-                    }
+                    nb200::store_chunk(yp, p.yStrideK, k0 + c0, p.K, bias, lane, p.act, p.alpha, pixelOk, v);
                 };
                 if (X3)
                 {
@@ -481,6 +544,226 @@ namespace nb200
                         store_chunk(c0, v);
                     }
                 }
+                if (dbgC.sink) dbgC.v[kDbgTotal] = clock64() - tConv;
+            }
+
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            if (warp == 1)
+            {
+                ptx::tc_fence_after_sync();
+                ptx::tmem_dealloc(tmemAcc, kTmemCols);
+            }
+            if (warp == 0) dbgP.flush();
+            if (warp == 1) dbgM.flush();
+            if (warp == 2) dbgX.flush();
+            if (warp == kFirstConvWarp) dbgC.flush();
+        }
+
+
+
+
+        // ---------------------------------------------------------------- forward kernel, 256-pixel tile (two M halves)
+        // Measured on B200 an SM ingests ~48 B/clk from L2 (profiles/r1_microbench_*): the 128-pixel tile streams a
+        // 128 B x BN filter tile per 4 MMAs, which for BN = 256 is 35 KB per 512 MMA cycles -- ingest-bound at ~70 %. This
+        // variant lets TWO 128-pixel halves (8 output rows x 32 columns) share every filter tile: one CTA per SM, accumulators
+        // D0 | D1 (2 x BN <= 256 TMEM columns), one A ring per half (4 x 32 columns each), converter group g owns half g for
+        // every tap, the MMA warp issues both halves against the same B stage. Filter bytes per MMA cycle halve
+        // (23 KB per 512 cycles at BN = 128), the halo tile grows to 8+R-1 rows.
+        constexpr int kHalfStages = 4;
+
+        template <int BN>
+        __global__ void __launch_bounds__(kFpropThreads, 1)
+        tc_fprop_m256_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, FpropParams p,
+                             const float* __restrict__ bias, float* __restrict__ y)
+        {
+            static_assert(BN <= 128, "two accumulators of BN columns plus two A rings must fit 512 TMEM columns");
+            constexpr uint32_t kBBytes = BN * kBlockC * 4;
+            constexpr uint32_t kTmemCols = 512;
+
+            extern __shared__ uint8_t smemRaw[];
+            uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+            const uint32_t xBytes = (uint32_t)(kBlockC * p.HR * p.WB * 4);
+            const uint32_t xBytesPad = (xBytes + 1023) & ~1023u;
+            uint8_t* bRing = smem;
+            uint8_t* xRing = smem + p.bStages * kBBytes;
+            uint64_t* bars = (uint64_t*)(xRing + p.xStages * xBytesPad);
+            uint64_t* bFull = bars;            // [bStages]
+            uint64_t* bEmpty = bFull + 8;
+            uint64_t* xFull = bEmpty + 8;      // [xStages]
+            uint64_t* xEmpty = xFull + 4;
+            uint64_t* aFull = xEmpty + 4;      // [2 halves][kHalfStages]
+            uint64_t* aEmpty = aFull + 2 * kHalfStages;
+            uint64_t* accBar = aEmpty + 2 * kHalfStages;
+            uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
+
+            const int warp = threadIdx.x >> 5;
+            const int lane = threadIdx.x & 31;
+
+            int t = blockIdx.x;
+            const int kt = t % p.tilesK; t /= p.tilesK;
+            const int tw = t % p.tilesW; t /= p.tilesW;
+            const int th = t % p.tilesH; t /= p.tilesH;
+            const int n = t;
+            const int ow0 = tw * kTileW, oh0 = th * (2 * kTileH), k0 = kt * BN;
+
+            if (warp == 0 && lane == 0)
+            {
+                ptx::prefetch_tensormap(&mapX);
+                ptx::prefetch_tensormap(&mapW);
+                for (int s = 0; s < p.bStages; ++s) { ptx::mbar_init(&bFull[s], 1); ptx::mbar_init(&bEmpty[s], 1); }
+                for (int s = 0; s < p.xStages; ++s) { ptx::mbar_init(&xFull[s], 1); ptx::mbar_init(&xEmpty[s], kTileH * kConvGroups); }
+                for (int s = 0; s < 2 * kHalfStages; ++s) { ptx::mbar_init(&aFull[s], kTileH); ptx::mbar_init(&aEmpty[s], 1); }
+                ptx::mbar_init(accBar, 1);
+                ptx::fence_mbar_init();
+            }
+            if (warp == 1)
+                ptx::tmem_alloc(tmemSlot, kTmemCols);
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            ptx::tc_fence_after_sync();
+            const uint32_t tmemAcc = *tmemSlot;            // D0 at +0, D1 at +BN
+            const uint32_t tmemA = tmemAcc + 2 * BN;       // half h, stage s at +(h * kHalfStages + s) * 32
+
+            const int taps = p.R * p.S;
+            const int iters = taps * p.Cblocks;
+
+            if (warp == 0)
+            {
+                if (lane == 0)
+                {
+                    int bs = 0;
+                    uint32_t bph = 0;
+                    for (int cb = 0; cb < p.Cblocks; ++cb)
+                        for (int tap = 0; tap < taps; ++tap)
+                        {
+                            ptx::mbar_wait(&bEmpty[bs], bph ^ 1);
+                            ptx::mbar_arrive_expect_tx(&bFull[bs], kBBytes);
+                            ptx::tma_load_3d(bRing + bs * kBBytes, &mapW, &bFull[bs], cb * kBlockC, k0, tap);
+                            if (++bs == p.bStages) { bs = 0; bph ^= 1; }
+                        }
+                }
+            }
+            else if (warp == 2)
+            {
+                if (lane == 0)
+                {
+                    int xs = 0;
+                    uint32_t xph = 0;
+                    for (int cb = 0; cb < p.Cblocks; ++cb)
+                    {
+                        ptx::mbar_wait(&xEmpty[xs], xph ^ 1);
+                        ptx::mbar_arrive_expect_tx(&xFull[xs], xBytes);
+                        ptx::tma_load_4d(xRing + xs * xBytesPad, &mapX, &xFull[xs], ow0 - p.wOff, oh0 - p.padY, cb * kBlockC, n);
+                        if (++xs == p.xStages) { xs = 0; xph ^= 1; }
+                    }
+                }
+            }
+            else if (warp == 1)
+            {
+                constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, 0, 0);
+                const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(bRing), 16, 1024);
+                int as = 0, bs = 0;
+                uint32_t aph = 0, bph = 0;
+                for (int it = 0; it < iters; ++it)
+                {
+                    ptx::mbar_wait(&bFull[bs], bph);
+                    const uint64_t db = descB0 + (uint64_t)((bs * kBBytes) >> 4);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                    {
+                        ptx::mbar_wait(&aFull[h * kHalfStages + as], aph);
+                        ptx::tc_fence_after_sync();
+                        if (ptx::elect_one())
+                        {
+                            const uint32_t ta = tmemA + (h * kHalfStages + as) * kBlockC;
+#pragma unroll
+                            for (int kk = 0; kk < kBlockC / 8; ++kk)
+                                ptx::mma_tf32_ts(tmemAcc + h * BN, ta + kk * 8, db + kk * 2, idesc, (it | kk) != 0);
+                            ptx::mma_commit(&aEmpty[h * kHalfStages + as]);
+                            if (h == 1)
+                                ptx::mma_commit(&bEmpty[bs]); // both halves have read this filter tile
+                        }
+                        __syncwarp();
+                    }
+                    if (++as == kHalfStages) { as = 0; aph ^= 1; }
+                    if (++bs == p.bStages) { bs = 0; bph ^= 1; }
+                }
+                if (ptx::elect_one())
+                    ptx::mma_commit(accBar);
+                __syncwarp();
+            }
+            else
+            {
+                // ===== converters: group g owns tile half g (output rows 4g .. 4g+3) for every tap =====
+                const int q = warp & 3;
+                const int g = (warp - kFirstConvWarp) >> 2;
+                const uint32_t laneSel = (uint32_t)(q * 32) << 16;
+                const uint32_t chanStrideB = (uint32_t)(p.HR * p.WB * 4);
+                const uint32_t xRing32 = ptx::smem_u32(xRing);
+                uint64_t* myFull = aFull + g * kHalfStages;
+                uint64_t* myEmpty = aEmpty + g * kHalfStages;
+                const uint32_t myA = tmemA + laneSel + g * kHalfStages * kBlockC;
+                bool pending = false;
+                int pendStage = 0;
+                int it = 0;
+                for (int cb = 0; cb < p.Cblocks; ++cb)
+                {
+                    const int xs = cb % p.xStages;
+                    ptx::mbar_wait(&xFull[xs], (uint32_t)(cb / p.xStages) & 1);
+                    const uint32_t xt = xRing32 + xs * xBytesPad;
+                    int r = 0, s = 0;
+                    for (int tap = 0; tap < taps; ++tap, ++it, (++s == p.S ? (s = 0, ++r) : 0))
+                    {
+                        const uint32_t src = xt + (uint32_t)(((g * kTileH + q + r) * p.WB + (lane + s - p.padX + p.wOff)) << 2);
+                        uint32_t v[kBlockC];
+#pragma unroll
+                        for (int c = 0; c < kBlockC; ++c)
+                            v[c] = ptx::tf32_round_bits(ptx::lds_b32(src + c * chanStrideB));
+                        if (pending)
+                        {
+                            ptx::tmem_st_wait();
+                            ptx::tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0)
+                                ptx::mbar_arrive(&myFull[pendStage]);
+                        }
+                        const int as = it & (kHalfStages - 1);
+                        ptx::mbar_wait(&myEmpty[as], ((uint32_t)(it / kHalfStages) & 1) ^ 1);
+                        ptx::tc_fence_after_sync();
+                        ptx::tmem_st_32x32b_x32(myA + as * kBlockC, v);
+                        pending = true;
+                        pendStage = as;
+                    }
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(&xEmpty[xs]);
+                }
+                if (pending)
+                {
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(&myFull[pendStage]);
+                }
+
+                // ----- epilogue: this group's half, all BN columns -----
+                const int oh = oh0 + g * kTileH + q, ow = ow0 + lane;
+                ptx::mbar_wait(accBar, 0);
+                ptx::tc_fence_after_sync();
+                const bool pixelOk = oh < p.Ho && ow < p.Wo;
+                float* yp = y + n * p.yStrideN + (long long)oh * p.Wo + ow;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32)
+                {
+                    if (k0 + c0 >= p.K)
+                        break;
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + g * BN + c0, v);
+                    ptx::tmem_ld_wait();
+                    nb200::store_chunk(yp, p.yStrideK, k0 + c0, p.K, bias, lane, p.act, p.alpha, pixelOk, v);
+                }
             }
 
             ptx::tc_fence_before_sync();
@@ -491,8 +774,6 @@ namespace nb200
                 ptx::tmem_dealloc(tmemAcc, kTmemCols);
             }
         }
-
-
 
         // ---------------------------------------------------------------- forward kernel, CTA-pair form (cta_group::2)
         // Same algorithm, but two CTAs of a cluster (one TPC = two SMs) cooperate on a 256-pixel x BN-filter tile:
@@ -565,10 +846,10 @@ namespace nb200
             const int taps = p.R * p.S;
             // per-CTA debug rows: [0] filter producer, [1] MMA issuer, [2] halo producer, [3] converter warp 3 lane 0
             long long* dbgBase = p.dbg ? p.dbg + (long long)blockIdx.x * 4 * kDbgSlots : nullptr;
-            WaitAcc dbgP((dbgBase && lane == 0) ? dbgBase : nullptr);
-            WaitAcc dbgM((dbgBase && lane == 0) ? dbgBase + kDbgSlots : nullptr);
-            WaitAcc dbgX((dbgBase && lane == 0) ? dbgBase + 2 * kDbgSlots : nullptr);
-            WaitAcc dbgC((dbgBase && warp == kFirstConvWarp && lane == 0) ? dbgBase + 3 * kDbgSlots : nullptr);
+            WaitAcc dbgP(dbgBase ? dbgBase : nullptr);
+            WaitAcc dbgM(dbgBase ? dbgBase + kDbgSlots : nullptr);
+            WaitAcc dbgX(dbgBase ? dbgBase + 2 * kDbgSlots : nullptr);
+            WaitAcc dbgC((dbgBase && warp == kFirstConvWarp) ? dbgBase + 3 * kDbgSlots : nullptr);
             const long long tStart = clock64();
 
             if (warp == 0)
@@ -716,21 +997,7 @@ namespace nb200
                     uint32_t v[32];
                     ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + c0, v);
                     ptx::tmem_ld_wait();
-                    if (pixelOk)
-                    {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                        {
-                            const int k = k0 + c0 + j;
-                            if (k < p.K)
-                            {
-                                float f = __uint_as_float(v[j]);
-                                if (bias)
-                                    f += __ldg(bias + k);
-                                yp[k * p.yStrideK] = apply_activation(p.act, p.alpha, f);
-                            }
-                        }
-                    }
+                    nb200::store_chunk(yp, p.yStrideK, k0 + c0, p.K, bias, lane, p.act, p.alpha, pixelOk, v);
                 }
             }
 
@@ -1543,6 +1810,7 @@ namespace nb200
         {
             int BN, wOff, WB, HR, xStages, bStages;
             bool pair; // CTA-pair (cta_group::2) kernel
+            bool m256; // 256-pixel tile: two M halves share each filter tile (one CTA per SM)
             size_t smemBytes;
             bool ok;
         };
@@ -1564,14 +1832,23 @@ namespace nb200
                 if (pl.BN == 256 && spatial * ceil_div(f.Kout, 256) <= 96)
                     pl.BN = 128;
             }
+            {
+                // 256-pixel tiles halve the filter bytes per MMA cycle (the L2->SM ingest limit); take them whenever
+                // they still give every SM work. NB200_FPROP_M256=0/1 overrides for profiling.
+                static const char* env = getenv("NB200_FPROP_M256");
+                const long long tiles256 = (long long)f.N * ceil_div(f.Hout, 2 * kTileH) * ceil_div(f.Wout, kTileW) * ceil_div(f.Kout, 128);
+                pl.m256 = !f.x3 && !pl.pair && f.Kout > 64 && tiles256 >= 120;
+                if (env) pl.m256 = !f.x3 && !pl.pair && env[0] == '1';
+                if (pl.m256 && pl.BN > 128) pl.BN = 128;
+            }
             pl.wOff = round_up(f.padX, 4);
             const int right = f.S - 1 - f.padX > 0 ? f.S - 1 - f.padX : 0;
             pl.WB = round_up(kTileW + pl.wOff + right, 4);
-            pl.HR = kTileH + f.R - 1;
+            pl.HR = (pl.m256 ? 2 * kTileH : kTileH) + f.R - 1;
             const size_t xBytes = ((size_t)kBlockC * pl.HR * pl.WB * 4 + 1023) & ~(size_t)1023;
             const size_t bBytes = (size_t)(pl.pair ? pl.BN / 2 : pl.BN) * kBlockC * 4 * (f.x3 ? 2 : 1);
             const size_t fixed = 1024 /*alignment slack*/ + 512 /*barriers*/;
-            const long long budget = (pl.BN > 128 || f.x3) ? kSmemBudget1 : kSmemBudget2;
+            const long long budget = (pl.BN > 128 || f.x3 || pl.m256) ? kSmemBudget1 : kSmemBudget2;
             pl.ok = false;
             // prefer two (three when alone on the SM) halo stages; give the rest to the filter ring (at least 2, at most 8)
             for (int xs = 2; xs >= 1 && !pl.ok; --xs)
@@ -1626,7 +1903,20 @@ namespace nb200
                 NB200_CUDA_TRY(cudaMemset(dbgDev, 0, ctas * 4 * kDbgSlots * sizeof(long long)));
                 pd.dbg = dbgDev;
             }
-            if (pl.pair && !X3)
+            if (pl.m256)
+            {
+                if constexpr (BN <= 128 && !X3)
+                {
+                    static bool attrSetM = false;
+                    if (!attrSetM)
+                    {
+                        NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop_m256_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1));
+                        attrSetM = true;
+                    }
+                    tc_fprop_m256_kernel<BN><<<(unsigned)tiles, kFpropThreads, pl.smemBytes, st>>>(mapX, mapW, pd, bias, out);
+                }
+            }
+            else if (pl.pair && !X3)
             {
                 static bool attrSet2 = false;
                 if (!attrSet2)
@@ -1661,9 +1951,9 @@ namespace nb200
                         for (int k = 0; k < kDbgSlots; ++k)
                             sum[r][k] += (double)h[((size_t)c * 4 + r) * kDbgSlots + k];
                 const double inv = 1.0 / (double)ctas;
-                fprintf(stderr, "[nb200 waits] BN=%d pair=%d ctas=%lld iters=%d | total %.0f cyc/CTA | filterTMA: bEmpty %.0f | MMA: loop %.0f issue %.0f bFull %.0f aFull %.0f | haloTMA: xEmpty %.0f | conv(w3): xFull %.0f aEmpty %.0f acc %.0f\n",
+                fprintf(stderr, "[nb200 waits] BN=%d pair=%d ctas=%lld iters=%d | total %.0f cyc/CTA | filterTMA: bEmpty %.0f | MMA: loop %.0f issue %.0f bFull %.0f aFull %.0f | haloTMA: xEmpty %.0f | conv(w3): total %.0f xFull %.0f aEmpty %.0f load %.0f stWait %.0f arrive %.0f stIssue %.0f acc %.0f\n",
                         BN, (int)pl.pair, ctas, p.Cblocks * p.R * p.S, sum[0][kDbgTotal] * inv, sum[0][kDbgBEmpty] * inv, sum[1][kDbgTotal] * inv, sum[1][kDbgAcc] * inv, sum[1][kDbgBFull] * inv,
-                        sum[1][kDbgAFull] * inv, sum[2][kDbgXEmpty] * inv, sum[3][kDbgXFull] * inv, sum[3][kDbgAEmpty] * inv, sum[3][kDbgAcc] * inv);
+                        sum[1][kDbgAFull] * inv, sum[2][kDbgXEmpty] * inv, sum[3][kDbgTotal] * inv, sum[3][kDbgXFull] * inv, sum[3][kDbgAEmpty] * inv, sum[3][kDbgAFull] * inv, sum[3][kDbgBFull] * inv, sum[3][kDbgXEmpty] * inv, sum[3][kDbgBEmpty] * inv, sum[3][kDbgAcc] * inv);
             }
             return NB200_OK;
         }
@@ -1712,7 +2002,7 @@ namespace nb200
             p.R = f.R; p.S = f.S; p.padX = f.padX; p.padY = f.padY;
             p.wOff = pl.wOff; p.WB = pl.WB; p.HR = pl.HR; p.xStages = pl.xStages; p.bStages = pl.bStages;
             p.Ho = f.Hout; p.Wo = f.Wout; p.K = f.Kout;
-            p.tilesW = ceil_div(f.Wout, kTileW); p.tilesH = ceil_div(f.Hout, pl.pair ? 2 * kTileH : kTileH); p.tilesK = ceil_div(f.Kout, pl.BN);
+            p.tilesW = ceil_div(f.Wout, kTileW); p.tilesH = ceil_div(f.Hout, (pl.pair || pl.m256) ? 2 * kTileH : kTileH); p.tilesK = ceil_div(f.Kout, pl.BN);
             p.act = act; p.alpha = alpha; p.dbg = nullptr;
             p.yStrideK = (long long)f.Hout * f.Wout;
             p.yStrideN = p.yStrideK * f.Kout;

@@ -136,6 +136,44 @@ namespace nb200
             }
         }
 
+
+        // ---- the same primitives on 32-bit shared-window addresses ----
+        // Kernels compute smem_u32() of each barrier array ONCE: passing generic pointers makes ptxas rebuild the generic
+        // address (S2UR CgaCtaId/SWINHI, ULEA ...) and convert it back around every call, ~15 instructions in loops whose
+        // whole body is ~100 (profiles/: the converter warps are instruction-issue-bound).
+        __device__ __forceinline__ void mbar_arrive(uint32_t bar)
+        {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        }
+        __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+        {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        }
+        __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity, uint32_t hintNs = 20000)
+        {
+            uint32_t done;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(parity), "r"(hintNs)
+                : "memory");
+            return done;
+        }
+        __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+        {
+            uint32_t polls = 0;
+            while (!mbar_try_wait(bar, parity))
+            {
+                if (++polls > (1u << 24))
+                {
+                    printf("nb200: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+                    __trap();
+                }
+            }
+        }
+
         // ---------------- TMA ----------------
         __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m)
         {
@@ -250,6 +288,10 @@ namespace nb200
         __device__ __forceinline__ void mma_commit(uint64_t* bar)
         {
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+        }
+        __device__ __forceinline__ void mma_commit(uint32_t bar)
+        {
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
         }
 
         // ---------------- tcgen05: TMEM -> registers ----------------
