@@ -1833,11 +1833,11 @@ namespace nb200
                     pl.BN = 128;
             }
             {
-                // 256-pixel tiles halve the filter bytes per MMA cycle (the L2->SM ingest limit); take them whenever
-                // they still give every SM work. NB200_FPROP_M256=0/1 overrides for profiling.
+                // 256-pixel tiles halve the filter bytes per MMA cycle. NB200_FPROP_M256=1 opts in (profiling).
                 static const char* env = getenv("NB200_FPROP_M256");
                 const long long tiles256 = (long long)f.N * ceil_div(f.Hout, 2 * kTileH) * ceil_div(f.Wout, kTileW) * ceil_div(f.Kout, 128);
-                pl.m256 = !f.x3 && !pl.pair && f.Kout > 64 && tiles256 >= 120;
+                (void)tiles256;
+                pl.m256 = false; // measured slower than the 128-pixel tile on every VGG16 layer (profiles/); opt-in only
                 if (env) pl.m256 = !f.x3 && !pl.pair && env[0] == '1';
                 if (pl.m256 && pl.BN > 128) pl.BN = 128;
             }

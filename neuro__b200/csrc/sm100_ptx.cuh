@@ -122,13 +122,13 @@ namespace nb200
 
         // Bounded wait: a protocol bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.
         // The bound is a poll count (no clock reads in the loop): each poll sleeps up to the hint, or returns within
-        // ~100 cycles if the hardware ignores it, so 2^24 polls is >= ~1 s either way.
+        // ~100 cycles if the hardware ignores it, so 2^20 polls is >= ~50 ms (hint ignored) and <= ~20 s (every poll sleeping the full hint).
         __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         {
             uint32_t polls = 0;
             while (!mbar_try_wait(bar, parity))
             {
-                if (++polls > (1u << 24))
+                if (++polls > (1u << 20))
                 {
                     printf("nb200: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
                     __trap();
@@ -166,7 +166,7 @@ namespace nb200
             uint32_t polls = 0;
             while (!mbar_try_wait(bar, parity))
             {
-                if (++polls > (1u << 24))
+                if (++polls > (1u << 20))
                 {
                     printf("nb200: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
                     __trap();
