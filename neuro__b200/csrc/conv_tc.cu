@@ -775,6 +775,436 @@ namespace nb200
             }
         }
 
+
+        // ---------------------------------------------------------------- forward kernel, horizontal taps folded into N
+        // For few filters (K <= 128) the main kernel is bound by its converter warps: every converted A tile (128 pixels x 32
+        // channels, ~90 instructions per warp) feeds only 4 MMAs of N = K columns. This kernel (3x3-style filters: S = 3,
+        // padX = 1) makes each A tile feed three times the columns. With lane p of a tile row standing for INPUT column
+        // xc = 32 tw + p,
+        //     P_s[p][k] = sum_{c,r} x[c][oh + r - padY][xc(p)] * f[k][c][r][s]            (one GEMM, N = 3 x 64 = 192)
+        //     y[32 tw + i][k] = P_0[i - 1][k] + P_1[i][k] + P_2[i + 1][k]
+        // so the A operand is not shifted per horizontal tap at all: one A tile per (channel block, filter ROW r), the three
+        // taps of that row side by side in the B tile (192 rows x 32 channels), and the epilogue adds the three partial
+        // products with lane shuffles. The tiles of a row cover input columns 0 .. W-1 exactly; the two columns they leave
+        // out are the zero padding. Column 0 of a tile needs P_0 of the previous tile's lane 31 and column 31 needs P_2 of the
+        // next tile's lane 0, so a CTA walks a strip (one image, 4 output rows, 64 filters) left to right, carries that one
+        // P_0 value and holds back the last 8-column sector of every tile in shared memory until the next tile completes it;
+        // each store instruction then writes 32 consecutive columns starting 8 left of the tile -- whole 32-byte sectors
+        // (a first version that stored 30-column tiles directly ran 3x slower end to end on partial-sector writes).
+        // The kernel is persistent (one CTA per SM, strips dealt round-robin) with two accumulators, so the epilogue of one
+        // tile overlaps the main loop of the next: at C = 64 a tile's main loop is only ~2300 MMA cycles.
+        //   warp 0 filter TMA | warp 1 MMA issue | warp 2 halo TMA | warps 4-11 converters (2 groups) | warps 12-19 epilogue
+        //   TMEM: accumulators at columns [0,192) and [256,448); A stages at 192, 224, 448, 480.
+        constexpr int kRtThreads = 640;
+        constexpr int kRtBNK = 64;                          // filters per tile
+        constexpr int kRtS = 3;                             // horizontal taps folded into N
+        constexpr int kRtN = kRtBNK * kRtS;                 // MMA N
+        constexpr int kRtWB = 32;                           // halo width = the tile's 32 input columns (16-byte aligned origin)
+        constexpr int kRtHold = 8;                          // columns held back per tile (one 32-byte sector)
+        constexpr int kRtHoldStride = kRtHold + 1;          // + the tile's P_0[lane 31], carried into the next tile's column 0
+        constexpr uint32_t kRtBBytes = kRtN * kBlockC * 4;  // one filter stage
+        constexpr uint32_t kRtHoldBytes = kTileH * kRtBNK * kRtHoldStride * 4; // [row][filter][8 columns + carry]
+        constexpr uint32_t kRtDummyBytes = 8 * 32 * 4;      // one scratch word per epilogue thread
+        constexpr int kRtFirstConvWarp = 4;
+        constexpr int kRtFirstEpiWarp = 12;
+
+        struct RowtapParams
+        {
+            int Cblocks, R, padX, padY, HR;
+            int xStages, bStages;
+            int Ho, Wo, K;
+            int tilesW, tilesH, tilesK, numStrips;
+            long long yStrideN, yStrideK;
+            int act;
+            float alpha;
+            int dbgFlags; // profiling only (NB200_RT_DEBUG): 1 = epilogue skips math + stores, 2 = converters skip the loads
+        };
+
+        __device__ __forceinline__ uint32_t rt_a_stage_col(uint32_t as) { return (as < 2 ? 192u : 448u - 64u) + as * 32u; }
+
+        __device__ __forceinline__ float rt_activate(int act, float alpha, float f)
+        {
+            if (act == NB200_ACT_RELU) return f > 0.f ? f : 0.f;
+            if (act == NB200_ACT_IDENTITY) return f;
+            return apply_activation(act, alpha, f);
+        }
+
+        // One 16-filter chunk of the row-tap epilogue for this thread's lane (see the kernel). Lanes 0-23 store this tile's columns
+        // 0-23; lanes 24-31 store the PREVIOUS tile's columns 24-31 (held in shared memory, same lane) and hold this tile's.
+        //   slotAddr:  this lane's hold slot for filter 0 of the chunk (lanes < 24: a private dummy word, so the exchange below
+        //              is branch-free); carryAddr: the chunk's P0[31] slot; 36-byte pitch per filter (dummy: pitch 0).
+        //   Shared accesses are volatile asm and stay in program order: lane 0 reads the previous tile's carry (phase 1) before
+        //   lane 31 overwrites it (phase 2). The phases keep 16 independent shuffles / loads in flight instead of one chain.
+        template <int ACT, bool FULL>
+        __device__ __forceinline__ void rt_epilogue_chunk(uint32_t (&p0)[16], uint32_t (&p1)[16], uint32_t (&p2)[16], float bl, uint32_t slotAddr,
+                                                          uint32_t slotPitch, uint32_t carryAddr, int lane, bool first, float* yptr, bool storeOk,
+                                                          long long strideK, int kLeft, int act, float alpha)
+        {
+            const bool upper = lane >= 32 - kRtHold;
+            // phase 1: o = P0[i-1] + P1[i] + P2[i+1] + bias -> p1;  P2[0] (completes the previous tile's column 31) -> p2
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+            {
+                const float f0 = __uint_as_float(p0[j]), f2 = __uint_as_float(p2[j]);
+                float a0 = __shfl_up_sync(0xffffffffu, f0, 1);            // P0[i-1]
+                const float a2 = __shfl_down_sync(0xffffffffu, f2, 1);     // P2[i+1]
+                const float c2 = __shfl_sync(0xffffffffu, f2, 0);          // P2[0]
+                const float bj = __shfl_sync(0xffffffffu, bl, j);
+                if (lane == 0)
+                    a0 = first ? 0.f : __uint_as_float(ptx::lds_b32(carryAddr + j * (kRtHoldStride * 4)));
+                float o = (a0 + __uint_as_float(p1[j])) + bj;
+                if (lane < 31)
+                    o += a2;
+                p1[j] = __float_as_uint(o);
+                p2[j] = __float_as_uint(c2);
+            }
+            // phase 2: swap with the held sector, finish, store
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+            {
+                const uint32_t sa = slotAddr + j * slotPitch;
+                const float held = __uint_as_float(ptx::lds_b32(sa));
+                ptx::sts_b32(sa, p1[j]);
+                if (lane == 31)
+                    ptx::sts_b32(carryAddr + j * (kRtHoldStride * 4), p0[j]);
+                float val = upper ? held : __uint_as_float(p1[j]);
+                if (lane == 31)
+                    val += __uint_as_float(p2[j]);
+                if constexpr (ACT == NB200_ACT_RELU) val = val > 0.f ? val : 0.f;
+                else if constexpr (ACT != NB200_ACT_IDENTITY) val = apply_activation(act, alpha, val);
+                if (storeOk && (FULL || j < kLeft))
+                    *yptr = val;
+                yptr += strideK;
+            }
+        }
+
+        __global__ void __launch_bounds__(kRtThreads, 1)
+        tc_rowtap_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, RowtapParams p,
+                         const float* __restrict__ bias, float* __restrict__ y)
+        {
+            extern __shared__ uint8_t smemRaw[];
+            uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+            const uint32_t xBytes = (uint32_t)(kBlockC * p.HR * kRtWB * 4);
+            const uint32_t xBytesPad = (xBytes + 1023) & ~1023u;
+            uint8_t* bRing = smem;
+            uint8_t* xRing = smem + p.bStages * kRtBBytes;
+            float* hold = (float*)(xRing + p.xStages * xBytesPad);
+            uint64_t* bars = (uint64_t*)((uint8_t*)hold + kRtHoldBytes + kRtDummyBytes);
+            uint64_t* bFull = bars;             // [bStages <= 8]
+            uint64_t* bEmpty = bFull + 8;
+            uint64_t* xFull = bEmpty + 8;       // [xStages <= 4]
+            uint64_t* xEmpty = xFull + 4;
+            uint64_t* aFull = xEmpty + 4;       // [4]
+            uint64_t* aEmpty = aFull + 4;
+            uint64_t* accFull = aEmpty + 4;     // [2]
+            uint64_t* accEmpty = accFull + 2;
+            uint32_t* tmemSlot = (uint32_t*)(accEmpty + 2);
+
+            const int warp = threadIdx.x >> 5;
+            const int lane = threadIdx.x & 31;
+
+            if (warp == 0 && lane == 0)
+            {
+                ptx::prefetch_tensormap(&mapX);
+                ptx::prefetch_tensormap(&mapW);
+                for (int s = 0; s < p.bStages; ++s) { ptx::mbar_init(&bFull[s], 1); ptx::mbar_init(&bEmpty[s], 1); }
+                for (int s = 0; s < p.xStages; ++s) { ptx::mbar_init(&xFull[s], 1); ptx::mbar_init(&xEmpty[s], 8); }
+                for (int s = 0; s < 4; ++s) { ptx::mbar_init(&aFull[s], 4); ptx::mbar_init(&aEmpty[s], 1); }
+                for (int s = 0; s < 2; ++s) { ptx::mbar_init(&accFull[s], 1); ptx::mbar_init(&accEmpty[s], 8); }
+                ptx::fence_mbar_init();
+            }
+            if (warp == 1)
+                ptx::tmem_alloc(tmemSlot, 512);
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            ptx::tc_fence_after_sync();
+            const uint32_t tmemBase = *tmemSlot;
+            const uint32_t bFull32 = ptx::smem_u32(bFull), bEmpty32 = ptx::smem_u32(bEmpty), xFull32 = ptx::smem_u32(xFull),
+                           xEmpty32 = ptx::smem_u32(xEmpty), aFull32 = ptx::smem_u32(aFull), aEmpty32 = ptx::smem_u32(aEmpty),
+                           accFull32 = ptx::smem_u32(accFull), accEmpty32 = ptx::smem_u32(accEmpty);
+            const int itersPerTile = p.Cblocks * p.R;
+
+            if (warp == 0)
+            {
+                if (lane == 0)
+                {
+                    // ===== filter TMA: one 192-row tile per (channel block, filter row), again for every tile of the strip =====
+                    int bs = 0;
+                    uint32_t bph = 0;
+                    for (int sp = blockIdx.x; sp < p.numStrips; sp += gridDim.x)
+                    {
+                        const int kt = sp % p.tilesK;
+                        for (int tw = 0; tw < p.tilesW; ++tw)
+                            for (int cb = 0; cb < p.Cblocks; ++cb)
+                                for (int r = 0; r < p.R; ++r)
+                                {
+                                    ptx::mbar_wait(bEmpty32 + 8u * bs, bph ^ 1);
+                                    ptx::mbar_arrive_expect_tx(bFull32 + 8u * bs, kRtBBytes);
+                                    ptx::tma_load_3d(bRing + bs * kRtBBytes, &mapW, &bFull[bs], cb * kBlockC, kt * kRtN, r);
+                                    if (++bs == p.bStages) { bs = 0; bph ^= 1; }
+                                }
+                    }
+                }
+            }
+            else if (warp == 2)
+            {
+                if (lane == 0)
+                {
+                    // ===== halo TMA: one tile per channel block (rows above / below the image read as zeros) =====
+                    int xs = 0;
+                    uint32_t xph = 0;
+                    for (int sp = blockIdx.x; sp < p.numStrips; sp += gridDim.x)
+                    {
+                        int u = sp / p.tilesK;
+                        const int th = u % p.tilesH;
+                        const int n = u / p.tilesH;
+                        for (int tw = 0; tw < p.tilesW; ++tw)
+                        {
+                            const int origin = tw * kTileW;
+                            for (int cb = 0; cb < p.Cblocks; ++cb)
+                            {
+                                ptx::mbar_wait(xEmpty32 + 8u * xs, xph ^ 1);
+                                ptx::mbar_arrive_expect_tx(xFull32 + 8u * xs, xBytes);
+                                ptx::tma_load_4d(xRing + xs * xBytesPad, &mapX, &xFull[xs], origin, th * kTileH - p.padY, cb * kBlockC, n);
+                                if (++xs == p.xStages) { xs = 0; xph ^= 1; }
+                            }
+                        }
+                    }
+                }
+            }
+            else if (warp == 1)
+            {
+                // ===== MMA issuer =====
+                constexpr uint32_t idesc = ptx::idesc_tf32(128, kRtN, 0, 0);
+                const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(bRing), 16, 1024);
+                int bs = 0;
+                uint32_t bph = 0, aCount = 0, tileCount = 0;
+                for (int sp = blockIdx.x; sp < p.numStrips; sp += gridDim.x)
+                    for (int tw = 0; tw < p.tilesW; ++tw, ++tileCount)
+                    {
+                        const uint32_t buf = tileCount & 1;
+                        ptx::mbar_wait(accEmpty32 + 8u * buf, ((tileCount >> 1) & 1) ^ 1); // the epilogue has drained this accumulator
+                        ptx::tc_fence_after_sync();
+                        const uint32_t tmemAcc = tmemBase + buf * 256;
+                        for (int it = 0; it < itersPerTile; ++it, ++aCount)
+                        {
+                            const uint32_t as = aCount & 3;
+                            ptx::mbar_wait(bFull32 + 8u * bs, bph);
+                            ptx::mbar_wait(aFull32 + 8u * as, (aCount >> 2) & 1);
+                            ptx::tc_fence_after_sync();
+                            if (ptx::elect_one())
+                            {
+                                const uint64_t db = descB0 + (uint64_t)((bs * kRtBBytes) >> 4);
+                                const uint32_t ta = tmemBase + rt_a_stage_col(as);
+#pragma unroll
+                                for (int kk = 0; kk < kBlockC / 8; ++kk)
+                                    ptx::mma_tf32_ts(tmemAcc, ta + kk * 8, db + kk * 2, idesc, (it | kk) != 0);
+                                ptx::mma_commit(aEmpty32 + 8u * as);
+                                ptx::mma_commit(bEmpty32 + 8u * bs);
+                                if (it == itersPerTile - 1)
+                                    ptx::mma_commit(accFull32 + 8u * buf);
+                            }
+                            __syncwarp();
+                            if (++bs == p.bStages) { bs = 0; bph ^= 1; }
+                        }
+                    }
+            }
+            else if (warp >= kRtFirstConvWarp && warp < kRtFirstEpiWarp)
+            {
+                // ===== converters: group g builds A tiles aCount = g (mod 2) into its own stages {g, g + 2} =====
+                const int q = warp & 3;
+                const int g = (warp - kRtFirstConvWarp) >> 2;
+                const uint32_t laneSel = (uint32_t)(q * 32) << 16;
+                const uint32_t chanStrideB = (uint32_t)(p.HR * kRtWB * 4);
+                const uint32_t xRing32 = ptx::smem_u32(xRing);
+                bool pending = false;
+                uint32_t pendStage = 0, aCount = 0, xCount = 0;
+                for (int sp = blockIdx.x; sp < p.numStrips; sp += gridDim.x)
+                    for (int tw = 0; tw < p.tilesW; ++tw)
+                    {
+                        for (int cb = 0; cb < p.Cblocks; ++cb, ++xCount)
+                        {
+                            const uint32_t xs = xCount % (uint32_t)p.xStages;
+                            ptx::mbar_wait(xFull32 + 8u * xs, (xCount / (uint32_t)p.xStages) & 1);
+                            const uint32_t xt = xRing32 + xs * xBytesPad;
+                            for (int r = 0; r < p.R; ++r, ++aCount)
+                            {
+                                if ((int)(aCount & 1) != g)
+                                    continue;
+                                const uint32_t src = xt + (uint32_t)(((q + r) * kRtWB + lane) << 2);
+                                uint32_t v[kBlockC];
+                                if (p.dbgFlags & 2)
+                                {
+#pragma unroll
+                                    for (int c = 0; c < kBlockC; ++c)
+                                        v[c] = 0x3f800000u;
+                                }
+                                else if (chanStrideB == 768u) // 3 filter rows: compile-time channel pitch -> immediate offsets
+                                {
+#pragma unroll
+                                    for (int c = 0; c < kBlockC; ++c)
+                                        v[c] = ptx::tf32_round_bits(ptx::lds_b32(src + c * 768u));
+                                }
+                                else
+                                {
+#pragma unroll
+                                    for (int c = 0; c < kBlockC; ++c)
+                                        v[c] = ptx::tf32_round_bits(ptx::lds_b32(src + c * chanStrideB));
+                                }
+                                if (pending)
+                                {
+                                    ptx::tmem_st_wait();
+                                    ptx::tc_fence_before_sync();
+                                    __syncwarp();
+                                    if (lane == 0)
+                                        ptx::mbar_arrive(aFull32 + 8u * pendStage);
+                                }
+                                const uint32_t as = aCount & 3;
+                                ptx::mbar_wait(aEmpty32 + 8u * as, ((aCount >> 2) & 1) ^ 1);
+                                ptx::tc_fence_after_sync();
+                                ptx::tmem_st_32x32b_x32(tmemBase + laneSel + rt_a_stage_col(as), v);
+                                pending = true;
+                                pendStage = as;
+                            }
+                            __syncwarp();
+                            if (lane == 0)
+                                ptx::mbar_arrive(xEmpty32 + 8u * xs);
+                        }
+                    }
+                if (pending)
+                {
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(aFull32 + 8u * pendStage);
+                }
+            }
+            else if (warp >= kRtFirstEpiWarp)
+            {
+                // ===== epilogue: warp (q, h) owns tile row q and filters [32 h, 32 h + 32) of the tile =====
+                // Per filter:  o[i]   = P0[i-1] + P1[i] + P2[i+1] + bias   (P0[-1] = carry of the previous tile; lane 31 lacks P2[32])
+                //              store  columns 32 tw - 8 + lane: lanes 0-7 the sector held back by the previous tile (+ P2[0] of
+                //                     this tile into its column 7), lanes 8-31 this tile's columns 0-23
+                //              hold   this tile's columns 24-31 and P0[31] for the next tile (after the last tile the sector is
+                //                     flushed as it is: the missing term multiplies zero padding)
+                const int q = warp & 3;
+                const int h = (warp - kRtFirstEpiWarp) >> 2;
+                const uint32_t laneSel = (uint32_t)(q * 32) << 16;
+                const bool upper = lane >= 32 - kRtHold;
+                const uint32_t myHold = ptx::smem_u32(hold) + (uint32_t)((q * kRtBNK + h * 32) * kRtHoldStride * 4);
+                const uint32_t holdLane = myHold + (uint32_t)((lane - (32 - kRtHold)) * 4); // meaningful for the upper lanes only
+                const uint32_t carry = myHold + kRtHold * 4;
+                // lanes 0-23 exchange with a private dummy word instead (keeps the epilogue branch-free)
+                const uint32_t dummy = ptx::smem_u32(hold) + kRtHoldBytes + (uint32_t)(((warp - kRtFirstEpiWarp) * 32 + lane) * 4);
+                uint32_t tileCount = 0;
+                for (int sp = blockIdx.x; sp < p.numStrips; sp += gridDim.x)
+                {
+                    int u = sp;
+                    const int kt = u % p.tilesK; u /= p.tilesK;
+                    const int th = u % p.tilesH;
+                    const int n = u / p.tilesH;
+                    const int k0 = kt * kRtBNK + h * 32;
+                    const int oh = th * kTileH + q;
+                    const bool rowOk = oh < p.Ho;
+                    float* yrow = y + n * p.yStrideN + (long long)oh * p.Wo + (long long)k0 * p.yStrideK;
+                    for (int tw = 0; tw < p.tilesW; ++tw, ++tileCount)
+                    {
+                        const uint32_t buf = tileCount & 1;
+                        const uint32_t acc = tmemBase + laneSel + buf * 256 + h * 32;
+                        const int col = (upper ? tw - 1 : tw) * kTileW + lane;        // output column this lane stores
+                        const bool storeOk = rowOk && col >= 0 && col < p.Wo;
+                        ptx::mbar_wait(accFull32 + 8u * buf, (tileCount >> 1) & 1);
+                        ptx::tc_fence_after_sync();
+#pragma unroll 1
+                        for (int c0 = 0; c0 < 32; c0 += 16)
+                        {
+                            const int kb = k0 + c0;
+                            // bias first: its latency hides behind the TMEM loads
+                            const float bl = (bias && lane < 16 && kb + lane < p.K) ? __ldg(bias + kb + lane) : 0.f;
+                            uint32_t p0[16], p1[16], p2[16];
+                            ptx::tmem_ld_32x32b_x16(acc + c0, p0);
+                            ptx::tmem_ld_32x32b_x16(acc + kRtBNK + c0, p1);
+                            ptx::tmem_ld_32x32b_x16(acc + 2 * kRtBNK + c0, p2);
+                            ptx::tmem_ld_wait();
+                            if (c0 == 16)
+                            {
+                                // every column this warp needs has been read: hand the accumulator back to the MMA warp
+                                ptx::tc_fence_before_sync();
+                                __syncwarp();
+                                if (lane == 0)
+                                    ptx::mbar_arrive(accEmpty32 + 8u * buf);
+                            }
+                            if (p.dbgFlags & 1)
+                                continue;
+                            float* yptr = yrow + (long long)c0 * p.yStrideK + col;
+                            const uint32_t ha = upper ? holdLane + (uint32_t)(c0 * kRtHoldStride * 4) : dummy;
+                            const uint32_t hp = upper ? (uint32_t)(kRtHoldStride * 4) : 0u;
+                            const uint32_t ca = carry + (uint32_t)(c0 * kRtHoldStride * 4);
+                            const int kLeft = p.K - kb;
+                            if (kLeft >= 16 && p.act == NB200_ACT_RELU)
+                                rt_epilogue_chunk<NB200_ACT_RELU, true>(p0, p1, p2, bl, ha, hp, ca, lane, tw == 0, yptr, storeOk, p.yStrideK, kLeft, p.act, p.alpha);
+                            else if (kLeft >= 16 && p.act == NB200_ACT_IDENTITY)
+                                rt_epilogue_chunk<NB200_ACT_IDENTITY, true>(p0, p1, p2, bl, ha, hp, ca, lane, tw == 0, yptr, storeOk, p.yStrideK, kLeft, p.act, p.alpha);
+                            else
+                                rt_epilogue_chunk<-1, false>(p0, p1, p2, bl, ha, hp, ca, lane, tw == 0, yptr, storeOk, p.yStrideK, kLeft, p.act, p.alpha);
+                        }
+                    }
+                    // flush the last tile's held sector (its column 31 lacks only a term that multiplies zero padding)
+                    if (!(p.dbgFlags & 1))
+                    {
+                        const int col = (p.tilesW - 1) * kTileW + lane;
+                        if (upper && rowOk && col < p.Wo)
+                        {
+                            for (int j = 0; j < 32; ++j)
+                                if (k0 + j < p.K)
+                                    yrow[(long long)j * p.yStrideK + col] =
+                                        rt_activate(p.act, p.alpha, __uint_as_float(ptx::lds_b32(holdLane + (uint32_t)(j * kRtHoldStride * 4))));
+                        }
+                    }
+                }
+            }
+
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            if (warp == 1)
+            {
+                ptx::tc_fence_after_sync();
+                ptx::tmem_dealloc(tmemBase, 512);
+            }
+        }
+
+        // filters for tc_rowtap_kernel: out[r][kt][s][kLocal 0..63][c] (TF32-rounded, zero padded); mode 0 forward, mode 1 input
+        // gradient (filters flipped, roles of K and C exchanged: GEMM filter index = input channel, reduction = K)
+        __global__ void repack_rowtap_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int C, int R, int S, int ktiles,
+                                             int outCp, int mode)
+        {
+            const int rowsPerR = ktiles * S * kRtBNK;
+            const long long total = (long long)R * rowsPerR * outCp;
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+            {
+                const int col = (int)(i % outCp);
+                const int row = (int)((i / outCp) % rowsPerR);
+                const int r = (int)(i / ((long long)outCp * rowsPerR));
+                const int kt = row / (S * kRtBNK), s = (row / kRtBNK) % S, kl = row % kRtBNK;
+                const int filt = kt * kRtBNK + kl;
+                float v = 0.f;
+                if (mode == 0)
+                {
+                    if (filt < K && col < C)
+                        v = w[(((long long)filt * C + col) * R + r) * S + s];
+                }
+                else
+                {
+                    if (filt < C && col < K)
+                        v = w[(((long long)col * C + filt) * R + (R - 1 - r)) * S + (S - 1 - s)];
+                }
+                uint32_t t;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+                out[i] = __uint_as_float(t);
+            }
+        }
+
         // ---------------------------------------------------------------- forward kernel, CTA-pair form (cta_group::2)
         // Same algorithm, but two CTAs of a cluster (one TPC = two SMs) cooperate on a 256-pixel x BN-filter tile:
         //   - each CTA converts the A tile of ITS 128 pixels (4 of the pair's 8 output rows) into its own TMEM;
@@ -1958,9 +2388,106 @@ namespace nb200
             return NB200_OK;
         }
 
+
+        // ---- horizontal-taps-in-N kernel (tc_rowtap_kernel): 3-column filters with few output filters ----
+        bool rowtap_wanted(const FwdShape& f)
+        {
+            static const char* env = getenv("NB200_ROWTAP"); // 0 / 1 override for profiling
+            if (f.x3 || f.S != kRtS || f.padX != 1 || f.R > 7)
+                return false;
+            if (env)
+                return env[0] == '1';
+            return f.Kout <= 64 && f.Wout >= 64 && f.Wout % 8 == 0 && (long long)f.N * ceil_div(f.Hout, kTileH) * ceil_div(f.Kout, kRtBNK) >= 148;
+        }
+
+        size_t rowtap_bytes(const FwdShape& f)
+        {
+            return (size_t)f.R * ceil_div(f.Kout, kRtBNK) * kRtN * round_up(f.Cin, kBlockC) * sizeof(float);
+        }
+
+        int run_rowtap(const FwdShape& f, int repackMode, int wK, int wC, const float* in, const float* w, const float* bias, int act,
+                       float alpha, float* out, void* ws, size_t wsBytes, cudaStream_t st)
+        {
+            const size_t need = rowtap_bytes(f);
+            if (wsBytes < need || !ws)
+                return fail(NB200_E_WORKSPACE, "tcgen05 conv needs %zu workspace bytes, got %zu", need, wsBytes);
+            if (((uintptr_t)in & 15) || ((uintptr_t)ws & 15))
+                return fail(NB200_E_INVALID, "tensor base addresses must be 16-byte aligned for TMA");
+            const int Cp = round_up(f.Cin, kBlockC);
+            const int ktiles = ceil_div(f.Kout, kRtBNK);
+            const int rowsPerR = ktiles * kRtN;
+            float* wr = (float*)ws;
+            {
+                const long long total = (long long)f.R * rowsPerR * Cp;
+                const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+                repack_rowtap_kernel<<<blocks, 256, 0, st>>>(w, wr, wK, wC, f.R, f.S, ktiles, Cp, repackMode);
+                NB200_CUDA_TRY(cudaGetLastError());
+                count_launch();
+            }
+            RowtapParams p;
+            p.Cblocks = Cp / kBlockC; p.R = f.R; p.padX = f.padX; p.padY = f.padY; p.HR = kTileH + f.R - 1;
+            const size_t xBytes = ((size_t)kBlockC * p.HR * kRtWB * 4 + 1023) & ~(size_t)1023;
+            p.xStages = 2;
+            long long rest = (long long)kSmemBudget1 - 1536 - kRtHoldBytes - kRtDummyBytes - 2 * (long long)xBytes;
+            p.bStages = (int)(rest / kRtBBytes);
+            if (p.bStages > 8) p.bStages = 8;
+            if (p.bStages < 2)
+                return fail(NB200_E_UNSUPPORTED, "no shared-memory plan for this filter size");
+            const size_t smemBytes = 1536 + kRtHoldBytes + kRtDummyBytes + 2 * xBytes + (size_t)p.bStages * kRtBBytes;
+            p.Ho = f.Hout; p.Wo = f.Wout; p.K = f.Kout;
+            p.tilesW = ceil_div(f.Wout, kTileW); p.tilesH = ceil_div(f.Hout, kTileH); p.tilesK = ktiles;
+            const long long tiles = (long long)f.N * p.tilesH * p.tilesK; // strips
+            if (tiles > 0x7fffffffLL)
+                return fail(NB200_E_UNSUPPORTED, "too many tiles");
+            p.numStrips = (int)tiles;
+            p.yStrideK = (long long)f.Hout * f.Wout;
+            p.yStrideN = p.yStrideK * f.Kout;
+            p.act = act; p.alpha = alpha;
+            {
+                static const char* dbgEnv = getenv("NB200_RT_DEBUG");
+                p.dbgFlags = dbgEnv ? atoi(dbgEnv) : 0;
+            }
+
+            CUtensorMap mapX, mapW;
+            {
+                cuuint64_t dims[4] = {(cuuint64_t)f.Win, (cuuint64_t)f.Hin, (cuuint64_t)f.Cin, (cuuint64_t)f.N};
+                cuuint64_t strides[3] = {(cuuint64_t)f.Win * 4, (cuuint64_t)f.Hin * f.Win * 4, (cuuint64_t)f.Cin * f.Hin * f.Win * 4};
+                cuuint32_t box[4] = {(cuuint32_t)kRtWB, (cuuint32_t)p.HR, kBlockC, 1};
+                int rc = make_map(&mapX, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+                if (rc) return rc;
+            }
+            {
+                cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)rowsPerR, (cuuint64_t)f.R};
+                cuuint64_t strides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * rowsPerR * 4};
+                cuuint32_t box[3] = {kBlockC, (cuuint32_t)kRtN, 1};
+                int rc = make_map(&mapW, wr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+                if (rc) return rc;
+            }
+            static bool attrSet = false;
+            if (!attrSet)
+            {
+                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_rowtap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1));
+                attrSet = true;
+            }
+            static int smCount = 0;
+            if (!smCount)
+            {
+                int dev = 0;
+                NB200_CUDA_TRY(cudaGetDevice(&dev));
+                NB200_CUDA_TRY(cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, dev));
+            }
+            const unsigned grid = (unsigned)(tiles < smCount ? tiles : smCount);
+            tc_rowtap_kernel<<<grid, kRtThreads, smemBytes, st>>>(mapX, mapW, p, bias, out);
+            NB200_CUDA_TRY(cudaGetLastError());
+            count_launch();
+            return NB200_OK;
+        }
+
         int run_fwd_shaped(const FwdShape& f, int repackMode, int wK, int wC, const float* in, const float* w, const float* bias, int act,
                            float alpha, float* out, void* ws, size_t wsBytes, cudaStream_t st)
         {
+            if (rowtap_wanted(f))
+                return run_rowtap(f, repackMode, wK, wC, in, w, bias, act, alpha, out, ws, wsBytes, st);
             const size_t need = repack_bytes(f);
             if (wsBytes < need || !ws)
                 return fail(NB200_E_WORKSPACE, "tcgen05 conv needs %zu workspace bytes, got %zu", need, wsBytes);
@@ -2341,12 +2868,18 @@ namespace nb200
 
     bool tc_kernels_gradient_supported(const nb200_conv_desc& d) { return wgrad_shape_ok(d); }
 
+    static size_t fwd_ws_bytes(const FwdShape& f)
+    {
+        const size_t a = repack_bytes(f), b = rowtap_wanted(f) ? rowtap_bytes(f) : 0;
+        return a > b ? a : b;
+    }
+
     size_t tc_workspace_bytes(int op, const nb200_conv_desc& d)
     {
         switch (op)
         {
-        case NB200_OP_FORWARD: return repack_bytes(fwd_shape(d));
-        case NB200_OP_INPUT_GRADIENT: return repack_bytes(dgrad_shape(d));
+        case NB200_OP_FORWARD: return fwd_ws_bytes(fwd_shape(d));
+        case NB200_OP_INPUT_GRADIENT: return fwd_ws_bytes(dgrad_shape(d));
         default: return wgrad_plan(d).wsBytes;
         }
     }

@@ -43,6 +43,11 @@ namespace nb200
             return v;
         }
 
+        __device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v)
+        {
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+        }
+
         __device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d)
         {
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
@@ -311,6 +316,18 @@ namespace nb200
         }
 
         // registers -> TMEM, same shape: thread t writes columns [col, col+32) of TMEM lane (base lane + t).
+        // 32 lanes x 16 consecutive columns
+        __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16])
+        {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr)
+                : "memory");
+        }
+
         __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32])
         {
             asm volatile(
