@@ -1084,8 +1084,8 @@ namespace nb200
             {
                 // ===== epilogue: warp (q, h) owns tile row q and filters [32 h, 32 h + 32) of the tile =====
                 // Per filter:  o[i]   = P0[i-1] + P1[i] + P2[i+1] + bias   (P0[-1] = carry of the previous tile; lane 31 lacks P2[32])
-                //              store  columns 32 tw - 8 + lane: lanes 0-7 the sector held back by the previous tile (+ P2[0] of
-                //                     this tile into its column 7), lanes 8-31 this tile's columns 0-23
+                //              store  lanes 0-23: this tile's columns 0-23; lanes 24-31: the sector held back by the previous tile
+                //                     (same lanes; + P2[0] of this tile into its column 31) -- one 128-byte span per instruction
                 //              hold   this tile's columns 24-31 and P0[31] for the next tile (after the last tile the sector is
                 //                     flushed as it is: the missing term multiplies zero padding)
                 const int q = warp & 3;
@@ -2397,7 +2397,7 @@ namespace nb200
                 return false;
             if (env)
                 return env[0] == '1';
-            return f.Kout <= 64 && f.Wout >= 64 && f.Wout % 8 == 0 && (long long)f.N * ceil_div(f.Hout, kTileH) * ceil_div(f.Kout, kRtBNK) >= 148;
+            return f.Kout <= 64 && f.Wout >= 64 && f.Wout % 8 == 0 && (long long)f.N * ceil_div(f.Hout, kTileH) * ceil_div(f.Kout, kRtBNK) >= 24; // strips for the persistent grid
         }
 
         size_t rowtap_bytes(const FwdShape& f)

@@ -78,6 +78,11 @@ TC_CASES = [
     (0, 4, 16, 4, 8, 16, 3, 3, 2, 1, 1),       # 2x4 output maps: 8-pixel reduction sub-tiles (SWIZZLE_32B rows)
     (0, 6, 200, 16, 16, 72, 4, 4, 2, 1, 1),    # two channel tiles, ragged filter tile, 16 taps in tap groups
     (0, 3, 16, 12, 12, 16, 3, 3, 2, 1, 1),     # 6x6 = 36-pixel output maps: last reduction chunk is partial
+    # row-tap kernel (<= 64 filters, 3 columns, pad 1, width >= 64 and % 8 == 0): strips of 32-column tiles with a held sector
+    (0, 2, 64, 48, 96, 64, 3, 3, 1, 1, 1),     # three full tiles per strip, fwd and dgrad both take the row-tap kernel
+    (0, 3, 40, 36, 72, 24, 3, 3, 1, 1, 1),     # ragged channels, 24 filters (generic epilogue), last tile 8 columns wide
+    (0, 3, 32, 38, 64, 64, 5, 3, 1, 1, 2),     # 5 filter rows x 3 columns, H not a multiple of 4
+    (0, 1, 128, 96, 128, 48, 3, 3, 1, 1, 1),   # four channel blocks, one image
 ]
 
 
@@ -99,7 +104,7 @@ def test_against_oracle(cfg, math):
 @pytest.mark.parametrize("act", [lib.ACT_IDENTITY, lib.ACT_SIGMOID, lib.ACT_RELU, lib.ACT_TANH, lib.ACT_ELU, lib.ACT_LEAKY_RELU])
 def test_bias_activation(act, math):
     """Conv2DBiasActivation (TensorOpGpuTests.cpp:1238-1252 uses ReLU; all epilogues are covered here)."""
-    for (N, C, H, W, K, F, st, p) in [(3, 3, 26, 26, 2, 3, 1, 0), (2, 64, 32, 32, 64, 3, 1, 1)]:
+    for (N, C, H, W, K, F, st, p) in [(3, 3, 26, 26, 2, 3, 1, 0), (2, 64, 32, 32, 64, 3, 1, 1), (2, 32, 48, 96, 40, 3, 1, 1)]:
         x = synth.uniform(synth.SEED_X, (N, C, H, W)); w = synth.glorot_uniform(synth.SEED_W, K, C, F, F)
         b = synth.uniform(synth.SEED_BIAS, (K,))
         ref = O.conv2d_bias_activation(x, w, b, st, p, act, 0.2)
