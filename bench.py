@@ -276,11 +276,20 @@ def run_ours(args):
         sampler.stop()
     fam_ms = {0: 0.0, 1: 0.0, 2: 0.0, 3: 0.0}
     tc_ms = {0: 0.0, 1: 0.0, 2: 0.0}; tc_fl = {0: 0.0, 1: 0.0, 2: 0.0}
+    kern = {}   # CUDA kernel -> [flops, ms, launches] over the instrumented pass
+    KERNEL_OF = {"tcgen05_fprop": "tc_fprop_kernel (forward + input gradient, >64 filters)",
+                 "tcgen05_dgrad": "tc_fprop_kernel (forward + input gradient, >64 filters)",
+                 "tcgen05_rowtap_fprop": "tc_rowtap_kernel (forward + input gradient, <=64 filters)",
+                 "tcgen05_rowtap_dgrad": "tc_rowtap_kernel (forward + input gradient, <=64 filters)",
+                 "tcgen05_wgrad": "tc_wgrad_kernel (kernel gradient)"}
     for (fam, i), e0, e1 in events:
         dt = e0.elapsed_time(e1)
         fam_ms[fam] += dt
         if fam < 3 and names[i][fam].startswith("tcgen05"):
             tc_ms[fam] += dt; tc_fl[fam] += layers[i]["desc"].flops()
+        if fam < 3:
+            k = kern.setdefault(KERNEL_OF.get(names[i][fam], names[i][fam]), [0.0, 0.0, 0])
+            k[0] += layers[i]["desc"].flops(); k[1] += dt; k[2] += 1
 
     # ---- e2e: the same step through the public API with HOST input and HOST result, copies inside the timed region ----
     # Every step's input batch comes from pinned host memory and its result (the image gradient, what style transfer reads
@@ -334,12 +343,14 @@ def run_ours(args):
     if rank == 0:
         peaks = read_peaks()
         tf32_peak = peaks["bf16_sustained"] / 2.0       # TF32 dense = half the bf16 rate; sustained: kernels timed inside a long step
-        # kernel level: forward and input gradient are the same kernel (tc_fprop_kernel); kernel gradient is tc_wgrad_kernel
-        kern = {"tc_fprop_kernel (forward + input gradient)": (tc_fl[0] + tc_fl[1], tc_ms[0] + tc_ms[1]),
-                "tc_wgrad_kernel (kernel gradient)": (tc_fl[2], tc_ms[2])}
+        # kernel level: the op-level event pairs are grouped by the CUDA kernel that op dispatched to (an op's pair also
+        # covers its helper launches: the filter repack before tc_fprop/tc_rowtap, the split-K reduce after tc_wgrad; < 3 %)
         dom_name = max(kern, key=lambda k: kern[k][1])
-        dom_fl, dom_ms = kern[dom_name]
+        dom_fl, dom_ms, dom_n = kern[dom_name]
         achieved = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        kernels = {k: {"ms_per_step": v[1] / op_steps, "launches_per_step": v[2] // op_steps,
+                       "tflops": v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None,
+                       "share_of_step": v[1] / sum(fam_ms.values())} for k, v in kern.items()}
         per_op = {n: {"ms_per_step": fam_ms[f] / op_steps,
                       "tflops": (B * SAMPLE_FLOPS_PER_OP) / (fam_ms[f] / op_steps * 1e-3) / 1e12,
                       "tensor_core_tflops": (tc_fl[f] / (tc_ms[f] * 1e-3) / 1e12) if tc_ms[f] > 0 else None,
@@ -351,9 +362,11 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
             "config": workload_config(B, world),
             "tflops_total": 3 * B * world * SAMPLE_FLOPS_PER_OP / (ms * 1e-3) / 1e12,
-            "per_op": per_op, "adam_ms_per_step": fam_ms[3] / op_steps,
+            "per_op": per_op, "kernels": kernels, "adam_ms_per_step": fam_ms[3] / op_steps,
             "roofline": {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf32_peak if tf32_peak else None, "traffic": None,
+                         "avg_launch_ms": dom_ms / dom_n if dom_n else None,
+                         "flops_per_launch": dom_fl / dom_n if dom_n else None,
                          "peak_source": "%s bf16_tflops_sustained / 2 (MEASURED_PEAKS.json has no TF32 entry; TF32 dense = 1/2 bf16)" % peaks["source"],
                          "share_of_step": dom_ms / sum(fam_ms.values()) if sum(fam_ms.values()) else None},
             "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": img_host.numel() * 4,

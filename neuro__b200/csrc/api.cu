@@ -169,7 +169,7 @@ extern "C"
         if (f == kTc)
             return tc_workspace_bytes(op, *d);
         if (f == kSmallC)
-            return op == NB200_OP_KERNELS_GRADIENT ? smallc_wgrad_workspace(*d) : 0;
+            return op != NB200_OP_KERNELS_GRADIENT ? 0 : tc_smallc_wgrad_supported(*d) ? tc_smallc_wgrad_workspace(*d) : smallc_wgrad_workspace(*d);
         if (f == kGather)
             return op == NB200_OP_KERNELS_GRADIENT ? tc_gather_kernels_gradient_workspace(*d) : tc_gather_workspace_bytes(op, *d);
         return op == NB200_OP_KERNELS_GRADIENT ? direct_kernels_gradient_workspace(*d) : 0;
@@ -182,9 +182,9 @@ extern "C"
         const Family f = pick(op, *d);
         switch (op)
         {
-        case NB200_OP_FORWARD: return f == kTc ? "tcgen05_fprop" : f == kGather ? "tcgen05_gather_fprop" : f == kSmallC ? "smallc_fprop" : "direct_fprop";
-        case NB200_OP_INPUT_GRADIENT: return f == kTc ? "tcgen05_dgrad" : f == kGather ? "tcgen05_gather_dgrad" : f == kSmallC ? "smallc_dgrad" : "direct_dgrad";
-        case NB200_OP_KERNELS_GRADIENT: return f == kTc ? "tcgen05_wgrad" : f == kGather ? "tcgen05_gather_wgrad" : f == kSmallC ? "smallc_wgrad" : "direct_wgrad";
+        case NB200_OP_FORWARD: return f == kTc ? (tc_uses_rowtap(op, *d) ? "tcgen05_rowtap_fprop" : "tcgen05_fprop") : f == kGather ? "tcgen05_gather_fprop" : f == kSmallC ? "smallc_fprop" : "direct_fprop";
+        case NB200_OP_INPUT_GRADIENT: return f == kTc ? (tc_uses_rowtap(op, *d) ? "tcgen05_rowtap_dgrad" : "tcgen05_dgrad") : f == kGather ? "tcgen05_gather_dgrad" : f == kSmallC ? "smallc_dgrad" : "direct_dgrad";
+        case NB200_OP_KERNELS_GRADIENT: return f == kTc ? "tcgen05_wgrad" : f == kGather ? "tcgen05_gather_wgrad" : f == kSmallC ? (tc_smallc_wgrad_supported(*d) ? "tcgen05_smallc_wgrad" : "smallc_wgrad") : "direct_wgrad";
         default: return "invalid";
         }
     }
@@ -252,7 +252,8 @@ extern "C"
         if (f == kTc)
             return tc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         if (f == kSmallC)
-            return smallc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
+            return tc_smallc_wgrad_supported(*d) ? tc_smallc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st)
+                                                 : smallc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         if (f == kGather)
             return tc_gather_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         return direct_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);

@@ -83,6 +83,11 @@ namespace nb200
     bool tc_input_gradient_supported(const nb200_conv_desc& d);
     bool tc_kernels_gradient_supported(const nb200_conv_desc& d);
     size_t tc_workspace_bytes(int op, const nb200_conv_desc& d);
+    // C <= 4 kernel gradient as an SS-form tcgen05 GEMM over the dy stream (TF32 mode, large maps)
+    bool tc_smallc_wgrad_supported(const nb200_conv_desc& d);
+    size_t tc_smallc_wgrad_workspace(const nb200_conv_desc& d);
+    int tc_smallc_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st);
+    bool tc_uses_rowtap(int op, const nb200_conv_desc& d); // forward / stride-1 input gradient take tc_rowtap_kernel
     int tc_forward(const nb200_conv_desc& d, const float* x, const float* w, const float* bias, int act, float alpha, float* y,
                    void* ws, size_t wsBytes, cudaStream_t st);
     int tc_input_gradient(const nb200_conv_desc& d, const float* dy, const float* w, float* dx, void* ws, size_t wsBytes,

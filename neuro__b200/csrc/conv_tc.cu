@@ -2188,6 +2188,224 @@ namespace nb200
             dw[((long long)k * C + c) * taps + tap] = acc;
         }
 
+
+        // ---------------------------------------------------------------- kernel gradient, few input channels (C <= 4, 3x3)
+        // First layers (RGB input): dw has only K x 27 elements but the reduction runs over every output pixel, so the op is a
+        // stream over dy (0.5 GB for VGG16 block1_conv1 at batch 8) -- HBM-bound, and far too slow on CUDA cores (measured
+        // 0.72 ms against a 0.09 ms stream time). GEMM view with the roles the tensor core wants:
+        //     D[M = 128 filters][N = round16(C*9)] += A[filter][pixel] * B[j = (c, r, s)][pixel],  32 pixels per step
+        //     A = the dy tile exactly as TMA lands it (K-major, SWIZZLE_128B): SS-form MMA straight from shared memory
+        //     B = the im2col rows of the step: J x 32 floats, written by a converter warp from the (C x 3 rows x 40 columns)
+        //         x segment TMA brings with the dy tile; TF32-rounded; laid out as the same swizzled K-major tile
+        // One CTA per SM walks a contiguous share of the (image, output row, 32-column segment) steps and writes one partial
+        // per CTA; a reduce kernel adds the partials in fixed order (deterministic, no atomics). dy is truncated to TF32 by the
+        // tensor core (its bits are never touched by a thread); x is rounded to nearest by the converters.
+        //   warp 0 TMA | warp 1 MMA issue | warps 2-5 converters (step it -> warp it % 4, B stage it % 4), then epilogue
+        constexpr int kScThreads = 192;
+        constexpr int kScXW = 40;                                // x segment: columns ow0 - 4 .. ow0 + 35
+        constexpr int kScABytes = 128 * 32 * 4;                  // dy tile
+        constexpr int kScXBytesMax = 4 * 3 * kScXW * 4;          // x segment, C <= 4
+        constexpr int kScStageBytes = kScABytes + 2048;          // x segment rounded up; keeps every A tile 1 KB aligned
+        constexpr int kScBStages = 4;
+        constexpr int kScBBytes = 48 * 128;                      // im2col tile: Jpad <= 48 rows of 128 bytes (6 KB, 1 KB aligned)
+
+        struct ScWgradParams
+        {
+            int C, K, J, Jpad;          // J = C * 9 live rows, Jpad = MMA N
+            int N, Ho, Wo, segs, padX, padY;
+            int stages, tilesK;
+            long long steps;            // N * Ho * segs
+            uint32_t xBytes;
+        };
+
+        __global__ void __launch_bounds__(kScThreads, 1)
+        tc_smallc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDy, ScWgradParams p,
+                               float* __restrict__ ws)
+        {
+            extern __shared__ uint8_t smemRaw[];
+            uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+            uint8_t* bRing = smem + p.stages * kScStageBytes;         // kScBStages x 5 KB
+            uint64_t* bars = (uint64_t*)(bRing + kScBStages * kScBBytes);
+            uint64_t* full = bars;               // [stages <= 8] TMA landed
+            uint64_t* empty = full + 8;          // [stages] converter done with x + MMA done with dy
+            uint64_t* bFull = empty + 8;         // [4]
+            uint64_t* bEmpty = bFull + 4;        // [4]
+            uint64_t* accBar = bEmpty + 4;
+            uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
+
+            const int warp = threadIdx.x >> 5;
+            const int lane = threadIdx.x & 31;
+            const int kt = blockIdx.x % p.tilesK;
+            const int split = blockIdx.x / p.tilesK;
+            const int splits = gridDim.x / p.tilesK;
+            const long long per = (p.steps + splits - 1) / splits;
+            const long long begin = (long long)split * per;
+            const long long end = begin + per < p.steps ? begin + per : p.steps;
+            const int steps = end > begin ? (int)(end - begin) : 0;
+
+            if (warp == 0 && lane == 0)
+            {
+                ptx::prefetch_tensormap(&mapX);
+                ptx::prefetch_tensormap(&mapDy);
+                for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 2); }
+                for (int s = 0; s < kScBStages; ++s) { ptx::mbar_init(&bFull[s], 1); ptx::mbar_init(&bEmpty[s], 1); }
+                ptx::mbar_init(accBar, 1);
+                ptx::fence_mbar_init();
+            }
+            if (warp == 1)
+                ptx::tmem_alloc(tmemSlot, 64);
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            ptx::tc_fence_after_sync();
+            const uint32_t tmemAcc = *tmemSlot;
+            const uint32_t full32 = ptx::smem_u32(full), empty32 = ptx::smem_u32(empty), bFull32 = ptx::smem_u32(bFull),
+                           bEmpty32 = ptx::smem_u32(bEmpty), accBar32 = ptx::smem_u32(accBar);
+
+            if (warp == 0)
+            {
+                if (lane == 0)
+                {
+                    int st = 0;
+                    uint32_t ph = 0;
+                    long long g = begin;
+                    int seg = (int)(g % p.segs);
+                    long long row = g / p.segs;
+                    int oh = (int)(row % p.Ho), n = (int)(row / p.Ho);
+                    for (int it = 0; it < steps; ++it)
+                    {
+                        ptx::mbar_wait(empty32 + 8u * st, ph ^ 1);
+                        uint8_t* a = smem + st * kScStageBytes;
+                        ptx::mbar_arrive_expect_tx(full32 + 8u * st, kScABytes + p.xBytes);
+                        // dy viewed as (Wo, K, Ho, N): [128 filters][32 pixels], rows past K read as zeros
+                        ptx::tma_load_4d(a, &mapDy, &full[st], seg * 32, kt * 128, oh, n);
+                        // x viewed as (W, H, C, N): [C][3 rows][40 columns]; everything outside the image reads as zeros
+                        ptx::tma_load_4d(a + kScABytes, &mapX, &full[st], seg * 32 - 4, oh - p.padY, 0, n);
+                        if (++st == p.stages) { st = 0; ph ^= 1; }
+                        if (++seg == p.segs) { seg = 0; if (++oh == p.Ho) { oh = 0; ++n; } }
+                    }
+                }
+            }
+            else if (warp == 1)
+            {
+                const uint32_t idesc = ptx::idesc_tf32(128, p.Jpad, 0, 0);
+                const uint64_t descA0 = ptx::smem_desc_sw128(ptx::smem_u32(smem), 16, 1024);
+                const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(bRing), 16, 1024);
+                int st = 0;
+                uint32_t ph = 0;
+                for (int it = 0; it < steps; ++it)
+                {
+                    const uint32_t bs = it & (kScBStages - 1);
+                    ptx::mbar_wait(full32 + 8u * st, ph);
+                    ptx::mbar_wait(bFull32 + 8u * bs, (it / kScBStages) & 1);
+                    ptx::tc_fence_after_sync();
+                    if (ptx::elect_one())
+                    {
+                        const uint64_t da = descA0 + (uint64_t)((st * kScStageBytes) >> 4);
+                        const uint64_t db = descB0 + (uint64_t)((bs * kScBBytes) >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            ptx::mma_tf32_ss(tmemAcc, da + kk * 2, db + kk * 2, idesc, (it | kk) != 0);
+                        ptx::mma_commit(bEmpty32 + 8u * bs);
+                        ptx::mma_commit(empty32 + 8u * st);
+                    }
+                    __syncwarp();
+                    if (++st == p.stages) { st = 0; ph ^= 1; }
+                }
+                if (ptx::elect_one())
+                    ptx::mma_commit(accBar32);
+                __syncwarp();
+            }
+            else
+            {
+                // ===== converters: lane = pixel of the step; row j = (c, r, s) of the im2col tile =====
+                const int cw = warp - 2;                       // also this warp's B stage
+                const uint32_t smem32 = ptx::smem_u32(smem);
+                const uint32_t bTile = ptx::smem_u32(bRing) + cw * kScBBytes;
+                // swizzled position of pixel `lane` in row j: 16-byte chunk (lane / 4) ^ (j % 8)
+                const uint32_t laneLo = (uint32_t)(lane & 3) * 4, laneChunk = (uint32_t)(lane >> 2);
+                if (steps > 0)
+                {
+                    // rows J .. Jpad-1 stay zero for the whole kernel (no other writer touches them)
+                    for (int j = p.J; j < p.Jpad; ++j)
+                        ptx::sts_b32(bTile + j * 128 + ((laneChunk ^ (uint32_t)(j & 7)) << 4) + laneLo, 0u);
+                }
+                for (int it = cw; it < steps; it += kScBStages)
+                {
+                    const int st = it % p.stages;
+                    ptx::mbar_wait(full32 + 8u * st, (uint32_t)(it / p.stages) & 1);
+                    ptx::mbar_wait(bEmpty32 + 8u * cw, ((uint32_t)(it / kScBStages) & 1) ^ 1);
+                    const uint32_t xs = smem32 + st * kScStageBytes + kScABytes + (uint32_t)(lane + 4 - p.padX) * 4;
+                    int j = 0;
+                    for (int c = 0; c < p.C; ++c)
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+#pragma unroll
+                            for (int s = 0; s < 3; ++s, ++j)
+                            {
+                                const uint32_t v = ptx::tf32_round_bits(ptx::lds_b32(xs + (uint32_t)((c * 3 + r) * kScXW + s) * 4));
+                                ptx::sts_b32(bTile + j * 128 + ((laneChunk ^ (uint32_t)(j & 7)) << 4) + laneLo, v);
+                            }
+                    // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0)
+                    {
+                        ptx::mbar_arrive(bFull32 + 8u * cw);
+                        ptx::mbar_arrive(empty32 + 8u * st);     // x segment consumed
+                    }
+                }
+
+                // ----- epilogue: partial[split][kt][filter][Jpad] -----
+                const int q = warp & 3;
+                ptx::mbar_wait(accBar32, 0);
+                ptx::tc_fence_after_sync();
+                float* dst = ws + (((long long)split * p.tilesK + kt) * 128 + q * 32 + lane) * p.Jpad;
+                for (int j0 = 0; j0 < p.Jpad; j0 += 8)
+                {
+                    uint32_t v[8];
+                    if (steps > 0)
+                    {
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                                     : "r"(tmemAcc + ((uint32_t)(q * 32) << 16) + j0)
+                                     : "memory");
+                        ptx::tmem_ld_wait();
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dst[j0 + j] = __uint_as_float(v[j]);
+                }
+            }
+
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            if (warp == 1)
+            {
+                ptx::tc_fence_after_sync();
+                ptx::tmem_dealloc(tmemAcc, 64);
+            }
+        }
+
+        // dw[k][j] = sum over splits of partial[split][k / 128][k % 128][j]   (j = (c, r, s) is already the KCRS order)
+        __global__ void smallc_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int K, int J, int Jpad, int tilesK, int splits)
+        {
+            const int i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= K * J)
+                return;
+            const int k = i / J, j = i - k * J;
+            const long long off = ((long long)(k / 128) * 128 + (k % 128)) * Jpad + j;
+            const long long stride = (long long)tilesK * 128 * Jpad;
+            float acc = 0.f;
+            for (int s = 0; s < splits; ++s)
+                acc += ws[s * stride + off];
+            dw[i] = acc;
+        }
+
         // ---------------------------------------------------------------- host side
         typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -2851,6 +3069,77 @@ namespace nb200
         return NB200_OK;
     }
 
+
+    // ---- small-channel kernel gradient on the tensor cores (tc_smallc_wgrad_kernel) ----
+    static int sc_splits(const nb200_conv_desc& d)
+    {
+        const int tilesK = ceil_div(d.K, 128);
+        const long long steps = (long long)d.N * d.Ho * ceil_div(d.Wo, 32);
+        long long splits = 148 / tilesK;
+        if (splits < 1) splits = 1;
+        if (splits > steps) splits = steps > 0 ? steps : 1;
+        return (int)splits;
+    }
+
+    bool tc_smallc_wgrad_supported(const nb200_conv_desc& d)
+    {
+        return d.math == NB200_MATH_TF32 && d.fmt == NB200_NCHW && d.C >= 1 && d.C <= 4 && d.R == 3 && d.S == 3 && d.stride == 1 &&
+               d.padX <= 2 && d.padY <= 2 && d.W % 4 == 0 && d.Wo % 4 == 0 && d.K >= 1 && d.Ho == d.H + 2 * d.padY - 2 &&
+               d.Wo == d.W + 2 * d.padX - 2 && (long long)d.N * d.Ho * d.Wo >= 64 * 1024;
+    }
+
+    size_t tc_smallc_wgrad_workspace(const nb200_conv_desc& d)
+    {
+        const int Jpad = round_up(d.C * 9, 16);
+        return (size_t)sc_splits(d) * ceil_div(d.K, 128) * 128 * Jpad * sizeof(float);
+    }
+
+    int tc_smallc_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st)
+    {
+        const size_t need = tc_smallc_wgrad_workspace(d);
+        if (wsBytes < need || !ws)
+            return fail(NB200_E_WORKSPACE, "kernel gradient needs %zu workspace bytes, got %zu", need, wsBytes);
+        if (((uintptr_t)x & 15) || ((uintptr_t)dy & 15))
+            return fail(NB200_E_INVALID, "tensor base addresses must be 16-byte aligned for TMA");
+        ScWgradParams p;
+        p.C = d.C; p.K = d.K; p.J = d.C * 9; p.Jpad = round_up(p.J, 16);
+        p.N = d.N; p.Ho = d.Ho; p.Wo = d.Wo; p.segs = ceil_div(d.Wo, 32); p.padX = d.padX; p.padY = d.padY;
+        p.tilesK = ceil_div(d.K, 128);
+        p.steps = (long long)d.N * d.Ho * p.segs;
+        p.xBytes = (uint32_t)(d.C * 3 * kScXW * 4);
+        p.stages = 8;
+        const size_t smemBytes = 1024 + (size_t)p.stages * kScStageBytes + kScBStages * kScBBytes + 512;
+        CUtensorMap mapX, mapDy;
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.C, (cuuint64_t)d.N};
+            cuuint64_t strides[3] = {(cuuint64_t)d.W * 4, (cuuint64_t)d.H * d.W * 4, (cuuint64_t)d.C * d.H * d.W * 4};
+            cuuint32_t box[4] = {(cuuint32_t)kScXW, 3, (cuuint32_t)d.C, 1};
+            int rc = make_map(&mapX, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc) return rc;
+        }
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)d.Wo, (cuuint64_t)d.K, (cuuint64_t)d.Ho, (cuuint64_t)d.N};
+            cuuint64_t strides[3] = {(cuuint64_t)d.Ho * d.Wo * 4, (cuuint64_t)d.Wo * 4, (cuuint64_t)d.K * d.Ho * d.Wo * 4};
+            cuuint32_t box[4] = {32, 128, 1, 1};
+            int rc = make_map(&mapDy, dy, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (rc) return rc;
+        }
+        static bool attrSet = false;
+        if (!attrSet)
+        {
+            NB200_CUDA_TRY(cudaFuncSetAttribute(tc_smallc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            attrSet = true;
+        }
+        const int splits = sc_splits(d);
+        tc_smallc_wgrad_kernel<<<(unsigned)(splits * p.tilesK), kScThreads, smemBytes, st>>>(mapX, mapDy, p, (float*)ws);
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        smallc_wgrad_reduce_kernel<<<ceil_div((long long)d.K * p.J, 256), 256, 0, st>>>((const float*)ws, dw, d.K, p.J, p.Jpad, p.tilesK, splits);
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        return NB200_OK;
+    }
+
     bool tc_forward_supported(const nb200_conv_desc& d)
     {
         return d.fmt == NB200_NCHW && (d.math == NB200_MATH_TF32 || d.math == NB200_MATH_3XTF32) && d.stride == 1 && shape_ok(fwd_shape(d));
@@ -2872,6 +3161,11 @@ namespace nb200
     {
         const size_t a = repack_bytes(f), b = rowtap_wanted(f) ? rowtap_bytes(f) : 0;
         return a > b ? a : b;
+    }
+
+    bool tc_uses_rowtap(int op, const nb200_conv_desc& d)
+    {
+        return op == NB200_OP_FORWARD ? rowtap_wanted(fwd_shape(d)) : op == NB200_OP_INPUT_GRADIENT ? rowtap_wanted(dgrad_shape(d)) : false;
     }
 
     size_t tc_workspace_bytes(int op, const nb200_conv_desc& d)

@@ -83,6 +83,10 @@ TC_CASES = [
     (0, 3, 40, 36, 72, 24, 3, 3, 1, 1, 1),     # ragged channels, 24 filters (generic epilogue), last tile 8 columns wide
     (0, 3, 32, 38, 64, 64, 5, 3, 1, 1, 2),     # 5 filter rows x 3 columns, H not a multiple of 4
     (0, 1, 128, 96, 128, 48, 3, 3, 1, 1, 1),   # four channel blocks, one image
+    # small-channel kernel gradient on the tensor cores (TF32 mode, >= 64K output pixels, W % 4 == 0, pad 1)
+    (0, 4, 3, 128, 128, 64, 3, 3, 1, 1, 1),    # RGB first layer: 27 im2col rows in a 32-row tile, filters fill half the M tile
+    (0, 2, 4, 128, 256, 160, 3, 3, 1, 1, 1),   # 36 rows in a 48-row tile, two filter tiles (the second ragged)
+    (0, 1, 1, 256, 260, 24, 3, 3, 1, 1, 1),    # one channel, last 32-column segment 4 columns wide
 ]
 
 
