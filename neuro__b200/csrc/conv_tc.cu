@@ -1710,7 +1710,11 @@ namespace nb200
         constexpr uint32_t kWgXBytes = 128 * kWgXW * 4;         // 22528
         constexpr int kWgAStages = 4;
 
-        template <int BN, bool PACK>
+        // OFF0 >= 0: three taps with compile-time window offsets OFF0 + s into the row segment (3-column filters, padX = 1:
+        // OFF0 = wOff - padX = 3). The segment is rounded once and every window is a fixed register range, which removes the
+        // runtime compare chain and two thirds of the rounding adds: ~175 instead of ~330 converter instructions per step
+        // (the converter warps run at ~5 cycles per instruction and were what held this kernel at ~70 % of the MMA rate).
+        template <int BN, bool PACK, int OFF0>
         __global__ void __launch_bounds__(kThreads, 1)
         tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDy, WgradParams p,
                         float* __restrict__ ws)
@@ -1839,12 +1843,45 @@ namespace nb200
 #pragma unroll
                     for (int i = 0; i < 10; ++i)
                         ptx::lds_v4(rowp + i * 16, row[4 * i + 0], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
-                    for (int grp = 0; grp < p.groups; ++grp)
+                    if constexpr (OFF0 >= 0)
                     {
+#pragma unroll
+                        for (int i = 0; i < 40; ++i)
+                            row[i] = ptx::tf32_round_bits(row[i]);
+                    }
+#pragma unroll
+                    for (int grp = 0; grp < (OFF0 >= 0 ? (PACK ? 2 : 3) : 8); ++grp)
+                    {
+                        if (OFF0 < 0 && grp >= p.groups)
+                            break;
+                        uint32_t v[32];
+                        if constexpr (OFF0 >= 0)
+                        {
+                            // fixed windows: tap s = grp, or (packed) taps 2 grp / 2 grp + 1 in the two lane halves
+                            if (!PACK || (cl >> 6) == 0)
+                            {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    v[j] = row[j + OFF0 + (PACK ? 2 * grp : grp)];
+                            }
+                            else if (grp == 0)
+                            {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    v[j] = row[j + OFF0 + 1];
+                            }
+                            else
+                            {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    v[j] = 0u; // the fourth tap does not exist
+                            }
+                        }
+                        else
+                        {
                         // tap column handled by this lane in this group (packed: the two lane halves take adjacent taps)
                         const int s = PACK ? 2 * grp + (cl >> 6) : grp;
                         const int off = s - p.padX + p.wOff; // 0..8 for a real tap
-                        uint32_t v[32];
                         if (PACK)
                         {
 #pragma unroll
@@ -1859,6 +1896,7 @@ namespace nb200
                                 for (int j = 0; j < 32; ++j)
                                     v[j] = ptx::tf32_round_bits(row[j + o]);
                             }
+                        }
                         if (pending)
                         {
                             ptx::tmem_st_wait();
@@ -2875,20 +2913,29 @@ namespace nb200
             return pl;
         }
 
-        template <int BN, bool PACK>
-        int launch_wgrad(const WgradPlan& pl, const CUtensorMap& mapX, const CUtensorMap& mapDy, const WgradParams& p, float* ws, cudaStream_t st)
+        template <int BN, bool PACK, int OFF0>
+        int launch_wgrad_t(const WgradPlan& pl, const CUtensorMap& mapX, const CUtensorMap& mapDy, const WgradParams& p, float* ws, cudaStream_t st)
         {
             static bool attrSet = false;
             if (!attrSet)
             {
-                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<BN, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<BN, PACK, OFF0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
                 attrSet = true;
             }
             const long long ctas = (long long)p.splits * p.tilesK * p.tilesC * p.R;
-            tc_wgrad_kernel<BN, PACK><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapX, mapDy, p, ws);
+            tc_wgrad_kernel<BN, PACK, OFF0><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapX, mapDy, p, ws);
             NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
             return NB200_OK;
+        }
+
+        template <int BN, bool PACK>
+        int launch_wgrad(const WgradPlan& pl, const CUtensorMap& mapX, const CUtensorMap& mapDy, const WgradParams& p, float* ws, cudaStream_t st)
+        {
+            static const bool generic = getenv("NB200_WGRAD_GENERIC") != nullptr; // profiling: force the runtime-offset converters
+            if (!generic && p.S == 3 && p.wOff - p.padX == 3)
+                return launch_wgrad_t<BN, PACK, 3>(pl, mapX, mapDy, p, ws, st);
+            return launch_wgrad_t<BN, PACK, -1>(pl, mapX, mapDy, p, ws, st);
         }
     }
 
