@@ -167,7 +167,7 @@ def workload_config(batch, gpus):
     return {"workload": "VGG16 conv stack @512x512x3 (13 layers 3x3 s1 p1): fwd(bias+ReLU) + input-gradient + kernel-gradient "
                         "+ gradient all-reduce + Adam",
             "per_gpu_batch": batch, "global_batch": batch * gpus, "parallelism": "dp%d (batch sharded)" % gpus,
-            "math": "tf32 tensor cores, fp32 accumulate (first layer C=3: fp32 CUDA cores)",
+            "math": "tf32 tensor cores, fp32 accumulate (first layer C=3: HBM-bound; forward / input gradient on fp32 CUDA cores, kernel gradient on tensor cores)",
             "l2": "inputs larger than L2: each step streams every layer's tensors once (%.1f GB of distinct tensors per step)" % (batch * 0.95)}
 
 
@@ -285,7 +285,7 @@ def run_ours(args):
     for (fam, i), e0, e1 in events:
         dt = e0.elapsed_time(e1)
         fam_ms[fam] += dt
-        if fam < 3 and names[i][fam].startswith("tcgen05"):
+        if fam < 3 and names[i][fam].startswith("tcgen05") and "smallc" not in names[i][fam]:   # tensor-bound launches only
             tc_ms[fam] += dt; tc_fl[fam] += layers[i]["desc"].flops()
         if fam < 3:
             k = kern.setdefault(KERNEL_OF.get(names[i][fam], names[i][fam]), [0.0, 0.0, 0])
