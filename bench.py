@@ -281,7 +281,9 @@ def run_ours(args):
                  "tcgen05_dgrad": "tc_fprop_kernel (forward + input gradient, >64 filters)",
                  "tcgen05_rowtap_fprop": "tc_rowtap_kernel (forward + input gradient, <=64 filters)",
                  "tcgen05_rowtap_dgrad": "tc_rowtap_kernel (forward + input gradient, <=64 filters)",
-                 "tcgen05_wgrad": "tc_wgrad_kernel (kernel gradient)"}
+                 "tcgen05_wgrad": "tc_wgrad_kernel (kernel gradient)",
+                 "tcgen05_rowfold_wgrad": "tc_wgrad_rowfold_kernel (kernel gradient, <=64 channels and filters)",
+                 "tcgen05_smallc_wgrad": "tc_smallc_wgrad_kernel (kernel gradient, <=4 channels, HBM-bound)"}
     for (fam, i), e0, e1 in events:
         dt = e0.elapsed_time(e1)
         fam_ms[fam] += dt

@@ -184,7 +184,7 @@ extern "C"
         {
         case NB200_OP_FORWARD: return f == kTc ? (tc_uses_rowtap(op, *d) ? "tcgen05_rowtap_fprop" : "tcgen05_fprop") : f == kGather ? "tcgen05_gather_fprop" : f == kSmallC ? "smallc_fprop" : "direct_fprop";
         case NB200_OP_INPUT_GRADIENT: return f == kTc ? (tc_uses_rowtap(op, *d) ? "tcgen05_rowtap_dgrad" : "tcgen05_dgrad") : f == kGather ? "tcgen05_gather_dgrad" : f == kSmallC ? "smallc_dgrad" : "direct_dgrad";
-        case NB200_OP_KERNELS_GRADIENT: return f == kTc ? "tcgen05_wgrad" : f == kGather ? "tcgen05_gather_wgrad" : f == kSmallC ? (tc_smallc_wgrad_supported(*d) ? "tcgen05_smallc_wgrad" : "smallc_wgrad") : "direct_wgrad";
+        case NB200_OP_KERNELS_GRADIENT: return f == kTc ? (tc_uses_rowfold(*d) ? "tcgen05_rowfold_wgrad" : "tcgen05_wgrad") : f == kGather ? "tcgen05_gather_wgrad" : f == kSmallC ? (tc_smallc_wgrad_supported(*d) ? "tcgen05_smallc_wgrad" : "smallc_wgrad") : "direct_wgrad";
         default: return "invalid";
         }
     }

@@ -1973,6 +1973,317 @@ namespace nb200
         }
 
 
+
+        // ---------------------------------------------------------------- kernel gradient, filter rows folded into N (C <= 64)
+        // With C <= 64 and K <= 64 a converted x tile feeds only 4 MMAs of N = 64 and tc_wgrad_kernel is converter-bound
+        // (220 TFLOP/s on VGG block1_conv2). A filter-row shift is a whole-row shift of dy, which TMA can express, so here
+        // the R filter rows share every converted tile: a step is one INPUT row y and one 32-column segment,
+        //     A_t  = the packed x windows of the step (lanes 0-63 tap s = 2t, lanes 64-127 tap s = 2t + 1), t = 0, 1
+        //     B_r  = dy[n][k][oh = y + padY - r][segment]                      (rows outside the image: TMA zero fill)
+        //     D[t][r][lane][k] += A_t . B_r^T                                   2 x R accumulators of 64 columns
+        // i.e. R times the MMA work per converted tile. A CTA walks its rows with y fastest inside a segment, so each dy tile is
+        // loaded once and used by R consecutive steps out of a ring in shared memory (a run of L rows loads L + R - 1 tiles).
+        // 3-column filters, padX = 1, R <= 3; grid = (row split, filter tile); partials and reduce as in tc_wgrad_kernel.
+        constexpr int kRfBN = 64;
+        constexpr int kRfXBytes = 64 * kWgXW * 4;          // 11264
+        constexpr int kRfDyBytes = kRfBN * 32 * 4;         // 8192
+        constexpr int kRfXSlots = 6, kRfDySlots = 12;
+
+        struct RowfoldParams
+        {
+            int R, padY, N, H, Ho, Wo, C, K, segs, tilesK, splits, rowsPerSplit;
+        };
+
+        __global__ void __launch_bounds__(kThreads, 1)
+        tc_wgrad_rowfold_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDy, RowfoldParams p,
+                                float* __restrict__ ws)
+        {
+            constexpr int S = 3, OFF0 = 3;
+            extern __shared__ uint8_t smemRaw[];
+            uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+            uint8_t* dyRing = smem;                                    // kRfDySlots x 8 KB (1 KB aligned: SW128 tiles)
+            uint8_t* xRing = smem + kRfDySlots * kRfDyBytes;           // kRfXSlots x 11 KB
+            uint64_t* bars = (uint64_t*)(xRing + kRfXSlots * kRfXBytes);
+            uint64_t* dyFull = bars;                   // [12]
+            uint64_t* dyEmpty = dyFull + 12;           // [12]
+            uint64_t* xFull = dyEmpty + 12;            // [6]
+            uint64_t* xEmpty = xFull + 6;              // [6]
+            uint64_t* aFull = xEmpty + 6;              // [4]
+            uint64_t* aEmpty = aFull + 4;              // [4]
+            uint64_t* accBar = aEmpty + 4;
+            uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
+
+            const int warp = threadIdx.x >> 5;
+            const int lane = threadIdx.x & 31;
+            const int split = blockIdx.x % p.splits;
+            const int kt = blockIdx.x / p.splits;
+            const int k0 = kt * kRfBN;
+            const int totalRows = p.N * p.H;
+            const int rowBegin = split * p.rowsPerSplit;
+            const int rowEnd = min(rowBegin + p.rowsPerSplit, totalRows);
+            const int steps = max(rowEnd - rowBegin, 0) * p.segs;
+            const int R = p.R;
+
+            if (warp == 0 && lane == 0)
+            {
+                ptx::prefetch_tensormap(&mapX);
+                ptx::prefetch_tensormap(&mapDy);
+                for (int s = 0; s < kRfDySlots; ++s) { ptx::mbar_init(&dyFull[s], 1); ptx::mbar_init(&dyEmpty[s], 1); }
+                for (int s = 0; s < kRfXSlots; ++s) { ptx::mbar_init(&xFull[s], 1); ptx::mbar_init(&xEmpty[s], kTileH); }
+                for (int s = 0; s < 4; ++s) { ptx::mbar_init(&aFull[s], kTileH); ptx::mbar_init(&aEmpty[s], 1); }
+                ptx::mbar_init(accBar, 1);
+                ptx::fence_mbar_init();
+            }
+            if (warp == 1)
+                ptx::tmem_alloc(tmemSlot, 512);
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            ptx::tc_fence_after_sync();
+            const uint32_t tmemAcc = *tmemSlot;
+            const uint32_t tmemA = tmemAcc + 512 - 4 * 32;
+            const uint32_t dyFull32 = ptx::smem_u32(dyFull), dyEmpty32 = ptx::smem_u32(dyEmpty), xFull32 = ptx::smem_u32(xFull),
+                           xEmpty32 = ptx::smem_u32(xEmpty), aFull32 = ptx::smem_u32(aFull), aEmpty32 = ptx::smem_u32(aEmpty),
+                           accBar32 = ptx::smem_u32(accBar);
+
+            if (warp == 0)
+            {
+                if (lane == 0)
+                {
+                    // ===== TMA producer: per run (image n, segment, rows y0..y1-1): R-1 leading dy tiles, then (x, dy) per row =====
+                    uint32_t dq = 0, xq = 0;
+                    auto load_dy = [&](int n, int ow0, int oh) {
+                        const uint32_t sl = dq % kRfDySlots;
+                        ptx::mbar_wait(dyEmpty32 + 8u * sl, ((dq / kRfDySlots) & 1) ^ 1);
+                        ptx::mbar_arrive_expect_tx(dyFull32 + 8u * sl, kRfDyBytes);
+                        ptx::tma_load_4d(dyRing + sl * kRfDyBytes, &mapDy, &dyFull[sl], ow0, k0, oh, n);
+                        ++dq;
+                    };
+                    for (int row = rowBegin; row < rowEnd;)
+                    {
+                        const int n = row / p.H, y0 = row - n * p.H;
+                        const int y1 = min(p.H, y0 + (rowEnd - row));
+                        for (int seg = 0; seg < p.segs; ++seg)
+                        {
+                            const int ow0 = seg * 32;
+                            for (int j = 0; j < R - 1; ++j)
+                                load_dy(n, ow0, y0 + p.padY - (R - 1) + j);
+                            for (int y = y0; y < y1; ++y)
+                            {
+                                const uint32_t sl = xq % kRfXSlots;
+                                ptx::mbar_wait(xEmpty32 + 8u * sl, ((xq / kRfXSlots) & 1) ^ 1);
+                                ptx::mbar_arrive_expect_tx(xFull32 + 8u * sl, kRfXBytes);
+                                // x viewed as (W, C, H, N): box {44, 64, 1, 1}; columns left of the image read as zeros
+                                ptx::tma_load_4d(xRing + sl * kRfXBytes, &mapX, &xFull[sl], ow0 - 4, 0, y, n);
+                                ++xq;
+                                load_dy(n, ow0, y + p.padY);
+                            }
+                        }
+                        row += y1 - y0;
+                    }
+                }
+            }
+            else if (warp == 1)
+            {
+                // ===== MMA issuer =====
+                // The R dy tiles of a step sit in consecutive ring slots (oldest = filter row R-1 first), so unless the ring
+                // wraps inside them they are ONE B operand of R x 64 rows: one N = 64 R MMA per K slice instead of R (the
+                // issuing lane is otherwise the bottleneck: 24 N = 64 MMAs per 768-cycle step). Accumulator columns of
+                // tile t: [(t R + e) 64, +64) for ring position e = R - 1 - r.
+                constexpr uint32_t idesc64 = ptx::idesc_tf32(128, kRfBN, 0, 0);
+                const uint32_t idescAll = ptx::idesc_tf32(128, kRfBN * R, 0, 0);
+                const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(dyRing), 16, 1024);
+                uint32_t dq = 0, dyWaited = 0, aCount = 0;
+                uint32_t accum = 0;
+                for (int row = rowBegin; row < rowEnd;)
+                {
+                    const int n = row / p.H, y0 = row - n * p.H;
+                    const int len = min(p.H, y0 + (rowEnd - row)) - y0;
+                    (void)n;
+                    for (int seg = 0; seg < p.segs; ++seg)
+                    {
+                        uint32_t slot = dq % kRfDySlots;   // ring slot of the oldest tile of the step
+                        for (int i = 0; i < len; ++i)
+                        {
+                            const uint32_t need = dq + i + R; // dy tiles dq+i .. dq+i+R-1 serve this row
+                            while (dyWaited < need)
+                            {
+                                ptx::mbar_wait(dyFull32 + 8u * (dyWaited % kRfDySlots), (dyWaited / kRfDySlots) & 1);
+                                ++dyWaited;
+                            }
+                            const bool contiguous = slot + R <= kRfDySlots;
+#pragma unroll 1
+                            for (int t = 0; t < 2; ++t, ++aCount)
+                            {
+                                const uint32_t as = aCount & 3;
+                                ptx::mbar_wait(aFull32 + 8u * as, (aCount >> 2) & 1);
+                                ptx::tc_fence_after_sync();
+                                if (ptx::elect_one())
+                                {
+                                    const uint32_t ta = tmemA + as * 32;
+                                    const uint32_t td = tmemAcc + t * R * kRfBN;
+                                    if (contiguous)
+                                    {
+                                        const uint64_t db = descB0 + (uint64_t)(slot * (kRfDyBytes >> 4));
+#pragma unroll
+                                        for (int kk = 0; kk < 4; ++kk)
+                                            ptx::mma_tf32_ts(td, ta + kk * 8, db + kk * 2, idescAll, accum | kk);
+                                    }
+                                    else
+                                    {
+                                        for (int e = 0; e < R; ++e)
+                                        {
+                                            uint32_t sl = slot + e;
+                                            if (sl >= kRfDySlots) sl -= kRfDySlots;
+                                            const uint64_t db = descB0 + (uint64_t)(sl * (kRfDyBytes >> 4));
+#pragma unroll
+                                            for (int kk = 0; kk < 4; ++kk)
+                                                ptx::mma_tf32_ts(td + e * kRfBN, ta + kk * 8, db + kk * 2, idesc64, accum | kk);
+                                        }
+                                    }
+                                    ptx::mma_commit(aEmpty32 + 8u * as);
+                                    if (t == 1)
+                                    {
+                                        // the oldest dy tile has served its last row; at the end of a run so have the others
+                                        ptx::mma_commit(dyEmpty32 + 8u * slot);
+                                        if (i == len - 1)
+                                            for (int e = 1; e < R; ++e)
+                                                ptx::mma_commit(dyEmpty32 + 8u * ((slot + e) % kRfDySlots));
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                            accum = 1;
+                            if (++slot == kRfDySlots) slot = 0;
+                        }
+                        dq += len + R - 1;
+                    }
+                    row += len;
+                }
+                if (ptx::elect_one())
+                    ptx::mma_commit(accBar32);
+                __syncwarp();
+            }
+            else
+            {
+                // ===== converters: thread = (tap half, channel); two groups of 4 warps alternate steps =====
+                const int q = warp & 3;
+                const int g = (warp - 2) >> 2;
+                const uint32_t laneSel = (uint32_t)(q * 32) << 16;
+                const int cl = q * 32 + lane;
+                const uint32_t xRing32 = ptx::smem_u32(xRing);
+                bool pending = false;
+                uint32_t pendStage = 0;
+                for (int it = g; it < steps; it += 2)
+                {
+                    const uint32_t sl = (uint32_t)it % kRfXSlots;
+                    ptx::mbar_wait(xFull32 + 8u * sl, ((uint32_t)it / kRfXSlots) & 1);
+                    const uint32_t rowp = xRing32 + sl * kRfXBytes + (cl & 63) * (kWgXW * 4);
+                    uint32_t row[40];
+#pragma unroll
+                    for (int i = 0; i < 10; ++i)
+                        ptx::lds_v4(rowp + i * 16, row[4 * i + 0], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+#pragma unroll
+                    for (int i = 0; i < 40; ++i)
+                        row[i] = ptx::tf32_round_bits(row[i]);
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
+                    {
+                        uint32_t v[32];
+                        if ((cl >> 6) == 0)
+                        {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                v[j] = row[j + OFF0 + 2 * t];
+                        }
+                        else if (t == 0)
+                        {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                v[j] = row[j + OFF0 + 1];
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                v[j] = 0u; // the fourth tap does not exist
+                        }
+                        if (pending)
+                        {
+                            ptx::tmem_st_wait();
+                            ptx::tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0)
+                                ptx::mbar_arrive(aFull32 + 8u * pendStage);
+                        }
+                        const uint32_t j = (uint32_t)it * 2 + t; // global A-tile number = MMA consumption order
+                        const uint32_t as = j & 3;
+                        ptx::mbar_wait(aEmpty32 + 8u * as, ((j >> 2) & 1) ^ 1);
+                        ptx::tc_fence_after_sync();
+                        ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * 32, v);
+                        pending = true;
+                        pendStage = as;
+                    }
+                    // publish the step's second tile now: this group owns only two A stages, and holding the tile back until
+                    // the next row segment is loaded and rounded would stall the MMA warp on it for most of a step
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0)
+                    {
+                        ptx::mbar_arrive(aFull32 + 8u * pendStage);
+                        ptx::mbar_arrive(xEmpty32 + 8u * sl);
+                    }
+                    pending = false;
+                }
+
+                // ----- epilogue: partial[split][tap = r*3 + s][k][c], lanes = consecutive channels -----
+                ptx::mbar_wait(accBar32, 0);
+                ptx::tc_fence_after_sync();
+                const int c = cl & 63;
+                for (int t = 0; t < 2; ++t)
+                {
+                    const int s = 2 * t + (cl >> 6);
+                    const bool tapOk = s < S;
+                    for (int r = 0; r < R; ++r)
+                    {
+                        float* dst = ws + ((long long)(split * R * S + r * S + (tapOk ? s : 0)) * p.K) * p.C + c;
+#pragma unroll 1
+                        for (int j0 = g * 32; j0 < kRfBN; j0 += 64)
+                        {
+                            if (k0 + j0 >= p.K)
+                                break;
+                            uint32_t v[32];
+                            if (steps > 0)
+                            {
+                                ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + (t * R + (R - 1 - r)) * kRfBN + j0, v);
+                                ptx::tmem_ld_wait();
+                            }
+                            else
+                            {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = 0u;
+                            }
+                            if (tapOk && c < p.C)
+                            {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (k0 + j0 + j < p.K)
+                                        dst[(long long)(k0 + j0 + j) * p.C] = __uint_as_float(v[j]);
+                            }
+                        }
+                    }
+                }
+            }
+
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            if (warp == 1)
+            {
+                ptx::tc_fence_after_sync();
+                ptx::tmem_dealloc(tmemAcc, 512);
+            }
+        }
+
         // ---------------------------------------------------------------- gathered kernel gradient (any stride / map size)
         //   dw[k][c][r][s] = sum over (n, oh, ow)  dy[n][k][oh][ow] * x[n][c][oh*st-pY+r][ow*st-pX+s]
         // Same GEMM view as tc_wgrad_kernel (M = 128 channels, N = BN filters, reduction = pixels, one accumulator per tap
@@ -3204,11 +3515,16 @@ namespace nb200
 
     bool tc_kernels_gradient_supported(const nb200_conv_desc& d) { return wgrad_shape_ok(d); }
 
+    static bool rowfold_wanted(const nb200_conv_desc& d);
+    static int rowfold_splits(const nb200_conv_desc& d);
+
     static size_t fwd_ws_bytes(const FwdShape& f)
     {
         const size_t a = repack_bytes(f), b = rowtap_wanted(f) ? rowtap_bytes(f) : 0;
         return a > b ? a : b;
     }
+
+    bool tc_uses_rowfold(const nb200_conv_desc& d) { return rowfold_wanted(d); }
 
     bool tc_uses_rowtap(int op, const nb200_conv_desc& d)
     {
@@ -3221,7 +3537,12 @@ namespace nb200
         {
         case NB200_OP_FORWARD: return fwd_ws_bytes(fwd_shape(d));
         case NB200_OP_INPUT_GRADIENT: return fwd_ws_bytes(dgrad_shape(d));
-        default: return wgrad_plan(d).wsBytes;
+        default:
+        {
+            const size_t a = wgrad_plan(d).wsBytes;
+            const size_t b = rowfold_wanted(d) ? (size_t)rowfold_splits(d) * d.R * d.S * d.K * d.C * sizeof(float) : 0;
+            return a > b ? a : b;
+        }
         }
     }
 
@@ -3236,8 +3557,77 @@ namespace nb200
         return run_fwd_shaped(dgrad_shape(d), 1, d.K, d.C, dy, w, nullptr, NB200_ACT_IDENTITY, 0.f, dx, ws, wsBytes, st);
     }
 
+
+    // ---- kernel gradient with the filter rows folded into N (tc_wgrad_rowfold_kernel) ----
+    static bool rowfold_wanted(const nb200_conv_desc& d)
+    {
+        static const char* env = getenv("NB200_WGRAD_ROWFOLD"); // 0 / 1 override for profiling
+        if (!wgrad_shape_ok(d) || d.S != 3 || d.padX != 1 || d.R > 3 || d.C > 64)
+            return false;
+        if (env)
+            return env[0] == '1';
+        return d.K <= 64 && (long long)d.N * d.H >= 64;
+    }
+
+    static int rowfold_splits(const nb200_conv_desc& d)
+    {
+        const int tilesK = ceil_div(d.K, kRfBN);
+        int splits = 148 / tilesK;
+        if (splits < 1) splits = 1;
+        const int rows = d.N * d.H;
+        if (splits > rows) splits = rows;
+        const int per = ceil_div(rows, splits);
+        return ceil_div(rows, per);
+    }
+
+    static int tc_rowfold_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st)
+    {
+        RowfoldParams p;
+        p.R = d.R; p.padY = d.padY; p.N = d.N; p.H = d.H; p.Ho = d.Ho; p.Wo = d.Wo; p.C = d.C; p.K = d.K;
+        p.segs = ceil_div(d.Wo, 32); p.tilesK = ceil_div(d.K, kRfBN);
+        p.splits = rowfold_splits(d);
+        p.rowsPerSplit = ceil_div(d.N * d.H, p.splits);
+        const size_t need = (size_t)p.splits * d.R * d.S * d.K * d.C * sizeof(float);
+        if (wsBytes < need || !ws)
+            return fail(NB200_E_WORKSPACE, "tcgen05 kernel gradient needs %zu workspace bytes, got %zu", need, wsBytes);
+        if (((uintptr_t)x & 15) || ((uintptr_t)dy & 15))
+            return fail(NB200_E_INVALID, "tensor base addresses must be 16-byte aligned for TMA");
+        CUtensorMap mapX, mapDy;
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)d.W, (cuuint64_t)d.C, (cuuint64_t)d.H, (cuuint64_t)d.N};
+            cuuint64_t strides[3] = {(cuuint64_t)d.H * d.W * 4, (cuuint64_t)d.W * 4, (cuuint64_t)d.C * d.H * d.W * 4};
+            cuuint32_t box[4] = {kWgXW, 64, 1, 1};
+            int rc = make_map(&mapX, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc) return rc;
+        }
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)d.Wo, (cuuint64_t)d.K, (cuuint64_t)d.Ho, (cuuint64_t)d.N};
+            cuuint64_t strides[3] = {(cuuint64_t)d.Ho * d.Wo * 4, (cuuint64_t)d.Wo * 4, (cuuint64_t)d.K * d.Ho * d.Wo * 4};
+            cuuint32_t box[4] = {32, (cuuint32_t)kRfBN, 1, 1};
+            int rc = make_map(&mapDy, dy, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (rc) return rc;
+        }
+        static bool attrSet = false;
+        if (!attrSet)
+        {
+            NB200_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_rowfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            attrSet = true;
+        }
+        const size_t smemBytes = 1024 + (size_t)kRfDySlots * kRfDyBytes + (size_t)kRfXSlots * kRfXBytes + 512;
+        tc_wgrad_rowfold_kernel<<<(unsigned)(p.splits * p.tilesK), kThreads, smemBytes, st>>>(mapX, mapDy, p, (float*)ws);
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        const long long total = (long long)d.K * d.C * d.R * d.S;
+        wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)ws, dw, d.K, d.C, d.R * d.S, p.splits);
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        return NB200_OK;
+    }
+
     int tc_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st)
     {
+        if (rowfold_wanted(d))
+            return tc_rowfold_kernels_gradient(d, x, dy, dw, ws, wsBytes, st);
         const WgradPlan pl = wgrad_plan(d);
         if (wsBytes < pl.wsBytes || !ws)
             return fail(NB200_E_WORKSPACE, "tcgen05 kernel gradient needs %zu workspace bytes, got %zu", pl.wsBytes, wsBytes);

@@ -87,6 +87,10 @@ TC_CASES = [
     (0, 4, 3, 128, 128, 64, 3, 3, 1, 1, 1),    # RGB first layer: 27 im2col rows in a 32-row tile, filters fill half the M tile
     (0, 2, 4, 128, 256, 160, 3, 3, 1, 1, 1),   # 36 rows in a 48-row tile, two filter tiles (the second ragged)
     (0, 1, 1, 256, 260, 24, 3, 3, 1, 1, 1),    # one channel, last 32-column segment 4 columns wide
+    # row-fold kernel gradient (C, K <= 64, 3 columns, padX 1, R <= 3; also taken by several cases above)
+    (0, 4, 16, 20, 32, 24, 2, 3, 1, 1, 0),     # two filter rows, no vertical padding
+    (0, 4, 32, 16, 64, 16, 1, 3, 1, 1, 0),     # one filter row
+    (0, 3, 64, 37, 40, 64, 3, 3, 1, 1, 1),     # rows split across images mid-run (3 x 37 rows over 111 CTAs), ragged segment
 ]
 
 

@@ -30,7 +30,7 @@ def test_loss_curve_tracks_reference(math, tol, optimizer):
     op = TensorOpB200(math)
     d = lib.ConvDesc(BATCH, 8, 32, 32, 16, 3, 3, 32, 32, 1, 1, 1, lib.NCHW, math)
     if math == lib.MATH_TF32:
-        assert op.kernel_name(lib.OP_FORWARD, d) == "tcgen05_fprop" and op.kernel_name(lib.OP_KERNELS_GRADIENT, d) == "tcgen05_wgrad"
+        assert op.kernel_name(lib.OP_FORWARD, d) == "tcgen05_fprop" and op.kernel_name(lib.OP_KERNELS_GRADIENT, d) == "tcgen05_rowfold_wgrad"
     losses, params = _run(op, torch.device("cuda", 0), optimizer)
     assert len(losses) == len(ref_losses) == (N // BATCH) * EPOCHS
     rel = np.abs(np.array(losses) - np.array(ref_losses)) / np.abs(np.array(ref_losses))
