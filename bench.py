@@ -188,6 +188,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / debug lines must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = lib.load()
     op = TensorOpB200(lib.MATH_TF32)
