@@ -278,6 +278,7 @@ def run_ours(args):
     fam_ms = {0: 0.0, 1: 0.0, 2: 0.0, 3: 0.0}
     tc_ms = {0: 0.0, 1: 0.0, 2: 0.0}; tc_fl = {0: 0.0, 1: 0.0, 2: 0.0}
     kern = {}   # CUDA kernel -> [flops, ms, launches] over the instrumented pass
+    kern_bytes = {}
     KERNEL_OF = {"tcgen05_fprop": "tc_fprop_kernel (forward + input gradient, >64 filters)",
                  "tcgen05_dgrad": "tc_fprop_kernel (forward + input gradient, >64 filters)",
                  "tcgen05_rowtap_fprop": "tc_rowtap_kernel (forward + input gradient, <=64 filters)",
@@ -293,6 +294,9 @@ def run_ours(args):
         if fam < 3:
             k = kern.setdefault(KERNEL_OF.get(names[i][fam], names[i][fam]), [0.0, 0.0, 0])
             k[0] += layers[i]["desc"].flops(); k[1] += dt; k[2] += 1
+            l = layers[i]   # algorithmic bytes of the call: the two activation-sized tensors it streams + the filters
+            kern_bytes[KERNEL_OF.get(names[i][fam], names[i][fam])] = kern_bytes.get(KERNEL_OF.get(names[i][fam], names[i][fam]), 0.0) + \
+                4.0 * (l["x"].numel() + l["y"].numel() + l["w"].numel())
 
     # ---- e2e: the same step through the public API with HOST input and HOST result, copies inside the timed region ----
     # Every step's input batch comes from pinned host memory and its result (the image gradient, what style transfer reads
@@ -351,6 +355,17 @@ def run_ours(args):
         dom_name = max(kern, key=lambda k: kern[k][1])
         dom_fl, dom_ms, dom_n = kern[dom_name]
         achieved = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        # DRAM traffic of the dominant kernel: from the committed ncu --set full capture of the same workload (never measured
+        # in this run: a profiler run is not a timing run); null when the capture has no row for the kernel
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_dram_traffic_per_launch.json")))
+            ent = tj["kernels"].get(dom_name.split(" ")[0])
+            if ent and B == 8:
+                traffic, traffic_src = ent["dram_bytes_per_launch"], tj["source"]
+        except (OSError, ValueError, KeyError):
+            pass
+        dom_bytes = kern_bytes.get(dom_name, 0.0)
         kernels = {k: {"ms_per_step": v[1] / op_steps, "launches_per_step": v[2] // op_steps,
                        "tflops": v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None,
                        "share_of_step": v[1] / sum(fam_ms.values())} for k, v in kern.items()}
@@ -367,7 +382,9 @@ def run_ours(args):
             "tflops_total": 3 * B * world * SAMPLE_FLOPS_PER_OP / (ms * 1e-3) / 1e12,
             "per_op": per_op, "kernels": kernels, "adam_ms_per_step": fam_ms[3] / op_steps,
             "roofline": {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf32_peak if tf32_peak else None, "traffic": None,
+                         "frac": achieved / tf32_peak if tf32_peak else None, "traffic": traffic,
+                         "traffic_unit": "DRAM bytes per launch (read + write)", "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": dom_bytes / dom_n if dom_n else None,
                          "avg_launch_ms": dom_ms / dom_n if dom_n else None,
                          "flops_per_launch": dom_fl / dom_n if dom_n else None,
                          "peak_source": "%s bf16_tflops_sustained / 2 (MEASURED_PEAKS.json has no TF32 entry; TF32 dense = 1/2 bf16)" % peaks["source"],

@@ -1979,19 +1979,24 @@ namespace nb200
         // (220 TFLOP/s on VGG block1_conv2). A filter-row shift is a whole-row shift of dy, which TMA can express, so here
         // the R filter rows share every converted tile: a step is one INPUT row y and one 32-column segment,
         //     A_t  = the packed x windows of the step (lanes 0-63 tap s = 2t, lanes 64-127 tap s = 2t + 1), t = 0, 1
-        //     B_r  = dy[n][k][oh = y + padY - r][segment]                      (rows outside the image: TMA zero fill)
-        //     D[t][r][lane][k] += A_t . B_r^T                                   2 x R accumulators of 64 columns
-        // i.e. R times the MMA work per converted tile. A CTA walks its rows with y fastest inside a segment, so each dy tile is
-        // loaded once and used by R consecutive steps out of a ring in shared memory (a run of L rows loads L + R - 1 tiles).
-        // 3-column filters, padX = 1, R <= 3; grid = (row split, filter tile); partials and reduce as in tc_wgrad_kernel.
+        //     B    = [dy[oh = y + padY - r][segment], r = 0 .. R-1]: R tiles of 64 filters landed back to back = one operand of
+        //            64 R rows (rows outside the image: TMA zero fill)
+        //     D[t][lane][r 64 + k] += A_t . B^T                                  one N = 64 R MMA per K slice
+        // i.e. R times the MMA work per converted tile and a third of the MMA instructions. A CTA walks its (image, input row)
+        // range row by row, all segments of a row in turn: consecutive steps then read adjacent 128-byte pieces of the same
+        // DRAM pages. (A first version walked y fastest inside a segment and kept the dy tiles in a ring for R steps: it was
+        // bound by DRAM page misses -- 0.44 ms with neither conversions nor MMAs issued.) Each dy tile is fetched R times, two
+        // of them from L2. 3-column filters, padX = 1, R <= 3; grid = (row split, filter tile); partials and reduce as in
+        // tc_wgrad_kernel.
         constexpr int kRfBN = 64;
         constexpr int kRfXBytes = 64 * kWgXW * 4;          // 11264
         constexpr int kRfDyBytes = kRfBN * 32 * 4;         // 8192
-        constexpr int kRfXSlots = 6, kRfDySlots = 12;
 
         struct RowfoldParams
         {
-            int R, padY, N, H, Ho, Wo, C, K, segs, tilesK, splits, rowsPerSplit;
+            int R, padY, N, H, Ho, Wo, C, K, segs, tilesK, splits, rowsPerSplit, stages;
+            uint32_t stageBytes;
+            int dbgFlags; // profiling only (NB200_RF_DEBUG): 1 = converters skip loads and rounding, 2 = no MMAs are issued
         };
 
         __global__ void __launch_bounds__(kThreads, 1)
@@ -2001,14 +2006,11 @@ namespace nb200
             constexpr int S = 3, OFF0 = 3;
             extern __shared__ uint8_t smemRaw[];
             uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
-            uint8_t* dyRing = smem;                                    // kRfDySlots x 8 KB (1 KB aligned: SW128 tiles)
-            uint8_t* xRing = smem + kRfDySlots * kRfDyBytes;           // kRfXSlots x 11 KB
-            uint64_t* bars = (uint64_t*)(xRing + kRfXSlots * kRfXBytes);
-            uint64_t* dyFull = bars;                   // [12]
-            uint64_t* dyEmpty = dyFull + 12;           // [12]
-            uint64_t* xFull = dyEmpty + 12;            // [6]
-            uint64_t* xEmpty = xFull + 6;              // [6]
-            uint64_t* aFull = xEmpty + 6;              // [4]
+            // stage = [R dy tiles (1 KB aligned, SW128)][x segment]
+            uint64_t* bars = (uint64_t*)(smem + p.stages * p.stageBytes);
+            uint64_t* full = bars;                     // [stages <= 8]
+            uint64_t* empty = full + 8;                // [stages] 4 converter warps + 1 MMA commit
+            uint64_t* aFull = empty + 8;               // [4]
             uint64_t* aEmpty = aFull + 4;              // [4]
             uint64_t* accBar = aEmpty + 4;
             uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
@@ -2023,13 +2025,13 @@ namespace nb200
             const int rowEnd = min(rowBegin + p.rowsPerSplit, totalRows);
             const int steps = max(rowEnd - rowBegin, 0) * p.segs;
             const int R = p.R;
+            const uint32_t xOff = (uint32_t)R * kRfDyBytes;   // x segment behind the dy tiles of the stage
 
             if (warp == 0 && lane == 0)
             {
                 ptx::prefetch_tensormap(&mapX);
                 ptx::prefetch_tensormap(&mapDy);
-                for (int s = 0; s < kRfDySlots; ++s) { ptx::mbar_init(&dyFull[s], 1); ptx::mbar_init(&dyEmpty[s], 1); }
-                for (int s = 0; s < kRfXSlots; ++s) { ptx::mbar_init(&xFull[s], 1); ptx::mbar_init(&xEmpty[s], kTileH); }
+                for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], kTileH + 1); }
                 for (int s = 0; s < 4; ++s) { ptx::mbar_init(&aFull[s], kTileH); ptx::mbar_init(&aEmpty[s], 1); }
                 ptx::mbar_init(accBar, 1);
                 ptx::fence_mbar_init();
@@ -2041,123 +2043,67 @@ namespace nb200
             ptx::tc_fence_after_sync();
             const uint32_t tmemAcc = *tmemSlot;
             const uint32_t tmemA = tmemAcc + 512 - 4 * 32;
-            const uint32_t dyFull32 = ptx::smem_u32(dyFull), dyEmpty32 = ptx::smem_u32(dyEmpty), xFull32 = ptx::smem_u32(xFull),
-                           xEmpty32 = ptx::smem_u32(xEmpty), aFull32 = ptx::smem_u32(aFull), aEmpty32 = ptx::smem_u32(aEmpty),
-                           accBar32 = ptx::smem_u32(accBar);
+            const uint32_t full32 = ptx::smem_u32(full), empty32 = ptx::smem_u32(empty), aFull32 = ptx::smem_u32(aFull),
+                           aEmpty32 = ptx::smem_u32(aEmpty), accBar32 = ptx::smem_u32(accBar);
 
             if (warp == 0)
             {
                 if (lane == 0)
                 {
-                    // ===== TMA producer: per run (image n, segment, rows y0..y1-1): R-1 leading dy tiles, then (x, dy) per row =====
-                    uint32_t dq = 0, xq = 0;
-                    auto load_dy = [&](int n, int ow0, int oh) {
-                        const uint32_t sl = dq % kRfDySlots;
-                        ptx::mbar_wait(dyEmpty32 + 8u * sl, ((dq / kRfDySlots) & 1) ^ 1);
-                        ptx::mbar_arrive_expect_tx(dyFull32 + 8u * sl, kRfDyBytes);
-                        ptx::tma_load_4d(dyRing + sl * kRfDyBytes, &mapDy, &dyFull[sl], ow0, k0, oh, n);
-                        ++dq;
-                    };
-                    for (int row = rowBegin; row < rowEnd;)
+                    // ===== TMA producer: per step the R dy tiles and the x segment of one (row, segment) =====
+                    int st = 0;
+                    uint32_t ph = 0;
+                    for (int row = rowBegin; row < rowEnd; ++row)
                     {
-                        const int n = row / p.H, y0 = row - n * p.H;
-                        const int y1 = min(p.H, y0 + (rowEnd - row));
+                        const int n = row / p.H, y = row - n * p.H;
                         for (int seg = 0; seg < p.segs; ++seg)
                         {
                             const int ow0 = seg * 32;
-                            for (int j = 0; j < R - 1; ++j)
-                                load_dy(n, ow0, y0 + p.padY - (R - 1) + j);
-                            for (int y = y0; y < y1; ++y)
-                            {
-                                const uint32_t sl = xq % kRfXSlots;
-                                ptx::mbar_wait(xEmpty32 + 8u * sl, ((xq / kRfXSlots) & 1) ^ 1);
-                                ptx::mbar_arrive_expect_tx(xFull32 + 8u * sl, kRfXBytes);
-                                // x viewed as (W, C, H, N): box {44, 64, 1, 1}; columns left of the image read as zeros
-                                ptx::tma_load_4d(xRing + sl * kRfXBytes, &mapX, &xFull[sl], ow0 - 4, 0, y, n);
-                                ++xq;
-                                load_dy(n, ow0, y + p.padY);
-                            }
+                            ptx::mbar_wait(empty32 + 8u * st, ph ^ 1);
+                            uint8_t* stage = smem + st * p.stageBytes;
+                            ptx::mbar_arrive_expect_tx(full32 + 8u * st, xOff + kRfXBytes);
+                            for (int r = 0; r < R; ++r) // dy viewed as (Wo, K, Ho, N): [64 filters][32 pixels] of output row y + padY - r
+                                ptx::tma_load_4d(stage + r * kRfDyBytes, &mapDy, &full[st], ow0, k0, y + p.padY - r, n);
+                            // x viewed as (W, C, H, N): box {44, 64, 1, 1}; columns left / right of the image read as zeros
+                            ptx::tma_load_4d(stage + xOff, &mapX, &full[st], ow0 - 4, 0, y, n);
+                            if (++st == p.stages) { st = 0; ph ^= 1; }
                         }
-                        row += y1 - y0;
                     }
                 }
             }
             else if (warp == 1)
             {
-                // ===== MMA issuer =====
-                // The R dy tiles of a step sit in consecutive ring slots (oldest = filter row R-1 first), so unless the ring
-                // wraps inside them they are ONE B operand of R x 64 rows: one N = 64 R MMA per K slice instead of R (the
-                // issuing lane is otherwise the bottleneck: 24 N = 64 MMAs per 768-cycle step). Accumulator columns of
-                // tile t: [(t R + e) 64, +64) for ring position e = R - 1 - r.
-                constexpr uint32_t idesc64 = ptx::idesc_tf32(128, kRfBN, 0, 0);
-                const uint32_t idescAll = ptx::idesc_tf32(128, kRfBN * R, 0, 0);
-                const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(dyRing), 16, 1024);
-                uint32_t dq = 0, dyWaited = 0, aCount = 0;
-                uint32_t accum = 0;
-                for (int row = rowBegin; row < rowEnd;)
+                // ===== MMA issuer: per step two A tiles x one B operand of 64 R rows =====
+                const uint32_t idesc = ptx::idesc_tf32(128, kRfBN * R, 0, 0);
+                const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(smem), 16, 1024);
+                int st = 0;
+                uint32_t ph = 0, aCount = 0;
+                for (int it = 0; it < steps; ++it)
                 {
-                    const int n = row / p.H, y0 = row - n * p.H;
-                    const int len = min(p.H, y0 + (rowEnd - row)) - y0;
-                    (void)n;
-                    for (int seg = 0; seg < p.segs; ++seg)
-                    {
-                        uint32_t slot = dq % kRfDySlots;   // ring slot of the oldest tile of the step
-                        for (int i = 0; i < len; ++i)
-                        {
-                            const uint32_t need = dq + i + R; // dy tiles dq+i .. dq+i+R-1 serve this row
-                            while (dyWaited < need)
-                            {
-                                ptx::mbar_wait(dyFull32 + 8u * (dyWaited % kRfDySlots), (dyWaited / kRfDySlots) & 1);
-                                ++dyWaited;
-                            }
-                            const bool contiguous = slot + R <= kRfDySlots;
+                    ptx::mbar_wait(full32 + 8u * st, ph);
+                    const uint64_t db = descB0 + (uint64_t)((st * p.stageBytes) >> 4);
 #pragma unroll 1
-                            for (int t = 0; t < 2; ++t, ++aCount)
+                    for (int t = 0; t < 2; ++t, ++aCount)
+                    {
+                        const uint32_t as = aCount & 3;
+                        ptx::mbar_wait(aFull32 + 8u * as, (aCount >> 2) & 1);
+                        ptx::tc_fence_after_sync();
+                        if (ptx::elect_one())
+                        {
+                            const uint32_t ta = tmemA + as * 32;
+                            if (!(p.dbgFlags & 2))
                             {
-                                const uint32_t as = aCount & 3;
-                                ptx::mbar_wait(aFull32 + 8u * as, (aCount >> 2) & 1);
-                                ptx::tc_fence_after_sync();
-                                if (ptx::elect_one())
-                                {
-                                    const uint32_t ta = tmemA + as * 32;
-                                    const uint32_t td = tmemAcc + t * R * kRfBN;
-                                    if (contiguous)
-                                    {
-                                        const uint64_t db = descB0 + (uint64_t)(slot * (kRfDyBytes >> 4));
 #pragma unroll
-                                        for (int kk = 0; kk < 4; ++kk)
-                                            ptx::mma_tf32_ts(td, ta + kk * 8, db + kk * 2, idescAll, accum | kk);
-                                    }
-                                    else
-                                    {
-                                        for (int e = 0; e < R; ++e)
-                                        {
-                                            uint32_t sl = slot + e;
-                                            if (sl >= kRfDySlots) sl -= kRfDySlots;
-                                            const uint64_t db = descB0 + (uint64_t)(sl * (kRfDyBytes >> 4));
-#pragma unroll
-                                            for (int kk = 0; kk < 4; ++kk)
-                                                ptx::mma_tf32_ts(td + e * kRfBN, ta + kk * 8, db + kk * 2, idesc64, accum | kk);
-                                        }
-                                    }
-                                    ptx::mma_commit(aEmpty32 + 8u * as);
-                                    if (t == 1)
-                                    {
-                                        // the oldest dy tile has served its last row; at the end of a run so have the others
-                                        ptx::mma_commit(dyEmpty32 + 8u * slot);
-                                        if (i == len - 1)
-                                            for (int e = 1; e < R; ++e)
-                                                ptx::mma_commit(dyEmpty32 + 8u * ((slot + e) % kRfDySlots));
-                                    }
-                                }
-                                __syncwarp();
+                                for (int kk = 0; kk < 4; ++kk)
+                                    ptx::mma_tf32_ts(tmemAcc + t * R * kRfBN, ta + kk * 8, db + kk * 2, idesc, (it | kk) != 0);
                             }
-                            accum = 1;
-                            if (++slot == kRfDySlots) slot = 0;
+                            ptx::mma_commit(aEmpty32 + 8u * as);
+                            if (t == 1)
+                                ptx::mma_commit(empty32 + 8u * st); // dy tiles consumed
                         }
-                        dq += len + R - 1;
+                        __syncwarp();
                     }
-                    row += len;
+                    if (++st == p.stages) { st = 0; ph ^= 1; }
                 }
                 if (ptx::elect_one())
                     ptx::mma_commit(accBar32);
@@ -2170,21 +2116,29 @@ namespace nb200
                 const int g = (warp - 2) >> 2;
                 const uint32_t laneSel = (uint32_t)(q * 32) << 16;
                 const int cl = q * 32 + lane;
-                const uint32_t xRing32 = ptx::smem_u32(xRing);
+                const uint32_t smem32 = ptx::smem_u32(smem);
                 bool pending = false;
                 uint32_t pendStage = 0;
                 for (int it = g; it < steps; it += 2)
                 {
-                    const uint32_t sl = (uint32_t)it % kRfXSlots;
-                    ptx::mbar_wait(xFull32 + 8u * sl, ((uint32_t)it / kRfXSlots) & 1);
-                    const uint32_t rowp = xRing32 + sl * kRfXBytes + (cl & 63) * (kWgXW * 4);
+                    const int st = it % p.stages;
+                    ptx::mbar_wait(full32 + 8u * st, (uint32_t)(it / p.stages) & 1);
+                    const uint32_t rowp = smem32 + st * p.stageBytes + xOff + (cl & 63) * (kWgXW * 4);
                     uint32_t row[40];
+                    if (p.dbgFlags & 1)
+                    {
 #pragma unroll
-                    for (int i = 0; i < 10; ++i)
-                        ptx::lds_v4(rowp + i * 16, row[4 * i + 0], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+                        for (int i = 0; i < 40; ++i) row[i] = 0x3f800000u;
+                    }
+                    else
+                    {
 #pragma unroll
-                    for (int i = 0; i < 40; ++i)
-                        row[i] = ptx::tf32_round_bits(row[i]);
+                        for (int i = 0; i < 10; ++i)
+                            ptx::lds_v4(rowp + i * 16, row[4 * i + 0], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+#pragma unroll
+                        for (int i = 0; i < 40; ++i)
+                            row[i] = ptx::tf32_round_bits(row[i]);
+                    }
 #pragma unroll
                     for (int t = 0; t < 2; ++t)
                     {
@@ -2216,24 +2170,24 @@ namespace nb200
                                 ptx::mbar_arrive(aFull32 + 8u * pendStage);
                         }
                         const uint32_t j = (uint32_t)it * 2 + t; // global A-tile number = MMA consumption order
-                        const uint32_t as = j & 3;
+                        const uint32_t as = j & 3;               // group g only ever touches stages 2g, 2g + 1
                         ptx::mbar_wait(aEmpty32 + 8u * as, ((j >> 2) & 1) ^ 1);
                         ptx::tc_fence_after_sync();
                         ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * 32, v);
                         pending = true;
                         pendStage = as;
                     }
-                    // publish the step's second tile now: this group owns only two A stages, and holding the tile back until
-                    // the next row segment is loaded and rounded would stall the MMA warp on it for most of a step
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(empty32 + 8u * st); // x segment is in registers / tensor memory
+                }
+                if (pending)
+                {
                     ptx::tmem_st_wait();
                     ptx::tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0)
-                    {
                         ptx::mbar_arrive(aFull32 + 8u * pendStage);
-                        ptx::mbar_arrive(xEmpty32 + 8u * sl);
-                    }
-                    pending = false;
                 }
 
                 // ----- epilogue: partial[split][tap = r*3 + s][k][c], lanes = consecutive channels -----
@@ -2255,7 +2209,7 @@ namespace nb200
                             uint32_t v[32];
                             if (steps > 0)
                             {
-                                ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + (t * R + (R - 1 - r)) * kRfBN + j0, v);
+                                ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + (t * R + r) * kRfBN + j0, v);
                                 ptx::tmem_ld_wait();
                             }
                             else
@@ -3197,6 +3151,10 @@ namespace nb200
                 return false;
             if (d.S > 6 || d.R > 16 || d.padX > 4 || d.S - 1 - d.padX > 4)
                 return false;
+            // A-ring discipline of tc_wgrad_kernel (see the kernel): at most 3 A tiles per step, i.e. S <= 3, or S <= 6 when
+            // two taps share a tile (C <= 64). Wider filters take the gathered kernel.
+            if ((d.C <= 64 ? (d.S + 1) / 2 : d.S) > 3)
+                return false;
             return true;
         }
 
@@ -3566,7 +3524,7 @@ namespace nb200
             return false;
         if (env)
             return env[0] == '1';
-        return d.K <= 64 && (long long)d.N * d.H >= 64;
+        return d.K <= 128 && (long long)d.N * d.H >= 64;
     }
 
     static int rowfold_splits(const nb200_conv_desc& d)
@@ -3586,6 +3544,10 @@ namespace nb200
         p.R = d.R; p.padY = d.padY; p.N = d.N; p.H = d.H; p.Ho = d.Ho; p.Wo = d.Wo; p.C = d.C; p.K = d.K;
         p.segs = ceil_div(d.Wo, 32); p.tilesK = ceil_div(d.K, kRfBN);
         p.splits = rowfold_splits(d);
+        {
+            static const char* dbgEnv = getenv("NB200_RF_DEBUG");
+            p.dbgFlags = dbgEnv ? atoi(dbgEnv) : 0;
+        }
         p.rowsPerSplit = ceil_div(d.N * d.H, p.splits);
         const size_t need = (size_t)p.splits * d.R * d.S * d.K * d.C * sizeof(float);
         if (wsBytes < need || !ws)
@@ -3613,7 +3575,10 @@ namespace nb200
             NB200_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_rowfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             attrSet = true;
         }
-        const size_t smemBytes = 1024 + (size_t)kRfDySlots * kRfDyBytes + (size_t)kRfXSlots * kRfXBytes + 512;
+        p.stageBytes = (uint32_t)((d.R * kRfDyBytes + kRfXBytes + 1023) & ~1023);
+        p.stages = (int)((200 * 1024) / p.stageBytes);
+        if (p.stages > 8) p.stages = 8;
+        const size_t smemBytes = 1024 + (size_t)p.stages * p.stageBytes + 512;
         tc_wgrad_rowfold_kernel<<<(unsigned)(p.splits * p.tilesK), kThreads, smemBytes, st>>>(mapX, mapDy, p, (float*)ws);
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();

@@ -91,6 +91,7 @@ TC_CASES = [
     (0, 4, 16, 20, 32, 24, 2, 3, 1, 1, 0),     # two filter rows, no vertical padding
     (0, 4, 32, 16, 64, 16, 1, 3, 1, 1, 0),     # one filter row
     (0, 3, 64, 37, 40, 64, 3, 3, 1, 1, 1),     # rows split across images mid-run (3 x 37 rows over 111 CTAs), ragged segment
+    (0, 1, 128, 24, 32, 32, 5, 5, 1, 2, 2),    # 5 columns with > 64 channels: 5 A tiles per step, kernel gradient must take the gathered kernel
 ]
 
 
