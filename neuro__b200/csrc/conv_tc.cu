@@ -817,7 +817,7 @@ namespace nb200
             long long yStrideN, yStrideK;
             int act;
             float alpha;
-            int dbgFlags; // profiling only (NB200_RT_DEBUG): 1 = epilogue skips math + stores, 2 = converters skip the loads
+            int dbgFlags; // profiling only (NB200_RT_DEBUG): 1 = epilogue skips math + stores, 2 = converters skip the loads, 4 = no global stores
         };
 
         __device__ __forceinline__ uint32_t rt_a_stage_col(uint32_t as) { return (as < 2 ? 192u : 448u - 64u) + as * 32u; }
@@ -1113,7 +1113,7 @@ namespace nb200
                         const uint32_t buf = tileCount & 1;
                         const uint32_t acc = tmemBase + laneSel + buf * 256 + h * 32;
                         const int col = (upper ? tw - 1 : tw) * kTileW + lane;        // output column this lane stores
-                        const bool storeOk = rowOk && col >= 0 && col < p.Wo;
+                        const bool storeOk = rowOk && col >= 0 && col < p.Wo && !(p.dbgFlags & 4);
                         ptx::mbar_wait(accFull32 + 8u * buf, (tileCount >> 1) & 1);
                         ptx::tc_fence_after_sync();
 #pragma unroll 1
