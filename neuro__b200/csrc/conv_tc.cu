@@ -2799,7 +2799,10 @@ namespace nb200
             const size_t xBytes = ((size_t)kBlockC * pl.HR * pl.WB * 4 + 1023) & ~(size_t)1023;
             const size_t bBytes = (size_t)(pl.pair ? pl.BN / 2 : pl.BN) * kBlockC * 4 * (f.x3 ? 2 : 1);
             const size_t fixed = 1024 /*alignment slack*/ + 512 /*barriers*/;
-            const long long budget = (pl.BN > 128 || f.x3 || pl.m256) ? kSmemBudget1 : kSmemBudget2;
+            // Grids of at most one CTA per SM (small batches, small maps) are latency-bound on the filter ring -- nothing else
+            // on the SM hides a TMA round trip -- so they take the whole shared memory for a deeper ring.
+            const long long ctasTotal = (long long)f.N * ceil_div(f.Hout, kTileH) * ceil_div(f.Wout, kTileW) * ceil_div(f.Kout, pl.BN);
+            const long long budget = (pl.BN > 128 || f.x3 || pl.m256 || ctasTotal <= 148) ? kSmemBudget1 : kSmemBudget2;
             pl.ok = false;
             // prefer two (three when alone on the SM) halo stages; give the rest to the filter ring (at least 2, at most 8)
             for (int xs = 2; xs >= 1 && !pl.ok; --xs)
@@ -2838,7 +2841,7 @@ namespace nb200
             static bool attrSet = false;
             if (!attrSet)
             {
-                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (BN > 128 || X3) ? kSmemBudget1 : kSmemBudget2));
+                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1));
                 attrSet = true;
             }
             const long long tiles = (long long)p.tilesK * p.tilesW * p.tilesH * f.N;
