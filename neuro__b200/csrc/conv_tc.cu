@@ -801,7 +801,7 @@ namespace nb200
         constexpr int kRtN = kRtBNK * kRtS;                 // MMA N
         constexpr int kRtWB = 32;                           // halo width = the tile's 32 input columns (16-byte aligned origin)
         constexpr int kRtHold = 8;                          // columns held back per tile (one 32-byte sector)
-        constexpr int kRtHoldStride = kRtHold + 1;          // + the tile's P_0[lane 31], carried into the next tile's column 0
+        constexpr int kRtHoldStride = kRtHold + 4;          // + P_0[lane 31] carry (two parities), P_2[lane 0], bias: see rt_epilogue_chunk
         constexpr uint32_t kRtBBytes = kRtN * kBlockC * 4;  // one filter stage
         constexpr uint32_t kRtHoldBytes = kTileH * kRtBNK * kRtHoldStride * 4; // [row][filter][8 columns + carry]
         constexpr uint32_t kRtDummyBytes = 8 * 32 * 4;      // one scratch word per epilogue thread
@@ -831,43 +831,76 @@ namespace nb200
 
         // One 16-filter chunk of the row-tap epilogue for this thread's lane (see the kernel). Lanes 0-23 store this tile's columns
         // 0-23; lanes 24-31 store the PREVIOUS tile's columns 24-31 (held in shared memory, same lane) and hold this tile's.
-        //   slotAddr:  this lane's hold slot for filter 0 of the chunk (lanes < 24: a private dummy word, so the exchange below
-        //              is branch-free); carryAddr: the chunk's P0[31] slot; 36-byte pitch per filter (dummy: pitch 0).
-        //   Shared accesses are volatile asm and stay in program order: lane 0 reads the previous tile's carry (phase 1) before
-        //   lane 31 overwrites it (phase 2). The phases keep 16 independent shuffles / loads in flight instead of one chain.
+        // Per (tile row, filter) the warp owns 12 words of shared memory at rowAddr + 48 j:
+        //     [0..7] held columns 24-31 | [8], [9] P0[lane 31] of the even / odd tiles (carry into the next tile's column 0)
+        //     [10] P2[lane 0] of this tile (completes the previous tile's column 31) | [11] bias
+        // The chunk is written as whole-array phases (16 independent shuffles / loads / stores each) so that no result is
+        // consumed right after it is requested: the warp issues in order, and a per-filter chain of shuffle -> add -> load ->
+        // store stalled on every link (ablation: the math alone cost 0.10 ms of the 0.41 ms C64->K64 layer).
+        // Shared accesses are volatile asm, i.e. they stay in program order within the warp.
         template <int ACT, bool FULL>
-        __device__ __forceinline__ void rt_epilogue_chunk(uint32_t (&p0)[16], uint32_t (&p1)[16], uint32_t (&p2)[16], float bl, uint32_t slotAddr,
-                                                          uint32_t slotPitch, uint32_t carryAddr, int lane, bool first, float* yptr, bool storeOk,
-                                                          long long strideK, int kLeft, int act, float alpha)
+        __device__ __forceinline__ void rt_epilogue_chunk(uint32_t (&p0)[16], uint32_t (&p1)[16], uint32_t (&p2)[16], uint32_t rowAddr, int lane,
+                                                          bool first, uint32_t parity, float* yptr, bool storeOk, long long strideK, int kLeft,
+                                                          int act, float alpha)
         {
+            constexpr uint32_t kPitch = kRtHoldStride * 4;
             const bool upper = lane >= 32 - kRtHold;
-            // phase 1: o = P0[i-1] + P1[i] + P2[i+1] + bias -> p1;  P2[0] (completes the previous tile's column 31) -> p2
+            const uint32_t heldAddr = rowAddr + (uint32_t)((lane - (32 - kRtHold)) * 4);
+            uint32_t t[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < 16; ++j)                      // bias (broadcast load)
+                t[j] = ptx::lds_b32(rowAddr + j * kPitch + 44);
+            if (lane == 31)
             {
-                const float f0 = __uint_as_float(p0[j]), f2 = __uint_as_float(p2[j]);
-                float a0 = __shfl_up_sync(0xffffffffu, f0, 1);            // P0[i-1]
-                const float a2 = __shfl_down_sync(0xffffffffu, f2, 1);     // P2[i+1]
-                const float c2 = __shfl_sync(0xffffffffu, f2, 0);          // P2[0]
-                const float bj = __shfl_sync(0xffffffffu, bl, j);
-                if (lane == 0)
-                    a0 = first ? 0.f : __uint_as_float(ptx::lds_b32(carryAddr + j * (kRtHoldStride * 4)));
-                float o = (a0 + __uint_as_float(p1[j])) + bj;
-                if (lane < 31)
-                    o += a2;
-                p1[j] = __float_as_uint(o);
-                p2[j] = __float_as_uint(c2);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)                  // this tile's P0[31] for the next tile
+                    ptx::sts_b32(rowAddr + j * kPitch + 32 + 4 * parity, p0[j]);
             }
-            // phase 2: swap with the held sector, finish, store
+            if (lane == 0)
+            {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)                  // this tile's P2[0] for lane 31 below
+                    ptx::sts_b32(rowAddr + j * kPitch + 40, p2[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                p0[j] = __float_as_uint(__shfl_up_sync(0xffffffffu, __uint_as_float(p0[j]), 1));      // P0[i-1]
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                p2[j] = __float_as_uint(__shfl_down_sync(0xffffffffu, __uint_as_float(p2[j]), 1));    // P2[i+1]
+            if (lane == 0)
+            {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)                  // column 0: the previous tile's P0[31] (zero padding for the first tile)
+                    p0[j] = first ? 0u : ptx::lds_b32(rowAddr + j * kPitch + 32 + 4 * (parity ^ 1));
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j)
             {
-                const uint32_t sa = slotAddr + j * slotPitch;
-                const float held = __uint_as_float(ptx::lds_b32(sa));
-                ptx::sts_b32(sa, p1[j]);
-                if (lane == 31)
-                    ptx::sts_b32(carryAddr + j * (kRtHoldStride * 4), p0[j]);
-                float val = upper ? held : __uint_as_float(p1[j]);
+                float o = (__uint_as_float(p0[j]) + __uint_as_float(p1[j])) + __uint_as_float(t[j]);
+                if (lane < 31)
+                    o += __uint_as_float(p2[j]);
+                p1[j] = __float_as_uint(o);
+            }
+            if (upper)
+            {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)                  // the sector the previous tile held back
+                    t[j] = ptx::lds_b32(heldAddr + j * kPitch);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    ptx::sts_b32(heldAddr + j * kPitch, p1[j]);
+            }
+            if (lane == 31)
+            {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    p2[j] = ptx::lds_b32(rowAddr + j * kPitch + 40);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+            {
+                float val = __uint_as_float(upper ? t[j] : p1[j]);
                 if (lane == 31)
                     val += __uint_as_float(p2[j]);
                 if constexpr (ACT == NB200_ACT_RELU) val = val > 0.f ? val : 0.f;
@@ -1094,9 +1127,6 @@ namespace nb200
                 const bool upper = lane >= 32 - kRtHold;
                 const uint32_t myHold = ptx::smem_u32(hold) + (uint32_t)((q * kRtBNK + h * 32) * kRtHoldStride * 4);
                 const uint32_t holdLane = myHold + (uint32_t)((lane - (32 - kRtHold)) * 4); // meaningful for the upper lanes only
-                const uint32_t carry = myHold + kRtHold * 4;
-                // lanes 0-23 exchange with a private dummy word instead (keeps the epilogue branch-free)
-                const uint32_t dummy = ptx::smem_u32(hold) + kRtHoldBytes + (uint32_t)(((warp - kRtFirstEpiWarp) * 32 + lane) * 4);
                 uint32_t tileCount = 0;
                 for (int sp = blockIdx.x; sp < p.numStrips; sp += gridDim.x)
                 {
@@ -1108,6 +1138,10 @@ namespace nb200
                     const int oh = th * kTileH + q;
                     const bool rowOk = oh < p.Ho;
                     float* yrow = y + n * p.yStrideN + (long long)oh * p.Wo + (long long)k0 * p.yStrideK;
+                    // this strip's 32 biases into the warp's rows (word 11 of each filter's 12)
+                    ptx::sts_b32(myHold + (uint32_t)(lane * kRtHoldStride * 4) + 44,
+                                 __float_as_uint((bias && k0 + lane < p.K) ? __ldg(bias + k0 + lane) : 0.f));
+                    __syncwarp();
                     for (int tw = 0; tw < p.tilesW; ++tw, ++tileCount)
                     {
                         const uint32_t buf = tileCount & 1;
@@ -1120,8 +1154,6 @@ namespace nb200
                         for (int c0 = 0; c0 < 32; c0 += 16)
                         {
                             const int kb = k0 + c0;
-                            // bias first: its latency hides behind the TMEM loads
-                            const float bl = (bias && lane < 16 && kb + lane < p.K) ? __ldg(bias + kb + lane) : 0.f;
                             uint32_t p0[16], p1[16], p2[16];
                             ptx::tmem_ld_32x32b_x16(acc + c0, p0);
                             ptx::tmem_ld_32x32b_x16(acc + kRtBNK + c0, p1);
@@ -1138,16 +1170,14 @@ namespace nb200
                             if (p.dbgFlags & 1)
                                 continue;
                             float* yptr = yrow + (long long)c0 * p.yStrideK + col;
-                            const uint32_t ha = upper ? holdLane + (uint32_t)(c0 * kRtHoldStride * 4) : dummy;
-                            const uint32_t hp = upper ? (uint32_t)(kRtHoldStride * 4) : 0u;
-                            const uint32_t ca = carry + (uint32_t)(c0 * kRtHoldStride * 4);
+                            const uint32_t ra = myHold + (uint32_t)(c0 * kRtHoldStride * 4);
                             const int kLeft = p.K - kb;
                             if (kLeft >= 16 && p.act == NB200_ACT_RELU)
-                                rt_epilogue_chunk<NB200_ACT_RELU, true>(p0, p1, p2, bl, ha, hp, ca, lane, tw == 0, yptr, storeOk, p.yStrideK, kLeft, p.act, p.alpha);
+                                rt_epilogue_chunk<NB200_ACT_RELU, true>(p0, p1, p2, ra, lane, tw == 0, (uint32_t)tw & 1, yptr, storeOk, p.yStrideK, kLeft, p.act, p.alpha);
                             else if (kLeft >= 16 && p.act == NB200_ACT_IDENTITY)
-                                rt_epilogue_chunk<NB200_ACT_IDENTITY, true>(p0, p1, p2, bl, ha, hp, ca, lane, tw == 0, yptr, storeOk, p.yStrideK, kLeft, p.act, p.alpha);
+                                rt_epilogue_chunk<NB200_ACT_IDENTITY, true>(p0, p1, p2, ra, lane, tw == 0, (uint32_t)tw & 1, yptr, storeOk, p.yStrideK, kLeft, p.act, p.alpha);
                             else
-                                rt_epilogue_chunk<-1, false>(p0, p1, p2, bl, ha, hp, ca, lane, tw == 0, yptr, storeOk, p.yStrideK, kLeft, p.act, p.alpha);
+                                rt_epilogue_chunk<-1, false>(p0, p1, p2, ra, lane, tw == 0, (uint32_t)tw & 1, yptr, storeOk, p.yStrideK, kLeft, p.act, p.alpha);
                         }
                     }
                     // flush the last tile's held sector (its column 31 lacks only a term that multiplies zero padding)
@@ -2507,8 +2537,7 @@ namespace nb200
         constexpr int kScThreads = 192;
         constexpr int kScXW = 40;                                // x segment: columns ow0 - 4 .. ow0 + 35
         constexpr int kScABytes = 128 * 32 * 4;                  // dy tile
-        constexpr int kScXBytesMax = 4 * 3 * kScXW * 4;          // x segment, C <= 4
-        constexpr int kScStageBytes = kScABytes + 2048;          // x segment rounded up; keeps every A tile 1 KB aligned
+        constexpr int kScStageBytes = kScABytes + 2048;          // + x segment (C <= 4: 1920 B) rounded up; keeps every A tile 1 KB aligned
         constexpr int kScBStages = 4;
         constexpr int kScBBytes = 48 * 128;                      // im2col tile: Jpad <= 48 rows of 128 bytes (6 KB, 1 KB aligned)
 
