@@ -159,6 +159,95 @@ namespace nb200
         // hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-22 relative), which recovers fp32-class accuracy
         // (<= 1e-5 max-normalised against the reference) at a third of the TF32 rate. A tiles carry [hi | lo] (64 columns),
         // filter stages carry a hi and a lo tile (the repack writes both).
+        // Tiled variants of the filter repack (taps <= 32): the element-wise kernel above reads w with a stride of R*S floats
+        // per thread (9x read amplification for 3x3) or writes 4-byte pieces; at 24 launches per VGG16 step that was 2.7 % of
+        // the step. These stage a tile in shared memory so that both the reads and the writes are contiguous runs.
+        __device__ __forceinline__ void repack_store(float* __restrict__ out, long long i, long long total, float v, int x3)
+        {
+            uint32_t t;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+            out[i] = __uint_as_float(t);
+            if (x3)
+            {
+                uint32_t tl;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tl) : "f"(v - __uint_as_float(t)));
+                out[total + i] = __uint_as_float(tl);
+            }
+        }
+
+        // mode 0: out[tap][k][c] = w[k][c][tap]. Block = (32-channel tile, filter k): reads 32*taps contiguous floats.
+        __global__ void repack_fwd_tiled_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int C, int taps, int outCp, int x3)
+        {
+            extern __shared__ float tile[]; // [32 channels][taps]
+            const int k = blockIdx.y, c0 = blockIdx.x * 32;
+            const int n = 32 * taps;
+            const long long base = ((long long)k * C + c0) * taps;
+            const int valid = (C - c0 < 32 ? (C - c0 > 0 ? C - c0 : 0) : 32) * taps;
+            for (int j = threadIdx.x; j < n; j += blockDim.x)
+                tile[j] = j < valid ? w[base + j] : 0.f;
+            __syncthreads();
+            const long long total = (long long)taps * K * outCp;
+            for (int j = threadIdx.x; j < n; j += blockDim.x)
+            {
+                const int tap = j >> 5, cl = j & 31;
+                repack_store(out, ((long long)tap * K + k) * outCp + c0 + cl, total, tile[cl * taps + tap], x3);
+            }
+        }
+
+        // modes 1 / 2: out[tap'][c][k] = w[k][c][tap] (mode 1: tap' = the flipped tap). Block = (8-channel tile, 32-filter
+        // tile): reads 32 runs of 8*taps floats, writes 8*taps runs of 32 floats.
+        __global__ void repack_dgrad_tiled_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int C, int R, int S, int outRows,
+                                                  int outCp, int flip, int x3)
+        {
+            extern __shared__ float tile[]; // [32 filters][8 * taps + 1]
+            const int taps = R * S, run = 8 * taps, pitch = run + 1;
+            const int c0 = blockIdx.x * 8, k0 = blockIdx.y * 32;
+            const int validRun = (C - c0 < 8 ? C - c0 : 8) * taps;
+            for (int j = threadIdx.x; j < 32 * run; j += blockDim.x)
+            {
+                const int kl = j / run, i = j - kl * run;
+                tile[kl * pitch + i] = (k0 + kl < K && i < validRun) ? w[((long long)(k0 + kl) * C + c0) * taps + i] : 0.f;
+            }
+            __syncthreads();
+            const long long total = (long long)taps * outRows * outCp;
+            for (int j = threadIdx.x; j < 32 * run; j += blockDim.x)
+            {
+                const int kl = j & 31, i = j >> 5;          // i = cl * taps + tap
+                const int cl = i / taps, tap = i - cl * taps;
+                if (c0 + cl >= outRows)
+                    continue;
+                const int tapOut = flip ? (R - 1 - tap / S) * S + (S - 1 - tap % S) : tap;
+                repack_store(out, ((long long)tapOut * outRows + c0 + cl) * outCp + k0 + kl, total, tile[kl * pitch + i], x3);
+            }
+        }
+
+        // dw[k][c][tap] = sum over splits of partial[split][tap][k][c]; block = (32-channel tile, filter k): coalesced reads
+        // along c, one contiguous run of 32*taps floats written (the element-wise reduce wrote with a stride of `taps` floats).
+        __global__ void wgrad_reduce_tiled_kernel(const float* __restrict__ ws, float* __restrict__ dw, int K, int C, int taps, int splits)
+        {
+            extern __shared__ float tile[]; // [32 channels][taps]
+            const int k = blockIdx.y, c0 = blockIdx.x * 32;
+            const int n = 32 * taps;
+            const long long total = (long long)K * C * taps;
+            for (int j = threadIdx.x; j < n; j += blockDim.x)
+            {
+                const int tap = j >> 5, cl = j & 31;
+                float acc = 0.f;
+                if (c0 + cl < C)
+                {
+                    const float* src = ws + ((long long)tap * K + k) * C + c0 + cl;
+                    for (int sp = 0; sp < splits; ++sp)
+                        acc += src[(long long)sp * total];
+                }
+                tile[cl * taps + tap] = acc;
+            }
+            __syncthreads();
+            const int valid = (C - c0 < 32 ? C - c0 : 32) * taps;
+            float* dst = dw + ((long long)k * C + c0) * taps;
+            for (int j = threadIdx.x; j < valid; j += blockDim.x)
+                dst[j] = tile[j];
+        }
+
         // Bias + activation + store of one 32-filter chunk of this thread's pixel (lanes = 32 consecutive output columns, so
         // every store instruction writes one full 128-byte line). The activation is a template parameter: the per-element
         // switch and the exp paths stay out of the identity / ReLU / leaky-ReLU instantiations (the epilogue used to cost
@@ -3036,6 +3125,51 @@ namespace nb200
             return NB200_OK;
         }
 
+        // out[tap][outRows][outCp] from w[wK][wC][R][S]; mode 0 forward, 1 flipped + transposed (input gradient), 2 transposed
+        int launch_repack(const float* w, float* out, int wK, int wC, int R, int S, int outRows, int outCp, int mode, int x3, cudaStream_t st)
+        {
+            const int taps = R * S;
+            if (taps <= 32 && outCp % 32 == 0)
+            {
+                if (mode == 0)
+                {
+                    dim3 grid((unsigned)(outCp / 32), (unsigned)wK);
+                    repack_fwd_tiled_kernel<<<grid, 288, 32 * taps * sizeof(float), st>>>(w, out, wK, wC, taps, outCp, x3);
+                }
+                else
+                {
+                    dim3 grid((unsigned)ceil_div(outRows, 8), (unsigned)(outCp / 32));
+                    repack_dgrad_tiled_kernel<<<grid, 256, 32 * (8 * taps + 1) * sizeof(float), st>>>(w, out, wK, wC, R, S, outRows, outCp, mode == 1, x3);
+                }
+            }
+            else
+            {
+                const long long total = (long long)taps * outRows * outCp;
+                const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+                repack_filters_kernel<<<blocks, 256, 0, st>>>(w, out, wK, wC, R, S, outRows, outCp, mode, x3);
+            }
+            NB200_CUDA_TRY(cudaGetLastError());
+            count_launch();
+            return NB200_OK;
+        }
+
+        int launch_wgrad_reduce(const float* ws, float* dw, int K, int C, int taps, int splits, cudaStream_t st)
+        {
+            if (taps <= 32)
+            {
+                dim3 grid((unsigned)ceil_div(C, 32), (unsigned)K);
+                wgrad_reduce_tiled_kernel<<<grid, 288, 32 * taps * sizeof(float), st>>>(ws, dw, K, C, taps, splits);
+            }
+            else
+            {
+                const long long total = (long long)K * C * taps;
+                wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ws, dw, K, C, taps, splits);
+            }
+            NB200_CUDA_TRY(cudaGetLastError());
+            count_launch();
+            return NB200_OK;
+        }
+
         int run_fwd_shaped(const FwdShape& f, int repackMode, int wK, int wC, const float* in, const float* w, const float* bias, int act,
                            float alpha, float* out, void* ws, size_t wsBytes, cudaStream_t st)
         {
@@ -3053,11 +3187,8 @@ namespace nb200
             const int Cp = round_up(f.Cin, kBlockC);
             float* wr = (float*)ws;
             {
-                const long long total = (long long)f.R * f.S * f.Kout * Cp;
-                const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-                repack_filters_kernel<<<blocks, 256, 0, st>>>(w, wr, wK, wC, f.R, f.S, f.Kout, Cp, repackMode, f.x3);
-                NB200_CUDA_TRY(cudaGetLastError());
-        count_launch();
+                const int rc = launch_repack(w, wr, wK, wC, f.R, f.S, f.Kout, Cp, repackMode, f.x3, st);
+                if (rc) return rc;
             }
 
             CUtensorMap mapX, mapW;
@@ -3124,11 +3255,10 @@ namespace nb200
                 return fail(NB200_E_WORKSPACE, "tcgen05 gather conv needs %zu workspace bytes, got %zu", need, wsBytes);
             if ((uintptr_t)ws & 15)
                 return fail(NB200_E_INVALID, "workspace must be 16-byte aligned for TMA");
-            const long long total = (long long)R * S * Kout * Cp;
-            const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-            repack_filters_kernel<<<blocks, 256, 0, st>>>(w, (float*)ws, wK, wC, R, S, Kout, Cp, repackMode, 0);
-            NB200_CUDA_TRY(cudaGetLastError());
-            count_launch();
+            {
+                const int rc = launch_repack(w, (float*)ws, wK, wC, R, S, Kout, Cp, repackMode, 0, st);
+                if (rc) return rc;
+            }
             *BN = pick_bn(Kout);
             cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)Kout, (cuuint64_t)(R * S)};
             cuuint64_t strides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * Kout * 4};
@@ -3410,11 +3540,7 @@ namespace nb200
         p.rowBytes = (uint32_t)pl.PXI * 4; p.layoutType = pl.PXI == 32 ? 2u : pl.PXI == 16 ? 4u : 6u;
         int rc = pl.BN == 64 ? launch_wgather<64>(pl, mapDy, p, x, (float*)ws, st) : launch_wgather<128>(pl, mapDy, p, x, (float*)ws, st);
         if (rc) return rc;
-        const long long total = (long long)d.K * d.C * d.R * d.S;
-        wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)ws, dw, d.K, d.C, d.R * d.S, pl.splits);
-        NB200_CUDA_TRY(cudaGetLastError());
-        count_launch();
-        return NB200_OK;
+        return launch_wgrad_reduce((const float*)ws, dw, d.K, d.C, d.R * d.S, pl.splits, st);
     }
 
 
@@ -3614,11 +3740,7 @@ namespace nb200
         tc_wgrad_rowfold_kernel<<<(unsigned)(p.splits * p.tilesK), kThreads, smemBytes, st>>>(mapX, mapDy, p, (float*)ws);
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
-        const long long total = (long long)d.K * d.C * d.R * d.S;
-        wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)ws, dw, d.K, d.C, d.R * d.S, p.splits);
-        NB200_CUDA_TRY(cudaGetLastError());
-        count_launch();
-        return NB200_OK;
+        return launch_wgrad_reduce((const float*)ws, dw, d.K, d.C, d.R * d.S, p.splits, st);
     }
 
     int tc_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st)
@@ -3654,10 +3776,6 @@ namespace nb200
         int rc = pl.pack ? (pl.BN == 64 ? launch_wgrad<64, true>(pl, mapX, mapDy, p, (float*)ws, st) : launch_wgrad<128, true>(pl, mapX, mapDy, p, (float*)ws, st))
                          : (pl.BN == 64 ? launch_wgrad<64, false>(pl, mapX, mapDy, p, (float*)ws, st) : launch_wgrad<128, false>(pl, mapX, mapDy, p, (float*)ws, st));
         if (rc) return rc;
-        const long long total = (long long)d.K * d.C * d.R * d.S;
-        wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)ws, dw, d.K, d.C, d.R * d.S, pl.splits);
-        NB200_CUDA_TRY(cudaGetLastError());
-        count_launch();
-        return NB200_OK;
+        return launch_wgrad_reduce((const float*)ws, dw, d.K, d.C, d.R * d.S, pl.splits, st);
     }
 }
