@@ -80,3 +80,48 @@ def test_product_does_not_touch_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower().replace("# oracle-free", ""), os.path.join(dirpath, f)
     assert "oracle" not in open(os.path.join(ROOT, "include", "neuro_b200.h")).read().lower()
+
+
+def _desc(N, C, H, W, K, R, S, stride, padX, padY, fmt=lib.NCHW, math=lib.MATH_TF32):
+    Ho = (H + 2 * padY - R) // stride + 1
+    Wo = (W + 2 * padX - S) // stride + 1
+    return lib.ConvDesc(N, C, H, W, K, R, S, Ho, Wo, stride, padX, padY, fmt, math)
+
+
+def test_kernel_dispatch_is_host_logic(L):
+    """Which kernel family serves a shape is decided on the host (no GPU needed): pin it for the shapes BASELINE.json names,
+    so that a heuristic change that silently drops a layer off the tensor cores shows up in the CPU suite."""
+    L.nb200_conv2d_kernel_name.restype = ctypes.c_char_p
+
+    def names(d):
+        return [L.nb200_conv2d_kernel_name(op, ctypes.byref(d)).decode() for op in (lib.OP_FORWARD, lib.OP_INPUT_GRADIENT, lib.OP_KERNELS_GRADIENT)]
+
+    # VGG16 @ 512x512, batch 8 (bench workload)
+    assert names(_desc(8, 3, 512, 512, 64, 3, 3, 1, 1, 1)) == ["smallc_fprop", "smallc_dgrad", "tcgen05_smallc_wgrad"]
+    assert names(_desc(8, 64, 512, 512, 64, 3, 3, 1, 1, 1)) == ["tcgen05_rowtap_fprop", "tcgen05_rowtap_dgrad", "tcgen05_rowfold_wgrad"]
+    assert names(_desc(8, 64, 256, 256, 128, 3, 3, 1, 1, 1)) == ["tcgen05_fprop", "tcgen05_rowtap_dgrad", "tcgen05_rowfold_wgrad"]
+    for (C, K, HW) in [(128, 128, 256), (128, 256, 128), (256, 256, 128), (256, 512, 64), (512, 512, 64), (512, 512, 32)]:
+        assert names(_desc(8, C, HW, HW, K, 3, 3, 1, 1, 1)) == ["tcgen05_fprop", "tcgen05_dgrad", "tcgen05_wgrad"]
+    # DCGAN / pix2pix geometry: strided, tiny maps, transposed convolutions -> gathered tensor-core kernels
+    assert names(_desc(128, 64, 32, 32, 128, 3, 3, 2, 1, 1)) == ["tcgen05_gather_fprop", "tcgen05_gather_dgrad", "tcgen05_gather_wgrad"]
+    assert names(_desc(128, 128, 8, 8, 256, 4, 4, 2, 1, 1))[0].startswith("tcgen05_gather")
+    # 3xTF32: forward / input gradient stay on tensor cores (no row-tap), kernel gradient on fp32 CUDA cores
+    n3 = names(_desc(8, 64, 512, 512, 64, 3, 3, 1, 1, 1, math=lib.MATH_3XTF32))
+    assert n3[0] == "tcgen05_fprop" and n3[1] == "tcgen05_dgrad" and n3[2] == "direct_wgrad"
+    # fp32 math and NHWC never touch the tensor-core families
+    assert all(n.startswith("direct_") for n in names(_desc(8, 64, 64, 64, 64, 3, 3, 1, 1, 1, math=lib.MATH_FP32)))
+    assert all(n.startswith("direct_") for n in names(_desc(8, 64, 64, 64, 64, 3, 3, 1, 1, 1, fmt=lib.NHWC)))
+
+
+def test_workspace_sizes_cover_every_kernel_of_an_op(L):
+    """nb200_conv2d_workspace_bytes must cover whichever kernel the dispatcher picks (filter repack for forward / input
+    gradient, split-K partials for the kernel gradient)."""
+    L.nb200_conv2d_workspace_bytes.restype = ctypes.c_size_t
+    d = _desc(8, 64, 512, 512, 64, 3, 3, 1, 1, 1)
+    fwd = L.nb200_conv2d_workspace_bytes(lib.OP_FORWARD, ctypes.byref(d))
+    assert fwd >= 3 * 192 * 64 * 4 and fwd >= 9 * 64 * 64 * 4        # row-tap layout and the generic [tap][k][c] layout
+    wg = L.nb200_conv2d_workspace_bytes(lib.OP_KERNELS_GRADIENT, ctypes.byref(d))
+    assert wg >= 147 * 9 * 64 * 64 * 4                                # one partial per CTA of the row-fold kernel (4096 rows / 28)
+    d0 = _desc(8, 3, 512, 512, 64, 3, 3, 1, 1, 1)
+    assert L.nb200_conv2d_workspace_bytes(lib.OP_KERNELS_GRADIENT, ctypes.byref(d0)) >= 148 * 128 * 32 * 4
+    assert L.nb200_conv2d_workspace_bytes(lib.OP_FORWARD, ctypes.byref(d0)) == 0
