@@ -109,6 +109,11 @@ namespace nb200
             float alpha;
             long long yStrideN, yStrideK; // elements
             long long* dbg;               // wait-time instrumentation sink or nullptr
+            // channel split (tc_fprop_kernel only): CTA sp of a tile reduces channel blocks [sp * cbPer, ...) and writes a raw
+            // partial to partial + sp * partialStride; fprop_split_reduce_kernel adds them, then bias and activation
+            int splits, cbPer;
+            float* partial;
+            long long partialStride;
         };
 
         // ---------------------------------------------------------------- filter repack
@@ -319,6 +324,9 @@ namespace nb200
 
             // tile coordinates: filter tile fastest so CTAs sharing the same activation tile run together (L2 reuse)
             int t = blockIdx.x;
+            const int sp = t % p.splits; t /= p.splits;           // channel split: this CTA's share of the reduction
+            const int cbBegin = sp * p.cbPer;
+            const int cbCount = min(p.cbPer, p.Cblocks - cbBegin);
             const int kt = t % p.tilesK; t /= p.tilesK;
             const int tw = t % p.tilesW; t /= p.tilesW;
             const int th = t % p.tilesH; t /= p.tilesH;
@@ -364,14 +372,14 @@ namespace nb200
                     // ===== TMA producer (filters): one tile per (channel block, tap) =====
                     int bs = 0;
                     uint32_t bph = 0;
-                    for (int cb = 0; cb < p.Cblocks; ++cb)
+                    for (int cb = 0; cb < cbCount; ++cb)
                         for (int tap = 0; tap < taps; ++tap)
                         {
                             timed_wait(&bEmpty[bs], bph ^ 1, dbgP, kDbgBEmpty);
                             ptx::mbar_arrive_expect_tx(&bFull[bs], kBBytes);
-                            ptx::tma_load_3d(bRing + bs * kBBytes, &mapW, &bFull[bs], cb * kBlockC, k0, tap);
+                            ptx::tma_load_3d(bRing + bs * kBBytes, &mapW, &bFull[bs], (cbBegin + cb) * kBlockC, k0, tap);
                             if (X3) // lo parts live behind the hi parts in the repacked tensor (tap index + taps)
-                                ptx::tma_load_3d(bRing + bs * kBBytes + kBTile, &mapW, &bFull[bs], cb * kBlockC, k0, taps + tap);
+                                ptx::tma_load_3d(bRing + bs * kBBytes + kBTile, &mapW, &bFull[bs], (cbBegin + cb) * kBlockC, k0, taps + tap);
                             if (++bs == p.bStages) { bs = 0; bph ^= 1; }
                         }
                 }
@@ -383,12 +391,12 @@ namespace nb200
                     // ===== TMA producer (activations): one halo tile per channel block, independent of the filter ring =====
                     int xs = 0;
                     uint32_t xph = 0;
-                    for (int cb = 0; cb < p.Cblocks; ++cb)
+                    for (int cb = 0; cb < cbCount; ++cb)
                     {
                         timed_wait(&xEmpty[xs], xph ^ 1, dbgX, kDbgXEmpty);
                         ptx::mbar_arrive_expect_tx(&xFull[xs], xBytes);
                         // x viewed as (W, H, C, N); origin 16-byte aligned in W; out-of-bounds elements read as 0 (= zero padding)
-                        ptx::tma_load_4d(xRing + xs * xBytesPad, &mapX, &xFull[xs], ow0 - p.wOff, oh0 - p.padY, cb * kBlockC, n);
+                        ptx::tma_load_4d(xRing + xs * xBytesPad, &mapX, &xFull[xs], ow0 - p.wOff, oh0 - p.padY, (cbBegin + cb) * kBlockC, n);
                         if (++xs == p.xStages) { xs = 0; xph ^= 1; }
                     }
                 }
@@ -402,7 +410,7 @@ namespace nb200
                 const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(bRing), /*LBO*/ 16, /*SBO*/ 1024);
                 int as = 0, bs = 0;
                 uint32_t aph = 0, bph = 0;
-                const int iters = taps * p.Cblocks;
+                const int iters = taps * cbCount;
                 const long long tLoop = dbgM.sink ? clock64() : 0;
                 int tapc = 0, cbc = 0; // position inside the current channel block (3xTF32 drains the accumulator per block)
                 for (int it = 0; it < iters; ++it)
@@ -469,7 +477,7 @@ namespace nb200
                         for (int j = 0; j < 32; ++j)
                             racc[ch][j] = 0.f;
                 }
-                for (int cb = 0; cb < p.Cblocks; ++cb)
+                for (int cb = 0; cb < cbCount; ++cb)
                 {
                     const int xs = cb % p.xStages;
                     timed_wait(xFull32 + 8u * xs, (uint32_t)(cb / p.xStages) & 1, dbgC, kDbgXFull);
@@ -599,10 +607,12 @@ namespace nb200
                     ptx::tc_fence_after_sync();
                 }
                 const bool pixelOk = oh < p.Ho && ow < p.Wo;
-                float* yp = y + n * p.yStrideN + (long long)oh * p.Wo + ow;
+                const bool split = p.splits > 1; // raw partial sums; bias and activation wait for the reduce kernel
+                float* yp = (split ? p.partial + sp * p.partialStride : y) + n * p.yStrideN + (long long)oh * p.Wo + ow;
                 // bias + activation + one full 128-byte line per store instruction (lanes = 32 consecutive output columns)
                 auto store_chunk = [&](int c0, const uint32_t (&v)[32]) {
-                    nb200::store_chunk(yp, p.yStrideK, k0 + c0, p.K, bias, lane, p.act, p.alpha, pixelOk, v);
+                    nb200::store_chunk(yp, p.yStrideK, k0 + c0, p.K, split ? nullptr : bias, lane, split ? (int)NB200_ACT_IDENTITY : p.act, p.alpha,
+                                       pixelOk, v);
                 };
                 if (X3)
                 {
@@ -2827,6 +2837,21 @@ namespace nb200
             dw[i] = acc;
         }
 
+        // y = activation(sum over channel splits of partial + bias): the second pass of a channel-split forward call
+        __global__ void fprop_split_reduce_kernel(const float* __restrict__ partial, long long stride, int splits, const float* __restrict__ bias,
+                                                  int act, float alpha, float* __restrict__ y, long long total, long long plane, int K)
+        {
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+            {
+                float acc = 0.f;
+                for (int sp = 0; sp < splits; ++sp)
+                    acc += partial[sp * stride + i];
+                if (bias)
+                    acc += __ldg(bias + (int)((i / plane) % K));
+                y[i] = apply_activation(act, alpha, acc);
+            }
+        }
+
         // ---------------------------------------------------------------- host side
         typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -2880,6 +2905,7 @@ namespace nb200
             int BN, wOff, WB, HR, xStages, bStages;
             bool pair; // CTA-pair (cta_group::2) kernel
             bool m256; // 256-pixel tile: two M halves share each filter tile (one CTA per SM)
+            int splits, cbPer; // channel split for grids that leave most SMs idle (small batches, small maps)
             size_t smemBytes;
             bool ok;
         };
@@ -2920,6 +2946,22 @@ namespace nb200
             // Grids of at most one CTA per SM (small batches, small maps) are latency-bound on the filter ring -- nothing else
             // on the SM hides a TMA round trip -- so they take the whole shared memory for a deeper ring.
             const long long ctasTotal = (long long)f.N * ceil_div(f.Hout, kTileH) * ceil_div(f.Wout, kTileW) * ceil_div(f.Kout, pl.BN);
+            {
+                // Too few tiles for the chip (batch-1 style transfer on the deep 32x32 / 64x64 layers): split the channel blocks
+                // of every tile over several CTAs; each writes a raw partial and a second kernel adds them in fixed order.
+                static const char* env = getenv("NB200_FPROP_SPLIT"); // 0 disables (profiling)
+                const int Cblocks = round_up(f.Cin, kBlockC) / kBlockC;
+                pl.splits = 1;
+                if (!f.x3 && !pl.pair && !pl.m256 && ctasTotal <= 74 && Cblocks >= 4 && !(env && env[0] == '0'))
+                {
+                    int want = (int)(148 / ctasTotal);
+                    if (want > Cblocks / 2) want = Cblocks / 2;
+                    if (want > 8) want = 8;
+                    if (want > 1) pl.splits = want;
+                }
+                pl.cbPer = ceil_div(Cblocks, pl.splits);
+                pl.splits = ceil_div(Cblocks, pl.cbPer);
+            }
             const long long budget = (pl.BN > 128 || f.x3 || pl.m256 || ctasTotal <= 148) ? kSmemBudget1 : kSmemBudget2;
             pl.ok = false;
             // prefer two (three when alone on the SM) halo stages; give the rest to the filter ring (at least 2, at most 8)
@@ -2962,7 +3004,7 @@ namespace nb200
                 NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1));
                 attrSet = true;
             }
-            const long long tiles = (long long)p.tilesK * p.tilesW * p.tilesH * f.N;
+            const long long tiles = (long long)p.tilesK * p.tilesW * p.tilesH * f.N * p.splits;
             if (tiles > 0x3FFFFFFFll)
                 return fail(NB200_E_UNSUPPORTED, "too many tiles");
             static const bool debugWaits = getenv("NB200_DEBUG_WAITS") != nullptr;
@@ -3175,14 +3217,16 @@ namespace nb200
         {
             if (rowtap_wanted(f))
                 return run_rowtap(f, repackMode, wK, wC, in, w, bias, act, alpha, out, ws, wsBytes, st);
-            const size_t need = repack_bytes(f);
+            const Plan pl = make_plan(f);
+            if (!pl.ok)
+                return fail(NB200_E_UNSUPPORTED, "no shared-memory plan for this filter size");
+            const size_t repackBytes = (repack_bytes(f) + 255) & ~(size_t)255;
+            const long long outElems = (long long)f.N * f.Kout * f.Hout * f.Wout;
+            const size_t need = repackBytes + (pl.splits > 1 ? (size_t)pl.splits * outElems * sizeof(float) : 0);
             if (wsBytes < need || !ws)
                 return fail(NB200_E_WORKSPACE, "tcgen05 conv needs %zu workspace bytes, got %zu", need, wsBytes);
             if (((uintptr_t)in & 15) || ((uintptr_t)ws & 15))
                 return fail(NB200_E_INVALID, "tensor base addresses must be 16-byte aligned for TMA");
-            const Plan pl = make_plan(f);
-            if (!pl.ok)
-                return fail(NB200_E_UNSUPPORTED, "no shared-memory plan for this filter size");
 
             const int Cp = round_up(f.Cin, kBlockC);
             float* wr = (float*)ws;
@@ -3217,11 +3261,20 @@ namespace nb200
             p.act = act; p.alpha = alpha; p.dbg = nullptr;
             p.yStrideK = (long long)f.Hout * f.Wout;
             p.yStrideN = p.yStrideK * f.Kout;
+            p.splits = pl.splits; p.cbPer = pl.cbPer;
+            p.partial = (float*)((uint8_t*)ws + repackBytes); p.partialStride = outElems;
             if (f.x3)
                 return pl.BN == 64 ? launch_fprop<64, true>(f, pl, mapX, mapW, p, bias, out, st) : launch_fprop<128, true>(f, pl, mapX, mapW, p, bias, out, st);
-            return pl.BN == 64 ? launch_fprop<64, false>(f, pl, mapX, mapW, p, bias, out, st)
-                 : pl.BN == 128 ? launch_fprop<128, false>(f, pl, mapX, mapW, p, bias, out, st)
-                                : launch_fprop<256, false>(f, pl, mapX, mapW, p, bias, out, st);
+            const int rc = pl.BN == 64 ? launch_fprop<64, false>(f, pl, mapX, mapW, p, bias, out, st)
+                         : pl.BN == 128 ? launch_fprop<128, false>(f, pl, mapX, mapW, p, bias, out, st)
+                                        : launch_fprop<256, false>(f, pl, mapX, mapW, p, bias, out, st);
+            if (rc || pl.splits == 1)
+                return rc;
+            const int blocks = (int)((outElems + 255) / 256 > 148 * 8 ? 148 * 8 : (outElems + 255) / 256);
+            fprop_split_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, outElems, pl.splits, bias, act, alpha, out, outElems, p.yStrideK, f.Kout);
+            NB200_CUDA_TRY(cudaGetLastError());
+            count_launch();
+            return NB200_OK;
         }
 
 
@@ -3636,7 +3689,14 @@ namespace nb200
 
     static size_t fwd_ws_bytes(const FwdShape& f)
     {
-        const size_t a = repack_bytes(f), b = rowtap_wanted(f) ? rowtap_bytes(f) : 0;
+        size_t a = repack_bytes(f);
+        if (shape_ok(f))
+        {
+            const Plan pl = make_plan(f);
+            if (pl.ok && pl.splits > 1) // channel-split forward: partials behind the (256-byte aligned) repacked filters
+                a = ((a + 255) & ~(size_t)255) + (size_t)pl.splits * f.N * f.Kout * f.Hout * f.Wout * sizeof(float);
+        }
+        const size_t b = rowtap_wanted(f) ? rowtap_bytes(f) : 0;
         return a > b ? a : b;
     }
 

@@ -92,6 +92,9 @@ TC_CASES = [
     (0, 4, 32, 16, 64, 16, 1, 3, 1, 1, 0),     # one filter row
     (0, 3, 64, 37, 40, 64, 3, 3, 1, 1, 1),     # rows split across images mid-run (3 x 37 rows over 111 CTAs), ragged segment
     (0, 1, 128, 24, 32, 32, 5, 5, 1, 2, 2),    # 5 columns with > 64 channels: 5 A tiles per step, kernel gradient must take the gathered kernel
+    # channel-split forward / input gradient (few tiles, many channels: batch-1 style transfer on the deep layers)
+    (0, 1, 256, 32, 32, 128, 3, 3, 1, 1, 1),   # 8 tiles x 4 channel splits (forward), 16 tiles x 2 splits (input gradient)
+    (0, 1, 160, 32, 64, 96, 3, 3, 1, 1, 1),    # 5 channel blocks: uneven split 3 + 2
 ]
 
 
@@ -113,7 +116,7 @@ def test_against_oracle(cfg, math):
 @pytest.mark.parametrize("act", [lib.ACT_IDENTITY, lib.ACT_SIGMOID, lib.ACT_RELU, lib.ACT_TANH, lib.ACT_ELU, lib.ACT_LEAKY_RELU])
 def test_bias_activation(act, math):
     """Conv2DBiasActivation (TensorOpGpuTests.cpp:1238-1252 uses ReLU; all epilogues are covered here)."""
-    for (N, C, H, W, K, F, st, p) in [(3, 3, 26, 26, 2, 3, 1, 0), (2, 64, 32, 32, 64, 3, 1, 1), (2, 32, 48, 96, 40, 3, 1, 1)]:
+    for (N, C, H, W, K, F, st, p) in [(3, 3, 26, 26, 2, 3, 1, 0), (2, 64, 32, 32, 64, 3, 1, 1), (2, 32, 48, 96, 40, 3, 1, 1), (1, 256, 32, 32, 72, 3, 1, 1)]:
         x = synth.uniform(synth.SEED_X, (N, C, H, W)); w = synth.glorot_uniform(synth.SEED_W, K, C, F, F)
         b = synth.uniform(synth.SEED_BIAS, (K,))
         ref = O.conv2d_bias_activation(x, w, b, st, p, act, 0.2)
