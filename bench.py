@@ -394,12 +394,103 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary() if sampler else None,
         }
+        if world == 1 and not args.no_extras:
+            line["style_transfer_batch1"] = style_transfer_pass()
+            line["style_transfer_batch1"]["frac_of_tf32_peak"] = line["style_transfer_batch1"]["tflops"] / tf32_peak
+            line["neighbours"] = neighbour_pass(B)
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_run(1, 1, 64)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def style_transfer_pass(iters=30):
+    """BASELINE configs[2] as the reference runs it: ONE image, frozen VGG16 weights, per iteration the forward
+    of the 13 conv layers (bias + ReLU fused) and then the input gradient of each back to the image -- no kernel gradient.
+    Constant weights => filters prepared once (nb200_conv2d_prepare_filters); the 26-launch chain is launch-latency
+    sensitive at batch 1 => also replayed as one CUDA graph. Returns ms per image for the three ways of issuing it."""
+    import torch
+    from neuro__b200 import lib, synth
+    from neuro__b200.tensor_op import TensorOpB200
+    dev = torch.device("cuda", torch.cuda.current_device())
+    op = TensorOpB200(lib.MATH_TF32)
+    gen = torch.Generator(device=dev); gen.manual_seed(synth.SEED_MODEL)
+    L = []
+    for (C, K, HW) in VGG16:
+        limit = (6.0 / (C * F * F + K * F * F)) ** 0.5
+        w = (torch.rand(K, C, F, F, device=dev, generator=gen) * 2 - 1) * limit
+        x = torch.rand(1, C, HW, HW, device=dev, generator=gen) * 2 - 1
+        dy = torch.rand(1, K, HW, HW, device=dev, generator=gen) * 2 - 1
+        L.append(dict(w=w, x=x, dy=dy, y=torch.empty(1, K, HW, HW, device=dev), dx=torch.empty(1, C, HW, HW, device=dev),
+                      bias=torch.zeros(K, device=dev)))
+    for l in L:
+        l["pf"] = op.PrepareKernels(lib.OP_FORWARD, l["x"], l["w"], l["y"], STRIDE, PAD, PAD)
+        l["pg"] = op.PrepareKernels(lib.OP_INPUT_GRADIENT, l["dx"], l["w"], l["dy"], STRIDE, PAD, PAD)
+
+    def chain(prepared):
+        for l in L:
+            op.Conv2DBiasActivation(l["x"], l["w"], STRIDE, PAD, PAD, l["bias"], lib.ACT_RELU, 0.0, l["y"], prepared=l["pf"] if prepared else None)
+        for l in reversed(L):
+            op.Conv2DInputGradient(l["dy"], l["w"], STRIDE, PAD, PAD, lib.NCHW, l["dx"], prepared=l["pg"] if prepared else None)
+
+    def time_it(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out = {"per_call_repack_ms": time_it(lambda: chain(False)), "prepared_filters_ms": time_it(lambda: chain(True))}
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            chain(True)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            chain(True)
+        out["prepared_filters_cuda_graph_ms"] = time_it(g.replay)
+    except Exception as e:  # noqa: BLE001 -- the graph is an extra; the two numbers above stand without it
+        out["prepared_filters_cuda_graph_ms"] = None
+        out["cuda_graph_error"] = str(e)[:200]
+        torch.cuda.synchronize()
+    best = min(v for k, v in out.items() if k.endswith("_ms") and v)
+    out["gflop_per_image"] = 2 * SAMPLE_FLOPS_PER_OP / 1e9
+    out["tflops"] = 2 * SAMPLE_FLOPS_PER_OP / (best * 1e-3) / 1e12
+    out["workload"] = "VGG16 @512x512x3, batch 1: 13 x forward(bias+ReLU) + 13 x input gradient, frozen weights"
+    return out
+
+
+def neighbour_pass(batch, iters=20):
+    """The HBM-bound backward prologue next to the conv ops: dz = relu'(y)*dy and db = sum(dz) in one
+    pass (nb200_conv2d_bias_activation_gradient) on VGG16 block1's activation (batch x 64 x 512 x 512). Algorithmic bytes =
+    12 per element (read y, read dy, write dz)."""
+    import torch
+    from neuro__b200 import lib
+    from neuro__b200.tensor_op import TensorOpB200
+    op = TensorOpB200()
+    y = torch.rand(batch, 64, 512, 512, device="cuda") - 0.5; dy = torch.rand_like(y); dz = torch.empty_like(y)
+    db = torch.empty(64, device="cuda")
+    for _ in range(3):
+        op.Conv2DBiasActivationGradient(y, dy, lib.ACT_RELU, 0.0, dz, db)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        op.Conv2DBiasActivationGradient(y, dy, lib.ACT_RELU, 0.0, dz, db)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    peaks = read_peaks()
+    gbs = 12.0 * y.numel() / (ms * 1e-3) / 1e9
+    return {"kernel": "act_bias_gradient_kernel (relu'(y)*dy + bias gradient, one pass)", "ms": ms, "achieved_gbs": gbs,
+            "peak_gbs": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"], "bytes": 12.0 * y.numel()}
 
 
 def main():
@@ -410,6 +501,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="images per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the batch-1 style-transfer and neighbour-kernel passes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -127,6 +127,34 @@ NB200_API int nb200_conv2d_kernels_gradient(const nb200_conv_desc* d, const floa
  * TensorOpCpu.cpp:1065 = Sum over _013Axes). Only N,K,Ho,Wo,fmt of the descriptor are read. */
 NB200_API int nb200_conv2d_bias_gradient(const nb200_conv_desc* d, const float* dy, float* db, void* stream);
 
+/* Backward prologue of the fused bias+activation convolution, Conv2dBiasActivationOp::ComputeGradientInternal
+ * (Neuro/src/ComputationalGraph/Operations/Conv2dBiasActivationOp.cpp:47-60), in one pass over HBM:
+ *   dz = act'(y) * dy   -- Tensor::ActivationGradient -> TensorOpCpu::{Sigmoid,Tanh,ReLU,Elu,LeakyReLU}Gradient
+ *                          (TensorOpCpu.cpp:813-864; the derivative is taken through the OUTPUT y, as there);
+ *   db[k] = sum_{n,ho,wo} dz   -- TensorOpCpu::Conv2DBiasGradient (TensorOpCpu.cpp:1065-1068); db may be NULL.
+ * dz is then the `gradient` argument of nb200_conv2d_input_gradient / nb200_conv2d_kernels_gradient.
+ * y, dy, dz have extent (N,K,Ho,Wo) in d->fmt; only N,K,Ho,Wo,fmt of the descriptor are read. dz must not alias y/dy.
+ * Workspace: nb200_conv2d_bias_activation_gradient_workspace_bytes (per-block partial sums, added in fixed order). */
+NB200_API size_t nb200_conv2d_bias_activation_gradient_workspace_bytes(const nb200_conv_desc* d);
+NB200_API int nb200_conv2d_bias_activation_gradient(const nb200_conv_desc* d, int32_t act, float alpha, const float* y,
+                                                    const float* dy, float* dz, float* db, void* workspace,
+                                                    size_t workspace_bytes, void* stream);
+
+/* Filters that do not change between calls (inference; style transfer runs forward and input gradient against frozen
+ * VGG weights, Neuro.Examples/include/NeuralStyleTransfer.h). The tensor-core kernels read the filters from a repacked
+ * TF32 copy at the head of the workspace; nb200_conv2d_forward / _input_gradient rebuild it on every call because the
+ * reference interface cannot tell them the filters are unchanged. nb200_conv2d_prepare_filters builds it once into a
+ * workspace the caller dedicates to this (op, descriptor, w) -- size nb200_conv2d_workspace_bytes(op, d) -- and the
+ * *_prepared calls skip the repack launch. op: NB200_OP_FORWARD or NB200_OP_INPUT_GRADIENT. Kernel families that read
+ * w directly (first-layer and fp32 kernels) make prepare a no-op, so w must stay valid and unchanged either way. */
+NB200_API int nb200_conv2d_prepare_filters(int32_t op, const nb200_conv_desc* d, const float* w, void* workspace,
+                                           size_t workspace_bytes, void* stream);
+NB200_API int nb200_conv2d_forward_prepared(const nb200_conv_desc* d, const float* x, const float* w, const float* bias,
+                                            int32_t act, float alpha, float* y, void* workspace, size_t workspace_bytes,
+                                            void* stream);
+NB200_API int nb200_conv2d_input_gradient_prepared(const nb200_conv_desc* d, const float* dy, const float* w, float* dx,
+                                                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* Optimiser updates that follow the gradient exchange in data-parallel Fit().
  * Replace TensorOpCpu::AdamStep / SgdStep (TensorOpCpu.h:75-76, TensorOpCpu.cpp:987-1009), with the
  * 1/replicas scaling of an all-reduced (summed) gradient folded in as grad_scale:

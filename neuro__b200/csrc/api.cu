@@ -272,6 +272,81 @@ extern "C"
         return bias_gradient(*d, dy, db, (cudaStream_t)stream);
     }
 
+    size_t nb200_conv2d_bias_activation_gradient_workspace_bytes(const nb200_conv_desc* d)
+    {
+        if (!d || d->N < 0 || d->K < 0 || d->Ho < 0 || d->Wo < 0)
+            return 0;
+        return bias_activation_gradient_workspace(*d);
+    }
+
+    int nb200_conv2d_bias_activation_gradient(const nb200_conv_desc* d, int32_t act, float alpha, const float* y, const float* dy,
+                                              float* dz, float* db, void* workspace, size_t workspace_bytes, void* stream)
+    {
+        if (!d || d->N < 0 || d->K < 0 || d->Ho < 0 || d->Wo < 0 || (d->fmt != NB200_NCHW && d->fmt != NB200_NHWC))
+            return fail(NB200_E_INVALID, "bad descriptor");
+        if (act < NB200_ACT_IDENTITY || act > NB200_ACT_LEAKY_RELU)
+            return fail(NB200_E_INVALID, "activation %d has no gradient here", act);
+        const long long n = (long long)d->N * d->K * d->Ho * d->Wo;
+        if (n > 0 && (!y || !dy || !dz))
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        int rc = require_device();
+        if (rc) return rc;
+        if (n == 0)
+        {
+            if (db && d->K > 0)
+                NB200_CUDA_TRY(cudaMemsetAsync(db, 0, d->K * sizeof(float), (cudaStream_t)stream)); // sum over nothing
+            return NB200_OK;
+        }
+        return bias_activation_gradient(*d, act, alpha, y, dy, dz, db, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
+
+    namespace
+    {
+        struct FilterModeScope
+        {
+            explicit FilterModeScope(int m) { g_tcFilterMode = m; }
+            ~FilterModeScope() { g_tcFilterMode = kFiltersRepack; }
+        };
+    }
+
+    int nb200_conv2d_prepare_filters(int32_t op, const nb200_conv_desc* d, const float* w, void* workspace, size_t workspace_bytes,
+                                     void* stream)
+    {
+        if (op != NB200_OP_FORWARD && op != NB200_OP_INPUT_GRADIENT)
+            return fail(NB200_E_INVALID, "filters are prepared for the forward or the input-gradient op");
+        int rc = validate(d, op);
+        if (rc) return rc;
+        if (empty_out(*d, op) || (long long)d->K * d->C == 0)
+            return NB200_OK;
+        if (!w)
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        if ((rc = require_device())) return rc;
+        const Family f = pick(op, *d);
+        if (f != kTc && f != kGather)
+            return NB200_OK; // these kernels read w as it is
+        FilterModeScope scope(kFiltersOnly);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (op == NB200_OP_FORWARD)
+            return f == kTc ? tc_forward(*d, nullptr, w, nullptr, NB200_ACT_IDENTITY, 0.f, nullptr, workspace, workspace_bytes, st)
+                            : tc_gather_forward(*d, nullptr, w, nullptr, NB200_ACT_IDENTITY, 0.f, nullptr, workspace, workspace_bytes, st);
+        return f == kTc ? tc_input_gradient(*d, nullptr, w, nullptr, workspace, workspace_bytes, st)
+                        : tc_gather_input_gradient(*d, nullptr, w, nullptr, workspace, workspace_bytes, st);
+    }
+
+    int nb200_conv2d_forward_prepared(const nb200_conv_desc* d, const float* x, const float* w, const float* bias, int32_t act,
+                                      float alpha, float* y, void* workspace, size_t workspace_bytes, void* stream)
+    {
+        FilterModeScope scope(kFiltersReady);
+        return nb200_conv2d_forward(d, x, w, bias, act, alpha, y, workspace, workspace_bytes, stream);
+    }
+
+    int nb200_conv2d_input_gradient_prepared(const nb200_conv_desc* d, const float* dy, const float* w, float* dx, void* workspace,
+                                             size_t workspace_bytes, void* stream)
+    {
+        FilterModeScope scope(kFiltersReady);
+        return nb200_conv2d_input_gradient(d, dy, w, dx, workspace, workspace_bytes, stream);
+    }
+
     int nb200_adam_step(float* param, const float* grad, float* m, float* v, size_t count, float grad_scale, float lr, float beta1,
                         float beta2, float epsilon, void* stream)
     {

@@ -96,6 +96,11 @@ namespace nb200
     int tc_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes,
                             cudaStream_t st);
 
+    // What the forward / input-gradient launchers do about the repacked filters at the head of the workspace:
+    // repack on every call (default), trust what nb200_conv2d_prepare_filters left there, or repack and return.
+    enum { kFiltersRepack = 0, kFiltersReady = 1, kFiltersOnly = 2 };
+    extern thread_local int g_tcFilterMode;
+
     // gathered-A tensor-core kernel: any stride / padding / map size, forward and input gradient. conv_tc.cu
     bool tc_gather_forward_supported(const nb200_conv_desc& d);
     bool tc_gather_input_gradient_supported(const nb200_conv_desc& d);
@@ -112,6 +117,10 @@ namespace nb200
 
     // elementwise.cu
     int bias_gradient(const nb200_conv_desc& d, const float* dy, float* db, cudaStream_t st);
+    // dz = act'(y) * dy and (optionally) db = sum over N,H,W of dz, one pass over HBM
+    size_t bias_activation_gradient_workspace(const nb200_conv_desc& d);
+    int bias_activation_gradient(const nb200_conv_desc& d, int act, float alpha, const float* y, const float* dy, float* dz, float* db,
+                                 void* ws, size_t wsBytes, cudaStream_t st);
     int adam_step(float* p, const float* g, float* m, float* v, size_t n, float gs, float lr, float b1, float b2, float eps,
                   cudaStream_t st);
     int sgd_step(float* p, const float* g, size_t n, float gs, float lr, cudaStream_t st);

@@ -31,6 +31,8 @@
 
 namespace nb200
 {
+    thread_local int g_tcFilterMode = kFiltersRepack; // set by the *_prepared / prepare_filters entry points (api.cu)
+
     namespace
     {
         constexpr int kTileW = 32;   // output columns per tile (= lanes of a converter warp)
@@ -3101,6 +3103,7 @@ namespace nb200
             const int ktiles = ceil_div(f.Kout, kRtBNK);
             const int rowsPerR = ktiles * kRtN;
             float* wr = (float*)ws;
+            if (g_tcFilterMode != kFiltersReady)
             {
                 const long long total = (long long)f.R * rowsPerR * Cp;
                 const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
@@ -3108,6 +3111,8 @@ namespace nb200
                 NB200_CUDA_TRY(cudaGetLastError());
                 count_launch();
             }
+            if (g_tcFilterMode == kFiltersOnly)
+                return NB200_OK;
             RowtapParams p;
             p.Cblocks = Cp / kBlockC; p.R = f.R; p.padX = f.padX; p.padY = f.padY; p.HR = kTileH + f.R - 1;
             const size_t xBytes = ((size_t)kBlockC * p.HR * kRtWB * 4 + 1023) & ~(size_t)1023;
@@ -3170,6 +3175,8 @@ namespace nb200
         // out[tap][outRows][outCp] from w[wK][wC][R][S]; mode 0 forward, 1 flipped + transposed (input gradient), 2 transposed
         int launch_repack(const float* w, float* out, int wK, int wC, int R, int S, int outRows, int outCp, int mode, int x3, cudaStream_t st)
         {
+            if (g_tcFilterMode == kFiltersReady)
+                return NB200_OK; // the caller's workspace already holds this layer's repacked filters (nb200_conv2d_prepare_filters)
             const int taps = R * S;
             if (taps <= 32 && outCp % 32 == 0)
             {
@@ -3234,6 +3241,8 @@ namespace nb200
                 const int rc = launch_repack(w, wr, wK, wC, f.R, f.S, f.Kout, Cp, repackMode, f.x3, st);
                 if (rc) return rc;
             }
+            if (g_tcFilterMode == kFiltersOnly)
+                return NB200_OK;
 
             CUtensorMap mapX, mapW;
             {
@@ -3442,6 +3451,7 @@ namespace nb200
         int BN, bStages, Cblocks;
         int rc = gather_prepare(d.K, d.C, d.R, d.S, 0, d.K, d.C, w, ws, wsBytes, st, &mapW, &BN, &bStages, &Cblocks);
         if (rc) return rc;
+        if (g_tcFilterMode == kFiltersOnly) return NB200_OK;
         GatherParams p{};
         p.Cblocks = Cblocks; p.ntaps = d.R * d.S;
         p.C = d.C; p.H = d.H; p.W = d.W; p.K = d.K; p.Ho = d.Ho; p.Wo = d.Wo;
@@ -3464,6 +3474,7 @@ namespace nb200
         int BN, bStages, Cblocks;
         int rc = gather_prepare(d.C, d.K, d.R, d.S, 2, d.K, d.C, w, ws, wsBytes, st, &mapW, &BN, &bStages, &Cblocks);
         if (rc) return rc;
+        if (g_tcFilterMode == kFiltersOnly) return NB200_OK;
         const int st2 = d.stride;
         for (int ph = 0; ph < st2; ++ph)
             for (int pw = 0; pw < st2; ++pw)

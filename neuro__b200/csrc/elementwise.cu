@@ -49,6 +49,150 @@ namespace nb200
             }
         }
 
+        // Derivative of the activation expressed through its OUTPUT, times the incoming gradient, exactly as the reference
+        // evaluates it (TensorOpCpu.cpp:813-864: SigmoidGradient, TanhGradient, ReLUGradient, EluGradient, LeakyReLUGradient).
+        template <int ACT>
+        __device__ __forceinline__ float activation_gradient(float y, float g, float alpha)
+        {
+            // explicit round-to-nearest steps: no FMA contraction, so the result is bit-identical to the reference's fp32 loop
+            if (ACT == NB200_ACT_SIGMOID) return __fmul_rn(__fmul_rn(y, __fsub_rn(1.f, y)), g);
+            if (ACT == NB200_ACT_RELU) return y > 0.f ? g : 0.f;
+            if (ACT == NB200_ACT_TANH) return __fmul_rn(__fsub_rn(1.f, __fmul_rn(y, y)), g);
+            if (ACT == NB200_ACT_ELU) return __fmul_rn(y > 0.f ? 1.f : __fadd_rn(y, alpha), g);
+            if (ACT == NB200_ACT_LEAKY_RELU) return __fmul_rn(y > 0.f ? 1.f : alpha, g);
+            return g;
+        }
+
+        constexpr int kAgThreads = 256;
+        constexpr int kAgSeg = 8192; // elements of one (n, k) plane handled by one block: 8 float4 per thread
+
+        __device__ __forceinline__ float block_sum_256(float acc)
+        {
+            __shared__ float red[kAgThreads / 32];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if ((threadIdx.x & 31) == 0)
+                red[threadIdx.x >> 5] = acc;
+            __syncthreads();
+            float v = threadIdx.x < kAgThreads / 32 ? red[threadIdx.x] : 0.f;
+            if (threadIdx.x < 32)
+            {
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1)
+                    v += __shfl_xor_sync(0xffffffffu, v, o);
+            }
+            return v; // valid in thread 0
+        }
+
+        // Backward prologue of Conv2dBiasActivationOp (Conv2dBiasActivationOp.cpp:47-60) in ONE pass over HBM:
+        //   dz = act'(y) * dy                              (Tensor::ActivationGradient)
+        //   partial[k][n * segs + seg] = sum of this block's dz   (first half of Conv2DBiasGradient, TensorOpCpu.cpp:1065-1068)
+        // NCHW: block (seg, k, n) owns elements [seg*kAgSeg, ...) of plane (n, k): every partial belongs to one channel.
+        template <int ACT, bool VEC>
+        __global__ void __launch_bounds__(kAgThreads)
+        act_bias_gradient_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dz,
+                                 float* __restrict__ partial, int HW, int K, int segs, float alpha)
+        {
+            const int seg = blockIdx.x, k = blockIdx.y, n = blockIdx.z;
+            const long long base = ((long long)n * K + k) * HW;
+            const int lo = seg * kAgSeg;
+            const int hi = min(HW, lo + kAgSeg);
+            float acc = 0.f;
+            if (VEC)
+            {
+                const float4* y4 = reinterpret_cast<const float4*>(y + base);
+                const float4* g4 = reinterpret_cast<const float4*>(dy + base);
+                float4* z4 = reinterpret_cast<float4*>(dz + base);
+                for (int i = lo / 4 + threadIdx.x; i < hi / 4; i += kAgThreads)
+                {
+                    const float4 a = __ldcs(y4 + i), g = __ldcs(g4 + i);
+                    float4 z;
+                    z.x = activation_gradient<ACT>(a.x, g.x, alpha);
+                    z.y = activation_gradient<ACT>(a.y, g.y, alpha);
+                    z.z = activation_gradient<ACT>(a.z, g.z, alpha);
+                    z.w = activation_gradient<ACT>(a.w, g.w, alpha);
+                    z4[i] = z;
+                    acc += (z.x + z.y) + (z.z + z.w);
+                }
+            }
+            else
+            {
+                for (int i = lo + threadIdx.x; i < hi; i += kAgThreads)
+                {
+                    const float z = activation_gradient<ACT>(y[base + i], dy[base + i], alpha);
+                    dz[base + i] = z;
+                    acc += z;
+                }
+            }
+            if (partial)
+            {
+                const float v = block_sum_256(acc);
+                if (threadIdx.x == 0)
+                    partial[(long long)k * gridDim.z * segs + (long long)n * segs + seg] = v;
+            }
+        }
+
+        // db[k] = partials of channel k added in index order by one warp (fixed order => deterministic)
+        __global__ void bias_partial_reduce_kernel(const float* __restrict__ partial, float* __restrict__ db, int K, int per)
+        {
+            const int k = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+            if (k >= K)
+                return;
+            const float* p = partial + (long long)k * per;
+            float acc = 0.f;
+            for (int i = threadIdx.x & 31; i < per; i += 32)
+                acc += p[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if ((threadIdx.x & 31) == 0)
+                db[k] = acc;
+        }
+
+        // any layout, no reduction (NHWC callers: the channel of an element is not a block-uniform)
+        template <int ACT>
+        __global__ void act_gradient_flat_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dz,
+                                                 long long n, float alpha)
+        {
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+                dz[i] = activation_gradient<ACT>(y[i], dy[i], alpha);
+        }
+
+        template <int ACT>
+        int launch_act_bias_gradient(const nb200_conv_desc& d, float alpha, const float* y, const float* dy, float* dz, float* db,
+                                     float* partial, cudaStream_t st)
+        {
+            const int HW = d.Ho * d.Wo;
+            if (d.fmt != NB200_NCHW)
+            {
+                const long long n = (long long)d.N * d.K * HW;
+                const long long blocks = (n + 255) / 256;
+                act_gradient_flat_kernel<ACT><<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, st>>>(y, dy, dz, n, alpha);
+                NB200_CUDA_TRY(cudaGetLastError());
+                count_launch();
+                return db ? bias_gradient(d, dz, db, st) : NB200_OK;
+            }
+            const int segs = ceil_div(HW, kAgSeg);
+            if (d.K > 65535 || d.N > 65535)
+                return fail(NB200_E_UNSUPPORTED, "more than 65535 filters or images");
+            const dim3 grid((unsigned)segs, (unsigned)d.K, (unsigned)d.N);
+            const bool vec = HW % 4 == 0 && (((uintptr_t)y | (uintptr_t)dy | (uintptr_t)dz) & 15) == 0;
+            if (vec)
+                act_bias_gradient_kernel<ACT, true><<<grid, kAgThreads, 0, st>>>(y, dy, dz, db ? partial : nullptr, HW, d.K, segs, alpha);
+            else
+                act_bias_gradient_kernel<ACT, false><<<grid, kAgThreads, 0, st>>>(y, dy, dz, db ? partial : nullptr, HW, d.K, segs, alpha);
+            NB200_CUDA_TRY(cudaGetLastError());
+            count_launch();
+            if (db)
+            {
+                bias_partial_reduce_kernel<<<ceil_div(d.K, 8), 256, 0, st>>>(partial, db, d.K, d.N * segs);
+                NB200_CUDA_TRY(cudaGetLastError());
+                count_launch();
+            }
+            return NB200_OK;
+        }
+
         // TensorOpCpu::AdamStep (TensorOpCpu.cpp:987-1003) with the gradient pre-scale folded in.
         __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                          float* __restrict__ v, size_t n, float gs, float lr, float b1, float b2, float eps)
@@ -82,6 +226,30 @@ namespace nb200
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
+    }
+
+    size_t bias_activation_gradient_workspace(const nb200_conv_desc& d)
+    {
+        if (d.fmt != NB200_NCHW)
+            return 0;
+        return (size_t)d.K * d.N * ceil_div((long long)d.Ho * d.Wo, kAgSeg) * sizeof(float);
+    }
+
+    int bias_activation_gradient(const nb200_conv_desc& d, int act, float alpha, const float* y, const float* dy, float* dz, float* db,
+                                 void* ws, size_t wsBytes, cudaStream_t st)
+    {
+        if (db && d.fmt == NB200_NCHW && (!ws || wsBytes < bias_activation_gradient_workspace(d)))
+            return fail(NB200_E_WORKSPACE, "bias/activation gradient needs %zu workspace bytes, got %zu", bias_activation_gradient_workspace(d), wsBytes);
+        float* partial = (float*)ws;
+        switch (act)
+        {
+        case NB200_ACT_SIGMOID: return launch_act_bias_gradient<NB200_ACT_SIGMOID>(d, alpha, y, dy, dz, db, partial, st);
+        case NB200_ACT_RELU: return launch_act_bias_gradient<NB200_ACT_RELU>(d, alpha, y, dy, dz, db, partial, st);
+        case NB200_ACT_TANH: return launch_act_bias_gradient<NB200_ACT_TANH>(d, alpha, y, dy, dz, db, partial, st);
+        case NB200_ACT_ELU: return launch_act_bias_gradient<NB200_ACT_ELU>(d, alpha, y, dy, dz, db, partial, st);
+        case NB200_ACT_LEAKY_RELU: return launch_act_bias_gradient<NB200_ACT_LEAKY_RELU>(d, alpha, y, dy, dz, db, partial, st);
+        default: return launch_act_bias_gradient<NB200_ACT_IDENTITY>(d, alpha, y, dy, dz, db, partial, st);
+        }
     }
 
     int adam_step(float* p, const float* g, float* m, float* v, size_t n, float gs, float lr, float b1, float b2, float eps,

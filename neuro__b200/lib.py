@@ -20,6 +20,8 @@ EXPORTS = [
     "nb200_conv2d_forward", "nb200_conv2d_input_gradient", "nb200_conv2d_kernels_gradient",
     "nb200_conv2d_bias_gradient", "nb200_adam_step", "nb200_sgd_step", "nb200_conv2d_forward_host",
     "nb200_conv2d_input_gradient_host", "nb200_conv2d_kernels_gradient_host",
+    "nb200_conv2d_bias_activation_gradient_workspace_bytes", "nb200_conv2d_bias_activation_gradient",
+    "nb200_conv2d_prepare_filters", "nb200_conv2d_forward_prepared", "nb200_conv2d_input_gradient_prepared",
 ]
 
 
@@ -75,6 +77,12 @@ def load():
     L.nb200_conv2d_forward_host.argtypes = [dp, c_p, c_p, c_p, c_i, c_f, c_p, c_p]
     L.nb200_conv2d_input_gradient_host.argtypes = [dp, c_p, c_p, c_p, c_p]
     L.nb200_conv2d_kernels_gradient_host.argtypes = [dp, c_p, c_p, c_p, c_p, c_p]
+    L.nb200_conv2d_bias_activation_gradient_workspace_bytes.argtypes = [dp]
+    L.nb200_conv2d_bias_activation_gradient_workspace_bytes.restype = c_sz
+    L.nb200_conv2d_bias_activation_gradient.argtypes = [dp, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]
+    L.nb200_conv2d_prepare_filters.argtypes = [c_i, dp, c_p, c_p, c_sz, c_p]
+    L.nb200_conv2d_forward_prepared.argtypes = L.nb200_conv2d_forward.argtypes
+    L.nb200_conv2d_input_gradient_prepared.argtypes = L.nb200_conv2d_input_gradient.argtypes
     _lib = L
     return L
 

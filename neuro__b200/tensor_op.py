@@ -58,6 +58,21 @@ def get_conv_transpose_output_shape(in_shape, output_depth, kernel_w, kernel_h, 
     return (n, output_depth, ho, wo) if fmt == NCHW else (n, ho, wo, output_depth)
 
 
+class PreparedKernels:
+    """Filters of one layer repacked once for one op (nb200_conv2d_prepare_filters): the handle owns the workspace the
+    *_prepared calls read them from. Valid while the kernels tensor is unchanged (inference, style transfer)."""
+
+    def __init__(self, op, desc, kernels, ws, nbytes):
+        self.op, self.desc, self.kernels, self.ws, self.nbytes = op, desc, kernels, ws, nbytes
+
+    def matches(self, op, d, kernels):
+        return (self.op == op and kernels.data_ptr() == self.kernels.data_ptr()
+                and all(getattr(d, f) == getattr(self.desc, f) for f, _ in ConvDesc._fields_))
+
+    def ptr(self):
+        return (ctypes.c_void_p(self.ws.data_ptr()) if self.ws is not None else None), self.nbytes
+
+
 class TensorOpB200:
     """Stateless apart from a grow-only device workspace per instance (reference: pooled workspace,
     TensorOpGpu.cpp:648)."""
@@ -86,31 +101,75 @@ class TensorOpB200:
     def kernel_name(self, op, d):
         return self._L.nb200_conv2d_kernel_name(op, ctypes.byref(d)).decode()
 
+    # -- constant filters: repack once, reuse (no reference counterpart; the reference re-derives cuDNN descriptors and
+    #    algorithms on every call, TensorOpGpu.cpp:629-668)
+    def PrepareKernels(self, op, inputLike, kernels, outputLike, stride, paddingX, paddingY, dataFormat=NCHW):
+        """op: lib.OP_FORWARD (inputLike = input, outputLike = output) or lib.OP_INPUT_GRADIENT (inputLike = the input
+        gradient, outputLike = the incoming gradient). Returns a PreparedKernels to pass as `prepared=`."""
+        d = self._desc(dataFormat, inputLike, kernels, outputLike, stride, paddingX, paddingY)
+        need = self._L.nb200_conv2d_workspace_bytes(op, ctypes.byref(d))
+        ws = torch.empty(need, dtype=torch.uint8, device="cuda") if need else None
+        h = PreparedKernels(op, d, kernels, ws, need)
+        p, n = h.ptr()
+        check(self._L.nb200_conv2d_prepare_filters(op, ctypes.byref(d), _ptr(kernels), p, n, _stream()))
+        return h
+
     # -- the op interface (TensorOpCpu.h:46-50)
-    def Conv2D(self, input, kernels, stride, paddingX, paddingY, dataFormat, output):
-        d = self._desc(dataFormat, input, kernels, output, stride, paddingX, paddingY)
-        ws, n = self._workspace(lib.OP_FORWARD, d)
-        check(self._L.nb200_conv2d_forward(ctypes.byref(d), _ptr(input), _ptr(kernels), None, lib.ACT_IDENTITY, 0.0,
-                                           _ptr(output), ws, n, _stream()))
+    def Conv2D(self, input, kernels, stride, paddingX, paddingY, dataFormat, output, prepared=None):
+        self._forward(input, kernels, stride, paddingX, paddingY, dataFormat, None, lib.ACT_IDENTITY, 0.0, output, prepared)
 
     def Conv2DBiasActivation(self, input, kernels, stride, paddingX, paddingY, bias, activation, activationAlpha, output,
-                             dataFormat=NCHW):
+                             dataFormat=NCHW, prepared=None):
         assert paddingX == paddingY  # TensorOpCpu.cpp:1057
+        self._forward(input, kernels, stride, paddingX, paddingY, dataFormat, bias, activation, activationAlpha, output, prepared)
+
+    def _forward(self, input, kernels, stride, paddingX, paddingY, dataFormat, bias, activation, alpha, output, prepared):
         d = self._desc(dataFormat, input, kernels, output, stride, paddingX, paddingY)
-        ws, n = self._workspace(lib.OP_FORWARD, d)
-        check(self._L.nb200_conv2d_forward(ctypes.byref(d), _ptr(input), _ptr(kernels), _ptr(bias), activation,
-                                           activationAlpha, _ptr(output), ws, n, _stream()))
+        if prepared is not None:
+            assert prepared.matches(lib.OP_FORWARD, d, kernels), "PreparedKernels belong to another problem"
+            ws, n = prepared.ptr()
+            fn = self._L.nb200_conv2d_forward_prepared
+        else:
+            ws, n = self._workspace(lib.OP_FORWARD, d)
+            fn = self._L.nb200_conv2d_forward
+        check(fn(ctypes.byref(d), _ptr(input), _ptr(kernels), _ptr(bias), activation, alpha, _ptr(output), ws, n, _stream()))
+
+    def ActivationGradient(self, activation, activationAlpha, output, outputGradient, inputGradient, dataFormat=NCHW):
+        """Tensor::ActivationGradient -> TensorOpCpu::{Sigmoid,Tanh,ReLU,Elu,LeakyReLU}Gradient (TensorOpCpu.cpp:813-864)."""
+        self.Conv2DBiasActivationGradient(output, outputGradient, activation, activationAlpha, inputGradient, None, dataFormat)
+
+    def Conv2DBiasActivationGradient(self, output, outputGradient, activation, activationAlpha, activationInputGradient,
+                                     biasGradient=None, dataFormat=NCHW):
+        """Backward prologue of Conv2dBiasActivationOp (Conv2dBiasActivationOp.cpp:47-60) in one pass:
+        activationInputGradient = act'(output) * outputGradient and biasGradient = its sum over N,H,W."""
+        N, K, Ho, Wo = _act_extent(dataFormat, outputGradient)
+        assert output.shape == outputGradient.shape == activationInputGradient.shape
+        d = ConvDesc(N, 0, 0, 0, K, 1, 1, Ho, Wo, 1, 0, 0, dataFormat, self.math)
+        need = self._L.nb200_conv2d_bias_activation_gradient_workspace_bytes(ctypes.byref(d)) if biasGradient is not None else 0
+        ws = None
+        if need:
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+            ws = ctypes.c_void_p(self._ws.data_ptr())
+        check(self._L.nb200_conv2d_bias_activation_gradient(ctypes.byref(d), activation, activationAlpha, _ptr(output),
+                                                            _ptr(outputGradient), _ptr(activationInputGradient),
+                                                            _ptr(biasGradient), ws, need, _stream()))
 
     def Conv2DBiasGradient(self, gradient, biasGradient, dataFormat=NCHW):
         N, K, Ho, Wo = _act_extent(dataFormat, gradient)
         d = ConvDesc(N, 0, 0, 0, K, 1, 1, Ho, Wo, 1, 0, 0, dataFormat, self.math)
         check(self._L.nb200_conv2d_bias_gradient(ctypes.byref(d), _ptr(gradient), _ptr(biasGradient), _stream()))
 
-    def Conv2DInputGradient(self, gradient, kernels, stride, paddingX, paddingY, dataFormat, inputGradient):
+    def Conv2DInputGradient(self, gradient, kernels, stride, paddingX, paddingY, dataFormat, inputGradient, prepared=None):
         d = self._desc(dataFormat, inputGradient, kernels, gradient, stride, paddingX, paddingY)
-        ws, n = self._workspace(lib.OP_INPUT_GRADIENT, d)
-        check(self._L.nb200_conv2d_input_gradient(ctypes.byref(d), _ptr(gradient), _ptr(kernels), _ptr(inputGradient),
-                                                  ws, n, _stream()))
+        if prepared is not None:
+            assert prepared.matches(lib.OP_INPUT_GRADIENT, d, kernels), "PreparedKernels belong to another problem"
+            ws, n = prepared.ptr()
+            fn = self._L.nb200_conv2d_input_gradient_prepared
+        else:
+            ws, n = self._workspace(lib.OP_INPUT_GRADIENT, d)
+            fn = self._L.nb200_conv2d_input_gradient
+        check(fn(ctypes.byref(d), _ptr(gradient), _ptr(kernels), _ptr(inputGradient), ws, n, _stream()))
 
     def Conv2DKernelsGradient(self, input, gradient, stride, paddingX, paddingY, dataFormat, kernelsGradient,
                               biasGradient=None):

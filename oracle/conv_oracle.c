@@ -276,6 +276,30 @@ API void oracle_conv2d_bias_gradient(const conv_dims* d, const float* dy, float*
     }
 }
 
+/* Activation gradient through the activation's OUTPUT y, times the incoming gradient. Follows
+ * TensorOpCpu::SigmoidGradient :813-816, TanhGradient :825-828, ReLUGradient :837-840, EluGradient :849-852,
+ * LeakyReLUGradient :861-864 (dispatched by Tensor::ActivationGradient from
+ * Conv2dBiasActivationOp::ComputeGradientInternal, Conv2dBiasActivationOp.cpp:47-53). act = EActivation. */
+API void oracle_activation_gradient(int act, float alpha, const float* y, const float* dy, float* dz, size_t n)
+{
+#pragma omp parallel for
+    for (long long i = 0; i < (long long)n; ++i)
+    {
+        const float x = y[i], x2 = dy[i];
+        float r;
+        switch (act)
+        {
+        case 1: r = x * (1 - x) * x2; break;
+        case 2: r = x > 0 ? x2 : 0; break;
+        case 3: r = (1 - x * x) * x2; break;
+        case 4: r = (x > 0 ? 1 : (x + alpha)) * x2; break;
+        case 5: r = (x > 0 ? 1 : alpha) * x2; break;
+        default: r = x2; break;
+        }
+        dz[i] = r;
+    }
+}
+
 /* Optimiser updates that follow the gradient exchange. Follow TensorOpCpu::AdamStep /
  * SgdStep, TensorOpCpu.cpp:987-1009:  m = b1*m + (1-b1)*g;  v = v*b2 + (1-b2)*g*g;
  * p = p - m / (sqrt(v) + eps) * lr   (sqrt evaluated in double, as `(float)::sqrt(x)`). */

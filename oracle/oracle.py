@@ -158,6 +158,13 @@ def conv2d_bias_gradient(dy, fmt=NCHW):
     return db
 
 
+def activation_gradient(act, alpha, y, dy):
+    """dz = act'(y) * dy, derivative taken through the output y (TensorOpCpu.cpp:813-864)."""
+    dz = np.empty_like(dy)
+    lib().oracle_activation_gradient(int(act), ctypes.c_float(alpha), _fp(y), _fp(dy), _fp(dz), ctypes.c_size_t(dy.size))
+    return dz
+
+
 def adam_step(p, g, m, v, lr, beta1, beta2, eps):
     """In place on p, m, v."""
     lib().oracle_adam_step(_fp(p), _fp(g), _fp(m), _fp(v), ctypes.c_size_t(p.size), ctypes.c_float(lr),
@@ -211,3 +218,11 @@ def ref_conv2d_kernels_gradient(x, dy, stride, padX, padY, filt_rs, fmt=NCHW, mt
     ref().neuro_ref_conv2d_kernels_gradient(int(mt), fmt, _fp(x), _shape4(fmt, x), _fp(dy), _shape4(fmt, dy),
                                             stride, padX, padY, _fp(dw), _shape4(fmt, dw))
     return dw
+
+
+def ref_activation_gradient(act, alpha, y, dy):
+    dz = np.empty_like(dy)
+    a = y.reshape(-1)
+    dims = (ctypes.c_uint32 * 4)(a.size, 1, 1, 1)
+    ref().neuro_ref_activation_gradient(int(act), ctypes.c_float(alpha), _fp(y), _fp(dy), _fp(dz), dims)
+    return dz

@@ -11,6 +11,7 @@
 //   TensorOpCpu::Conv2DInputGradient    Neuro/src/Tensors/TensorOpCpu.cpp:1071
 //   TensorOpCpu::Conv2DKernelsGradient  Neuro/src/Tensors/TensorOpCpu.cpp:1129
 //   TensorOpCpuMt::{same three}         Neuro/src/Tensors/TensorOpCpuMt.cpp:173,220,278
+//   TensorOpCpu::{Sigmoid,Tanh,ReLU,Elu,LeakyReLU}Gradient   Neuro/src/Tensors/TensorOpCpu.cpp:813-864
 #include <cstdlib>
 #include <cstring>
 #include <omp.h>
@@ -72,6 +73,13 @@ namespace Neuro
     void Tensor::Zero()
     {
         memset(m_Storage.Data(), 0, sizeof(float) * m_Shape.Length);
+    }
+
+    // Tensor::Map (Tensor.cpp:814-818) forwards to the op; the op's own loop (TensorOpCpu.cpp:773-800) is the reference's.
+    void Tensor::Map(const function<float(float, float)>& func, const Tensor& other, Tensor& result) const
+    {
+        alignas(16) static char dummy[64];
+        reinterpret_cast<const TensorOpCpu*>(dummy)->TensorOpCpu::Map(func, *this, other, result);
     }
 
     // Same bounds semantics as the reference accessor (Tensor.cpp:2078-2084), including its
@@ -154,4 +162,22 @@ REF_API void neuro_ref_conv2d_kernels_gradient(int mt, int fmt, const float* x, 
     else
         OpSt()->TensorOpCpu::Conv2DKernelsGradient(tx, tdy, stride, padX, padY, (EDataFormat)fmt, tdw);
     Store(tdw, dw);
+}
+
+// dz = act'(y) * dy through the reference's own activation-gradient ops (what Tensor::ActivationGradient dispatches to,
+// Conv2dBiasActivationOp.cpp:52). act follows EActivation; dims = Shape of all three tensors.
+REF_API void neuro_ref_activation_gradient(int act, float alpha, const float* y, const float* dy, float* dz, const uint32_t* dims)
+{
+    Tensor ty(MakeShape(dims)), tg(MakeShape(dims)), tz(MakeShape(dims));
+    Load(ty, y); Load(tg, dy);
+    switch (act)
+    {
+    case 1: OpSt()->TensorOpCpu::SigmoidGradient(ty, tg, tz); break;
+    case 2: OpSt()->TensorOpCpu::ReLUGradient(ty, tg, tz); break;
+    case 3: OpSt()->TensorOpCpu::TanhGradient(ty, tg, tz); break;
+    case 4: OpSt()->TensorOpCpu::EluGradient(ty, tg, alpha, tz); break;
+    case 5: OpSt()->TensorOpCpu::LeakyReLUGradient(ty, tg, alpha, tz); break;
+    default: memcpy(tz.Values(), tg.Values(), sizeof(float) * tg.Length()); break;
+    }
+    Store(tz, dz);
 }

@@ -242,3 +242,70 @@ def test_host_buffer_entry_points():
     assert max_norm_err(dx, O.conv2d_input_gradient(dy, w, 1, 1, 1, (H, W))) <= 1e-5
     assert max_norm_err(dw, O.conv2d_kernels_gradient(x, dy, 1, 1, 1, (F, F))) <= 1e-5
     assert np.abs(db - O.conv2d_bias_gradient(dy)).max() <= 1e-4
+
+
+ACTS = [lib.ACT_IDENTITY, lib.ACT_SIGMOID, lib.ACT_RELU, lib.ACT_TANH, lib.ACT_ELU, lib.ACT_LEAKY_RELU]
+
+
+@pytest.mark.parametrize("fmt", [lib.NCHW, lib.NHWC])
+@pytest.mark.parametrize("act", ACTS)
+def test_bias_activation_gradient(act, fmt):
+    """Backward prologue of Conv2dBiasActivationOp (Conv2dBiasActivationOp.cpp:47-60): dz = act'(y)*dy is element-wise
+    fp32 with the reference's operation order, so it must be BIT-exact; db = sum(dz) within the reference's own
+    CPU-vs-GPU eps (1e-4, TensorOpGpuTests.cpp:1254-1268) relative to the largest sum."""
+    op = TensorOpB200()
+    # (N, K, Ho, Wo): vector path, ragged scalar path, several 8192-element segments per plane, tiny maps
+    for shape in [(3, 5, 24, 24), (2, 64, 32, 32), (2, 7, 13, 9), (2, 4, 96, 100), (16, 24, 4, 4), (1, 1, 1, 1)]:
+        y = O.conv2d_bias_activation(synth.uniform(synth.SEED_X, (shape[0], 2, shape[2], shape[3])),
+                                     synth.uniform(synth.SEED_W, (shape[1], 2, 1, 1)), synth.uniform(synth.SEED_BIAS, (shape[1],)),
+                                     1, 0, act, 0.2)                     # y in the activation's range
+        dy = synth.uniform(synth.SEED_DY, shape)
+        if fmt == lib.NHWC:
+            y = np.ascontiguousarray(y.transpose(0, 2, 3, 1)); dy = np.ascontiguousarray(dy.transpose(0, 2, 3, 1))
+        ref_dz = O.activation_gradient(act, 0.2, y, dy)
+        ref_db = O.conv2d_bias_gradient(ref_dz, fmt)
+        dz = torch.full(dy.shape, float("nan"), device="cuda"); db = torch.full((shape[1],), float("nan"), device="cuda")
+        op.Conv2DBiasActivationGradient(dev(y), dev(dy), act, 0.2, dz, db, fmt)
+        assert np.array_equal(dz.cpu().numpy(), ref_dz)
+        assert np.abs(db.cpu().numpy() - ref_db).max() <= 1e-4 * max(1.0, float(np.abs(ref_db).max()))
+        dz2 = torch.full(dy.shape, float("nan"), device="cuda")
+        op.ActivationGradient(act, 0.2, dev(y), dev(dy), dz2, fmt)      # without the bias gradient
+        assert np.array_equal(dz2.cpu().numpy(), ref_dz)
+
+
+# (N, C, H, W, K, F, stride, pad): one per kernel family that keeps repacked filters in the workspace, plus one that does not
+PREPARED_CASES = [
+    (2, 64, 32, 32, 128, 3, 1, 1),    # tcgen05_fprop BN=128
+    (1, 64, 48, 96, 64, 3, 1, 1),     # row-tap kernel
+    (1, 256, 32, 32, 128, 3, 1, 1),   # channel split: partials live behind the filters in the same workspace
+    (4, 64, 32, 32, 128, 3, 2, 1),    # gathered kernel (stride 2; the input gradient runs one launch per parity class)
+    (8, 128, 8, 8, 256, 4, 2, 1),     # DCGAN deconv geometry
+    (2, 3, 64, 64, 64, 3, 1, 1),      # first-layer kernels read w directly: prepare is a no-op
+]
+
+
+@pytest.mark.parametrize("math", [lib.MATH_TF32, lib.MATH_3XTF32], ids=["tf32", "3xtf32"])
+@pytest.mark.parametrize("cfg", PREPARED_CASES, ids=["-".join(map(str, c)) for c in PREPARED_CASES])
+def test_prepared_filters_match_per_call_repack(cfg, math):
+    """nb200_conv2d_prepare_filters + *_prepared run the same kernels on the same repacked filters as the plain calls,
+    so results must be bit-identical -- also on reuse, and whatever happens to the op's shared workspace in between."""
+    N, C, H, W, K, F, st, p = cfg
+    x, w, dy = make_inputs(lib.NCHW, N, C, H, W, K, F, F, st, p, p, glorot=True)
+    b = synth.uniform(synth.SEED_BIAS, (K,))
+    op = TensorOpB200(math)
+    xd, wd, bd, dyd = dev(x), dev(w), dev(b), dev(dy)
+    y0 = torch.empty(dy.shape, device="cuda"); dx0 = torch.empty(x.shape, device="cuda")
+    op.Conv2DBiasActivation(xd, wd, st, p, p, bd, lib.ACT_RELU, 0.0, y0)
+    op.Conv2DInputGradient(dyd, wd, st, p, p, lib.NCHW, dx0)
+    assert max_norm_err(y0, O.conv2d_bias_activation(x, w, b, st, p, O.RELU)) <= TOL[math]
+    hf = op.PrepareKernels(lib.OP_FORWARD, xd, wd, y0, st, p, p)
+    hg = op.PrepareKernels(lib.OP_INPUT_GRADIENT, dx0, wd, dyd, st, p, p)
+    for _ in range(2):
+        if op._ws is not None:
+            op._ws.fill_(0xFF)      # the shared per-call workspace is not what the prepared calls read
+        y1 = torch.full(dy.shape, float("nan"), device="cuda"); dx1 = torch.full(x.shape, float("nan"), device="cuda")
+        op.Conv2DBiasActivation(xd, wd, st, p, p, bd, lib.ACT_RELU, 0.0, y1, prepared=hf)
+        op.Conv2DInputGradient(dyd, wd, st, p, p, lib.NCHW, dx1, prepared=hg)
+        assert torch.equal(y1, y0) and torch.equal(dx1, dx0)
+    with pytest.raises(AssertionError):
+        op.Conv2DInputGradient(dyd, wd, st, p, p, lib.NCHW, dx1, prepared=hf)   # a forward handle is not an input-gradient handle

@@ -133,3 +133,18 @@ def test_optimizer_steps():
     assert np.allclose(p, p0 - 0.01 * m / (np.sqrt(v) + 1e-8), atol=1e-5)
     q = p.copy(); O.sgd_step(q, g, 0.1)
     assert np.allclose(q, p - 0.1 * g, atol=1e-7)
+
+
+@pytest.mark.parametrize("act", [O.IDENTITY, O.SIGMOID, O.RELU, O.TANH, O.ELU, O.LEAKY_RELU])
+def test_activation_gradient_restatement(act):
+    """dz = act'(y)*dy through the output (TensorOpCpu.cpp:813-864): analytic formulas, and bit-for-bit equality with
+    the reference's own ops where oracle/_ref is built."""
+    y = O.conv2d_bias_activation(synth.uniform(11, (2, 3, 9, 7)), synth.uniform(12, (4, 3, 1, 1)), synth.uniform(14, (4,)), 1, 0, act, 0.2)
+    dy = synth.uniform(13, y.shape)
+    got = O.activation_gradient(act, 0.2, y, dy)
+    y64 = y.astype(np.float64)
+    want = {O.IDENTITY: np.ones_like(y64), O.SIGMOID: y64 * (1 - y64), O.RELU: (y64 > 0) * 1.0, O.TANH: 1 - y64 * y64,
+            O.ELU: np.where(y64 > 0, 1.0, y64 + np.float32(0.2)), O.LEAKY_RELU: np.where(y64 > 0, 1.0, np.float32(0.2))}[act] * dy
+    assert np.allclose(got, want, atol=1e-6)
+    if O.have_ref():
+        assert np.array_equal(got, O.ref_activation_gradient(act, 0.2, y, dy))
