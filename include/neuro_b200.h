@@ -155,6 +155,41 @@ NB200_API int nb200_conv2d_forward_prepared(const nb200_conv_desc* d, const floa
 NB200_API int nb200_conv2d_input_gradient_prepared(const nb200_conv_desc* d, const float* dy, const float* w, float* dx,
                                                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- spatial resamplers on either side of the convolutions; HBM-bound, bit-exact vs the reference ----
+ * EPoolingMode, Neuro/include/Types.h:56-60 */
+enum { NB200_POOL_MAX = 0, NB200_POOL_AVG = 1 };
+
+/* (N,C,H,W) = input extent, (Ho,Wo) = pooled extent = Tensor::GetPooling2DOutputShape (Tensor.cpp:1988-2007). */
+typedef struct nb200_pool_desc
+{
+    int32_t N, C, H, W;
+    int32_t Ho, Wo;
+    int32_t filter, stride;
+    int32_t padX, padY;
+    int32_t mode; /* NB200_POOL_* */
+    int32_t fmt;  /* NB200_NCHW | NB200_NHWC */
+} nb200_pool_desc;
+
+/* y = pool(x). Replaces TensorOpCpu::Pool2D (TensorOpCpu.h:51, TensorOpCpu.cpp:1187-1246; Mt :336-404): padded taps read
+ * -FLT_MAX (max) or 0 (avg); the average divides by filter*filter whatever the padding. */
+NB200_API int nb200_pool2d(const nb200_pool_desc* d, const float* x, float* y, void* stream);
+/* dx = pool gradient. Replaces TensorOpCpu::Pool2DGradient (TensorOpCpu.h:52, TensorOpCpu.cpp:1249-1338): max -> the first
+ * window element (row-major) equal to the pooled value receives dy; avg -> every in-range element receives dy/filter^2;
+ * overlapping windows add in (oh, ow) order. dx is overwritten (the reference zeroes it first). y, x may be NULL for avg. */
+NB200_API int nb200_pool2d_gradient(const nb200_pool_desc* d, const float* y, const float* x, const float* dy, float* dx,
+                                    void* stream);
+/* y[n,c,oh,ow] = x[n,c,oh/scale,ow/scale]; (N,C,H,W) = INPUT extent, NCHW planes. Replaces TensorOpCpu::UpSample2D
+ * (TensorOpCpu.h:53, TensorOpCpu.cpp:1340-1354). */
+NB200_API int nb200_upsample2d(int32_t N, int32_t C, int32_t H, int32_t W, int32_t scale, const float* x, float* y, void* stream);
+/* dx[n,c,h,w] = sum of the scale x scale block of dy, added row by row. Replaces TensorOpCpu::UpSample2DGradient
+ * (TensorOpCpu.h:54, TensorOpCpu.cpp:1357-1369). (N,C,H,W) = extent of dx. */
+NB200_API int nb200_upsample2d_gradient(int32_t N, int32_t C, int32_t H, int32_t W, int32_t scale, const float* dy, float* dx,
+                                        void* stream);
+/* y = x framed by `value`; (N,C,H,W) = INPUT extent, output (H+top+bottom) x (W+left+right). Replaces
+ * TensorOpCpu::ConstantPad2D (TensorOpCpu.cpp:528-546; PatchGAN's ZeroPadding2D). */
+NB200_API int nb200_constant_pad2d(int32_t N, int32_t C, int32_t H, int32_t W, int32_t left, int32_t right, int32_t top,
+                                   int32_t bottom, float value, const float* x, float* y, void* stream);
+
 /* Optimiser updates that follow the gradient exchange in data-parallel Fit().
  * Replace TensorOpCpu::AdamStep / SgdStep (TensorOpCpu.h:75-76, TensorOpCpu.cpp:987-1009), with the
  * 1/replicas scaling of an all-reduced (summed) gradient folded in as grad_scale:

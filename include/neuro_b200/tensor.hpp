@@ -86,6 +86,14 @@ namespace NeuroB200
         virtual void Conv2DBiasGradient(const Tensor& gradient, Tensor& biasGradient) = 0;
         virtual void Conv2DInputGradient(const Tensor& gradient, const Tensor& kernels, uint32_t stride, uint32_t paddingX, uint32_t paddingY, EDataFormat dataFormat, Tensor& inputGradient) const = 0;
         virtual void Conv2DKernelsGradient(const Tensor& input, const Tensor& gradient, uint32_t stride, uint32_t paddingX, uint32_t paddingY, EDataFormat dataFormat, Tensor& kernelsGradient) const = 0;
+        // Tensor::ActivationGradient's targets (TensorOpCpu.h: SigmoidGradient ... LeakyReLUGradient; TensorOpCpu.cpp:813-864) behind one entry
+        virtual void ActivationGradient(EActivation, float, const Tensor&, const Tensor&, Tensor&) const { throw std::runtime_error("ActivationGradient: not implemented by this backend"); }
+        // the backward prologue of Conv2dBiasActivationOp (Conv2dBiasActivationOp.cpp:47-60); backends may fuse the two passes
+        virtual void Conv2DBiasActivationGradient(const Tensor& output, const Tensor& outputGradient, EActivation activation, float activationAlpha, Tensor& activationInputGradient, Tensor& biasGradient)
+        {
+            ActivationGradient(activation, activationAlpha, output, outputGradient, activationInputGradient);
+            Conv2DBiasGradient(activationInputGradient, biasGradient);
+        }
         virtual void AdamStep(Tensor& parameter, const Tensor& gradient, Tensor& mGrad, Tensor& vGrad, float lr, float beta1, float beta2, float epsilon) const = 0;
         virtual void SgdStep(Tensor& parameter, const Tensor& gradient, float lr) const = 0;
     };
@@ -236,6 +244,16 @@ namespace NeuroB200
             return output;
         }
         void Conv2DBiasGradient(const Tensor& gradient, Tensor& biasGradient) const { Op()->Conv2DBiasGradient(gradient, biasGradient); }
+        // Tensor::ActivationGradient as Conv2dBiasActivationOp calls it: grad.ActivationGradient(act, alpha, output, grad, inputGrad)
+        void ActivationGradient(EActivation activation, float alpha, const Tensor& output, const Tensor& outputGradient, Tensor& inputGradient) const
+        {
+            if (output.GetShape() != outputGradient.GetShape() || output.GetShape() != inputGradient.GetShape()) throw std::runtime_error("ActivationGradient: shapes differ");
+            Op()->ActivationGradient(activation, alpha, output, outputGradient, inputGradient);
+        }
+        void Conv2DBiasActivationGradient(const Tensor& output, const Tensor& outputGradient, EActivation activation, float alpha, Tensor& activationInputGradient, Tensor& biasGradient) const
+        {
+            Op()->Conv2DBiasActivationGradient(output, outputGradient, activation, alpha, activationInputGradient, biasGradient);
+        }
         void Conv2DInputsGradient(const Tensor& gradient, const Tensor& kernels, uint32_t stride, uint32_t padding, EDataFormat fmt, Tensor& inputsGradient) const
         {
             Op()->Conv2DInputGradient(gradient, kernels, stride, padding, padding, fmt, inputsGradient);

@@ -42,6 +42,17 @@ namespace NeuroB200
             Nb200Check(nb200_conv2d_bias_gradient(&d, gradient.GetDevicePtr(), biasGradient.GetDevicePtr(), m_Stream));
         }
 
+        void ActivationGradient(EActivation activation, float alpha, const Tensor& output, const Tensor& outputGradient, Tensor& inputGradient) const override
+        {
+            BiasActivationGradient(output, outputGradient, activation, alpha, inputGradient, nullptr);
+        }
+
+        // one pass over HBM instead of the reference's two (ActivationGradient, then Conv2DBiasGradient re-reading its result)
+        void Conv2DBiasActivationGradient(const Tensor& output, const Tensor& outputGradient, EActivation activation, float alpha, Tensor& activationInputGradient, Tensor& biasGradient) override
+        {
+            BiasActivationGradient(output, outputGradient, activation, alpha, activationInputGradient, &biasGradient);
+        }
+
         void Conv2DInputGradient(const Tensor& gradient, const Tensor& kernels, uint32_t stride, uint32_t paddingX, uint32_t paddingY, EDataFormat dataFormat, Tensor& inputGradient) const override
         {
             gradient.CopyToDevice(); kernels.CopyToDevice(); inputGradient.OverrideDevice();
@@ -89,17 +100,32 @@ namespace NeuroB200
             size_t ws = 0; void* w = Workspace(NB200_OP_FORWARD, d, ws);
             Nb200Check(nb200_conv2d_forward(&d, input.GetDevicePtr(), kernels.GetDevicePtr(), bias ? bias->GetDevicePtr() : nullptr, (int)act, alpha, output.GetDevicePtr(), w, ws, m_Stream));
         }
+        void BiasActivationGradient(const Tensor& output, const Tensor& outputGradient, EActivation act, float alpha, Tensor& dz, Tensor* db) const
+        {
+            output.CopyToDevice(); outputGradient.CopyToDevice(); dz.OverrideDevice(); if (db) db->OverrideDevice();
+            nb200_conv_desc d{};
+            d.N = outputGradient.Batch(); d.K = outputGradient.Depth(); d.Ho = outputGradient.Height(); d.Wo = outputGradient.Width();
+            d.R = d.S = 1; d.stride = 1; d.fmt = NB200_NCHW; d.math = m_Math;
+            const size_t need = db ? nb200_conv2d_bias_activation_gradient_workspace_bytes(&d) : 0;
+            void* w = need ? Grow(need) : nullptr;
+            Nb200Check(nb200_conv2d_bias_activation_gradient(&d, (int)act, alpha, output.GetDevicePtr(), outputGradient.GetDevicePtr(), dz.GetDevicePtr(),
+                                                             db ? db->GetDevicePtr() : nullptr, w, need, m_Stream));
+        }
         // grow-only scratch (reference: pooled workspace per call, TensorOpGpu.cpp:648)
         void* Workspace(int op, const nb200_conv_desc& d, size_t& bytes) const
         {
             bytes = nb200_conv2d_workspace_bytes(op, &d);
+            return bytes ? Grow(bytes) : nullptr;
+        }
+        void* Grow(size_t bytes) const
+        {
             if (bytes > m_WorkspaceBytes)
             {
                 if (m_Workspace) { CudaCheck(cudaDeviceSynchronize(), "workspace sync"); cudaFree(m_Workspace); }
                 CudaCheck(cudaMalloc(&m_Workspace, bytes), "workspace");
                 m_WorkspaceBytes = bytes;
             }
-            return bytes ? m_Workspace : nullptr;
+            return m_Workspace;
         }
 
         int m_Math;

@@ -91,12 +91,59 @@ namespace nb200
             }
         }
 
-        enum Family { kDirect, kTc, kSmallC, kGather };
+        enum Family { kDirect, kTc, kSmallC, kGather, kSmallK };
+
+        inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+        inline size_t smallk_filter_bytes(const nb200_conv_desc& d) { return align256((size_t)d.K * d.C * 9 * sizeof(float)); }
+
+        size_t smallk_workspace(int op, const nb200_conv_desc& d)
+        {
+            if (op != NB200_OP_KERNELS_GRADIENT)
+                return smallk_filter_bytes(d); // w'[c][k][2-r][2-s]
+            const nb200_conv_desc s = smallk_swapped(d);
+            return smallk_filter_bytes(d) + (tc_smallc_wgrad_supported(s) ? tc_smallc_wgrad_workspace(s) : smallc_wgrad_workspace(s));
+        }
+
+        // forward / input gradient of a few-filter layer through the small-channel kernels with the roles exchanged (conv_smallc.cu)
+        int smallk_run(int op, const nb200_conv_desc& d, const float* in, const float* w, const float* bias, int act, float alpha, float* out,
+                       void* ws, size_t wsBytes, cudaStream_t st)
+        {
+            if (!ws || wsBytes < smallk_filter_bytes(d))
+                return fail(NB200_E_WORKSPACE, "few-filter conv needs %zu workspace bytes, got %zu", smallk_filter_bytes(d), wsBytes);
+            float* wsw = (float*)ws;
+            if (g_tcFilterMode != kFiltersReady)
+            {
+                const int rc = smallc_swap_filters(w, wsw, d.K, d.C, st);
+                if (rc) return rc;
+            }
+            if (g_tcFilterMode == kFiltersOnly)
+                return NB200_OK;
+            const nb200_conv_desc s = smallk_swapped(d);
+            return op == NB200_OP_FORWARD ? smallc_input_gradient_epilogue(s, in, wsw, bias, act, alpha, out, st)
+                                          : smallc_forward(s, in, wsw, nullptr, NB200_ACT_IDENTITY, 0.f, out, st);
+        }
+
+        int smallk_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st)
+        {
+            const size_t need = smallk_workspace(NB200_OP_KERNELS_GRADIENT, d);
+            if (!ws || wsBytes < need)
+                return fail(NB200_E_WORKSPACE, "few-filter kernel gradient needs %zu workspace bytes, got %zu", need, wsBytes);
+            const nb200_conv_desc s = smallk_swapped(d);
+            float* dws = (float*)ws;                                  // dw'[c][k][r][s]
+            void* inner = (uint8_t*)ws + smallk_filter_bytes(d);
+            const size_t innerBytes = wsBytes - smallk_filter_bytes(d);
+            const int rc = tc_smallc_wgrad_supported(s) ? tc_smallc_kernels_gradient(s, dy, x, dws, inner, innerBytes, st)
+                                                        : smallc_kernels_gradient(s, dy, x, dws, inner, innerBytes, st);
+            if (rc) return rc;
+            return smallc_swap_filters(dws, dw, d.C, d.K, st);
+        }
 
         Family pick(int op, const nb200_conv_desc& d)
         {
             if (smallc_supported(d))
                 return kSmallC; // fp32 CUDA cores, HBM-bound: serves every math mode
+            if (smallk_supported(d))
+                return kSmallK; // few filters: the same kernels with x and y exchanged
             if (d.math == NB200_MATH_FP32)
                 return kDirect;
             // The halo-tile kernels tile 32 output columns per row; on narrower maps (or where they do not apply at all:
@@ -170,6 +217,8 @@ extern "C"
             return tc_workspace_bytes(op, *d);
         if (f == kSmallC)
             return op != NB200_OP_KERNELS_GRADIENT ? 0 : tc_smallc_wgrad_supported(*d) ? tc_smallc_wgrad_workspace(*d) : smallc_wgrad_workspace(*d);
+        if (f == kSmallK)
+            return smallk_workspace(op, *d);
         if (f == kGather)
             return op == NB200_OP_KERNELS_GRADIENT ? tc_gather_kernels_gradient_workspace(*d) : tc_gather_workspace_bytes(op, *d);
         return op == NB200_OP_KERNELS_GRADIENT ? direct_kernels_gradient_workspace(*d) : 0;
@@ -180,6 +229,12 @@ extern "C"
         if (!d || validate(d, -1) != NB200_OK)
             return "invalid";
         const Family f = pick(op, *d);
+        if (f == kSmallK)
+        {
+            if (op == NB200_OP_FORWARD) return "smallk_fprop";
+            if (op == NB200_OP_INPUT_GRADIENT) return "smallk_dgrad";
+            return tc_smallc_wgrad_supported(smallk_swapped(*d)) ? "tcgen05_smallk_wgrad" : "smallk_wgrad";
+        }
         switch (op)
         {
         case NB200_OP_FORWARD: return f == kTc ? (tc_uses_rowtap(op, *d) ? "tcgen05_rowtap_fprop" : "tcgen05_fprop") : f == kGather ? "tcgen05_gather_fprop" : f == kSmallC ? "smallc_fprop" : "direct_fprop";
@@ -207,6 +262,8 @@ extern "C"
             return tc_forward(*d, x, w, bias, act, alpha, y, workspace, workspace_bytes, st);
         if (f == kSmallC)
             return smallc_forward(*d, x, w, bias, act, alpha, y, st);
+        if (f == kSmallK)
+            return smallk_run(NB200_OP_FORWARD, *d, x, w, bias, act, alpha, y, workspace, workspace_bytes, st);
         if (f == kGather)
             return tc_gather_forward(*d, x, w, bias, act, alpha, y, workspace, workspace_bytes, st);
         return direct_forward(*d, x, w, bias, act, alpha, y, st);
@@ -228,6 +285,8 @@ extern "C"
             return tc_input_gradient(*d, dy, w, dx, workspace, workspace_bytes, st);
         if (f == kSmallC)
             return smallc_input_gradient(*d, dy, w, dx, st);
+        if (f == kSmallK)
+            return smallk_run(NB200_OP_INPUT_GRADIENT, *d, dy, w, nullptr, NB200_ACT_IDENTITY, 0.f, dx, workspace, workspace_bytes, st);
         if (f == kGather)
             return tc_gather_input_gradient(*d, dy, w, dx, workspace, workspace_bytes, st);
         return direct_input_gradient(*d, dy, w, dx, st);
@@ -254,6 +313,8 @@ extern "C"
         if (f == kSmallC)
             return tc_smallc_wgrad_supported(*d) ? tc_smallc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st)
                                                  : smallc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
+        if (f == kSmallK)
+            return smallk_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         if (f == kGather)
             return tc_gather_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         return direct_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
@@ -322,10 +383,12 @@ extern "C"
             return fail(NB200_E_INVALID, "null tensor pointer");
         if ((rc = require_device())) return rc;
         const Family f = pick(op, *d);
-        if (f != kTc && f != kGather)
+        if (f != kTc && f != kGather && f != kSmallK)
             return NB200_OK; // these kernels read w as it is
         FilterModeScope scope(kFiltersOnly);
         cudaStream_t st = (cudaStream_t)stream;
+        if (f == kSmallK)
+            return smallk_run(op, *d, nullptr, w, nullptr, NB200_ACT_IDENTITY, 0.f, nullptr, workspace, workspace_bytes, st);
         if (op == NB200_OP_FORWARD)
             return f == kTc ? tc_forward(*d, nullptr, w, nullptr, NB200_ACT_IDENTITY, 0.f, nullptr, workspace, workspace_bytes, st)
                             : tc_gather_forward(*d, nullptr, w, nullptr, NB200_ACT_IDENTITY, 0.f, nullptr, workspace, workspace_bytes, st);

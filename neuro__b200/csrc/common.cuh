@@ -78,6 +78,13 @@ namespace nb200
     int smallc_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes,
                                 cudaStream_t st);
 
+    int smallc_input_gradient_epilogue(const nb200_conv_desc& d, const float* dy, const float* w, const float* bias, int act, float alpha,
+                                       float* dx, cudaStream_t st);
+    // few-filter layers (K <= 4) = the small-channel problem with its activation tensors exchanged. conv_smallc.cu
+    bool smallk_supported(const nb200_conv_desc& d);
+    nb200_conv_desc smallk_swapped(const nb200_conv_desc& d);
+    int smallc_swap_filters(const float* in, float* out, int A, int B, cudaStream_t st); // out[b][a][2-r][2-s] = in[a][b][r][s]
+
     // tcgen05/TMA implicit-GEMM kernels (NCHW). conv_tc.cu
     bool tc_forward_supported(const nb200_conv_desc& d);
     bool tc_input_gradient_supported(const nb200_conv_desc& d);

@@ -115,7 +115,8 @@ namespace nb200
         // dx[n][c][h][w] = sum_k sum_{r,s} dy[n][k][h+pad-r][w+pad-s] * w[k][c][r][s]
         template <int C>
         __global__ void __launch_bounds__(kSmallThreads)
-        smallc_dgrad_kernel(SmallGeo g, const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx)
+        smallc_dgrad_kernel(SmallGeo g, const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ bias, int act,
+                            float alpha, float* __restrict__ dx)
         {
             constexpr int T = C * 9;
             constexpr int TP = (T + 3) & ~3;
@@ -208,6 +209,18 @@ namespace nb200
                         }
             }
 
+            if (bias != nullptr || act != NB200_ACT_IDENTITY)
+            {
+                // only when this kernel serves as the FORWARD of a few-filter layer (roles swapped, see smallk_* below)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                {
+                    const float b = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        acc[c][j] = apply_activation(act, alpha, acc[c][j] + b);
+                }
+            }
             const bool vec = g.aligned && (g.W & 3) == 0;
 #pragma unroll
             for (int c = 0; c < C; ++c)
@@ -331,6 +344,16 @@ namespace nb200
             out[i] = v;
         }
 
+        // out[b][a][2-r][2-s] = in[a][b][r][s]: filters transposed and rotated by 180 degrees (3x3 taps: index t -> 8 - t)
+        __global__ void swap_filters_kernel(const float* __restrict__ in, float* __restrict__ out, int A, int B)
+        {
+            const int i = blockIdx.x * blockDim.x + threadIdx.x;
+            if (i >= A * B * 9)
+                return;
+            const int t = i % 9, ab = i / 9, b = ab % B, a = ab / B;
+            out[(b * A + a) * 9 + (8 - t)] = in[i];
+        }
+
         SmallGeo small_geo(const nb200_conv_desc& d, const void* a, const void* b, const void* c)
         {
             const int aligned = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
@@ -388,13 +411,19 @@ namespace nb200
 
     int smallc_input_gradient(const nb200_conv_desc& d, const float* dy, const float* w, float* dx, cudaStream_t st)
     {
+        return smallc_input_gradient_epilogue(d, dy, w, nullptr, NB200_ACT_IDENTITY, 0.f, dx, st);
+    }
+
+    int smallc_input_gradient_epilogue(const nb200_conv_desc& d, const float* dy, const float* w, const float* bias, int act, float alpha,
+                                       float* dx, cudaStream_t st)
+    {
         const SmallGeo g = small_geo(d, dy, dx, nullptr);
         const long long quads = (long long)d.N * d.H * ((d.W + 3) / 4);
         const size_t smem = (size_t)d.K * ((d.C * 9 + 3) & ~3) * 4;
 #define CALL(CC)                                                                                                              \
         if (smem > 48 * 1024)                                                                                                  \
             NB200_CUDA_TRY(cudaFuncSetAttribute(smallc_dgrad_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        smallc_dgrad_kernel<CC><<<ceil_div(quads, kSmallThreads), kSmallThreads, smem, st>>>(g, dy, w, dx);
+        smallc_dgrad_kernel<CC><<<ceil_div(quads, kSmallThreads), kSmallThreads, smem, st>>>(g, dy, w, bias, act, alpha, dx);
         SMALLC_DISPATCH(CALL)
 #undef CALL
         NB200_CUDA_TRY(cudaGetLastError());
@@ -419,6 +448,37 @@ namespace nb200
         count_launch();
         const int count = d.K * d.C * 9;
         smallc_reduce_kernel<<<ceil_div(count, 256), 256, 0, st>>>((const float*)ws, dw, count, slices);
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        return NB200_OK;
+    }
+    // ---- few-FILTER layers (K <= 4: the RGB / mask output convolutions of the GAN generators and the autoencoder) ----
+    // A 3x3 stride-1 convolution with many channels and a few filters is the small-channel problem with the roles of its
+    // two activation tensors exchanged: with w'[c][k][r][s] = w[k][c][2-r][2-s] and pad' = 2 - pad
+    //   forward(x -> y)        = small-channel INPUT GRADIENT of (dy' = x) giving (dx' = y)      [+ bias / activation]
+    //   input gradient(dy->dx) = small-channel FORWARD of (x' = dy) giving (y' = dx)
+    //   kernel gradient        = small-channel KERNEL GRADIENT with (x' = dy, dy' = x), then dw[k][c][r][s] = dw'[c][k][2-r][2-s]
+    // so these HBM-bound layers stream their big tensor once through the kernels above instead of running as a GEMM with
+    // 3 of 64 accumulator columns in use.
+    nb200_conv_desc smallk_swapped(const nb200_conv_desc& d)
+    {
+        nb200_conv_desc s = d;
+        s.C = d.K; s.K = d.C;
+        s.H = d.Ho; s.W = d.Wo; s.Ho = d.H; s.Wo = d.W;
+        s.padX = 2 - d.padX; s.padY = 2 - d.padY;
+        return s;
+    }
+
+    bool smallk_supported(const nb200_conv_desc& d)
+    {
+        if (!(d.K >= 1 && d.K <= 4 && d.C > 4 && d.R == 3 && d.S == 3 && d.stride == 1 && d.padX <= 2 && d.padY <= 2))
+            return false;
+        return smallc_supported(smallk_swapped(d));
+    }
+
+    int smallc_swap_filters(const float* in, float* out, int A, int B, cudaStream_t st)
+    {
+        swap_filters_kernel<<<ceil_div((long long)A * B * 9, 256), 256, 0, st>>>(in, out, A, B);
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;

@@ -3520,19 +3520,42 @@ namespace nb200
         {
             int BN, PXI, tapsPerGroup, groups, tilesC, tilesK, splits, stages;
             long long chunks, chunksPerSplit;
-            size_t wsBytes, smemBytes;
+            size_t wsBytes, smemBytes, partialBytes;
+            int hwPad; // dy plane pitch the tensor map needs (multiple of 4 floats); != Ho*Wo => a pitched copy of dy in the workspace
             bool ok;
         };
+
+        // dst[plane][0 .. hwPad) = src[plane][0 .. hw), tail zero: gives dy planes the 16-byte pitch TMA requires
+        __global__ void pitch_planes_kernel(const float* __restrict__ src, float* __restrict__ dst, long long planes, int hw, int hwPad)
+        {
+            const long long total = planes * hwPad;
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+            {
+                const long long pl = i / hwPad;
+                const int j = (int)(i - pl * hwPad);
+                dst[i] = j < hw ? __ldg(src + pl * hw + j) : 0.f;
+            }
+        }
 
         WgatherPlan wgather_plan(const nb200_conv_desc& d)
         {
             WgatherPlan pl{};
             const int hw = d.Ho * d.Wo;
-            pl.PXI = hw >= 32 ? 32 : hw;
-            // maps of >= 32 pixels: 32-pixel chunks inside one image, the last one padded by the TMA zero fill (needs the
-            // 16-byte stride rule: Ho*Wo % 4 == 0); smaller maps: 16 or 8 pixels from each of 2 or 4 images
-            pl.ok = d.fmt == NB200_NCHW && d.math == NB200_MATH_TF32 && (pl.PXI == 32 ? hw % 4 == 0 : (pl.PXI == 16 || pl.PXI == 8)) &&
+            // maps of > 16 pixels: 32-pixel chunks inside one image; smaller maps: 16 or 8 pixel slots from each of 2 or 4
+            // images. Slots past the end of a map are zero on the dy side (TMA fills out-of-range box elements) and masked on
+            // the x side. TMA needs a 16-byte plane pitch: when Ho*Wo % 4 != 0 (31x31 PatchGAN maps, 1x1 U-Net bottleneck) dy
+            // is first copied into the workspace with its planes pitched to a multiple of 4 floats.
+            pl.PXI = hw > 16 ? 32 : hw > 8 ? 16 : 8;
+            pl.hwPad = round_up(hw, 4);
+            pl.ok = d.fmt == NB200_NCHW && d.math == NB200_MATH_TF32 && hw >= 1 &&
                     d.R * d.S <= 32 && d.C >= 1 && d.K >= 1 && d.N >= 1 && d.H >= 1 && d.W >= 1;
+            {
+                // tiny channel counts fill a sliver of the 128 x BN tile; below this K*C the CUDA-core kernel is used instead
+                static const char* env = getenv("NB200_WGRAD_GATHER_MIN_KC");
+                static const long long minKC = env ? atoll(env) : 0;
+                if ((long long)d.K * d.C < minKC)
+                    pl.ok = false;
+            }
             if (!pl.ok)
                 return pl;
             pl.BN = d.K > 64 ? 128 : 64;
@@ -3552,7 +3575,8 @@ namespace nb200
             pl.splits = (int)((pl.chunks + pl.chunksPerSplit - 1) / pl.chunksPerSplit);
             pl.stages = 6;
             pl.smemBytes = 1024 + 512 + (size_t)pl.stages * pl.BN * 128 + 8 * kWgScratchFloats * sizeof(float);
-            pl.wsBytes = (size_t)pl.splits * ntaps * d.K * d.C * sizeof(float);
+            pl.partialBytes = ((size_t)pl.splits * ntaps * d.K * d.C * sizeof(float) + 255) & ~(size_t)255;
+            pl.wsBytes = pl.partialBytes + (pl.hwPad != hw ? (size_t)d.N * d.K * pl.hwPad * sizeof(float) : 0);
             return pl;
         }
 
@@ -3583,13 +3607,23 @@ namespace nb200
             return fail(NB200_E_UNSUPPORTED, "gathered kernel gradient does not take this shape");
         if (wsBytes < pl.wsBytes || !ws)
             return fail(NB200_E_WORKSPACE, "tcgen05 kernel gradient needs %zu workspace bytes, got %zu", pl.wsBytes, wsBytes);
-        if ((uintptr_t)dy & 15)
+        if (((uintptr_t)dy & 15) || ((uintptr_t)ws & 15))
             return fail(NB200_E_INVALID, "tensor base addresses must be 16-byte aligned for TMA");
         const int hw = d.Ho * d.Wo;
+        if (pl.hwPad != hw)
+        {
+            float* pitched = (float*)((uint8_t*)ws + pl.partialBytes);
+            const long long total = (long long)d.N * d.K * pl.hwPad;
+            const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+            pitch_planes_kernel<<<blocks, 256, 0, st>>>(dy, pitched, (long long)d.N * d.K, hw, pl.hwPad);
+            NB200_CUDA_TRY(cudaGetLastError());
+            count_launch();
+            dy = pitched;
+        }
         CUtensorMap mapDy;
         {
             cuuint64_t dims[3] = {(cuuint64_t)hw, (cuuint64_t)d.K, (cuuint64_t)d.N};
-            cuuint64_t strides[2] = {(cuuint64_t)hw * 4, (cuuint64_t)d.K * hw * 4};
+            cuuint64_t strides[2] = {(cuuint64_t)pl.hwPad * 4, (cuuint64_t)d.K * pl.hwPad * 4};
             cuuint32_t box[3] = {(cuuint32_t)pl.PXI, (cuuint32_t)pl.BN, (cuuint32_t)(32 / pl.PXI)};
             const CUtensorMapSwizzle sw = pl.PXI == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : pl.PXI == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
             int rc = make_map(&mapDy, dy, 3, dims, strides, box, sw);

@@ -22,6 +22,7 @@ EXPORTS = [
     "nb200_conv2d_input_gradient_host", "nb200_conv2d_kernels_gradient_host",
     "nb200_conv2d_bias_activation_gradient_workspace_bytes", "nb200_conv2d_bias_activation_gradient",
     "nb200_conv2d_prepare_filters", "nb200_conv2d_forward_prepared", "nb200_conv2d_input_gradient_prepared",
+    "nb200_pool2d", "nb200_pool2d_gradient", "nb200_upsample2d", "nb200_upsample2d_gradient", "nb200_constant_pad2d",
 ]
 
 
@@ -38,6 +39,14 @@ class ConvDesc(ctypes.Structure):
         """4*(|x|+|w|+|y|): each tensor touched once."""
         return 4.0 * (self.N * self.C * self.H * self.W + self.K * self.C * self.R * self.S
                       + self.N * self.K * self.Ho * self.Wo)
+
+
+POOL_MAX, POOL_AVG = 0, 1
+
+
+class PoolDesc(ctypes.Structure):
+    """struct nb200_pool_desc"""
+    _fields_ = [(n, ctypes.c_int32) for n in ("N", "C", "H", "W", "Ho", "Wo", "filter", "stride", "padX", "padY", "mode", "fmt")]
 
 
 class NeuroB200Error(RuntimeError):
@@ -83,6 +92,12 @@ def load():
     L.nb200_conv2d_prepare_filters.argtypes = [c_i, dp, c_p, c_p, c_sz, c_p]
     L.nb200_conv2d_forward_prepared.argtypes = L.nb200_conv2d_forward.argtypes
     L.nb200_conv2d_input_gradient_prepared.argtypes = L.nb200_conv2d_input_gradient.argtypes
+    pp = ctypes.POINTER(PoolDesc)
+    L.nb200_pool2d.argtypes = [pp, c_p, c_p, c_p]
+    L.nb200_pool2d_gradient.argtypes = [pp, c_p, c_p, c_p, c_p, c_p]
+    L.nb200_upsample2d.argtypes = [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
+    L.nb200_upsample2d_gradient.argtypes = [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
+    L.nb200_constant_pad2d.argtypes = [c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p]
     _lib = L
     return L
 

@@ -190,6 +190,36 @@ class TensorOpB200:
         """note the swapped (gradient, input) order, as in Tensor.cpp:1827-1830"""
         self.Conv2DKernelsGradient(gradient, input, stride, padding, padding, dataFormat, kernelsGradient)
 
+    # -- spatial resamplers around the convolutions (TensorOpCpu.h:51-54; ConstantPad2D TensorOpCpu.cpp:528)
+    def _pool_desc(self, input, filterSize, stride, type, paddingX, paddingY, dataFormat, output):
+        N, C, H, W = _act_extent(dataFormat, input)
+        N2, C2, Ho, Wo = _act_extent(dataFormat, output)
+        assert N2 == N and C2 == C
+        return lib.PoolDesc(N, C, H, W, Ho, Wo, filterSize, stride, paddingX, paddingY, type, dataFormat)
+
+    def Pool2D(self, input, filterSize, stride, type, paddingX, paddingY, dataFormat, output):
+        d = self._pool_desc(input, filterSize, stride, type, paddingX, paddingY, dataFormat, output)
+        check(self._L.nb200_pool2d(ctypes.byref(d), _ptr(input), _ptr(output), _stream()))
+
+    def Pool2DGradient(self, output, input, outputGradient, filterSize, stride, type, paddingX, paddingY, dataFormat, inputGradient):
+        d = self._pool_desc(input, filterSize, stride, type, paddingX, paddingY, dataFormat, output)
+        check(self._L.nb200_pool2d_gradient(ctypes.byref(d), _ptr(output), _ptr(input), _ptr(outputGradient), _ptr(inputGradient), _stream()))
+
+    def UpSample2D(self, input, scaleFactor, output):
+        N, C, H, W = input.shape
+        assert tuple(output.shape) == (N, C, H * scaleFactor, W * scaleFactor)   # Tensor.cpp:1859
+        check(self._L.nb200_upsample2d(N, C, H, W, scaleFactor, _ptr(input), _ptr(output), _stream()))
+
+    def UpSample2DGradient(self, outputGradient, scaleFactor, inputGradient):
+        N, C, H, W = inputGradient.shape
+        assert tuple(outputGradient.shape) == (N, C, H * scaleFactor, W * scaleFactor)   # Tensor.cpp:1874
+        check(self._L.nb200_upsample2d_gradient(N, C, H, W, scaleFactor, _ptr(outputGradient), _ptr(inputGradient), _stream()))
+
+    def ConstantPad2D(self, input, left, right, top, bottom, value, output):
+        N, C, H, W = input.shape
+        assert tuple(output.shape) == (N, C, H + top + bottom, W + left + right)   # Tensor.cpp:1502
+        check(self._L.nb200_constant_pad2d(N, C, H, W, left, right, top, bottom, value, _ptr(input), _ptr(output), _stream()))
+
     # -- optimiser tail (TensorOpCpu.h:75-76)
     def AdamStep(self, parameter, gradient, mGrad, vGrad, lr, beta1, beta2, epsilon, gradScale=1.0):
         check(self._L.nb200_adam_step(_ptr(parameter), _ptr(gradient), _ptr(mGrad), _ptr(vGrad), parameter.numel(),

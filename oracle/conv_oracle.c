@@ -321,3 +321,124 @@ API void oracle_sgd_step(float* p, const float* g, size_t n, float lr)
     for (long long i = 0; i < (long long)n; ++i)
         p[i] = 1 * p[i] + -lr * g[i];
 }
+
+
+/* ---- spatial resamplers ---- */
+#include <float.h>
+
+typedef struct pool_dims { int N, C, H, W, Ho, Wo, filter, stride, padX, padY, mode, fmt; } pool_dims;
+
+static inline size_t ai(int fmt, int C, int H, int W, int n, int c, int h, int w)
+{
+    return fmt == 0 ? (((size_t)n * C + c) * H + h) * W + w : (((size_t)n * H + h) * W + w) * C + c;
+}
+
+/* Pooling. Follows TensorOpCpu::Pool2D, TensorOpCpu.cpp:1187-1246: window scanned (poolY, poolX); TryGet outside the
+ * tensor returns -FLT_MAX (max) or 0 (avg); the average divides by filter*filter. mode 0 = MaxPool, 1 = AvgPool. */
+API void oracle_pool2d(const pool_dims* d, const float* x, float* y)
+{
+#pragma omp parallel for collapse(2)
+    for (int n = 0; n < d->N; ++n)
+    for (int c = 0; c < d->C; ++c)
+    for (int oh = 0; oh < d->Ho; ++oh)
+    for (int ow = 0; ow < d->Wo; ++ow)
+    {
+        const int h = oh * d->stride - d->padY, w = ow * d->stride - d->padX;
+        float acc = d->mode == 0 ? -FLT_MAX : 0.f;
+        for (int py = 0; py < d->filter; ++py)
+        for (int px = 0; px < d->filter; ++px)
+        {
+            const int in = h + py >= 0 && h + py < d->H && w + px >= 0 && w + px < d->W;
+            if (d->mode == 0)
+            {
+                const float v = in ? x[ai(d->fmt, d->C, d->H, d->W, n, c, h + py, w + px)] : -FLT_MAX;
+                acc = acc > v ? acc : v;
+            }
+            else
+                acc += in ? x[ai(d->fmt, d->C, d->H, d->W, n, c, h + py, w + px)] : 0.f;
+        }
+        y[ai(d->fmt, d->C, d->Ho, d->Wo, n, c, oh, ow)] = d->mode == 0 ? acc : acc / (float)(d->filter * d->filter);
+    }
+}
+
+/* Pooling gradient. Follows TensorOpCpu::Pool2DGradient, TensorOpCpu.cpp:1249-1338: dx zeroed, then windows visited in
+ * (outH, outW) order; max: the first element (poolH, poolW order) whose value equals the pooled output gets += dy (a
+ * match on an out-of-range tap is dropped by TrySet but still ends the search); avg: every in-range element gets
+ * += dy / filter^2. */
+API void oracle_pool2d_gradient(const pool_dims* d, const float* y, const float* x, const float* dy, float* dx)
+{
+    memset(dx, 0, sizeof(float) * (size_t)d->N * d->C * d->H * d->W);
+#pragma omp parallel for collapse(2)
+    for (int n = 0; n < d->N; ++n)
+    for (int c = 0; c < d->C; ++c)
+    for (int oh = 0; oh < d->Ho; ++oh)
+    for (int ow = 0; ow < d->Wo; ++ow)
+    {
+        const int h = oh * d->stride - d->padY, w = ow * d->stride - d->padX;
+        const size_t yo = ai(d->fmt, d->C, d->Ho, d->Wo, n, c, oh, ow);
+        if (d->mode == 0)
+        {
+            int found = 0;
+            for (int py = 0; py < d->filter && !found; ++py)
+            for (int px = 0; px < d->filter; ++px)
+            {
+                const int in = h + py >= 0 && h + py < d->H && w + px >= 0 && w + px < d->W;
+                const float v = in ? x[ai(d->fmt, d->C, d->H, d->W, n, c, h + py, w + px)] : -FLT_MAX;
+                if (v == y[yo])
+                {
+                    if (in)
+                        dx[ai(d->fmt, d->C, d->H, d->W, n, c, h + py, w + px)] += dy[yo];
+                    found = 1;
+                    break;
+                }
+            }
+        }
+        else
+        {
+            const float f2 = (float)(d->filter * d->filter);
+            for (int py = 0; py < d->filter; ++py)
+            for (int px = 0; px < d->filter; ++px)
+                if (h + py >= 0 && h + py < d->H && w + px >= 0 && w + px < d->W)
+                    dx[ai(d->fmt, d->C, d->H, d->W, n, c, h + py, w + px)] += dy[yo] / f2;
+        }
+    }
+}
+
+/* Nearest-neighbour up-sampling. Follows TensorOpCpu::UpSample2D, TensorOpCpu.cpp:1340-1354 (NCHW planes). */
+API void oracle_upsample2d(int planes, int H, int W, int s, const float* x, float* y)
+{
+#pragma omp parallel for
+    for (int p = 0; p < planes; ++p)
+    for (int h = 0; h < H; ++h)
+    for (int w = 0; w < W; ++w)
+        for (int oh = h * s; oh < (h + 1) * s; ++oh)
+        for (int ow = w * s; ow < (w + 1) * s; ++ow)
+            y[((size_t)p * H * s + oh) * W * s + ow] = x[((size_t)p * H + h) * W + w];
+}
+
+/* Follows TensorOpCpu::UpSample2DGradient, TensorOpCpu.cpp:1357-1369: dx zeroed, dx(w/s, h/s) += dy(w, h) walking h then w. */
+API void oracle_upsample2d_gradient(int planes, int H, int W, int s, const float* dy, float* dx)
+{
+    memset(dx, 0, sizeof(float) * (size_t)planes * H * W);
+#pragma omp parallel for
+    for (int p = 0; p < planes; ++p)
+    for (int oh = 0; oh < H * s; ++oh)
+    for (int ow = 0; ow < W * s; ++ow)
+        dx[((size_t)p * H + oh / s) * W + ow / s] += dy[((size_t)p * H * s + oh) * W * s + ow];
+}
+
+/* Follows TensorOpCpu::ConstantPad2D, TensorOpCpu.cpp:528-546 (NCHW planes). */
+API void oracle_constant_pad2d(int planes, int H, int W, int left, int right, int top, int bottom, float value, const float* x, float* y)
+{
+    const int Ho = H + top + bottom, Wo = W + left + right;
+#pragma omp parallel for
+    for (int p = 0; p < planes; ++p)
+    for (int h = 0; h < Ho; ++h)
+    for (int w = 0; w < Wo; ++w)
+    {
+        float v = value;
+        if (w >= left && h >= top && w < W + left && h < H + top)
+            v = x[((size_t)p * H + (h - top)) * W + (w - left)];
+        y[((size_t)p * Ho + h) * Wo + w] = v;
+    }
+}

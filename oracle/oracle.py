@@ -175,6 +175,60 @@ def sgd_step(p, g, lr):
     lib().oracle_sgd_step(_fp(p), _fp(g), ctypes.c_size_t(p.size), ctypes.c_float(lr))
 
 
+MAX_POOL, AVG_POOL = 0, 1
+
+
+class PoolDims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("N", "C", "H", "W", "Ho", "Wo", "filter", "stride", "padX", "padY", "mode", "fmt")]
+
+
+def pool_out_size(size, f, stride, pad):
+    """Tensor::GetPooling2DOutputShape, Neuro/src/Tensors/Tensor.cpp:1988-2007."""
+    return (size + 2 * pad - f) // stride + 1
+
+
+def _pool_dims(x, f, stride, mode, padX, padY, fmt):
+    N, C, H, W = _xshape(fmt, x)
+    return PoolDims(N, C, H, W, pool_out_size(H, f, stride, padY), pool_out_size(W, f, stride, padX), f, stride, padX, padY, mode, fmt)
+
+
+def pool2d(x, f, stride, mode, padX=0, padY=None, fmt=NCHW):
+    padY = padX if padY is None else padY
+    d = _pool_dims(x, f, stride, mode, padX, padY, fmt)
+    y = np.empty(_mk(fmt, d.N, 0, d.Ho, d.Wo, d.C), np.float32)
+    lib().oracle_pool2d(ctypes.byref(d), _fp(x), _fp(y))
+    return y
+
+
+def pool2d_gradient(y, x, dy, f, stride, mode, padX=0, padY=None, fmt=NCHW):
+    padY = padX if padY is None else padY
+    d = _pool_dims(x, f, stride, mode, padX, padY, fmt)
+    dx = np.empty_like(x)
+    lib().oracle_pool2d_gradient(ctypes.byref(d), _fp(y), _fp(x), _fp(dy), _fp(dx))
+    return dx
+
+
+def upsample2d(x, s):
+    N, C, H, W = x.shape
+    y = np.empty((N, C, H * s, W * s), np.float32)
+    lib().oracle_upsample2d(N * C, H, W, s, _fp(x), _fp(y))
+    return y
+
+
+def upsample2d_gradient(dy, s):
+    N, C, Ho, Wo = dy.shape
+    dx = np.empty((N, C, Ho // s, Wo // s), np.float32)
+    lib().oracle_upsample2d_gradient(N * C, Ho // s, Wo // s, s, _fp(dy), _fp(dx))
+    return dx
+
+
+def constant_pad2d(x, left, right, top, bottom, value):
+    N, C, H, W = x.shape
+    y = np.empty((N, C, H + top + bottom, W + left + right), np.float32)
+    lib().oracle_constant_pad2d(N * C, H, W, left, right, top, bottom, ctypes.c_float(value), _fp(x), _fp(y))
+    return y
+
+
 # ---------------------------------------------------------------- the reference itself
 
 def _shape4(fmt, a, kernels=False):
@@ -226,3 +280,39 @@ def ref_activation_gradient(act, alpha, y, dy):
     dims = (ctypes.c_uint32 * 4)(a.size, 1, 1, 1)
     ref().neuro_ref_activation_gradient(int(act), ctypes.c_float(alpha), _fp(y), _fp(dy), _fp(dz), dims)
     return dz
+
+
+def ref_pool2d(x, f, stride, mode, padX=0, padY=None, fmt=NCHW):
+    padY = padX if padY is None else padY
+    d = _pool_dims(x, f, stride, mode, padX, padY, fmt)
+    y = np.empty(_mk(fmt, d.N, 0, d.Ho, d.Wo, d.C), np.float32)
+    ref().neuro_ref_pool2d(fmt, _fp(x), _shape4(fmt, x), f, stride, mode, padX, padY, _fp(y), _shape4(fmt, y))
+    return y
+
+
+def ref_pool2d_gradient(y, x, dy, f, stride, mode, padX=0, padY=None, fmt=NCHW):
+    padY = padX if padY is None else padY
+    dx = np.empty_like(x)
+    ref().neuro_ref_pool2d_gradient(fmt, _fp(y), _shape4(fmt, y), _fp(x), _shape4(fmt, x), _fp(dy), f, stride, mode, padX, padY, _fp(dx))
+    return dx
+
+
+def ref_upsample2d(x, s):
+    N, C, H, W = x.shape
+    y = np.empty((N, C, H * s, W * s), np.float32)
+    ref().neuro_ref_upsample2d(_fp(x), _shape4(NCHW, x), s, _fp(y), _shape4(NCHW, y))
+    return y
+
+
+def ref_upsample2d_gradient(dy, s):
+    N, C, Ho, Wo = dy.shape
+    dx = np.empty((N, C, Ho // s, Wo // s), np.float32)
+    ref().neuro_ref_upsample2d_gradient(_fp(dy), _shape4(NCHW, dy), s, _fp(dx), _shape4(NCHW, dx))
+    return dx
+
+
+def ref_constant_pad2d(x, left, right, top, bottom, value):
+    N, C, H, W = x.shape
+    y = np.empty((N, C, H + top + bottom, W + left + right), np.float32)
+    ref().neuro_ref_constant_pad2d(_fp(x), _shape4(NCHW, x), left, right, top, bottom, ctypes.c_float(value), _fp(y), _shape4(NCHW, y))
+    return y

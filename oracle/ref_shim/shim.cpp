@@ -75,6 +75,14 @@ namespace Neuro
         memset(m_Storage.Data(), 0, sizeof(float) * m_Shape.Length);
     }
 
+    // Same bounds semantics as the reference (Tensor.cpp:2087-2093); used by Pool2DGradient's scatter.
+    void Tensor::TrySet(float value, int w, int h, int d, int n)
+    {
+        if (h < 0 || h >= (int)Height() || w < 0 || w >= (int)Width() || d < 0 || d >= (int)Depth() || n < 0 || n > (int)Batch())
+            return;
+        Set(value, w, h, d, n);
+    }
+
     // Tensor::Map (Tensor.cpp:814-818) forwards to the op; the op's own loop (TensorOpCpu.cpp:773-800) is the reference's.
     void Tensor::Map(const function<float(float, float)>& func, const Tensor& other, Tensor& result) const
     {
@@ -180,4 +188,48 @@ REF_API void neuro_ref_activation_gradient(int act, float alpha, const float* y,
     default: memcpy(tz.Values(), tg.Values(), sizeof(float) * tg.Length()); break;
     }
     Store(tz, dz);
+}
+
+// ---- spatial resamplers (TensorOpCpu.cpp:1187-1369, 528-546), single-thread class; shapes as above ----
+REF_API void neuro_ref_pool2d(int fmt, const float* x, const uint32_t* xDims, uint32_t filter, uint32_t stride, int mode, uint32_t padX, uint32_t padY,
+                              float* y, const uint32_t* yDims)
+{
+    Tensor tx(MakeShape(xDims)), ty(MakeShape(yDims));
+    Load(tx, x);
+    OpSt()->TensorOpCpu::Pool2D(tx, filter, stride, (EPoolingMode)mode, padX, padY, (EDataFormat)fmt, ty);
+    Store(ty, y);
+}
+
+REF_API void neuro_ref_pool2d_gradient(int fmt, const float* y, const uint32_t* yDims, const float* x, const uint32_t* xDims, const float* dy,
+                                       uint32_t filter, uint32_t stride, int mode, uint32_t padX, uint32_t padY, float* dx)
+{
+    Tensor tx(MakeShape(xDims)), ty(MakeShape(yDims)), tdy(MakeShape(yDims)), tdx(MakeShape(xDims));
+    Load(tx, x); Load(ty, y); Load(tdy, dy);
+    OpSt()->TensorOpCpu::Pool2DGradient(ty, tx, tdy, filter, stride, (EPoolingMode)mode, padX, padY, (EDataFormat)fmt, tdx);
+    Store(tdx, dx);
+}
+
+REF_API void neuro_ref_upsample2d(const float* x, const uint32_t* xDims, uint32_t scale, float* y, const uint32_t* yDims)
+{
+    Tensor tx(MakeShape(xDims)), ty(MakeShape(yDims));
+    Load(tx, x);
+    OpSt()->TensorOpCpu::UpSample2D(tx, scale, ty);
+    Store(ty, y);
+}
+
+REF_API void neuro_ref_upsample2d_gradient(const float* dy, const uint32_t* yDims, uint32_t scale, float* dx, const uint32_t* xDims)
+{
+    Tensor tdy(MakeShape(yDims)), tdx(MakeShape(xDims));
+    Load(tdy, dy);
+    OpSt()->TensorOpCpu::UpSample2DGradient(tdy, scale, tdx);
+    Store(tdx, dx);
+}
+
+REF_API void neuro_ref_constant_pad2d(const float* x, const uint32_t* xDims, uint32_t left, uint32_t right, uint32_t top, uint32_t bottom, float value,
+                                      float* y, const uint32_t* yDims)
+{
+    Tensor tx(MakeShape(xDims)), ty(MakeShape(yDims));
+    Load(tx, x);
+    OpSt()->TensorOpCpu::ConstantPad2D(tx, left, right, top, bottom, value, ty);
+    Store(ty, y);
 }

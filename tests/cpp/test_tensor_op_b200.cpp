@@ -19,6 +19,7 @@ extern "C"
     void oracle_conv2d_kernels_gradient(const conv_dims*, const float*, const float*, float*);
     void oracle_conv2d_bias_activation(const conv_dims*, const float*, const float*, const float*, int, float, float*);
     void oracle_conv2d_bias_gradient(const conv_dims*, const float*, float*);
+    void oracle_activation_gradient(int, float, const float*, const float*, float*, size_t);
     void oracle_adam_step(float*, const float*, float*, float*, size_t, float, float, float, float);
     void oracle_sgd_step(float*, const float*, size_t, float);
 }
@@ -47,6 +48,8 @@ public:
     { const conv_dims d = Dims(dx, k, g, s, px, py, f); dx.OverrideHost(); oracle_conv2d_input_gradient(&d, g.Values(), k.Values(), dx.Values()); }
     void Conv2DKernelsGradient(const Tensor& x, const Tensor& g, uint32_t s, uint32_t px, uint32_t py, EDataFormat f, Tensor& dw) const override
     { const conv_dims d = Dims(x, dw, g, s, px, py, f); dw.OverrideHost(); oracle_conv2d_kernels_gradient(&d, x.Values(), g.Values(), dw.Values()); }
+    void ActivationGradient(EActivation a, float alpha, const Tensor& y, const Tensor& g, Tensor& dz) const override
+    { dz.OverrideHost(); oracle_activation_gradient((int)a, alpha, y.Values(), g.Values(), dz.Values(), g.Length()); }
     void AdamStep(Tensor& p, const Tensor& g, Tensor& m, Tensor& v, float lr, float b1, float b2, float eps) const override
     { oracle_adam_step(p.Values(), g.Values(), m.Values(), v.Values(), p.Length(), lr, b1, b2, eps); }
     void SgdStep(Tensor& p, const Tensor& g, float lr) const override { oracle_sgd_step(p.Values(), g.Values(), p.Length(), lr); }
@@ -144,6 +147,28 @@ TEST_METHOD(Conv2DBiasGradient_CompareWithCpuResult)
     Tensor biasGradient2(Shape(1, 1, features, 1));
     gradient.Conv2DBiasGradient(gradient, biasGradient2);
     IsTrue(biasGradient.Equals(biasGradient2, 0.0001f));
+}
+
+// Conv2dBiasActivationOp::ComputeGradientInternal (Conv2dBiasActivationOp.cpp:47-60): ActivationGradient, then Conv2DBiasGradient of
+// its result -- the CPU side runs them as the reference does (two passes), TensorOpB200 in one fused pass.
+TEST_METHOD(Conv2DBiasActivationGradient_CompareWithCpuResult)
+{
+    const EActivation acts[] = { _Sigmoid, _ReLU, _TanH, _ELU, _LeakyReLU };
+    for (EActivation act : acts)
+    {
+        Tensor output(Shape(24, 24, 5, 3)); output.FillWithRand(15, act == _Sigmoid ? 0.f : -1.f, 1.f);
+        Tensor gradient(Shape(24, 24, 5, 3)); gradient.FillWithRand(13);
+        Tensor::SetForcedOpMode(CPU);
+        Tensor dz(output.GetShape()), db(Shape(1, 1, 5, 1));
+        gradient.Conv2DBiasActivationGradient(output, gradient, act, 0.2f, dz, db);
+        Tensor::SetForcedOpMode(B200);
+        Tensor dz2(output.GetShape()), db2(Shape(1, 1, 5, 1)), dz3(output.GetShape());
+        gradient.Conv2DBiasActivationGradient(output, gradient, act, 0.2f, dz2, db2);
+        gradient.ActivationGradient(act, 0.2f, output, gradient, dz3);
+        IsTrue(dz.Equals(dz2, 0.f));    // element-wise fp32 in the reference's operation order: bit-exact
+        IsTrue(dz.Equals(dz3, 0.f));
+        IsTrue(db.Equals(db2, 0.0001f));
+    }
 }
 
 TEST_METHOD(Conv2DInputGradient_CompareWithCpuResult)

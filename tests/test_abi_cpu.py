@@ -105,6 +105,14 @@ def test_kernel_dispatch_is_host_logic(L):
     # DCGAN / pix2pix geometry: strided, tiny maps, transposed convolutions -> gathered tensor-core kernels
     assert names(_desc(128, 64, 32, 32, 128, 3, 3, 2, 1, 1)) == ["tcgen05_gather_fprop", "tcgen05_gather_dgrad", "tcgen05_gather_wgrad"]
     assert names(_desc(128, 128, 8, 8, 256, 4, 4, 2, 1, 1))[0].startswith("tcgen05_gather")
+    # pix2pix shapes that used to fall off the tensor cores in the kernel gradient: 31x31 PatchGAN maps (odd plane size), U-Net bottleneck
+    assert names(_desc(8, 256, 34, 34, 512, 4, 4, 1, 0, 0))[2] == "tcgen05_gather_wgrad"
+    assert names(_desc(8, 512, 4, 4, 512, 3, 3, 2, 1, 1))[2] == "tcgen05_gather_wgrad"
+    assert names(_desc(8, 512, 2, 2, 512, 3, 3, 2, 1, 1))[2] == "tcgen05_gather_wgrad"
+    # few-filter output convolutions (DCGAN G out, pix2pix last, autoencoder dec3): small-channel kernels with x and y exchanged
+    assert names(_desc(128, 128, 32, 32, 3, 3, 3, 1, 1, 1)) == ["smallk_fprop", "smallk_dgrad", "tcgen05_smallk_wgrad"]
+    assert names(_desc(8, 128, 256, 256, 3, 3, 3, 1, 1, 1)) == ["smallk_fprop", "smallk_dgrad", "tcgen05_smallk_wgrad"]
+    assert names(_desc(256, 16, 28, 28, 1, 3, 3, 1, 1, 1))[:2] == ["smallk_fprop", "smallk_dgrad"]
     # 3xTF32: forward / input gradient stay on tensor cores (no row-tap), kernel gradient on fp32 CUDA cores
     n3 = names(_desc(8, 64, 512, 512, 64, 3, 3, 1, 1, 1, math=lib.MATH_3XTF32))
     assert n3[0] == "tcgen05_fprop" and n3[1] == "tcgen05_dgrad" and n3[2] == "direct_wgrad"

@@ -92,6 +92,18 @@ TC_CASES = [
     (0, 4, 32, 16, 64, 16, 1, 3, 1, 1, 0),     # one filter row
     (0, 3, 64, 37, 40, 64, 3, 3, 1, 1, 1),     # rows split across images mid-run (3 x 37 rows over 111 CTAs), ragged segment
     (0, 1, 128, 24, 32, 32, 5, 5, 1, 2, 2),    # 5 columns with > 64 channels: 5 A tiles per step, kernel gradient must take the gathered kernel
+    # few-filter layers (K <= 4): the small-channel kernels with x and y exchanged (GAN generator / autoencoder output convs)
+    (0, 2, 128, 32, 32, 3, 3, 3, 1, 1, 1),     # DCGAN G conv out 128 -> 3
+    (0, 2, 16, 28, 28, 1, 3, 3, 1, 1, 1),      # conv autoencoder dec conv3 16 -> 1
+    (0, 1, 64, 256, 256, 3, 3, 3, 1, 1, 1),    # pix2pix last conv geometry: >= 64K pixels, kernel gradient on the tensor cores
+    (0, 2, 24, 20, 24, 4, 3, 3, 1, 0, 0),      # valid padding (pad' = 2)
+    (0, 2, 24, 20, 22, 2, 3, 3, 1, 2, 2),      # full padding (pad' = 0), ragged width
+    # gathered kernel gradient on maps whose planes TMA cannot address directly (pitched copy of dy) and on tiny maps
+    (0, 2, 32, 34, 34, 48, 4, 4, 1, 0, 0),     # PatchGAN 31x31 maps: Ho*Wo = 961, odd
+    (0, 8, 64, 4, 4, 64, 3, 3, 2, 1, 1),       # U-Net bottleneck: 2x2 maps, 4 pixels in 8-pixel slots
+    (0, 8, 64, 2, 2, 64, 3, 3, 2, 1, 1),       # 1x1 maps
+    (0, 4, 32, 3, 3, 32, 3, 3, 1, 1, 1),       # 9 pixels in 16-pixel slots, planes pitched to 12
+    (0, 2, 16, 5, 5, 16, 3, 3, 1, 1, 1),       # 25 pixels in one 32-pixel chunk, planes pitched to 28
     # channel-split forward / input gradient (few tiles, many channels: batch-1 style transfer on the deep layers)
     (0, 1, 256, 32, 32, 128, 3, 3, 1, 1, 1),   # 8 tiles x 4 channel splits (forward), 16 tiles x 2 splits (input gradient)
     (0, 1, 160, 32, 64, 96, 3, 3, 1, 1, 1),    # 5 channel blocks: uneven split 3 + 2
@@ -116,7 +128,7 @@ def test_against_oracle(cfg, math):
 @pytest.mark.parametrize("act", [lib.ACT_IDENTITY, lib.ACT_SIGMOID, lib.ACT_RELU, lib.ACT_TANH, lib.ACT_ELU, lib.ACT_LEAKY_RELU])
 def test_bias_activation(act, math):
     """Conv2DBiasActivation (TensorOpGpuTests.cpp:1238-1252 uses ReLU; all epilogues are covered here)."""
-    for (N, C, H, W, K, F, st, p) in [(3, 3, 26, 26, 2, 3, 1, 0), (2, 64, 32, 32, 64, 3, 1, 1), (2, 32, 48, 96, 40, 3, 1, 1), (1, 256, 32, 32, 72, 3, 1, 1)]:
+    for (N, C, H, W, K, F, st, p) in [(3, 3, 26, 26, 2, 3, 1, 0), (2, 64, 32, 32, 64, 3, 1, 1), (2, 32, 48, 96, 40, 3, 1, 1), (1, 256, 32, 32, 72, 3, 1, 1), (2, 24, 20, 20, 3, 3, 1, 1)]:
         x = synth.uniform(synth.SEED_X, (N, C, H, W)); w = synth.glorot_uniform(synth.SEED_W, K, C, F, F)
         b = synth.uniform(synth.SEED_BIAS, (K,))
         ref = O.conv2d_bias_activation(x, w, b, st, p, act, 0.2)
@@ -281,6 +293,7 @@ PREPARED_CASES = [
     (4, 64, 32, 32, 128, 3, 2, 1),    # gathered kernel (stride 2; the input gradient runs one launch per parity class)
     (8, 128, 8, 8, 256, 4, 2, 1),     # DCGAN deconv geometry
     (2, 3, 64, 64, 64, 3, 1, 1),      # first-layer kernels read w directly: prepare is a no-op
+    (2, 128, 32, 32, 3, 3, 1, 1),     # few-filter layer: the transposed + rotated filters are what is prepared
 ]
 
 

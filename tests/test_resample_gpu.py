@@ -1,0 +1,87 @@
+"""GPU parity for the resamplers next to the convolutions (Pool2D / UpSample2D / ConstantPad2D and gradients): the CUDA
+kernels add in the reference's order, so every result must be BIT-identical to the oracle (itself pinned to the
+reference's literal vectors and compiled loops in tests/test_resample_oracle.py). Mirrors
+Neuro.Tests/src/TensorOpGpuTests.cpp (Pool2D_*_CompareWithCpuResult, UpSample2D_*)."""
+import numpy as np
+import pytest
+import torch
+
+from neuro__b200 import lib, synth
+from neuro__b200.tensor_op import TensorOpB200
+from oracle import oracle as O
+from tests.gpu_util import dev
+
+pytestmark = pytest.mark.gpu
+
+POOL_CASES = [  # (fmt, N, C, H, W, filter, stride, pad)
+    (0, 2, 3, 8, 8, 2, 2, 0), (0, 2, 3, 9, 7, 3, 2, 1), (0, 1, 2, 7, 7, 3, 1, 1), (1, 2, 3, 8, 6, 2, 2, 0), (1, 1, 4, 9, 9, 3, 2, 1),
+    (0, 1, 1, 5, 5, 5, 1, 2), (0, 3, 16, 28, 28, 2, 2, 0),       # conv autoencoder MaxPool2 (config 1)
+    (0, 2, 64, 64, 64, 2, 2, 0), (1, 2, 64, 32, 32, 2, 2, 0),     # VGG block pooling geometry (2x2 s2), both formats
+    (0, 1, 8, 33, 31, 3, 3, 0), (0, 2, 4, 12, 12, 4, 2, 1)]
+
+
+@pytest.mark.parametrize("mode", [O.MAX_POOL, O.AVG_POOL], ids=["max", "avg"])
+@pytest.mark.parametrize("cfg", POOL_CASES, ids=["-".join(map(str, c)) for c in POOL_CASES])
+def test_pool2d_and_gradient(cfg, mode):
+    fmt, N, C, H, W, f, st, p = cfg
+    x = synth.uniform(21, (N, C, H, W))
+    if mode == O.MAX_POOL:
+        x = np.round(x * 4) / 4            # ties inside windows: only the first (row-major) maximum may receive the gradient
+    if fmt == lib.NHWC:
+        x = np.ascontiguousarray(x.transpose(0, 2, 3, 1))
+    y_ref = O.pool2d(x, f, st, mode, p, p, fmt)
+    dy = synth.uniform(22, y_ref.shape)
+    dx_ref = O.pool2d_gradient(y_ref, x, dy, f, st, mode, p, p, fmt)
+    op = TensorOpB200()
+    xd = dev(x)
+    y = torch.full(y_ref.shape, float("nan"), device="cuda"); dx = torch.full(x.shape, float("nan"), device="cuda")
+    op.Pool2D(xd, f, st, mode, p, p, fmt, y)
+    op.Pool2DGradient(y, xd, dev(dy), f, st, mode, p, p, fmt, dx)
+    assert np.array_equal(y.cpu().numpy(), y_ref)
+    assert np.array_equal(dx.cpu().numpy(), dx_ref)
+
+
+def test_pool_reference_literal_vectors():
+    """TensorTests.cpp:427-492 on the device."""
+    op = TensorOpB200()
+    t = torch.arange(72, dtype=torch.float32, device="cuda").view(2, 1, 6, 6)
+    y = torch.empty(2, 1, 3, 3, device="cuda")
+    op.Pool2D(t, 2, 2, lib.POOL_MAX, 0, 0, lib.NCHW, y)
+    assert y.flatten().tolist() == [7, 9, 11, 19, 21, 23, 31, 33, 35, 43, 45, 47, 55, 57, 59, 67, 69, 71]
+    g = torch.arange(1, 19, dtype=torch.float32, device="cuda").view(2, 1, 3, 3)
+    dx = torch.empty_like(t)
+    op.Pool2DGradient(y, t, g, 2, 2, lib.POOL_MAX, 0, 0, lib.NCHW, dx)
+    want = torch.zeros_like(t); want[:, :, 1::2, 1::2] = g
+    assert torch.equal(dx, want)
+    op.Pool2D(t, 2, 2, lib.POOL_AVG, 0, 0, lib.NCHW, y)
+    assert y.flatten().tolist() == [3.5, 5.5, 7.5, 15.5, 17.5, 19.5, 27.5, 29.5, 31.5, 39.5, 41.5, 43.5, 51.5, 53.5, 55.5, 63.5, 65.5, 67.5]
+    op.Pool2DGradient(y, t, g, 2, 2, lib.POOL_AVG, 0, 0, lib.NCHW, dx)
+    assert torch.equal(dx, (g / 4).repeat_interleave(2, 2).repeat_interleave(2, 3))
+
+
+@pytest.mark.parametrize("shape,s", [((2, 1, 2, 2), 2), ((2, 3, 5, 4), 3), ((4, 8, 14, 14), 2), ((1, 2, 7, 9), 1), ((2, 16, 32, 32), 2)])
+def test_upsample2d_and_gradient(shape, s):
+    x = synth.uniform(23, shape)
+    y_ref = O.upsample2d(x, s)
+    dy = synth.uniform(24, y_ref.shape)
+    op = TensorOpB200()
+    y = torch.full(y_ref.shape, float("nan"), device="cuda"); dx = torch.full(shape, float("nan"), device="cuda")
+    op.UpSample2D(dev(x), s, y)
+    op.UpSample2DGradient(dev(dy), s, dx)
+    assert np.array_equal(y.cpu().numpy(), y_ref)
+    assert np.array_equal(dx.cpu().numpy(), O.upsample2d_gradient(dy, s))
+    if shape == (2, 1, 2, 2):   # TensorTests.cpp:494-504
+        t = torch.arange(8, dtype=torch.float32, device="cuda").view(2, 1, 2, 2)
+        op.UpSample2D(t, 2, y)
+        assert y.flatten().tolist() == [0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3, 4, 4, 5, 5, 4, 4, 5, 5, 6, 6, 7, 7, 6, 6, 7, 7]
+
+
+@pytest.mark.parametrize("pads", [(1, 1, 1, 1, 0.0), (0, 3, 2, 0, -1.5), (2, 0, 0, 1, 7.0), (1, 2, 1, 2, 0.0)])
+def test_constant_pad2d(pads):
+    """PatchGAN's ZeroPadding2D in front of its 4x4 pad-0 convolutions (Pix2Pix.cpp)."""
+    l, r, t, b, v = pads
+    x = synth.uniform(25, (2, 6, 32, 31))
+    ref = O.constant_pad2d(x, l, r, t, b, v)
+    y = torch.full(ref.shape, float("nan"), device="cuda")
+    TensorOpB200().ConstantPad2D(dev(x), l, r, t, b, v, y)
+    assert np.array_equal(y.cpu().numpy(), ref)
