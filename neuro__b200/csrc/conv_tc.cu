@@ -1600,14 +1600,34 @@ namespace nb200
             int tilesK, bStages;
             int act;
             float alpha;
+            // channel split (few tiles, many channels: the weight-bound U-Net bottleneck layers): split sp of a tile reduces
+            // channel blocks [sp*cbPer, (sp+1)*cbPer) and writes a raw partial; fprop_split_reduce_kernel adds them
+            int splits, cbPer;
+            float* partial;
+            long long partialStride;
             short iyAdd[32], ixAdd[32], wtap[32];
+        };
+
+        // Several pixel lists served by ONE launch: the stride^2 parity classes of a strided input gradient (transposed
+        // convolution) differ only in their tap lists and pixel-list geometry, and each alone fills a fraction of the chip.
+        constexpr int kGatherMaxClasses = 9;
+        struct GatherBatch
+        {
+            int count;
+            int tileStart[kGatherMaxClasses + 1]; // first CTA of each class; tileStart[count] = grid size
+            GatherParams cls[kGatherMaxClasses];
         };
 
         template <int BN>
         __global__ void __launch_bounds__(kFpropThreads, (BN > 128 ? 1 : 2))
-        tc_gather_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ GatherParams p, const float* __restrict__ in,
+        tc_gather_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ GatherBatch batch, const float* __restrict__ in,
                          const float* __restrict__ bias, float* __restrict__ out)
         {
+            int cls = 0;
+            while (cls + 1 < batch.count && (int)blockIdx.x >= batch.tileStart[cls + 1])
+                ++cls;
+            const GatherParams& p = batch.cls[cls];
+            const int bid = (int)blockIdx.x - batch.tileStart[cls];
             constexpr uint32_t kBBytes = BN * kBlockC * 4;
             constexpr int kAStages = a_stages(BN);
             constexpr uint32_t kTmemCols = BN > 128 ? 512 : 256;
@@ -1625,9 +1645,12 @@ namespace nb200
 
             const int warp = threadIdx.x >> 5;
             const int lane = threadIdx.x & 31;
-            const int kt = blockIdx.x % p.tilesK;
-            const long long tile = blockIdx.x / p.tilesK;
+            const int split = bid % p.splits;
+            const int kt = (bid / p.splits) % p.tilesK;
+            const long long tile = bid / (p.splits * p.tilesK);
             const int k0 = kt * BN;
+            const int cbBegin = split * p.cbPer;
+            const int cbEnd = min(p.Cblocks, cbBegin + p.cbPer);
 
             if (warp == 0 && lane == 0)
             {
@@ -1644,7 +1667,7 @@ namespace nb200
             ptx::tc_fence_after_sync();
             const uint32_t tmemAcc = *tmemSlot;
             const uint32_t tmemA = tmemAcc + BN;
-            const int iters = p.ntaps * p.Cblocks;
+            const int iters = p.ntaps * max(cbEnd - cbBegin, 0);
 
             if (warp == 0)
             {
@@ -1652,7 +1675,7 @@ namespace nb200
                 {
                     int bs = 0;
                     uint32_t bph = 0;
-                    for (int cb = 0; cb < p.Cblocks; ++cb)
+                    for (int cb = cbBegin; cb < cbEnd; ++cb)
                         for (int t = 0; t < p.ntaps; ++t)
                         {
                             ptx::mbar_wait(&bEmpty[bs], bph ^ 1);
@@ -1709,10 +1732,10 @@ namespace nb200
                 int pendStage = 0;
                 for (int it = g; it < iters; it += kConvGroups)
                 {
-                    const int cb = it / p.ntaps, t = it - cb * p.ntaps;
+                    const int cbRel = it / p.ntaps, t = it - cbRel * p.ntaps;
                     const int iy = a * p.iyMul + p.iyAdd[t], ix = b * p.ixMul + p.ixAdd[t];
                     const bool ok = pixOk && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                    const int cbase = cb * kBlockC;
+                    const int cbase = (cbBegin + cbRel) * kBlockC;
                     uint32_t v[kBlockC];
                     if (ok)
                     {
@@ -1764,7 +1787,8 @@ namespace nb200
                 const int oy = a * p.oyMul + p.oyAdd, ox = b * p.oxMul + p.oxAdd;
                 const bool outOk = pixOk && oy < p.Ho && ox < p.Wo;
                 const long long oplane = (long long)p.Ho * p.Wo;
-                float* op = out + n * p.K * oplane + (long long)oy * p.Wo + ox;
+                const bool raw = p.splits > 1; // partial sums: no bias, no activation
+                float* op = (raw ? p.partial + split * p.partialStride : out) + n * p.K * oplane + (long long)oy * p.Wo + ox;
                 ptx::mbar_wait(accBar, 0);
                 ptx::tc_fence_after_sync();
 #pragma unroll 1
@@ -1792,6 +1816,11 @@ namespace nb200
                             if (k < p.K)
                             {
                                 float f = __uint_as_float(v[j]);
+                                if (raw)
+                                {
+                                    op[k * oplane] = f;
+                                    continue;
+                                }
                                 if (bias)
                                     f += __ldg(bias + k);
                                 op[k * oplane] = apply_activation(p.act, p.alpha, f);
@@ -3289,7 +3318,7 @@ namespace nb200
 
         // ---------------------------------------------------------------- gather kernel, host side
         template <int BN>
-        int launch_gather(const CUtensorMap& mapW, const GatherParams& p, int bStages, const float* in, const float* bias, float* out, cudaStream_t st)
+        int launch_gather(const CUtensorMap& mapW, const GatherBatch& b, int bStages, const float* in, const float* bias, float* out, cudaStream_t st)
         {
             static bool attrSet = false;
             if (!attrSet)
@@ -3297,22 +3326,69 @@ namespace nb200
                 NB200_CUDA_TRY(cudaFuncSetAttribute(tc_gather_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, BN > 128 ? kSmemBudget1 : kSmemBudget2));
                 attrSet = true;
             }
-            const long long tiles = (p.totalPix + 127) / 128 * p.tilesK;
-            if (tiles > 0x7FFFFFFFll)
-                return fail(NB200_E_UNSUPPORTED, "too many tiles");
+            const long long tiles = b.tileStart[b.count];
             const size_t smemBytes = 1024 + 512 + (size_t)bStages * BN * kBlockC * 4;
-            tc_gather_kernel<BN><<<(unsigned)tiles, kFpropThreads, smemBytes, st>>>(mapW, p, in, bias, out);
+            tc_gather_kernel<BN><<<(unsigned)tiles, kFpropThreads, smemBytes, st>>>(mapW, b, in, bias, out);
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             return NB200_OK;
         }
 
-        // Repack filters and build the filter tensor map; returns BN.
-        int gather_prepare(int Kout, int Cin, int R, int S, int repackMode, int wK, int wC, const float* w, void* ws, size_t wsBytes, cudaStream_t st,
-                           CUtensorMap* mapW, int* BN, int* bStages, int* Cblocks)
+        // Tile width and channel split of a gathered forward / input gradient. Few pixel tiles (small maps, small batches) with
+        // many channels are bound by streaming the filters: with BN = 256 two CTAs would each read half of a 19 MB filter
+        // tensor. So the filter tile narrows until the grid covers the chip, and what is still missing comes from splitting the
+        // channel blocks of every tile over several CTAs (raw partials behind the repacked filters, fixed-order reduce).
+        struct GatherPlan
+        {
+            int BN, splits, cbPer, Cblocks;
+            long long outElems;
+            size_t repackBytes, wsBytes;
+        };
+
+        GatherPlan gather_plan(int op, const nb200_conv_desc& d)
+        {
+            GatherPlan pl{};
+            const bool fwd = op == NB200_OP_FORWARD;
+            const int Kout = fwd ? d.K : d.C, Cin = fwd ? d.C : d.K;
+            long long tilesM = 0;
+            if (fwd)
+                tilesM = ((long long)d.N * d.Ho * d.Wo + 127) / 128;
+            else
+                for (int ph = 0; ph < d.stride && ph < d.H; ++ph)
+                    for (int pw = 0; pw < d.stride && pw < d.W; ++pw)
+                        tilesM += ((long long)d.N * ((d.H - ph + d.stride - 1) / d.stride) * ((d.W - pw + d.stride - 1) / d.stride) + 127) / 128;
+            const int Cp = round_up(Cin, kBlockC);
+            pl.Cblocks = Cp / kBlockC;
+            pl.BN = pick_bn(Kout);
+            pl.splits = 1;
+            static const char* env = getenv("NB200_GATHER_SPLIT"); // 0 disables (profiling)
+            if (!(env && env[0] == '0'))
+            {
+                while (pl.BN > 64 && tilesM * ceil_div(Kout, pl.BN) < 148)
+                    pl.BN /= 2;
+                const long long ctas = tilesM * ceil_div(Kout, pl.BN);
+                if (ctas <= 74 && pl.Cblocks >= 4)
+                {
+                    int want = (int)(148 / (ctas > 0 ? ctas : 1));
+                    if (want > pl.Cblocks / 2) want = pl.Cblocks / 2;
+                    if (want > 8) want = 8;
+                    if (want > 1) pl.splits = want;
+                }
+            }
+            pl.cbPer = ceil_div(pl.Cblocks, pl.splits);
+            pl.splits = ceil_div(pl.Cblocks, pl.cbPer);
+            pl.outElems = fwd ? (long long)d.N * d.K * d.Ho * d.Wo : (long long)d.N * d.C * d.H * d.W;
+            pl.repackBytes = ((size_t)d.R * d.S * Kout * Cp * sizeof(float) + 255) & ~(size_t)255;
+            pl.wsBytes = pl.repackBytes + (pl.splits > 1 ? (size_t)pl.splits * pl.outElems * sizeof(float) : 0);
+            return pl;
+        }
+
+        // Repack filters and build the filter tensor map.
+        int gather_prepare(const GatherPlan& pl, int Kout, int Cin, int R, int S, int repackMode, int wK, int wC, const float* w, void* ws, size_t wsBytes,
+                           cudaStream_t st, CUtensorMap* mapW, int* BN, int* bStages, int* Cblocks)
         {
             const int Cp = round_up(Cin, kBlockC);
-            const size_t need = (size_t)R * S * Kout * Cp * sizeof(float);
+            const size_t need = pl.wsBytes;
             if (wsBytes < need || !ws)
                 return fail(NB200_E_WORKSPACE, "tcgen05 gather conv needs %zu workspace bytes, got %zu", need, wsBytes);
             if ((uintptr_t)ws & 15)
@@ -3321,7 +3397,7 @@ namespace nb200
                 const int rc = launch_repack(w, (float*)ws, wK, wC, R, S, Kout, Cp, repackMode, 0, st);
                 if (rc) return rc;
             }
-            *BN = pick_bn(Kout);
+            *BN = pl.BN;
             cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)Kout, (cuuint64_t)(R * S)};
             cuuint64_t strides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * Kout * 4};
             cuuint32_t box[3] = {kBlockC, (cuuint32_t)*BN, 1};
@@ -3342,11 +3418,33 @@ namespace nb200
                    d.H >= 1 && d.W >= 1 && d.Ho >= 1 && d.Wo >= 1 && d.R <= 127 && d.S <= 127 && d.padX <= 127 && d.padY <= 127;
         }
 
+        // append one pixel list to a batch; false when the batch (or the grid) is full
+        bool gather_batch_add(GatherBatch& b, const GatherParams& p)
+        {
+            const long long tiles = (p.totalPix + 127) / 128 * p.tilesK * p.splits;
+            if (b.count == kGatherMaxClasses || (long long)b.tileStart[b.count] + tiles > 0x3FFFFFFFll)
+                return false;
+            b.cls[b.count] = p;
+            b.tileStart[b.count + 1] = b.tileStart[b.count] + (int)tiles;
+            ++b.count;
+            return true;
+        }
+
+        int dispatch_gather(int BN, const CUtensorMap& mapW, const GatherBatch& b, int bStages, const float* in, const float* bias, float* out, cudaStream_t st)
+        {
+            if (b.count == 0 || b.tileStart[b.count] == 0)
+                return NB200_OK;
+            return BN == 64 ? launch_gather<64>(mapW, b, bStages, in, bias, out, st)
+                 : BN == 128 ? launch_gather<128>(mapW, b, bStages, in, bias, out, st)
+                             : launch_gather<256>(mapW, b, bStages, in, bias, out, st);
+        }
+
         int dispatch_gather(int BN, const CUtensorMap& mapW, const GatherParams& p, int bStages, const float* in, const float* bias, float* out, cudaStream_t st)
         {
-            return BN == 64 ? launch_gather<64>(mapW, p, bStages, in, bias, out, st)
-                 : BN == 128 ? launch_gather<128>(mapW, p, bStages, in, bias, out, st)
-                             : launch_gather<256>(mapW, p, bStages, in, bias, out, st);
+            GatherBatch b{};
+            if (!gather_batch_add(b, p))
+                return fail(NB200_E_UNSUPPORTED, "too many tiles");
+            return dispatch_gather(BN, mapW, b, bStages, in, bias, out, st);
         }
 
         FwdShape fwd_shape(const nb200_conv_desc& d)
@@ -3437,11 +3535,19 @@ namespace nb200
     bool tc_gather_forward_supported(const nb200_conv_desc& d) { return gather_ok(d); }
     bool tc_gather_input_gradient_supported(const nb200_conv_desc& d) { return gather_ok(d); }
 
-    size_t tc_gather_workspace_bytes(int op, const nb200_conv_desc& d)
+    size_t tc_gather_workspace_bytes(int op, const nb200_conv_desc& d) { return gather_plan(op, d).wsBytes; }
+
+    static int gather_split_reduce(const GatherPlan& pl, void* ws, const float* bias, int act, float alpha, float* out, long long plane, int Kout,
+                                   cudaStream_t st)
     {
-        if (op == NB200_OP_FORWARD)
-            return (size_t)d.R * d.S * d.K * round_up(d.C, kBlockC) * sizeof(float);
-        return (size_t)d.R * d.S * d.C * round_up(d.K, kBlockC) * sizeof(float);
+        if (pl.splits == 1)
+            return NB200_OK;
+        const float* partial = (const float*)((const uint8_t*)ws + pl.repackBytes);
+        const int blocks = (int)((pl.outElems + 255) / 256 > 148 * 8 ? 148 * 8 : (pl.outElems + 255) / 256);
+        fprop_split_reduce_kernel<<<blocks, 256, 0, st>>>(partial, pl.outElems, pl.splits, bias, act, alpha, out, pl.outElems, plane, Kout);
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        return NB200_OK;
     }
 
     int tc_gather_forward(const nb200_conv_desc& d, const float* x, const float* w, const float* bias, int act, float alpha, float* y, void* ws,
@@ -3449,10 +3555,12 @@ namespace nb200
     {
         CUtensorMap mapW;
         int BN, bStages, Cblocks;
-        int rc = gather_prepare(d.K, d.C, d.R, d.S, 0, d.K, d.C, w, ws, wsBytes, st, &mapW, &BN, &bStages, &Cblocks);
+        const GatherPlan pl = gather_plan(NB200_OP_FORWARD, d);
+        int rc = gather_prepare(pl, d.K, d.C, d.R, d.S, 0, d.K, d.C, w, ws, wsBytes, st, &mapW, &BN, &bStages, &Cblocks);
         if (rc) return rc;
         if (g_tcFilterMode == kFiltersOnly) return NB200_OK;
         GatherParams p{};
+        p.splits = pl.splits; p.cbPer = pl.cbPer; p.partial = (float*)((uint8_t*)ws + pl.repackBytes); p.partialStride = pl.outElems;
         p.Cblocks = Cblocks; p.ntaps = d.R * d.S;
         p.C = d.C; p.H = d.H; p.W = d.W; p.K = d.K; p.Ho = d.Ho; p.Wo = d.Wo;
         p.PH = d.Ho; p.PW = d.Wo; p.oyMul = 1; p.oyAdd = 0; p.oxMul = 1; p.oxAdd = 0; p.iyMul = d.stride; p.ixMul = d.stride;
@@ -3464,7 +3572,9 @@ namespace nb200
                 const int t = r * d.S + s2;
                 p.iyAdd[t] = (short)(r - d.padY); p.ixAdd[t] = (short)(s2 - d.padX); p.wtap[t] = (short)t;
             }
-        return dispatch_gather(BN, mapW, p, bStages, x, bias, y, st);
+        rc = dispatch_gather(BN, mapW, p, bStages, x, bias, y, st);
+        if (rc) return rc;
+        return gather_split_reduce(pl, ws, bias, act, alpha, y, (long long)d.Ho * d.Wo, d.K, st);
     }
 
     int tc_gather_input_gradient(const nb200_conv_desc& d, const float* dy, const float* w, float* dx, void* ws, size_t wsBytes, cudaStream_t st)
@@ -3472,10 +3582,15 @@ namespace nb200
         // produced tensor = dx (C channels, H x W); gathered tensor = dy (K channels, Ho x Wo); filters [tap][c][k]
         CUtensorMap mapW;
         int BN, bStages, Cblocks;
-        int rc = gather_prepare(d.C, d.K, d.R, d.S, 2, d.K, d.C, w, ws, wsBytes, st, &mapW, &BN, &bStages, &Cblocks);
+        const GatherPlan pl = gather_plan(NB200_OP_INPUT_GRADIENT, d);
+        int rc = gather_prepare(pl, d.C, d.K, d.R, d.S, 2, d.K, d.C, w, ws, wsBytes, st, &mapW, &BN, &bStages, &Cblocks);
         if (rc) return rc;
         if (g_tcFilterMode == kFiltersOnly) return NB200_OK;
         const int st2 = d.stride;
+        // NB200_GATHER_BATCH=0: one launch per parity class (profiling)
+        static const char* batchEnv = getenv("NB200_GATHER_BATCH");
+        const bool batched = !(batchEnv && batchEnv[0] == '0');
+        GatherBatch batch{};
         for (int ph = 0; ph < st2; ++ph)
             for (int pw = 0; pw < st2; ++pw)
             {
@@ -3483,6 +3598,7 @@ namespace nb200
                     continue;
                 GatherParams p{};
                 p.Cblocks = Cblocks;
+                p.splits = pl.splits; p.cbPer = pl.cbPer; p.partial = (float*)((uint8_t*)ws + pl.repackBytes); p.partialStride = pl.outElems;
                 p.C = d.K; p.H = d.Ho; p.W = d.Wo; p.K = d.C; p.Ho = d.H; p.Wo = d.W;
                 p.PH = (d.H - ph + st2 - 1) / st2; p.PW = (d.W - pw + st2 - 1) / st2;
                 p.oyMul = st2; p.oyAdd = ph; p.oxMul = st2; p.oxAdd = pw; p.iyMul = 1; p.ixMul = 1;
@@ -3506,10 +3622,18 @@ namespace nb200
                     }
                 }
                 p.ntaps = nt;
-                rc = dispatch_gather(BN, mapW, p, bStages, dy, nullptr, dx, st);
+                if (batched && gather_batch_add(batch, p))
+                    continue;
+                // batch full (stride > 3) or batching disabled: flush what is queued, then start over with this class
+                rc = dispatch_gather(BN, mapW, batch, bStages, dy, nullptr, dx, st);
                 if (rc) return rc;
+                batch = GatherBatch{};
+                if (!gather_batch_add(batch, p))
+                    return fail(NB200_E_UNSUPPORTED, "too many tiles");
             }
-        return NB200_OK;
+        rc = dispatch_gather(BN, mapW, batch, bStages, dy, nullptr, dx, st);
+        if (rc) return rc;
+        return gather_split_reduce(pl, ws, nullptr, NB200_ACT_IDENTITY, 0.f, dx, (long long)d.H * d.W, d.C, st);
     }
 
 
@@ -3552,7 +3676,7 @@ namespace nb200
             {
                 // tiny channel counts fill a sliver of the 128 x BN tile; below this K*C the CUDA-core kernel is used instead
                 static const char* env = getenv("NB200_WGRAD_GATHER_MIN_KC");
-                static const long long minKC = env ? atoll(env) : 0;
+                static const long long minKC = env ? atoll(env) : 128; // measured: 8 -> 8 @7x7 batch 256: 0.032 ms direct, 0.056 ms gathered
                 if ((long long)d.K * d.C < minKC)
                     pl.ok = false;
             }

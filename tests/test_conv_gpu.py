@@ -104,6 +104,10 @@ TC_CASES = [
     (0, 8, 64, 2, 2, 64, 3, 3, 2, 1, 1),       # 1x1 maps
     (0, 4, 32, 3, 3, 32, 3, 3, 1, 1, 1),       # 9 pixels in 16-pixel slots, planes pitched to 12
     (0, 2, 16, 5, 5, 16, 3, 3, 1, 1, 1),       # 25 pixels in one 32-pixel chunk, planes pitched to 28
+    # gathered forward / input gradient with a narrowed filter tile and channel splits (weight-bound U-Net bottleneck layers)
+    (0, 2, 256, 4, 4, 128, 3, 3, 1, 1, 1),     # one pixel tile: forward 2 filter tiles x 4 channel splits, input gradient 4 x 2
+    (0, 4, 128, 8, 8, 128, 3, 3, 2, 1, 1),     # stride 2: the four parity classes of the input gradient share one split launch
+    (0, 3, 200, 6, 6, 40, 4, 4, 2, 1, 1),      # ragged channel blocks (7 -> splits of 3 + 3 + 1), 16 taps, transposed-conv geometry
     # channel-split forward / input gradient (few tiles, many channels: batch-1 style transfer on the deep layers)
     (0, 1, 256, 32, 32, 128, 3, 3, 1, 1, 1),   # 8 tiles x 4 channel splits (forward), 16 tiles x 2 splits (input gradient)
     (0, 1, 160, 32, 64, 96, 3, 3, 1, 1, 1),    # 5 channel blocks: uneven split 3 + 2
@@ -128,7 +132,7 @@ def test_against_oracle(cfg, math):
 @pytest.mark.parametrize("act", [lib.ACT_IDENTITY, lib.ACT_SIGMOID, lib.ACT_RELU, lib.ACT_TANH, lib.ACT_ELU, lib.ACT_LEAKY_RELU])
 def test_bias_activation(act, math):
     """Conv2DBiasActivation (TensorOpGpuTests.cpp:1238-1252 uses ReLU; all epilogues are covered here)."""
-    for (N, C, H, W, K, F, st, p) in [(3, 3, 26, 26, 2, 3, 1, 0), (2, 64, 32, 32, 64, 3, 1, 1), (2, 32, 48, 96, 40, 3, 1, 1), (1, 256, 32, 32, 72, 3, 1, 1), (2, 24, 20, 20, 3, 3, 1, 1)]:
+    for (N, C, H, W, K, F, st, p) in [(3, 3, 26, 26, 2, 3, 1, 0), (2, 64, 32, 32, 64, 3, 1, 1), (2, 32, 48, 96, 40, 3, 1, 1), (1, 256, 32, 32, 72, 3, 1, 1), (2, 24, 20, 20, 3, 3, 1, 1), (2, 256, 4, 4, 72, 3, 1, 1)]:
         x = synth.uniform(synth.SEED_X, (N, C, H, W)); w = synth.glorot_uniform(synth.SEED_W, K, C, F, F)
         b = synth.uniform(synth.SEED_BIAS, (K,))
         ref = O.conv2d_bias_activation(x, w, b, st, p, act, 0.2)
@@ -294,6 +298,7 @@ PREPARED_CASES = [
     (8, 128, 8, 8, 256, 4, 2, 1),     # DCGAN deconv geometry
     (2, 3, 64, 64, 64, 3, 1, 1),      # first-layer kernels read w directly: prepare is a no-op
     (2, 128, 32, 32, 3, 3, 1, 1),     # few-filter layer: the transposed + rotated filters are what is prepared
+    (2, 256, 4, 4, 128, 3, 1, 1),     # gathered kernel with channel splits: partials behind the prepared filters
 ]
 
 
