@@ -3364,7 +3364,8 @@ namespace nb200
             static const char* env = getenv("NB200_GATHER_SPLIT"); // 0 disables (profiling)
             if (!(env && env[0] == '0'))
             {
-                while (pl.BN > 64 && tilesM * ceil_div(Kout, pl.BN) < 148)
+                // (only below half a wave: 122 CTAs of BN = 256 beat 244 of BN = 128 -- 256 -> 512 @ 31x31: 0.093 vs 0.120 ms)
+                while (pl.BN > 64 && tilesM * ceil_div(Kout, pl.BN) <= 74)
                     pl.BN /= 2;
                 const long long ctas = tilesM * ceil_div(Kout, pl.BN);
                 if (ctas <= 74 && pl.Cblocks >= 4)

@@ -17,8 +17,8 @@ the identical update -- replicas stay in lock-step without a broadcast. All-redu
 layer's kernel gradient is ready (backward visits layers last to first), so communication overlaps the remaining
 input-gradient / kernel-gradient kernels.
 
-`op` is any object with the TensorOpB200 method set (neuro__b200/tensor_op.py); elementwise neighbours that are not on
-the hot path (activation gradient, loss) use torch on the same device. Nothing here falls back to a CPU convolution.
+`op` is any object with the TensorOpB200 method set (neuro__b200/tensor_op.py); the loss (MSE against a target, not on
+the path) uses torch on the same device. Nothing here falls back to a CPU convolution.
 """
 import math
 from dataclasses import dataclass
@@ -38,23 +38,6 @@ class ConvLayerSpec:
     padding: int = 0
     activation: int = lib.ACT_RELU
     alpha: float = 0.0
-
-
-def _activation_gradient(act, alpha, output, output_grad):
-    """TensorOpCpu::{Sigmoid,Tanh,ReLU,Elu,LeakyReLU}Gradient, TensorOpCpu.cpp:812-864 (functions of the OUTPUT)."""
-    if act == lib.ACT_IDENTITY:
-        return output_grad
-    if act == lib.ACT_RELU:
-        return torch.where(output > 0, output_grad, torch.zeros_like(output_grad))
-    if act == lib.ACT_LEAKY_RELU:
-        return torch.where(output > 0, output_grad, alpha * output_grad)
-    if act == lib.ACT_SIGMOID:
-        return output * (1 - output) * output_grad
-    if act == lib.ACT_TANH:
-        return (1 - output * output) * output_grad
-    if act == lib.ACT_ELU:
-        return torch.where(output > 0, output_grad, (output + alpha) * output_grad)
-    raise ValueError(act)
 
 
 class ConvStackTrainer:
@@ -116,9 +99,12 @@ class ConvStackTrainer:
         works = []
         for i in reversed(range(len(self.layers))):
             l, v = self.layers[i], self.views[i]
-            grad = _activation_gradient(l.activation, l.alpha, acts[i + 1], grad).contiguous()
-            # kernel gradient with the bias gradient folded into the same call (Conv2dBiasActivationOp.cpp:47-60)
-            op.Conv2DKernelsGradient(acts[i], grad, l.stride, l.padding, l.padding, NCHW, v["dw"], v["db"])
+            # backward of Conv2dBiasActivationOp (Conv2dBiasActivationOp.cpp:47-60): activation gradient and bias gradient
+            # in one pass over the output gradient, then kernel gradient and input gradient of the result
+            dz = torch.empty_like(grad)
+            op.Conv2DBiasActivationGradient(acts[i + 1], grad.contiguous(), l.activation, l.alpha, dz, v["db"])
+            grad = dz
+            op.Conv2DKernelsGradient(acts[i], grad, l.stride, l.padding, l.padding, NCHW, v["dw"])
             if self.world > 1:
                 works.append(dist.all_reduce(self.grads[v["lo"]:v["hi"]], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
             if i > 0:

@@ -30,6 +30,14 @@ class OracleOp:
         if biasGradient is not None:
             biasGradient.copy_(torch.from_numpy(O.conv2d_bias_gradient(_np(gradient), dataFormat)))
 
+    def Conv2DBiasActivationGradient(self, output, outputGradient, activation, activationAlpha, activationInputGradient,
+                                     biasGradient=None, dataFormat=0):
+        # the reference's two passes (Conv2dBiasActivationOp.cpp:47-60): ActivationGradient, then Conv2DBiasGradient of its result
+        dz = O.activation_gradient(activation, activationAlpha, _np(output), _np(outputGradient))
+        activationInputGradient.copy_(torch.from_numpy(dz))
+        if biasGradient is not None:
+            biasGradient.copy_(torch.from_numpy(O.conv2d_bias_gradient(dz, dataFormat)))
+
     def AdamStep(self, parameter, gradient, mGrad, vGrad, lr, beta1, beta2, epsilon, gradScale=1.0):
         p, g, m, v = _np(parameter), _np(gradient) * np.float32(gradScale), _np(mGrad), _np(vGrad)
         O.adam_step(p, g, m, v, lr, beta1, beta2, epsilon)
