@@ -28,20 +28,22 @@ namespace nb200
             int nhwc;
         };
 
-        // decompose a flat index of a (N, C, h, w) tensor stored in the caller's format into its coordinates
-        __device__ __forceinline__ void coords(long long i, int nhwc, int C, int Hh, int Ww, int& n, int& c, int& h, int& w)
+        // decompose a flat index of a (N, C, h, w) tensor stored in the caller's format into its coordinates. Tensors hold
+        // < 2^32 elements (Neuro::Shape::Length is uint32_t), so the index arithmetic is 32-bit: a 64-bit division costs
+        // ~100 instructions on the CUDA cores and made the first version of these kernels issue-bound at 0.5-1.7 TB/s.
+        __device__ __forceinline__ void coords(unsigned i, int nhwc, unsigned C, unsigned Hh, unsigned Ww, unsigned& n, unsigned& c, unsigned& h, unsigned& w)
         {
             if (nhwc)
             {
-                c = (int)(i % C); i /= C;
-                w = (int)(i % Ww); i /= Ww;
-                h = (int)(i % Hh); n = (int)(i / Hh);
+                c = i % C; i /= C;
+                w = i % Ww; i /= Ww;
+                h = i % Hh; n = i / Hh;
             }
             else
             {
-                w = (int)(i % Ww); i /= Ww;
-                h = (int)(i % Hh); i /= Hh;
-                c = (int)(i % C); n = (int)(i / C);
+                w = i % Ww; i /= Ww;
+                h = i % Hh; i /= Hh;
+                c = i % C; n = i / C;
             }
         }
 
@@ -50,12 +52,13 @@ namespace nb200
         template <bool MAX>
         __global__ void __launch_bounds__(kThreads) pool2d_kernel(const float* __restrict__ x, float* __restrict__ y, Geo g, long long total)
         {
-            for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads)
+            for (long long i64 = (long long)blockIdx.x * kThreads + threadIdx.x; i64 < total; i64 += (long long)gridDim.x * kThreads)
             {
-                int n, c, oh, ow;
+                const unsigned i = (unsigned)i64;
+                unsigned n, c, oh, ow;
                 coords(i, g.nhwc, g.C, g.Ho, g.Wo, n, c, oh, ow);
                 const float* xp = x + n * g.xs.n + c * g.xs.c;
-                const int h0 = oh * g.stride - g.padY, w0 = ow * g.stride - g.padX;
+                const int h0 = (int)oh * g.stride - g.padY, w0 = (int)ow * g.stride - g.padX;
                 float acc = MAX ? -FLT_MAX : 0.f;
                 for (int py = 0; py < g.F; ++py)
                     for (int px = 0; px < g.F; ++px)
@@ -69,6 +72,77 @@ namespace nb200
             }
         }
 
+        // The pooling every model in the reference uses (VGG16/19, the conv autoencoder): 2x2 windows, stride 2, no padding,
+        // NCHW, even H, W % 8 == 0. Thread = 4 consecutive outputs of one row = two aligned float4 loads from each of the two
+        // input rows and one float4 store: every byte moves once, fully coalesced. Same operation order as above.
+        template <bool MAX>
+        __global__ void __launch_bounds__(kThreads)
+        pool2x2_kernel(const float4* __restrict__ x, float4* __restrict__ y, unsigned H, unsigned W4, unsigned Ho, unsigned Wo4, long long quads)
+        {
+            for (long long q64 = (long long)blockIdx.x * kThreads + threadIdx.x; q64 < quads; q64 += (long long)gridDim.x * kThreads)
+            {
+                const unsigned q = (unsigned)q64;
+                const unsigned ow4 = q % Wo4, t = q / Wo4, oh = t % Ho, plane = t / Ho;
+                const float4* r0 = x + ((size_t)plane * H + 2 * oh) * W4 + 2 * ow4;
+                const float4 a0 = __ldcs(r0), a1 = __ldcs(r0 + 1), b0 = __ldcs(r0 + W4), b1 = __ldcs(r0 + W4 + 1);
+                float4 o;
+                if (MAX)
+                {
+                    o.x = fmaxf(fmaxf(fmaxf(fmaxf(-FLT_MAX, a0.x), a0.y), b0.x), b0.y);
+                    o.y = fmaxf(fmaxf(fmaxf(fmaxf(-FLT_MAX, a0.z), a0.w), b0.z), b0.w);
+                    o.z = fmaxf(fmaxf(fmaxf(fmaxf(-FLT_MAX, a1.x), a1.y), b1.x), b1.y);
+                    o.w = fmaxf(fmaxf(fmaxf(fmaxf(-FLT_MAX, a1.z), a1.w), b1.z), b1.w);
+                }
+                else
+                {
+                    o.x = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a0.x, a0.y), b0.x), b0.y), 4.f);   // 0 + a is a, exactly
+                    o.y = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a0.z, a0.w), b0.z), b0.w), 4.f);
+                    o.z = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a1.x, a1.y), b1.x), b1.y), 4.f);
+                    o.w = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a1.z, a1.w), b1.z), b1.w), 4.f);
+                }
+                y[q] = o;
+            }
+        }
+
+        // first-match rule of the reference's max-pool gradient on one 2x2 window (scan order e00, e01, e10, e11)
+        __device__ __forceinline__ void first_max(float e00, float e01, float e10, float e11, float m, float g, float& d00, float& d01, float& d10,
+                                                  float& d11)
+        {
+            const bool m0 = e00 == m, m1 = !m0 && e01 == m, m2 = !m0 && !m1 && e10 == m, m3 = !m0 && !m1 && !m2 && e11 == m;
+            d00 = m0 ? g : 0.f; d01 = m1 ? g : 0.f; d10 = m2 ? g : 0.f; d11 = m3 ? g : 0.f;
+        }
+
+        template <bool MAX>
+        __global__ void __launch_bounds__(kThreads)
+        pool2x2_gradient_kernel(const float4* __restrict__ y, const float4* __restrict__ x, const float4* __restrict__ dy, float4* __restrict__ dx,
+                                unsigned H, unsigned W4, unsigned Ho, unsigned Wo4, long long quads)
+        {
+            for (long long q64 = (long long)blockIdx.x * kThreads + threadIdx.x; q64 < quads; q64 += (long long)gridDim.x * kThreads)
+            {
+                const unsigned q = (unsigned)q64;
+                const unsigned ow4 = q % Wo4, t = q / Wo4, oh = t % Ho, plane = t / Ho;
+                const size_t r0 = ((size_t)plane * H + 2 * oh) * W4 + 2 * ow4;
+                const float4 g = __ldcs(dy + q);
+                float4 t0, t1, u0, u1; // dx rows 2*oh (t) and 2*oh+1 (u), two float4 each
+                if (MAX)
+                {
+                    const float4 m = __ldcs(y + q);
+                    const float4 a0 = __ldcs(x + r0), a1 = __ldcs(x + r0 + 1), b0 = __ldcs(x + r0 + W4), b1 = __ldcs(x + r0 + W4 + 1);
+                    first_max(a0.x, a0.y, b0.x, b0.y, m.x, g.x, t0.x, t0.y, u0.x, u0.y);
+                    first_max(a0.z, a0.w, b0.z, b0.w, m.y, g.y, t0.z, t0.w, u0.z, u0.w);
+                    first_max(a1.x, a1.y, b1.x, b1.y, m.z, g.z, t1.x, t1.y, u1.x, u1.y);
+                    first_max(a1.z, a1.w, b1.z, b1.w, m.w, g.w, t1.z, t1.w, u1.z, u1.w);
+                }
+                else
+                {
+                    const float qx = __fdiv_rn(g.x, 4.f), qy = __fdiv_rn(g.y, 4.f), qz = __fdiv_rn(g.z, 4.f), qw = __fdiv_rn(g.w, 4.f);
+                    t0 = make_float4(qx, qx, qy, qy); t1 = make_float4(qz, qz, qw, qw);
+                    u0 = t0; u1 = t1;
+                }
+                __stcs(dx + r0, t0); __stcs(dx + r0 + 1, t1); __stcs(dx + r0 + W4, u0); __stcs(dx + r0 + W4 + 1, u1);
+            }
+        }
+
         // TensorOpCpu::Pool2DGradient (TensorOpCpu.cpp:1249-1338) in gather form. The reference walks the windows in (outH, outW)
         // order and scatters: max -> the FIRST window element (poolH, poolW order) equal to the pooled value receives the
         // gradient; avg -> every in-range element receives gradient / (F*F). Here each input element visits the windows
@@ -78,10 +152,12 @@ namespace nb200
         pool2d_gradient_kernel(const float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, Geo g,
                                long long total)
         {
-            for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads)
+            for (long long i64 = (long long)blockIdx.x * kThreads + threadIdx.x; i64 < total; i64 += (long long)gridDim.x * kThreads)
             {
-                int n, c, h, w;
-                coords(i, g.nhwc, g.C, g.H, g.W, n, c, h, w);
+                const unsigned i = (unsigned)i64;
+                unsigned n, c, hu, wu;
+                coords(i, g.nhwc, g.C, g.H, g.W, n, c, hu, wu);
+                const int h = (int)hu, w = (int)wu;
                 const float* xp = x + n * g.xs.n + c * g.xs.c;
                 const long long yb = n * g.ys.n + c * g.ys.c;
                 // windows with oh*stride - padY <= h < oh*stride - padY + F
@@ -131,54 +207,83 @@ namespace nb200
             }
         }
 
-        // TensorOpCpu::UpSample2D (TensorOpCpu.cpp:1340-1354): nearest neighbour, NCHW planes. One thread per output element.
-        __global__ void __launch_bounds__(kThreads) upsample2d_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int s, long long total)
+        // TensorOpCpu::UpSample2D (TensorOpCpu.cpp:1340-1354): nearest neighbour, NCHW planes. Thread = VEC consecutive outputs
+        // of one row (VEC = 4: one 16-byte store; the 1-2 source values they replicate come from L1).
+        template <int VEC>
+        __global__ void __launch_bounds__(kThreads)
+        upsample2d_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned H, unsigned W, unsigned s, long long groups)
         {
-            const int Wo = W * s, Ho = H * s;
-            for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads)
+            const unsigned Wo = W * s, Ho = H * s, WoG = Wo / VEC;
+            for (long long i64 = (long long)blockIdx.x * kThreads + threadIdx.x; i64 < groups; i64 += (long long)gridDim.x * kThreads)
             {
-                const int ow = (int)(i % Wo);
-                const long long r = i / Wo;
-                const int oh = (int)(r % Ho);
-                const long long plane = r / Ho;
-                y[i] = __ldg(x + (plane * H + oh / s) * W + ow / s);
+                const unsigned i = (unsigned)i64;
+                const unsigned ow0 = (i % WoG) * VEC, r = i / WoG, oh = r % Ho, plane = r / Ho;
+                const float* src = x + ((size_t)plane * H + oh / s) * W;
+                float v[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                    v[j] = __ldg(src + (ow0 + j) / s);
+                float* dst = y + (size_t)r * Wo + ow0;
+                if (VEC == 4)
+                    __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+                else
+                    dst[0] = v[0];
             }
         }
 
         // TensorOpCpu::UpSample2DGradient (TensorOpCpu.cpp:1357-1369): dx(w/s, h/s) += dy(w, h) walking h then w, i.e. each input
         // element adds its s x s block row by row, left to right, starting from 0.
         __global__ void __launch_bounds__(kThreads)
-        upsample2d_gradient_kernel(const float* __restrict__ dy, float* __restrict__ dx, int H, int W, int s, long long total)
+        upsample2d_gradient_kernel(const float* __restrict__ dy, float* __restrict__ dx, unsigned H, unsigned W, unsigned s, long long total)
         {
-            const int Wo = W * s;
-            for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads)
+            const unsigned Wo = W * s;
+            for (long long i64 = (long long)blockIdx.x * kThreads + threadIdx.x; i64 < total; i64 += (long long)gridDim.x * kThreads)
             {
-                const int w = (int)(i % W);
-                const long long r = i / W;
-                const int h = (int)(r % H);
-                const long long plane = r / H;
-                const float* p = dy + ((plane * H + h) * s) * (long long)Wo + (long long)w * s;
+                const unsigned i = (unsigned)i64;
+                const unsigned w = i % W, r = i / W, h = r % H, plane = r / H;
+                const float* p = dy + ((size_t)plane * H + h) * s * Wo + (size_t)w * s;
                 float acc = 0.f;
-                for (int a = 0; a < s; ++a)
-                    for (int b = 0; b < s; ++b)
-                        acc = __fadd_rn(acc, __ldg(p + (long long)a * Wo + b));
+                for (unsigned a = 0; a < s; ++a)
+                    for (unsigned b = 0; b < s; ++b)
+                        acc = __fadd_rn(acc, __ldg(p + (size_t)a * Wo + b));
                 dx[i] = acc;
             }
         }
 
-        // TensorOpCpu::ConstantPad2D (TensorOpCpu.cpp:528-546), NCHW planes.
+        // TensorOpCpu::ConstantPad2D (TensorOpCpu.cpp:528-546), NCHW planes. Thread = VEC consecutive outputs of one row.
+        template <int VEC>
         __global__ void __launch_bounds__(kThreads)
-        constant_pad2d_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int left, int top, int Ho, int Wo, float value, long long total)
+        constant_pad2d_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int left, int top, unsigned Ho, unsigned Wo, float value,
+                              long long groups)
         {
-            for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads)
+            const unsigned WoG = Wo / VEC;
+            for (long long i64 = (long long)blockIdx.x * kThreads + threadIdx.x; i64 < groups; i64 += (long long)gridDim.x * kThreads)
             {
-                const int ow = (int)(i % Wo);
-                const long long r = i / Wo;
-                const int oh = (int)(r % Ho);
-                const long long plane = r / Ho;
-                const int h = oh - top, w = ow - left;
-                y[i] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(x + (plane * H + h) * W + w) : value;
+                const unsigned i = (unsigned)i64;
+                const unsigned ow0 = (i % WoG) * VEC, r = i / WoG, oh = r % Ho, plane = r / Ho;
+                const int h = (int)oh - top;
+                const bool rowIn = h >= 0 && h < H;
+                const float* src = x + ((size_t)plane * H + (rowIn ? h : 0)) * W;
+                float v[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+                {
+                    const int w = (int)(ow0 + j) - left;
+                    v[j] = (rowIn && w >= 0 && w < W) ? __ldg(src + w) : value;
+                }
+                float* dst = y + (size_t)r * Wo + ow0;
+                if (VEC == 4)
+                    __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+                else
+                    dst[0] = v[0];
             }
+        }
+
+        // 2x2 stride-2 unpadded NCHW pooling on rows of whole float4 pairs; every pointer that is passed must be 16-byte aligned
+        bool pool2x2_fast(const nb200_pool_desc& d, const void* a, const void* b, const void* c, const void* e)
+        {
+            return d.fmt == NB200_NCHW && d.filter == 2 && d.stride == 2 && d.padX == 0 && d.padY == 0 && d.H % 2 == 0 && d.W % 8 == 0 &&
+                   (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)e) & 15) == 0;
         }
 
         int check_pool(const nb200_pool_desc* d)
@@ -239,7 +344,15 @@ extern "C"
         if (!x || !y) return fail(NB200_E_INVALID, "null tensor pointer");
         if ((rc = device_ok())) return rc;
         const Geo g = make_geo(*d);
-        if (d->mode == NB200_POOL_MAX)
+        if (pool2x2_fast(*d, x, y, nullptr, nullptr))
+        {
+            const long long quads = total / 4;
+            if (d->mode == NB200_POOL_MAX)
+                pool2x2_kernel<true><<<grid_for(quads), kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, d->H, d->W / 4, d->Ho, d->Wo / 4, quads);
+            else
+                pool2x2_kernel<false><<<grid_for(quads), kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, d->H, d->W / 4, d->Ho, d->Wo / 4, quads);
+        }
+        else if (d->mode == NB200_POOL_MAX)
             pool2d_kernel<true><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(x, y, g, total);
         else
             pool2d_kernel<false><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(x, y, g, total);
@@ -257,7 +370,17 @@ extern "C"
         if (!dy || !dx || (d->mode == NB200_POOL_MAX && (!x || !y))) return fail(NB200_E_INVALID, "null tensor pointer");
         if ((rc = device_ok())) return rc;
         const Geo g = make_geo(*d);
-        if (d->mode == NB200_POOL_MAX)
+        if (pool2x2_fast(*d, d->mode == NB200_POOL_MAX ? x : dy, d->mode == NB200_POOL_MAX ? y : dy, dy, dx))
+        {
+            const long long quads = (long long)d->N * d->C * d->Ho * d->Wo / 4;
+            if (d->mode == NB200_POOL_MAX)
+                pool2x2_gradient_kernel<true><<<grid_for(quads), kThreads, 0, (cudaStream_t)stream>>>((const float4*)y, (const float4*)x, (const float4*)dy, (float4*)dx,
+                                                                                                       d->H, d->W / 4, d->Ho, d->Wo / 4, quads);
+            else
+                pool2x2_gradient_kernel<false><<<grid_for(quads), kThreads, 0, (cudaStream_t)stream>>>(nullptr, nullptr, (const float4*)dy, (float4*)dx,
+                                                                                                        d->H, d->W / 4, d->Ho, d->Wo / 4, quads);
+        }
+        else if (d->mode == NB200_POOL_MAX)
             pool2d_gradient_kernel<true><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(y, x, dy, dx, g, total);
         else
             pool2d_gradient_kernel<false><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(y, x, dy, dx, g, total);
@@ -275,7 +398,10 @@ extern "C"
         if (!x || !y) return fail(NB200_E_INVALID, "null tensor pointer");
         int rc = device_ok();
         if (rc) return rc;
-        upsample2d_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(x, y, H, W, scale, total);
+        if ((W * scale) % 4 == 0 && ((uintptr_t)y & 15) == 0)
+            upsample2d_kernel<4><<<grid_for(total / 4), kThreads, 0, (cudaStream_t)stream>>>(x, y, H, W, scale, total / 4);
+        else
+            upsample2d_kernel<1><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(x, y, H, W, scale, total);
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -307,7 +433,10 @@ extern "C"
         if (!y || (!x && (long long)H * W > 0)) return fail(NB200_E_INVALID, "null tensor pointer");
         int rc = device_ok();
         if (rc) return rc;
-        constant_pad2d_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(x, y, H, W, left, top, Ho, Wo, value, total);
+        if (Wo % 4 == 0 && ((uintptr_t)y & 15) == 0)
+            constant_pad2d_kernel<4><<<grid_for(total / 4), kThreads, 0, (cudaStream_t)stream>>>(x, y, H, W, left, top, Ho, Wo, value, total / 4);
+        else
+            constant_pad2d_kernel<1><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(x, y, H, W, left, top, Ho, Wo, value, total);
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;

@@ -25,6 +25,9 @@ with open(out, "w", newline="") as f:
             v = r[col[h]] if h in col else ""
             if n == "kernel":
                 v = v.split("(")[0].replace("void nb200::<unnamed>::", "")
+            if n == "dur_us" and v:
+                u = units[col[h]]   # ncu picks the unit per report: ns / us / ms / s
+                v = "%.3f" % (float(v) * {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}.get(u, 1.0))
             if n in ("dram_rd_MB", "dram_wr_MB") and v:
                 u = units[col[h]]
                 v = "%.2f" % (float(v) * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1.0))
