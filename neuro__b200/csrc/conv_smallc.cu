@@ -11,6 +11,8 @@
 //   kernel gradient  warp = one filter k, lanes = pixels: streams dy[k] once with coalesced float4 loads, x windows come
 //                    from L1 (shared by the 8 warps of the block), 9*C running sums per lane, one shuffle reduction at the
 //                    end; deterministic split over output rows + fixed-order second pass.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nb200
@@ -237,6 +239,159 @@ namespace nb200
             }
         }
 
+        // ------------------------------------------------------------ input gradient, filters split over the warps of a block
+        // Same arithmetic as smallc_dgrad_kernel for grids that would leave most of the chip idle (few pixels, many filters:
+        // the forward of a few-filter output layer, e.g. DCGAN's 128 -> 3 at 32x32): all 8 warps of a block work on the SAME 32
+        // pixel quads, warp w reducing filters [w*K/8, (w+1)*K/8); the eight partial sums meet in shared memory and are added in
+        // warp order (deterministic). 8x the blocks, 1/8 of the serial filter loop per thread.
+        template <int C>
+        __global__ void __launch_bounds__(kSmallThreads)
+        smallc_dgrad_ksplit_kernel(SmallGeo g, const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ bias, int act,
+                            float alpha, float* __restrict__ dx)
+        {
+            constexpr int T = C * 9;
+            constexpr int TP = (T + 3) & ~3;
+            extern __shared__ float sw[];         // [K][TP], taps flipped: sw[k][(c*3+a)*3+b] = w[k][c][2-a][2-b]
+            for (int i = threadIdx.x; i < g.K * TP; i += kSmallThreads)
+            {
+                const int k = i / TP, t = i - k * TP;
+                float v = 0.f;
+                if (t < T)
+                {
+                    const int c = t / 9, a = (t % 9) / 3, b = t % 3;
+                    v = w[(k * C + c) * 9 + (2 - a) * 3 + (2 - b)];
+                }
+                sw[i] = v;
+            }
+            __syncthreads();
+
+            const int quadsPerRow = (g.W + 3) >> 2;
+            const long long quads = (long long)g.N * g.H * quadsPerRow;
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            const long long qRaw = (long long)blockIdx.x * 32 + lane;
+            const bool live = qRaw < quads;
+            const long long q = live ? qRaw : quads - 1;   // idle lanes shadow the last quad (no early return: block-wide barriers below)
+            const int qw = (int)(q % quadsPerRow);
+            const int h = (int)((q / quadsPerRow) % g.H);
+            const int n = (int)(q / ((long long)quadsPerRow * g.H));
+            const int kPer = (g.K + 7) >> 3;
+            const int kBegin = warp * kPer, kEnd = min(g.K, kBegin + kPer);
+            const int w0 = qw * 4;
+            // with flipped taps this is a forward conv of dy with pad' = 2 - pad: window rows h-pad'+a, cols w0-pad'+j
+            const int pp = 2 - g.pad;
+
+            float acc[C][4];
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    acc[c][j] = 0.f;
+
+            const long long plane = (long long)g.Ho * g.Wo;
+            const float* dyn = dy + (long long)n * g.K * plane;
+            const bool fast = g.aligned && pp == 1 && (g.Wo & 3) == 0 && w0 + 4 <= g.Wo; // aligned float4 centre + 2 edge scalars
+            for (int k = kBegin; k < kEnd; ++k)
+            {
+                float win[3][6];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                {
+                    const int oh = h - pp + a;
+                    const bool rowOk = oh >= 0 && oh < g.Ho;
+                    const float* row = dyn + k * plane + (long long)oh * g.Wo;
+                    if (fast)
+                    {
+                        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float l = 0.f, rr = 0.f;
+                        if (rowOk)
+                        {
+                            f = __ldcs((const float4*)(row + w0));
+                            if (w0 > 0) l = __ldg(row + w0 - 1);
+                            if (w0 + 4 < g.Wo) rr = __ldg(row + w0 + 4);
+                        }
+                        win[a][0] = l; win[a][1] = f.x; win[a][2] = f.y; win[a][3] = f.z; win[a][4] = f.w; win[a][5] = rr;
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j)
+                        {
+                            const int ow = w0 - pp + j;
+                            win[a][j] = (rowOk && ow >= 0 && ow < g.Wo) ? __ldg(row + ow) : 0.f;
+                        }
+                    }
+                }
+                float wk[TP];
+                const float4* wp = (const float4*)(sw + k * TP);
+#pragma unroll
+                for (int i = 0; i < TP / 4; ++i)
+                {
+                    const float4 f = wp[i];
+                    wk[4 * i] = f.x; wk[4 * i + 1] = f.y; wk[4 * i + 2] = f.z; wk[4 * i + 3] = f.w;
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b)
+                        {
+                            const float wv = wk[(c * 3 + a) * 3 + b];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                acc[c][j] = fmaf(win[a][b + j], wv, acc[c][j]);
+                        }
+            }
+
+            // partial sums of the 8 filter slices -> warp 0 adds them in slice order
+            float* red = sw + g.K * TP;               // [8 warps][C * 4][32 lanes]
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    red[(warp * C * 4 + c * 4 + j) * 32 + lane] = acc[c][j];
+            __syncthreads();
+            if (warp != 0 || !live)
+                return;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    float v = 0.f;
+#pragma unroll
+                    for (int wv = 0; wv < 8; ++wv)
+                        v += red[(wv * C * 4 + c * 4 + j) * 32 + lane];
+                    acc[c][j] = v;
+                }
+            if (bias != nullptr || act != NB200_ACT_IDENTITY)
+            {
+                // only when this kernel serves as the FORWARD of a few-filter layer (roles swapped, see smallk_* below)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                {
+                    const float b = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        acc[c][j] = apply_activation(act, alpha, acc[c][j] + b);
+                }
+            }
+            const bool vec = g.aligned && (g.W & 3) == 0;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+            {
+                float* dst = dx + (((long long)n * C + c) * g.H + h) * g.W + w0;
+                if (vec)
+                    *(float4*)dst = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (w0 + j < g.W) dst[j] = acc[c][j];
+                }
+            }
+        }
+
         // ------------------------------------------------------------ kernel gradient
         // dw[k][c][r][s] = sum_{n,oh,ow} dy[n][k][oh][ow] * x[n][c][oh+r-pad][ow+s-pad]
         // grid (ceil(K/8), slices): warp wIdx of the block owns filter k = blockIdx.x*8 + wIdx and the slice's output rows.
@@ -420,6 +575,21 @@ namespace nb200
         const SmallGeo g = small_geo(d, dy, dx, nullptr);
         const long long quads = (long long)d.N * d.H * ((d.W + 3) / 4);
         const size_t smem = (size_t)d.K * ((d.C * 9 + 3) & ~3) * 4;
+        // fewer than two blocks per SM and enough filters to share out: split the filters over the warps of a block instead
+        static const char* env = getenv("NB200_SMALLC_KSPLIT"); // 0 disables (profiling)
+        if (ceil_div(quads, kSmallThreads) < 2 * 148 && d.K >= 32 && !(env && env[0] == '0'))
+        {
+            const size_t smem2 = smem + (size_t)8 * d.C * 4 * 32 * sizeof(float);
+#define CALL(CC)                                                                                                              \
+            if (smem2 > 48 * 1024)                                                                                              \
+                NB200_CUDA_TRY(cudaFuncSetAttribute(smallc_dgrad_ksplit_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+            smallc_dgrad_ksplit_kernel<CC><<<ceil_div(quads, 32), kSmallThreads, smem2, st>>>(g, dy, w, bias, act, alpha, dx);
+            SMALLC_DISPATCH(CALL)
+#undef CALL
+            NB200_CUDA_TRY(cudaGetLastError());
+            count_launch();
+            return NB200_OK;
+        }
 #define CALL(CC)                                                                                                              \
         if (smem > 48 * 1024)                                                                                                  \
             NB200_CUDA_TRY(cudaFuncSetAttribute(smallc_dgrad_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

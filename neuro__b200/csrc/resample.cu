@@ -250,6 +250,24 @@ namespace nb200
             }
         }
 
+        // scale 2 (every model in the reference): thread = 2 consecutive dx elements = one aligned float4 from each of the two
+        // dy rows; same order of additions (row a = 0: left, right; row a = 1: left, right)
+        __global__ void __launch_bounds__(kThreads)
+        upsample2x_gradient_kernel(const float4* __restrict__ dy, float2* __restrict__ dx, unsigned H, unsigned W2, long long pairs)
+        {
+            for (long long i64 = (long long)blockIdx.x * kThreads + threadIdx.x; i64 < pairs; i64 += (long long)gridDim.x * kThreads)
+            {
+                const unsigned i = (unsigned)i64;
+                const unsigned w2 = i % W2, r = i / W2; // r = plane * H + h
+                const float4* p = dy + (size_t)r * 2 * W2 + w2; // dy row 2h of this plane: W2 float4 per row
+                const float4 a = __ldcs(p), b = __ldcs(p + W2);
+                float2 o;
+                o.x = __fadd_rn(__fadd_rn(__fadd_rn(a.x, a.y), b.x), b.y);
+                o.y = __fadd_rn(__fadd_rn(__fadd_rn(a.z, a.w), b.z), b.w);
+                dx[i] = o;
+            }
+        }
+
         // TensorOpCpu::ConstantPad2D (TensorOpCpu.cpp:528-546), NCHW planes. Thread = VEC consecutive outputs of one row.
         template <int VEC>
         __global__ void __launch_bounds__(kThreads)
@@ -416,7 +434,10 @@ extern "C"
         if (!dy || !dx) return fail(NB200_E_INVALID, "null tensor pointer");
         int rc = device_ok();
         if (rc) return rc;
-        upsample2d_gradient_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(dy, dx, H, W, scale, total);
+        if (scale == 2 && W % 2 == 0 && (((uintptr_t)dy & 15) | ((uintptr_t)dx & 7)) == 0)
+            upsample2x_gradient_kernel<<<grid_for(total / 2), kThreads, 0, (cudaStream_t)stream>>>((const float4*)dy, (float2*)dx, H, W / 2, total / 2);
+        else
+            upsample2d_gradient_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(dy, dx, H, W, scale, total);
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;

@@ -98,6 +98,7 @@ TC_CASES = [
     (0, 1, 64, 256, 256, 3, 3, 3, 1, 1, 1),    # pix2pix last conv geometry: >= 64K pixels, kernel gradient on the tensor cores
     (0, 2, 24, 20, 24, 4, 3, 3, 1, 0, 0),      # valid padding (pad' = 2)
     (0, 2, 24, 20, 22, 2, 3, 3, 1, 2, 2),      # full padding (pad' = 0), ragged width
+    (0, 3, 40, 18, 22, 3, 3, 3, 1, 1, 1),      # forward with the 40 channels split over the 8 warps of a block (5 each), ragged width
     # gathered kernel gradient on maps whose planes TMA cannot address directly (pitched copy of dy) and on tiny maps
     (0, 2, 32, 34, 34, 48, 4, 4, 1, 0, 0),     # PatchGAN 31x31 maps: Ho*Wo = 961, odd
     (0, 8, 64, 4, 4, 64, 3, 3, 2, 1, 1),       # U-Net bottleneck: 2x2 maps, 4 pixels in 8-pixel slots
@@ -132,7 +133,7 @@ def test_against_oracle(cfg, math):
 @pytest.mark.parametrize("act", [lib.ACT_IDENTITY, lib.ACT_SIGMOID, lib.ACT_RELU, lib.ACT_TANH, lib.ACT_ELU, lib.ACT_LEAKY_RELU])
 def test_bias_activation(act, math):
     """Conv2DBiasActivation (TensorOpGpuTests.cpp:1238-1252 uses ReLU; all epilogues are covered here)."""
-    for (N, C, H, W, K, F, st, p) in [(3, 3, 26, 26, 2, 3, 1, 0), (2, 64, 32, 32, 64, 3, 1, 1), (2, 32, 48, 96, 40, 3, 1, 1), (1, 256, 32, 32, 72, 3, 1, 1), (2, 24, 20, 20, 3, 3, 1, 1), (2, 256, 4, 4, 72, 3, 1, 1)]:
+    for (N, C, H, W, K, F, st, p) in [(3, 3, 26, 26, 2, 3, 1, 0), (2, 64, 32, 32, 64, 3, 1, 1), (2, 32, 48, 96, 40, 3, 1, 1), (1, 256, 32, 32, 72, 3, 1, 1), (2, 24, 20, 20, 3, 3, 1, 1), (2, 64, 20, 20, 3, 3, 1, 1), (2, 256, 4, 4, 72, 3, 1, 1)]:
         x = synth.uniform(synth.SEED_X, (N, C, H, W)); w = synth.glorot_uniform(synth.SEED_W, K, C, F, F)
         b = synth.uniform(synth.SEED_BIAS, (K,))
         ref = O.conv2d_bias_activation(x, w, b, st, p, act, 0.2)

@@ -1,6 +1,6 @@
 """Diagnostic: per-layer times of the three conv ops on the layer shapes of a BASELINE config.
 
-  python tools/layer_probe.py dcgan|pix2pix|vgg1|autoenc [--prepared]
+  python tools/layer_probe.py dcgan|pix2pix|vgg1|autoenc [--prepared] [--graph]
 
 Rows: conv y = conv(x[N,C,H,H], w[K,C,F,F], stride, pad). Conv2DTranspose layers are listed as the conv whose input
 gradient is their forward. --prepared times forward / input gradient with filters prepared once (constant weights)."""
@@ -34,6 +34,7 @@ CONFIGS = {
 }
 name = sys.argv[1] if len(sys.argv) > 1 else "dcgan"
 prepared = "--prepared" in sys.argv
+graph = "--graph" in sys.argv
 N, LAYERS = CONFIGS[name]
 op = TensorOpB200(lib.MATH_TF32)
 tot = [0.0, 0.0, 0.0]; totfl = 0.0
@@ -49,14 +50,25 @@ for (lname, C, H, K, F, st, p) in LAYERS:
     out = []
     for i, fn in enumerate(fns):
         fn(); fn(); torch.cuda.synchronize()
+        run = lambda: [fn() for _ in range(10)]
+        if graph:   # GPU time without the host's per-call cost (ctypes, tensor-map encode, launches): 10 calls replayed as one CUDA graph
+            side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                run()
+            run = gr.replay
+            run(); torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(10): fn()
+        run()
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         tot[i] += ms
         out.append("%s %7.3f ms %6.1f TF/s %6.0f GB/s" % (op.kernel_name(i, d)[:20], ms, d.flops() / ms / 1e9, d.bytes() / ms / 1e6))
     totfl += d.flops()
     print("%-36s %6.2f GF | " % (lname, d.flops() / 1e9) + " | ".join(out), flush=True)
-print("TOTAL %s N=%d prepared=%d: fwd %.3f ms dgrad %.3f ms wgrad %.3f ms; %.1f GF per op -> %.1f / %.1f / %.1f TF/s" %
-      (name, N, prepared, tot[0], tot[1], tot[2], totfl / 1e9, totfl / tot[0] / 1e9, totfl / tot[1] / 1e9, totfl / tot[2] / 1e9))
+print("TOTAL %s N=%d prepared=%d graph=%d: fwd %.3f ms dgrad %.3f ms wgrad %.3f ms; %.1f GF per op -> %.1f / %.1f / %.1f TF/s" %
+      (name, N, prepared, graph, tot[0], tot[1], tot[2], totfl / 1e9, totfl / tot[0] / 1e9, totfl / tot[1] / 1e9, totfl / tot[2] / 1e9))
