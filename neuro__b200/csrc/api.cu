@@ -91,7 +91,7 @@ namespace nb200
             }
         }
 
-        enum Family { kDirect, kTc, kSmallC, kGather, kSmallK };
+        enum Family { kDirect, kTc, kSmallC, kGather, kSmallK, kStrided };
 
         inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
         inline size_t smallk_filter_bytes(const nb200_conv_desc& d) { return align256((size_t)d.K * d.C * 9 * sizeof(float)); }
@@ -144,6 +144,8 @@ namespace nb200
                 return kSmallC; // fp32 CUDA cores, HBM-bound: serves every math mode
             if (smallk_supported(d))
                 return kSmallK; // few filters: the same kernels with x and y exchanged
+            if (op == NB200_OP_KERNELS_GRADIENT && strided_wgrad_supported(d))
+                return kStrided; // stride 2, 1-6 channels: HBM-bound, fp32 CUDA cores (forward / input gradient stay gathered)
             if (d.math == NB200_MATH_FP32)
                 return kDirect;
             // The halo-tile kernels tile 32 output columns per row; on narrower maps (or where they do not apply at all:
@@ -219,6 +221,8 @@ extern "C"
             return op != NB200_OP_KERNELS_GRADIENT ? 0 : tc_smallc_wgrad_supported(*d) ? tc_smallc_wgrad_workspace(*d) : smallc_wgrad_workspace(*d);
         if (f == kSmallK)
             return smallk_workspace(op, *d);
+        if (f == kStrided)
+            return strided_wgrad_workspace(*d);
         if (f == kGather)
             return op == NB200_OP_KERNELS_GRADIENT ? tc_gather_kernels_gradient_workspace(*d) : tc_gather_workspace_bytes(op, *d);
         return op == NB200_OP_KERNELS_GRADIENT ? direct_kernels_gradient_workspace(*d) : 0;
@@ -229,6 +233,8 @@ extern "C"
         if (!d || validate(d, -1) != NB200_OK)
             return "invalid";
         const Family f = pick(op, *d);
+        if (f == kStrided)
+            return "strided_smallc_wgrad";
         if (f == kSmallK)
         {
             if (op == NB200_OP_FORWARD) return "smallk_fprop";
@@ -315,6 +321,8 @@ extern "C"
                                                  : smallc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         if (f == kSmallK)
             return smallk_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
+        if (f == kStrided)
+            return strided_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         if (f == kGather)
             return tc_gather_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         return direct_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);

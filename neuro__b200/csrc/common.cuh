@@ -85,6 +85,11 @@ namespace nb200
     nb200_conv_desc smallk_swapped(const nb200_conv_desc& d);
     int smallc_swap_filters(const float* in, float* out, int A, int B, cudaStream_t st); // out[b][a][2-r][2-s] = in[a][b][r][s]
 
+    // stride-2 kernel gradient with 1-6 channels (first layers of the GAN discriminators / U-Net encoder). conv_smallc.cu
+    bool strided_wgrad_supported(const nb200_conv_desc& d);
+    size_t strided_wgrad_workspace(const nb200_conv_desc& d);
+    int strided_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st);
+
     // tcgen05/TMA implicit-GEMM kernels (NCHW). conv_tc.cu
     bool tc_forward_supported(const nb200_conv_desc& d);
     bool tc_input_gradient_supported(const nb200_conv_desc& d);

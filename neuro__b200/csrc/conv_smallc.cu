@@ -499,6 +499,98 @@ namespace nb200
             out[i] = v;
         }
 
+        // ------------------------------------------------------------ strided kernel gradient, few channels
+        // dw[k][c][r][s] = sum_{n,oh,ow} dy[n][k][oh][ow] * x[n][c][oh*st+r-padY][ow*st+s-padX]   (first layers of the GAN
+        // discriminators / U-Net encoder: 3 or 6 channels, 3x3 or 4x4 filters, stride 2 -- HBM-bound, and 10-60x off their HBM
+        // time on the gathered tensor-core kernel, whose 128-channel A tile holds 3 real channels). Warp = KPW filters, lanes =
+        // output pixels of a row; the C*F*F*KPW running sums live in registers, x comes from L1 (the 8 warps of a block read the
+        // same rows), dy is streamed once with coalesced loads. Deterministic split over output rows + fixed-order second pass.
+        struct StridedGeo
+        {
+            int N, H, W, K, Ho, Wo, stride, padX, padY;
+        };
+
+        template <int C, int F, int KPW>
+        __global__ void __launch_bounds__(kSmallThreads)
+        strided_wgrad_kernel(StridedGeo g, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part, int rowsPerSlice)
+        {
+            constexpr int T = C * F * F;
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            const int kBase = (blockIdx.x * 8 + warp) * KPW;
+            const int slice = blockIdx.y;
+            const int rows = g.N * g.Ho;
+            const int rowBegin = slice * rowsPerSlice;
+            const int rowEnd = min(rowBegin + rowsPerSlice, rows);
+
+            float acc[KPW][T];
+#pragma unroll
+            for (int j = 0; j < KPW; ++j)
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                    acc[j][t] = 0.f;
+
+            if (kBase < g.K)
+            {
+                const long long plane = (long long)g.Ho * g.Wo;
+                for (int row = rowBegin; row < rowEnd; ++row)
+                {
+                    const int n = row / g.Ho, oh = row - n * g.Ho;
+                    for (int ow = lane; ow < g.Wo; ow += 32)
+                    {
+                        float d[KPW];
+#pragma unroll
+                        for (int j = 0; j < KPW; ++j)
+                            d[j] = kBase + j < g.K ? __ldcs(dy + ((long long)n * g.K + kBase + j) * plane + (long long)oh * g.Wo + ow) : 0.f;
+                        const int iw0 = ow * g.stride - g.padX;
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+#pragma unroll
+                            for (int r = 0; r < F; ++r)
+                            {
+                                const int ih = oh * g.stride - g.padY + r;
+                                if (ih < 0 || ih >= g.H)
+                                    continue; // warp-uniform
+                                const float* xr = x + (((long long)n * C + c) * g.H + ih) * g.W;
+#pragma unroll
+                                for (int s2 = 0; s2 < F; ++s2)
+                                {
+                                    const int iw = iw0 + s2;
+                                    const float xv = (iw >= 0 && iw < g.W) ? __ldg(xr + iw) : 0.f;
+#pragma unroll
+                                    for (int j = 0; j < KPW; ++j)
+                                        acc[j][(c * F + r) * F + s2] = fmaf(d[j], xv, acc[j][(c * F + r) * F + s2]);
+                                }
+                            }
+                    }
+                }
+            }
+
+#pragma unroll
+            for (int j = 0; j < KPW; ++j)
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                {
+                    float v = acc[j][t];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                        v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0 && kBase + j < g.K)
+                        part[((long long)slice * g.K + kBase + j) * T + t] = v;
+                }
+        }
+
+        constexpr int strided_kpw(int C, int F) { return C * F * F <= 27 ? 4 : C * F * F <= 54 ? 2 : 1; }
+
+        int strided_slices(const nb200_conv_desc& d)
+        {
+            const int kpw = strided_kpw(d.C, d.R);
+            const int kBlocks = ceil_div(d.K, 8 * kpw);
+            const int rows = d.N * d.Ho;
+            int want = ceil_div(148 * 4, kBlocks);
+            if (want > rows) want = rows;
+            return want < 1 ? 1 : want;
+        }
+
         // out[b][a][2-r][2-s] = in[a][b][r][s]: filters transposed and rotated by 180 degrees (3x3 taps: index t -> 8 - t)
         __global__ void swap_filters_kernel(const float* __restrict__ in, float* __restrict__ out, int A, int B)
         {
@@ -575,9 +667,11 @@ namespace nb200
         const SmallGeo g = small_geo(d, dy, dx, nullptr);
         const long long quads = (long long)d.N * d.H * ((d.W + 3) / 4);
         const size_t smem = (size_t)d.K * ((d.C * 9 + 3) & ~3) * 4;
-        // fewer than two blocks per SM and enough filters to share out: split the filters over the warps of a block instead
+        // less than one block per SM and enough filters to share out: split the filters over the warps of a block instead
+        // (DCGAN 128 -> 3 @32x32 batch 128, 128 blocks: 0.089 -> 0.070 ms; at 256 blocks -- VGG 64 -> 3 @512x512 batch 1 -- the
+        // split is slower, 0.067 vs 0.050 ms, because every block reloads the filters)
         static const char* env = getenv("NB200_SMALLC_KSPLIT"); // 0 disables (profiling)
-        if (ceil_div(quads, kSmallThreads) < 2 * 148 && d.K >= 32 && !(env && env[0] == '0'))
+        if (ceil_div(quads, kSmallThreads) < 148 && d.K >= 32 && !(env && env[0] == '0'))
         {
             const size_t smem2 = smem + (size_t)8 * d.C * 4 * 32 * sizeof(float);
 #define CALL(CC)                                                                                                              \
@@ -649,6 +743,50 @@ namespace nb200
     int smallc_swap_filters(const float* in, float* out, int A, int B, cudaStream_t st)
     {
         swap_filters_kernel<<<ceil_div((long long)A * B * 9, 256), 256, 0, st>>>(in, out, A, B);
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        return NB200_OK;
+    }
+    // ---- strided few-channel kernel gradient (strided_wgrad_kernel) ----
+    bool strided_wgrad_supported(const nb200_conv_desc& d)
+    {
+        const bool cOk = d.C == 1 || d.C == 2 || d.C == 3 || d.C == 4 || d.C == 6;
+        return d.fmt == NB200_NCHW && cOk && d.R == d.S && (d.R == 3 || d.R == 4) && d.stride == 2 && d.K >= 1 && d.N >= 1 && d.Ho >= 1 &&
+               d.Wo >= 1 && d.H >= 1 && d.W >= 1 && (long long)d.N * d.Ho <= 0x7fffffffll;
+    }
+
+    size_t strided_wgrad_workspace(const nb200_conv_desc& d)
+    {
+        return (size_t)strided_slices(d) * d.K * d.C * d.R * d.S * sizeof(float);
+    }
+
+    int strided_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st)
+    {
+        const size_t need = strided_wgrad_workspace(d);
+        if (wsBytes < need || !ws)
+            return fail(NB200_E_WORKSPACE, "strided few-channel kernel gradient needs %zu workspace bytes, got %zu", need, wsBytes);
+        const StridedGeo g{d.N, d.H, d.W, d.K, d.Ho, d.Wo, d.stride, d.padX, d.padY};
+        const int slices = strided_slices(d);
+        const int rowsPerSlice = ceil_div(d.N * d.Ho, slices);
+#define SW_CALL(CC, FF)                                                                                                        \
+        {                                                                                                                      \
+            constexpr int kpw = strided_kpw(CC, FF);                                                                           \
+            dim3 grid(ceil_div(d.K, 8 * kpw), slices);                                                                         \
+            strided_wgrad_kernel<CC, FF, kpw><<<grid, kSmallThreads, 0, st>>>(g, x, dy, (float*)ws, rowsPerSlice);            \
+        }
+        if (d.R == 3)
+        {
+            switch (d.C) { case 1: SW_CALL(1, 3) break; case 2: SW_CALL(2, 3) break; case 3: SW_CALL(3, 3) break; case 4: SW_CALL(4, 3) break; default: SW_CALL(6, 3) break; }
+        }
+        else
+        {
+            switch (d.C) { case 1: SW_CALL(1, 4) break; case 2: SW_CALL(2, 4) break; case 3: SW_CALL(3, 4) break; case 4: SW_CALL(4, 4) break; default: SW_CALL(6, 4) break; }
+        }
+#undef SW_CALL
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        const int count = d.K * d.C * d.R * d.S;
+        smallc_reduce_kernel<<<ceil_div(count, 256), 256, 0, st>>>((const float*)ws, dw, count, slices);
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
