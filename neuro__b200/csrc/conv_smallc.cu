@@ -512,15 +512,16 @@ namespace nb200
 
         template <int C, int F, int KPW>
         __global__ void __launch_bounds__(kSmallThreads)
-        strided_wgrad_kernel(StridedGeo g, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part, int rowsPerSlice)
+        strided_wgrad_kernel(StridedGeo g, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part, int pixPerSlice)
         {
             constexpr int T = C * F * F;
             const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
             const int kBase = (blockIdx.x * 8 + warp) * KPW;
             const int slice = blockIdx.y;
-            const int rows = g.N * g.Ho;
-            const int rowBegin = slice * rowsPerSlice;
-            const int rowEnd = min(rowBegin + rowsPerSlice, rows);
+            const unsigned plane = (unsigned)(g.Ho * g.Wo);
+            const unsigned total = (unsigned)g.N * plane;               // output pixels, flattened (n, oh, ow): lanes stay busy on narrow maps
+            const unsigned pBegin = (unsigned)slice * (unsigned)pixPerSlice;
+            const unsigned pEnd = min(pBegin + (unsigned)pixPerSlice, total);
 
             float acc[KPW][T];
 #pragma unroll
@@ -531,37 +532,33 @@ namespace nb200
 
             if (kBase < g.K)
             {
-                const long long plane = (long long)g.Ho * g.Wo;
-                for (int row = rowBegin; row < rowEnd; ++row)
+                for (unsigned p = pBegin + lane; p < pEnd; p += 32)
                 {
-                    const int n = row / g.Ho, oh = row - n * g.Ho;
-                    for (int ow = lane; ow < g.Wo; ow += 32)
-                    {
-                        float d[KPW];
+                    const unsigned n = p / plane, rem = p - n * plane;
+                    const int oh = (int)(rem / (unsigned)g.Wo), ow = (int)(rem - (unsigned)oh * (unsigned)g.Wo);
+                    float d[KPW];
 #pragma unroll
-                        for (int j = 0; j < KPW; ++j)
-                            d[j] = kBase + j < g.K ? __ldcs(dy + ((long long)n * g.K + kBase + j) * plane + (long long)oh * g.Wo + ow) : 0.f;
-                        const int iw0 = ow * g.stride - g.padX;
+                    for (int j = 0; j < KPW; ++j)
+                        d[j] = kBase + j < g.K ? __ldcs(dy + ((long long)n * g.K + kBase + j) * plane + rem) : 0.f;
+                    const int ih0 = oh * g.stride - g.padY, iw0 = ow * g.stride - g.padX;
 #pragma unroll
-                        for (int c = 0; c < C; ++c)
+                    for (int c = 0; c < C; ++c)
 #pragma unroll
-                            for (int r = 0; r < F; ++r)
+                        for (int r = 0; r < F; ++r)
+                        {
+                            const int ih = ih0 + r;
+                            const bool rowOk = ih >= 0 && ih < g.H;
+                            const float* xr = x + (((long long)n * C + c) * g.H + (rowOk ? ih : 0)) * g.W;
+#pragma unroll
+                            for (int s2 = 0; s2 < F; ++s2)
                             {
-                                const int ih = oh * g.stride - g.padY + r;
-                                if (ih < 0 || ih >= g.H)
-                                    continue; // warp-uniform
-                                const float* xr = x + (((long long)n * C + c) * g.H + ih) * g.W;
+                                const int iw = iw0 + s2;
+                                const float xv = (rowOk && iw >= 0 && iw < g.W) ? __ldg(xr + iw) : 0.f;
 #pragma unroll
-                                for (int s2 = 0; s2 < F; ++s2)
-                                {
-                                    const int iw = iw0 + s2;
-                                    const float xv = (iw >= 0 && iw < g.W) ? __ldg(xr + iw) : 0.f;
-#pragma unroll
-                                    for (int j = 0; j < KPW; ++j)
-                                        acc[j][(c * F + r) * F + s2] = fmaf(d[j], xv, acc[j][(c * F + r) * F + s2]);
-                                }
+                                for (int j = 0; j < KPW; ++j)
+                                    acc[j][(c * F + r) * F + s2] = fmaf(d[j], xv, acc[j][(c * F + r) * F + s2]);
                             }
-                    }
+                        }
                 }
             }
 
@@ -585,10 +582,10 @@ namespace nb200
         {
             const int kpw = strided_kpw(d.C, d.R);
             const int kBlocks = ceil_div(d.K, 8 * kpw);
-            const int rows = d.N * d.Ho;
-            int want = ceil_div(148 * 4, kBlocks);
-            if (want > rows) want = rows;
-            return want < 1 ? 1 : want;
+            const long long chunks = ((long long)d.N * d.Ho * d.Wo + 31) / 32; // a slice is a whole number of 32-pixel steps
+            long long want = ceil_div(148 * 4, kBlocks);
+            if (want > chunks) want = chunks;
+            return want < 1 ? 1 : (int)want;
         }
 
         // out[b][a][2-r][2-s] = in[a][b][r][s]: filters transposed and rotated by 180 degrees (3x3 taps: index t -> 8 - t)
@@ -750,9 +747,11 @@ namespace nb200
     // ---- strided few-channel kernel gradient (strided_wgrad_kernel) ----
     bool strided_wgrad_supported(const nb200_conv_desc& d)
     {
-        const bool cOk = d.C == 1 || d.C == 2 || d.C == 3 || d.C == 4 || d.C == 6;
+        // measured (profiles/README.md): 3 channels x 3x3 (27 sums, 4 filters per warp) halves the gathered kernel's time; 6 channels x 4x4
+        // (96 sums, 237 registers, one block per SM) is 2.4x SLOWER than it, so the family stops at 36 running sums per filter
+        const bool cOk = d.C >= 1 && d.C <= 4 && d.C * d.R * d.S <= 36;
         return d.fmt == NB200_NCHW && cOk && d.R == d.S && (d.R == 3 || d.R == 4) && d.stride == 2 && d.K >= 1 && d.N >= 1 && d.Ho >= 1 &&
-               d.Wo >= 1 && d.H >= 1 && d.W >= 1 && (long long)d.N * d.Ho <= 0x7fffffffll;
+               d.Wo >= 1 && d.H >= 1 && d.W >= 1 && (long long)d.N * d.Ho * d.Wo <= 0x7fffffffll;
     }
 
     size_t strided_wgrad_workspace(const nb200_conv_desc& d)
@@ -767,7 +766,8 @@ namespace nb200
             return fail(NB200_E_WORKSPACE, "strided few-channel kernel gradient needs %zu workspace bytes, got %zu", need, wsBytes);
         const StridedGeo g{d.N, d.H, d.W, d.K, d.Ho, d.Wo, d.stride, d.padX, d.padY};
         const int slices = strided_slices(d);
-        const int rowsPerSlice = ceil_div(d.N * d.Ho, slices);
+        const long long chunks = ((long long)d.N * d.Ho * d.Wo + 31) / 32;
+        const int rowsPerSlice = (int)((chunks + slices - 1) / slices) * 32; // pixels per slice
 #define SW_CALL(CC, FF)                                                                                                        \
         {                                                                                                                      \
             constexpr int kpw = strided_kpw(CC, FF);                                                                           \
@@ -776,11 +776,11 @@ namespace nb200
         }
         if (d.R == 3)
         {
-            switch (d.C) { case 1: SW_CALL(1, 3) break; case 2: SW_CALL(2, 3) break; case 3: SW_CALL(3, 3) break; case 4: SW_CALL(4, 3) break; default: SW_CALL(6, 3) break; }
+            switch (d.C) { case 1: SW_CALL(1, 3) break; case 2: SW_CALL(2, 3) break; case 3: SW_CALL(3, 3) break; default: SW_CALL(4, 3) break; }
         }
         else
         {
-            switch (d.C) { case 1: SW_CALL(1, 4) break; case 2: SW_CALL(2, 4) break; case 3: SW_CALL(3, 4) break; case 4: SW_CALL(4, 4) break; default: SW_CALL(6, 4) break; }
+            switch (d.C) { case 1: SW_CALL(1, 4) break; default: SW_CALL(2, 4) break; }
         }
 #undef SW_CALL
         NB200_CUDA_TRY(cudaGetLastError());

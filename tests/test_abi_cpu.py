@@ -111,7 +111,7 @@ def test_kernel_dispatch_is_host_logic(L):
     assert names(_desc(8, 512, 2, 2, 512, 3, 3, 2, 1, 1))[2] == "tcgen05_gather_wgrad"
     # stride-2 first layers with 3 / 6 channels (pix2pix enc1, PatchGAN d1, DCGAN D conv1): HBM-bound kernel gradient off the GEMM path
     assert names(_desc(8, 3, 256, 256, 64, 3, 3, 2, 1, 1)) == ["tcgen05_gather_fprop", "tcgen05_gather_dgrad", "strided_smallc_wgrad"]
-    assert names(_desc(8, 6, 259, 259, 64, 4, 4, 2, 0, 0))[2] == "strided_smallc_wgrad"
+    assert names(_desc(8, 6, 259, 259, 64, 4, 4, 2, 0, 0))[2] == "tcgen05_gather_wgrad"   # 96 running sums per filter: measured slower there
     assert names(_desc(128, 3, 32, 32, 64, 3, 3, 2, 1, 1))[2] == "strided_smallc_wgrad"
     # few-filter output convolutions (DCGAN G out, pix2pix last, autoencoder dec3): small-channel kernels with x and y exchanged
     assert names(_desc(128, 128, 32, 32, 3, 3, 3, 1, 1, 1)) == ["smallk_fprop", "smallk_dgrad", "tcgen05_smallk_wgrad"]

@@ -107,9 +107,10 @@ TC_CASES = [
     (0, 2, 16, 5, 5, 16, 3, 3, 1, 1, 1),       # 25 pixels in one 32-pixel chunk, planes pitched to 28
     # stride-2 first layers with 1-6 channels: kernel gradient on the strided few-channel CUDA-core kernel
     (0, 2, 3, 32, 32, 64, 3, 3, 2, 1, 1),      # DCGAN D conv1 / pix2pix enc1 geometry (3 channels, 4 filters per warp)
-    (0, 2, 6, 35, 35, 24, 4, 4, 2, 0, 0),      # PatchGAN d1 geometry: 6 channels, 4x4, odd extent, ragged stride
+    (0, 2, 6, 35, 35, 24, 4, 4, 2, 0, 0),      # PatchGAN d1 geometry: 6 channels, 4x4, odd extent, ragged stride (stays on the gathered kernel)
+    (0, 2, 2, 19, 23, 24, 4, 4, 2, 0, 0),      # 2 channels, 4x4 (32 running sums, 2 filters per warp), odd extent, ragged stride
     (0, 3, 1, 28, 28, 20, 3, 3, 2, 1, 1),      # MNIST DCGAN first conv: one channel, filter count not a multiple of 32
-    (0, 2, 4, 18, 22, 70, 4, 4, 2, 1, 1),      # 64 running sums per filter, one filter per warp, ragged filter blocks
+    (0, 2, 4, 18, 22, 70, 3, 3, 2, 1, 1),      # 36 running sums per filter, two filters per warp, ragged filter blocks
     # gathered forward / input gradient with a narrowed filter tile and channel splits (weight-bound U-Net bottleneck layers)
     (0, 2, 256, 4, 4, 128, 3, 3, 1, 1, 1),     # one pixel tile: forward 2 filter tiles x 4 channel splits, input gradient 4 x 2
     (0, 4, 128, 8, 8, 128, 3, 3, 2, 1, 1),     # stride 2: the four parity classes of the input gradient share one split launch
