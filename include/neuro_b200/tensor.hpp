@@ -35,6 +35,7 @@ namespace NeuroB200
     enum ELocation { None, Host, Device };                                   // Types.h:42-47
     enum EPaddingMode { Valid, Same, Full };                                 // Types.h:49-54
     enum EDataFormat { NCHW = NB200_NCHW, NHWC = NB200_NHWC };               // Types.h:94-98
+    enum EPoolingMode { MaxPool = NB200_POOL_MAX, AvgPool = NB200_POOL_AVG };  // Types.h:56-60
     enum EActivation { _Identity, _Sigmoid, _ReLU, _TanH, _ELU, _LeakyReLU, _Softmax }; // Types.h:83-92
 
     inline void CudaCheck(cudaError_t e, const char* what)
@@ -94,6 +95,12 @@ namespace NeuroB200
             ActivationGradient(activation, activationAlpha, output, outputGradient, activationInputGradient);
             Conv2DBiasGradient(activationInputGradient, biasGradient);
         }
+        // resamplers around the convolutions (TensorOpCpu.h:51-54; ConstantPad2D TensorOpCpu.cpp:528)
+        virtual void Pool2D(const Tensor&, uint32_t, uint32_t, EPoolingMode, uint32_t, uint32_t, EDataFormat, Tensor&) const { throw std::runtime_error("Pool2D: not implemented by this backend"); }
+        virtual void Pool2DGradient(const Tensor&, const Tensor&, const Tensor&, uint32_t, uint32_t, EPoolingMode, uint32_t, uint32_t, EDataFormat, Tensor&) const { throw std::runtime_error("Pool2DGradient: not implemented by this backend"); }
+        virtual void UpSample2D(const Tensor&, uint32_t, Tensor&) const { throw std::runtime_error("UpSample2D: not implemented by this backend"); }
+        virtual void UpSample2DGradient(const Tensor&, uint32_t, Tensor&) const { throw std::runtime_error("UpSample2DGradient: not implemented by this backend"); }
+        virtual void ConstantPad2D(const Tensor&, uint32_t, uint32_t, uint32_t, uint32_t, float, Tensor&) const { throw std::runtime_error("ConstantPad2D: not implemented by this backend"); }
         virtual void AdamStep(Tensor& parameter, const Tensor& gradient, Tensor& mGrad, Tensor& vGrad, float lr, float beta1, float beta2, float epsilon) const = 0;
         virtual void SgdStep(Tensor& parameter, const Tensor& gradient, float lr) const = 0;
     };
@@ -261,6 +268,53 @@ namespace NeuroB200
         void Conv2DKernelsGradient(const Tensor& input, const Tensor& gradient, uint32_t stride, uint32_t padding, EDataFormat fmt, Tensor& kernelsGradient) const
         {
             Op()->Conv2DKernelsGradient(input, gradient, stride, padding, padding, fmt, kernelsGradient);
+        }
+        // ---- resampler wrappers (Tensor.cpp:1833-1876, 1500-1512): shape checks + dispatch ----
+        static Shape GetPooling2DOutputShape(const Shape& in, uint32_t kernelWidth, uint32_t kernelHeight, uint32_t stride, uint32_t paddingX, uint32_t paddingY, EDataFormat fmt)
+        {
+            if (fmt == NCHW)
+                return Shape((in.Width() + 2 * paddingX - kernelWidth) / stride + 1, (in.Height() + 2 * paddingY - kernelHeight) / stride + 1, in.Depth(), in.Batch());
+            return Shape(in.Len(0), (in.Len(1) + 2 * paddingX - kernelWidth) / stride + 1, (in.Len(2) + 2 * paddingY - kernelHeight) / stride + 1, in.Len(3));
+        }
+        void Pool2D(uint32_t filterSize, uint32_t stride, EPoolingMode type, uint32_t padding, EDataFormat fmt, Tensor& output) const
+        {
+            if (GetPooling2DOutputShape(m_Shape, filterSize, filterSize, stride, padding, padding, fmt) != output.GetShape())
+                throw std::runtime_error("Output shape doesn't match input shape.");
+            Op()->Pool2D(*this, filterSize, stride, type, padding, padding, fmt, output);
+        }
+        Tensor Pool2D(uint32_t filterSize, uint32_t stride, EPoolingMode type, uint32_t padding, EDataFormat fmt) const
+        {
+            Tensor result(GetPooling2DOutputShape(m_Shape, filterSize, filterSize, stride, padding, padding, fmt));
+            Pool2D(filterSize, stride, type, padding, fmt, result);
+            return result;
+        }
+        void Pool2DGradient(const Tensor& output, const Tensor& input, const Tensor& outputGradient, uint32_t filterSize, uint32_t stride, EPoolingMode type, uint32_t padding, EDataFormat fmt, Tensor& result) const
+        {
+            Op()->Pool2DGradient(output, input, outputGradient, filterSize, stride, type, padding, padding, fmt, result);
+        }
+        void UpSample2D(uint32_t scaleFactor, Tensor& output) const
+        {
+            if (Shape(Width() * scaleFactor, Height() * scaleFactor, Depth(), Batch()) != output.GetShape())
+                throw std::runtime_error("Output shape doesn't match input shape.");
+            Op()->UpSample2D(*this, scaleFactor, output);
+        }
+        Tensor UpSample2D(uint32_t scaleFactor) const
+        {
+            Tensor result(Shape(Width() * scaleFactor, Height() * scaleFactor, Depth(), Batch()));
+            UpSample2D(scaleFactor, result);
+            return result;
+        }
+        void UpSample2DGradient(const Tensor& outputGradient, uint32_t scaleFactor, Tensor& inputGradient) const
+        {
+            if (Shape(inputGradient.Width() * scaleFactor, inputGradient.Height() * scaleFactor, inputGradient.Depth(), inputGradient.Batch()) != outputGradient.GetShape())
+                throw std::runtime_error("Input gradient shape doesn't match input shape.");
+            Op()->UpSample2DGradient(outputGradient, scaleFactor, inputGradient);
+        }
+        Tensor ConstantPad2D(uint32_t left, uint32_t right, uint32_t top, uint32_t bottom, float value) const
+        {
+            Tensor output(Shape(Width() + left + right, Height() + top + bottom, Depth(), Batch()));
+            Op()->ConstantPad2D(*this, left, right, top, bottom, value, output);
+            return output;
         }
         // transposed convolution identities (Tensor.cpp:1806-1830)
         void Conv2DTransposed(const Tensor& kernels, uint32_t stride, uint32_t padding, EDataFormat fmt, Tensor& result) const

@@ -69,6 +69,40 @@ namespace NeuroB200
             Nb200Check(nb200_conv2d_kernels_gradient(&d, input.GetDevicePtr(), gradient.GetDevicePtr(), kernelsGradient.GetDevicePtr(), nullptr, w, ws, m_Stream));
         }
 
+        void Pool2D(const Tensor& input, uint32_t filterSize, uint32_t stride, EPoolingMode type, uint32_t paddingX, uint32_t paddingY, EDataFormat dataFormat, Tensor& output) const override
+        {
+            input.CopyToDevice(); output.OverrideDevice();
+            const nb200_pool_desc d = DescribePool(input, output, filterSize, stride, type, paddingX, paddingY, dataFormat);
+            Nb200Check(nb200_pool2d(&d, input.GetDevicePtr(), output.GetDevicePtr(), m_Stream));
+        }
+
+        void Pool2DGradient(const Tensor& output, const Tensor& input, const Tensor& outputGradient, uint32_t filterSize, uint32_t stride, EPoolingMode type, uint32_t paddingX, uint32_t paddingY, EDataFormat dataFormat, Tensor& inputGradient) const override
+        {
+            output.CopyToDevice(); input.CopyToDevice(); outputGradient.CopyToDevice(); inputGradient.OverrideDevice();
+            const nb200_pool_desc d = DescribePool(input, output, filterSize, stride, type, paddingX, paddingY, dataFormat);
+            Nb200Check(nb200_pool2d_gradient(&d, output.GetDevicePtr(), input.GetDevicePtr(), outputGradient.GetDevicePtr(), inputGradient.GetDevicePtr(), m_Stream));
+        }
+
+        void UpSample2D(const Tensor& input, uint32_t scaleFactor, Tensor& output) const override
+        {
+            input.CopyToDevice(); output.OverrideDevice();
+            Nb200Check(nb200_upsample2d(input.Batch(), input.Depth(), input.Height(), input.Width(), scaleFactor, input.GetDevicePtr(), output.GetDevicePtr(), m_Stream));
+        }
+
+        void UpSample2DGradient(const Tensor& outputGradient, uint32_t scaleFactor, Tensor& inputGradient) const override
+        {
+            outputGradient.CopyToDevice(); inputGradient.OverrideDevice();
+            Nb200Check(nb200_upsample2d_gradient(inputGradient.Batch(), inputGradient.Depth(), inputGradient.Height(), inputGradient.Width(), scaleFactor,
+                                                 outputGradient.GetDevicePtr(), inputGradient.GetDevicePtr(), m_Stream));
+        }
+
+        void ConstantPad2D(const Tensor& input, uint32_t left, uint32_t right, uint32_t top, uint32_t bottom, float value, Tensor& output) const override
+        {
+            input.CopyToDevice(); output.OverrideDevice();
+            Nb200Check(nb200_constant_pad2d(input.Batch(), input.Depth(), input.Height(), input.Width(), left, right, top, bottom, value, input.GetDevicePtr(),
+                                            output.GetDevicePtr(), m_Stream));
+        }
+
         void AdamStep(Tensor& parameter, const Tensor& gradient, Tensor& mGrad, Tensor& vGrad, float lr, float beta1, float beta2, float epsilon) const override
         {
             parameter.CopyToDevice(); gradient.CopyToDevice(); mGrad.CopyToDevice(); vGrad.CopyToDevice();
@@ -99,6 +133,14 @@ namespace NeuroB200
             const nb200_conv_desc d = Describe(input, kernels, output, stride, paddingX, paddingY, fmt);
             size_t ws = 0; void* w = Workspace(NB200_OP_FORWARD, d, ws);
             Nb200Check(nb200_conv2d_forward(&d, input.GetDevicePtr(), kernels.GetDevicePtr(), bias ? bias->GetDevicePtr() : nullptr, (int)act, alpha, output.GetDevicePtr(), w, ws, m_Stream));
+        }
+        static nb200_pool_desc DescribePool(const Tensor& x, const Tensor& y, uint32_t filterSize, uint32_t stride, EPoolingMode type, uint32_t paddingX, uint32_t paddingY, EDataFormat fmt)
+        {
+            nb200_pool_desc d{};
+            if (fmt == NCHW) { d.W = x.Len(0); d.H = x.Len(1); d.C = x.Len(2); d.Wo = y.Len(0); d.Ho = y.Len(1); }
+            else { d.C = x.Len(0); d.W = x.Len(1); d.H = x.Len(2); d.Wo = y.Len(1); d.Ho = y.Len(2); }
+            d.N = x.Len(3); d.filter = filterSize; d.stride = stride; d.padX = paddingX; d.padY = paddingY; d.mode = (int)type; d.fmt = fmt;
+            return d;
         }
         void BiasActivationGradient(const Tensor& output, const Tensor& outputGradient, EActivation act, float alpha, Tensor& dz, Tensor* db) const
         {

@@ -20,6 +20,12 @@ extern "C"
     void oracle_conv2d_bias_activation(const conv_dims*, const float*, const float*, const float*, int, float, float*);
     void oracle_conv2d_bias_gradient(const conv_dims*, const float*, float*);
     void oracle_activation_gradient(int, float, const float*, const float*, float*, size_t);
+    struct pool_dims { int N, C, H, W, Ho, Wo, filter, stride, padX, padY, mode, fmt; };
+    void oracle_pool2d(const pool_dims*, const float*, float*);
+    void oracle_pool2d_gradient(const pool_dims*, const float*, const float*, const float*, float*);
+    void oracle_upsample2d(int, int, int, int, const float*, float*);
+    void oracle_upsample2d_gradient(int, int, int, int, const float*, float*);
+    void oracle_constant_pad2d(int, int, int, int, int, int, int, float, const float*, float*);
     void oracle_adam_step(float*, const float*, float*, float*, size_t, float, float, float, float);
     void oracle_sgd_step(float*, const float*, size_t, float);
 }
@@ -50,6 +56,24 @@ public:
     { const conv_dims d = Dims(x, dw, g, s, px, py, f); dw.OverrideHost(); oracle_conv2d_kernels_gradient(&d, x.Values(), g.Values(), dw.Values()); }
     void ActivationGradient(EActivation a, float alpha, const Tensor& y, const Tensor& g, Tensor& dz) const override
     { dz.OverrideHost(); oracle_activation_gradient((int)a, alpha, y.Values(), g.Values(), dz.Values(), g.Length()); }
+    static pool_dims PoolDims(const Tensor& x, const Tensor& y, uint32_t f, uint32_t s, EPoolingMode t, uint32_t px, uint32_t py, EDataFormat fmt)
+    {
+        pool_dims d{};
+        if (fmt == NCHW) { d.W = x.Len(0); d.H = x.Len(1); d.C = x.Len(2); d.Wo = y.Len(0); d.Ho = y.Len(1); }
+        else { d.C = x.Len(0); d.W = x.Len(1); d.H = x.Len(2); d.Wo = y.Len(1); d.Ho = y.Len(2); }
+        d.N = x.Len(3); d.filter = f; d.stride = s; d.padX = px; d.padY = py; d.mode = (int)t; d.fmt = fmt;
+        return d;
+    }
+    void Pool2D(const Tensor& x, uint32_t f, uint32_t s, EPoolingMode t, uint32_t px, uint32_t py, EDataFormat fmt, Tensor& y) const override
+    { const pool_dims d = PoolDims(x, y, f, s, t, px, py, fmt); y.OverrideHost(); oracle_pool2d(&d, x.Values(), y.Values()); }
+    void Pool2DGradient(const Tensor& y, const Tensor& x, const Tensor& g, uint32_t f, uint32_t s, EPoolingMode t, uint32_t px, uint32_t py, EDataFormat fmt, Tensor& dx) const override
+    { const pool_dims d = PoolDims(x, y, f, s, t, px, py, fmt); dx.OverrideHost(); oracle_pool2d_gradient(&d, y.Values(), x.Values(), g.Values(), dx.Values()); }
+    void UpSample2D(const Tensor& x, uint32_t s, Tensor& y) const override
+    { y.OverrideHost(); oracle_upsample2d(x.Batch() * x.Depth(), x.Height(), x.Width(), s, x.Values(), y.Values()); }
+    void UpSample2DGradient(const Tensor& g, uint32_t s, Tensor& dx) const override
+    { dx.OverrideHost(); oracle_upsample2d_gradient(dx.Batch() * dx.Depth(), dx.Height(), dx.Width(), s, g.Values(), dx.Values()); }
+    void ConstantPad2D(const Tensor& x, uint32_t l, uint32_t r, uint32_t t, uint32_t b, float v, Tensor& y) const override
+    { y.OverrideHost(); oracle_constant_pad2d(x.Batch() * x.Depth(), x.Height(), x.Width(), l, r, t, b, v, x.Values(), y.Values()); }
     void AdamStep(Tensor& p, const Tensor& g, Tensor& m, Tensor& v, float lr, float b1, float b2, float eps) const override
     { oracle_adam_step(p.Values(), g.Values(), m.Values(), v.Values(), p.Length(), lr, b1, b2, eps); }
     void SgdStep(Tensor& p, const Tensor& g, float lr) const override { oracle_sgd_step(p.Values(), g.Values(), p.Length(), lr); }
@@ -169,6 +193,53 @@ TEST_METHOD(Conv2DBiasActivationGradient_CompareWithCpuResult)
         IsTrue(dz.Equals(dz3, 0.f));
         IsTrue(db.Equals(db2, 0.0001f));
     }
+}
+
+// ---- TensorTests.cpp:427-504 literal vectors on the device, and TensorOpGpuTests-style CPU-vs-device comparisons (exact) ----
+TEST_METHOD(Pool_Max_Valid_2Batches_Stride2)
+{
+    Tensor::SetForcedOpMode(B200);
+    Tensor t1(Shape(6, 6, 1, 2)); t1.FillWithRange(0);
+    Tensor r = t1.Pool2D(2, 2, MaxPool, 0, NCHW);
+    Tensor correct({ 7, 9, 11, 19, 21, 23, 31, 33, 35, 43, 45, 47, 55, 57, 59, 67, 69, 71 }, Shape(3, 3, 1, 2));
+    IsTrue(r.Equals(correct, 0.f));
+    Tensor a = t1.Pool2D(2, 2, AvgPool, 0, NCHW);
+    Tensor correctAvg({ 3.5f, 5.5f, 7.5f, 15.5f, 17.5f, 19.5f, 27.5f, 29.5f, 31.5f, 39.5f, 41.5f, 43.5f, 51.5f, 53.5f, 55.5f, 63.5f, 65.5f, 67.5f }, Shape(3, 3, 1, 2));
+    IsTrue(a.Equals(correctAvg, 0.f));
+}
+
+TEST_METHOD(UpSample2D_2)
+{
+    Tensor::SetForcedOpMode(B200);
+    Tensor t1(Shape(2, 2, 1, 2)); t1.FillWithRange(0);
+    Tensor r = t1.UpSample2D(2);
+    Tensor correct({ 0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3, 4, 4, 5, 5, 4, 4, 5, 5, 6, 6, 7, 7, 6, 6, 7, 7 }, Shape(4, 4, 1, 2));
+    IsTrue(r.Equals(correct, 0.f));
+}
+
+TEST_METHOD(Resamplers_CompareWithCpuResult)
+{
+    Tensor x(Shape(16, 12, 5, 3)); x.FillWithRand(21);
+    for (EPoolingMode mode : { MaxPool, AvgPool })
+        for (uint32_t cfg = 0; cfg < 2; ++cfg)
+        {
+            const uint32_t f = cfg ? 3 : 2, st = 2, pad = cfg ? 1 : 0;   // cfg 0 takes the float4 2x2 fast path
+            Tensor::SetForcedOpMode(CPU);
+            Tensor y = x.Pool2D(f, st, mode, pad, NCHW);
+            Tensor g(y.GetShape()); g.FillWithRand(22);
+            Tensor dx(x.GetShape()); x.Pool2DGradient(y, x, g, f, st, mode, pad, NCHW, dx);
+            Tensor::SetForcedOpMode(B200);
+            Tensor y2 = x.Pool2D(f, st, mode, pad, NCHW);
+            Tensor dx2(x.GetShape()); x.Pool2DGradient(y2, x, g, f, st, mode, pad, NCHW, dx2);
+            IsTrue(y.Equals(y2, 0.f)); IsTrue(dx.Equals(dx2, 0.f));
+        }
+    Tensor::SetForcedOpMode(CPU);
+    Tensor u = x.UpSample2D(2); Tensor du(x.GetShape()); x.UpSample2DGradient(u, 2, du);
+    Tensor p = x.ConstantPad2D(1, 2, 0, 3, -1.5f);
+    Tensor::SetForcedOpMode(B200);
+    Tensor u2 = x.UpSample2D(2); Tensor du2(x.GetShape()); x.UpSample2DGradient(u2, 2, du2);
+    Tensor p2 = x.ConstantPad2D(1, 2, 0, 3, -1.5f);
+    IsTrue(u.Equals(u2, 0.f)); IsTrue(du.Equals(du2, 0.f)); IsTrue(p.Equals(p2, 0.f));
 }
 
 TEST_METHOD(Conv2DInputGradient_CompareWithCpuResult)
