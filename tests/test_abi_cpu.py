@@ -57,6 +57,35 @@ def test_descriptor_validation(L):
     assert L.nb200_conv2d_forward(ctypes.byref(empty), None, None, None, 0, 0.0, None, None, 0, None) == 0
 
 
+def test_neighbour_entry_points_validate_before_touching_a_device(L):
+    """Resamplers, the fused activation/bias gradient and filter preparation reject bad arguments with NB200_E_INVALID (host logic),
+    accept empty tensors, and -- like every compute call -- refuse to run without a device rather than falling back."""
+    good = lib.PoolDesc(2, 3, 8, 8, 4, 4, 2, 2, 0, 0, lib.POOL_MAX, lib.NCHW)
+    bad_out = lib.PoolDesc(2, 3, 8, 8, 5, 4, 2, 2, 0, 0, lib.POOL_MAX, lib.NCHW)        # GetPooling2DOutputShape gives 4x4
+    bad_mode = lib.PoolDesc(2, 3, 8, 8, 4, 4, 2, 2, 0, 0, 7, lib.NCHW)
+    too_big = lib.PoolDesc(2, 3, 2, 2, 1, 1, 5, 1, 0, 0, lib.POOL_AVG, lib.NCHW)         # window larger than the padded input
+    for d in (bad_out, bad_mode, too_big):
+        assert L.nb200_pool2d(ctypes.byref(d), None, None, None) == -1
+        assert L.nb200_pool2d_gradient(ctypes.byref(d), None, None, None, None, None) == -1
+    assert L.nb200_pool2d(ctypes.byref(good), None, None, None) == -1                    # null tensors
+    empty = lib.PoolDesc(0, 3, 8, 8, 4, 4, 2, 2, 0, 0, lib.POOL_MAX, lib.NCHW)
+    assert L.nb200_pool2d(ctypes.byref(empty), None, None, None) == 0
+    assert L.nb200_upsample2d(0, 3, 4, 4, 2, None, None, None) == 0 and L.nb200_upsample2d(1, 3, 4, 4, 0, None, None, None) == -1
+    assert L.nb200_upsample2d_gradient(1, 1, 40000, 40000, 2, None, None, None) == -1    # exceeds Shape::Length (uint32)
+    assert L.nb200_constant_pad2d(1, 1, 4, 4, -1, 0, 0, 0, 0.0, None, None, None) == -1
+    d = _desc(2, 8, 16, 16, 8, 3, 3, 1, 1, 1)
+    assert L.nb200_conv2d_bias_activation_gradient(ctypes.byref(d), 6, 0.0, None, None, None, None, None, 0, None) == -1   # _Softmax has no gradient here
+    assert L.nb200_conv2d_prepare_filters(lib.OP_KERNELS_GRADIENT, ctypes.byref(d), None, None, 0, None) == -1
+    assert L.nb200_conv2d_prepare_filters(lib.OP_FORWARD, ctypes.byref(d), None, None, 0, None) == -1                      # null filters
+    import torch
+    if not torch.cuda.is_available():
+        one = ctypes.c_float(0.0)
+        p = ctypes.cast(ctypes.pointer(one), ctypes.c_void_p)
+        assert L.nb200_pool2d(ctypes.byref(good), p, p, None) == -2                       # NB200_E_NO_DEVICE, never a CPU loop
+        assert L.nb200_upsample2d(1, 1, 2, 2, 2, p, p, None) == -2
+        assert L.nb200_conv2d_bias_activation_gradient(ctypes.byref(d), 2, 0.0, p, p, p, None, None, 0, None) == -2
+
+
 def test_no_cpu_fallback(L):
     import torch
     if torch.cuda.is_available():

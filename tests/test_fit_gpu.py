@@ -40,3 +40,34 @@ def test_loss_curve_tracks_reference(math, tol, optimizer):
     # so parameters are compared loosely there; SGD parameters track tightly.
     ptol = {("adam", lib.MATH_TF32): 5e-2, ("adam", lib.MATH_FP32): 1e-3, ("sgd", lib.MATH_TF32): 5e-3, ("sgd", lib.MATH_FP32): 1e-5}
     assert np.abs(params - ref_params).max() <= ptol[(optimizer, math)]
+
+
+# DCGAN-discriminator-like stack (BASELINE configs[1]): RGB input, stride-2 3x3 convolutions with LeakyReLU(0.2) -- the first layer's
+# kernel gradient runs on the strided few-channel kernel, the others on the gathered tensor-core kernels, every backward step goes
+# through the fused activation-gradient + bias-gradient pass.
+GAN_LAYERS = [ConvLayerSpec(16, 3, 2, 1, lib.ACT_LEAKY_RELU, 0.2), ConvLayerSpec(32, 3, 2, 1, lib.ACT_LEAKY_RELU, 0.2),
+              ConvLayerSpec(8, 3, 1, 1, lib.ACT_TANH)]
+GAN_IN = (3, 32, 32)
+
+
+def _run_gan(op, device):
+    tr = ConvStackTrainer(op, GAN_IN, GAN_LAYERS, device, optimizer="sgd", lr=0.05)
+    x = torch.from_numpy(synth.uniform(synth.SEED_X, (N,) + GAN_IN))
+    t = torch.from_numpy(synth.uniform(synth.SEED_DY, (N,) + tr.out_shape, -0.5, 0.5))
+    return tr.fit(x, t, BATCH, epochs=EPOCHS), tr.params.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("math,tol", [(lib.MATH_TF32, 5e-3), (lib.MATH_FP32, 1e-4)], ids=["tf32", "fp32"])
+def test_strided_stack_loss_curve_tracks_reference(math, tol):
+    ref_losses, ref_params = _run_gan(OracleOp(), torch.device("cpu"))
+    op = TensorOpB200(math)
+    d0 = lib.ConvDesc(BATCH, 3, 32, 32, 16, 3, 3, 16, 16, 2, 1, 1, lib.NCHW, math)
+    assert op.kernel_name(lib.OP_KERNELS_GRADIENT, d0) == "strided_smallc_wgrad"
+    if math == lib.MATH_TF32:
+        d1 = lib.ConvDesc(BATCH, 16, 16, 16, 32, 3, 3, 8, 8, 2, 1, 1, lib.NCHW, math)
+        assert [op.kernel_name(o, d1) for o in (0, 1, 2)] == ["tcgen05_gather_fprop", "tcgen05_gather_dgrad", "tcgen05_gather_wgrad"]
+    losses, params = _run_gan(op, torch.device("cuda", 0))
+    rel = np.abs(np.array(losses) - np.array(ref_losses)) / np.abs(np.array(ref_losses))
+    assert rel.max() <= tol, (losses, ref_losses)
+    assert ref_losses[-1] < ref_losses[0]
+    assert np.abs(params - ref_params).max() <= (5e-3 if math == lib.MATH_TF32 else 1e-5)
