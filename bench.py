@@ -398,6 +398,7 @@ def run_ours(args):
             line["style_transfer_batch1"] = style_transfer_pass()
             line["style_transfer_batch1"]["frac_of_tf32_peak"] = line["style_transfer_batch1"]["tflops"] / tf32_peak
             line["neighbours"] = neighbour_pass(B)
+            line["other_configs"] = other_configs_pass()
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_run(1, 1, 64)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -465,6 +466,60 @@ def style_transfer_pass(iters=30):
     out["gflop_per_image"] = 2 * SAMPLE_FLOPS_PER_OP / 1e9
     out["tflops"] = 2 * SAMPLE_FLOPS_PER_OP / (best * 1e-3) / 1e12
     out["workload"] = "VGG16 @512x512x3, batch 1: 13 x forward(bias+ReLU) + 13 x input gradient, frozen weights"
+    return out
+
+
+def other_configs_pass(iters=10):
+    """The other BASELINE configs, per op over all their conv / transposed-conv layers (neuro__b200/shapes.py): DCGAN batch 128,
+    pix2pix 256x256 batch 8, conv autoencoder batch 256. One layer's op is issued `iters` times back to back between a CUDA-event
+    pair; a second measurement replays the same calls as one CUDA graph (GPU time without the host's per-call cost)."""
+    import torch
+    from neuro__b200 import lib
+    from neuro__b200.shapes import CONFIGS
+    from neuro__b200.tensor_op import TensorOpB200
+    op = TensorOpB200(lib.MATH_TF32)
+    peaks = read_peaks()
+    tf32_peak = peaks["bf16_sustained"] / 2.0
+    out = {}
+    for cfg in ("dcgan", "pix2pix", "autoenc"):
+        N, layers = CONFIGS[cfg]
+        tot = {"issued": [0.0, 0.0, 0.0], "graph": [0.0, 0.0, 0.0]}
+        flops = 0.0
+        for (_, C, H, K, Fs, st, pd) in layers:
+            Ho = (H + 2 * pd - Fs) // st + 1
+            x = torch.randn(N, C, H, H, device="cuda"); w = torch.randn(K, C, Fs, Fs, device="cuda") * 0.05
+            y = torch.empty(N, K, Ho, Ho, device="cuda"); dy = torch.randn_like(y); dx = torch.empty_like(x); dw = torch.empty_like(w)
+            flops += 2.0 * N * K * Ho * Ho * C * Fs * Fs
+            fns = [lambda: op.Conv2D(x, w, st, pd, pd, lib.NCHW, y), lambda: op.Conv2DInputGradient(dy, w, st, pd, pd, lib.NCHW, dx),
+                   lambda: op.Conv2DKernelsGradient(x, dy, st, pd, pd, lib.NCHW, dw)]
+            for i, fn in enumerate(fns):
+                fn(); fn(); torch.cuda.synchronize()
+                runs = {"issued": lambda fn=fn: [fn() for _ in range(iters)]}
+                try:
+                    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        fn()
+                    torch.cuda.current_stream().wait_stream(side)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        for _ in range(iters):
+                            fn()
+                    g.replay(); torch.cuda.synchronize()
+                    runs["graph"] = g.replay
+                except Exception:  # noqa: BLE001
+                    torch.cuda.synchronize()
+                for how, run in runs.items():
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(); run(); e1.record(); torch.cuda.synchronize()
+                    tot[how][i] += e0.elapsed_time(e1) / iters
+            del x, w, y, dy, dx, dw
+        names = ("forward", "input_gradient", "kernels_gradient")
+        out[cfg] = {"batch": N, "layers": len(layers), "gflop_per_op": flops / 1e9,
+                    "ms": {n: tot["issued"][i] for i, n in enumerate(names)},
+                    "ms_cuda_graph": {n: tot["graph"][i] for i, n in enumerate(names)},
+                    "tflops_cuda_graph": {n: (flops / (tot["graph"][i] * 1e-3) / 1e12 if tot["graph"][i] > 0 else None) for i, n in enumerate(names)},
+                    "frac_of_tf32_peak_cuda_graph": {n: (flops / (tot["graph"][i] * 1e-3) / 1e12 / tf32_peak if tot["graph"][i] > 0 else None)
+                                                     for i, n in enumerate(names)}}
     return out
 
 

@@ -334,3 +334,31 @@ def test_prepared_filters_match_per_call_repack(cfg, math):
         assert torch.equal(y1, y0) and torch.equal(dx1, dx0)
     with pytest.raises(AssertionError):
         op.Conv2DInputGradient(dyd, wd, st, p, p, lib.NCHW, dx1, prepared=hf)   # a forward handle is not an input-gradient handle
+
+
+FULL_SIZE = [  # (name, N, C, H, W, K, F, stride, pad): BASELINE-size layers of configs 2 and 4, too slow for the scalar oracle
+    ("dcgan_g_deconv3", 128, 128, 32, 32, 128, 4, 2, 1),      # as a conv 32x32 -> 16x16; its input gradient is the 16 -> 32 transposed conv
+    ("pix2pix_patchgan_d4", 8, 256, 34, 34, 512, 4, 1, 0),    # 31x31 output maps: kernel gradient through the pitched copy of dy
+    ("pix2pix_unet_dec2", 8, 1024, 4, 4, 512, 3, 1, 1),       # weight-bound: narrowed filter tile + channel splits
+    ("pix2pix_last", 8, 128, 256, 256, 3, 3, 1, 1),           # few-filter layer (roles exchanged)
+    ("pix2pix_enc1", 8, 3, 256, 256, 64, 3, 2, 1),            # strided few-channel kernel gradient
+]
+
+
+@pytest.mark.parametrize("cfg", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_gan_layers_adjoint_identities(cfg):
+    """<dy, conv(x,w)> = <dgrad(dy,w), x> = <wgrad(x,dy), w> in fp64 at BASELINE sizes (size-independent property), TF32 bound."""
+    _, N, C, H, W, K, F, st, p = cfg
+    x, w, dy = make_inputs(lib.NCHW, N, C, H, W, K, F, F, st, p, p, glorot=True)
+    y, dx, dw = run_all_three(TensorOpB200(lib.MATH_TF32), lib.NCHW, x, w, dy, st, p, p)
+    f64 = lambda a: a.ravel().astype(np.float64)
+    a, b, c = np.dot(f64(dy), f64(y)), np.dot(f64(dx), f64(x)), np.dot(f64(dw), f64(w))
+    scale = np.linalg.norm(f64(dy)) * np.linalg.norm(f64(y))
+    assert abs(a - b) <= 2e-3 * scale and abs(a - c) <= 2e-3 * scale
+    assert np.isfinite(dx).all() and np.isfinite(dw).all()
+    # one output pixel per image against a direct fp64 evaluation of the definition
+    oh, ow = y.shape[2] // 2, y.shape[3] // 3
+    xp = np.pad(x, ((0, 0), (0, 0), (p, p), (p, p))).astype(np.float64)
+    patch = xp[:, :, oh * st:oh * st + F, ow * st:ow * st + F]
+    ref = np.einsum("ncrs,kcrs->nk", patch, w.astype(np.float64))
+    assert np.abs(y[:, :, oh, ow] - ref).max() <= 2e-3 * np.abs(ref).max()

@@ -85,3 +85,30 @@ def test_constant_pad2d(pads):
     y = torch.full(ref.shape, float("nan"), device="cuda")
     TensorOpB200().ConstantPad2D(dev(x), l, r, t, b, v, y)
     assert np.array_equal(y.cpu().numpy(), ref)
+
+
+def test_full_size_round_trips():
+    """BASELINE-size activations (VGG16 block1 at batch 8: 8 x 64 x 512 x 512) through size-independent exact properties:
+    pooling undoes nearest-neighbour up-sampling (max and average of four equal values), the up-sampling gradient of a constant
+    block is 4x, padding then cropping is the identity, and the max-pool gradient routes every dy to exactly one input."""
+    op = TensorOpB200()
+    x = torch.rand(8, 64, 256, 256, device="cuda") - 0.5
+    up = torch.empty(8, 64, 512, 512, device="cuda")
+    op.UpSample2D(x, 2, up)
+    back = torch.empty_like(x)
+    for mode in (lib.POOL_MAX, lib.POOL_AVG):
+        op.Pool2D(up, 2, 2, mode, 0, 0, lib.NCHW, back)
+        assert torch.equal(back, x)
+    g = torch.empty_like(x)
+    op.UpSample2DGradient(up, 2, g)
+    assert torch.equal(g, 4 * x)                      # ((a + a) + a) + a is exactly 4a
+    padded = torch.empty(8, 64, 516, 516, device="cuda")
+    op.ConstantPad2D(up, 1, 3, 2, 2, -7.0, padded)
+    assert torch.equal(padded[:, :, 2:514, 1:513], up) and float(padded[:, :, :2].max()) == -7.0 and float(padded[:, :, :, 513:].min()) == -7.0
+    r = torch.rand(8, 64, 512, 512, device="cuda")
+    pooled = torch.empty_like(x); op.Pool2D(r, 2, 2, lib.POOL_MAX, 0, 0, lib.NCHW, pooled)
+    dy = torch.rand_like(x) + 1.0
+    dx = torch.empty_like(r); op.Pool2DGradient(pooled, r, dy, 2, 2, lib.POOL_MAX, 0, 0, lib.NCHW, dx)
+    assert int((dx != 0).sum()) == dy.numel()                                    # one receiver per window
+    assert torch.equal(dx.view(8, 64, 256, 2, 256, 2).sum(dim=(3, 5)), dy)      # and it receives dy itself
+    assert torch.equal((dx != 0) * r, (dx != 0) * pooled.repeat_interleave(2, 2).repeat_interleave(2, 3))   # at the maximum
