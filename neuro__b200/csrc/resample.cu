@@ -314,6 +314,8 @@ namespace nb200
                 return fail(NB200_E_INVALID, "unknown data format %d", d->fmt);
             if (d->mode != NB200_POOL_MAX && d->mode != NB200_POOL_AVG)
                 return fail(NB200_E_INVALID, "unknown pooling mode %d", d->mode);
+            if ((long long)d->N * d->C * d->H * d->W > 0xFFFFFFFFll || (long long)d->N * d->C * d->Ho * d->Wo > 0xFFFFFFFFll)
+                return fail(NB200_E_INVALID, "tensor exceeds 2^32-1 elements"); // Neuro::Shape::Length is uint32_t; the kernels index with 32 bits
             if ((long long)d->N * d->C * d->H * d->W > 0)
             {
                 // Tensor::GetPooling2DOutputShape (Tensor.cpp:1988-2007)

@@ -67,6 +67,8 @@ def test_neighbour_entry_points_validate_before_touching_a_device(L):
     for d in (bad_out, bad_mode, too_big):
         assert L.nb200_pool2d(ctypes.byref(d), None, None, None) == -1
         assert L.nb200_pool2d_gradient(ctypes.byref(d), None, None, None, None, None) == -1
+    huge = lib.PoolDesc(64, 64, 2048, 2048, 1024, 1024, 2, 2, 0, 0, lib.POOL_MAX, lib.NCHW)  # 2^34 elements: beyond Shape::Length (uint32)
+    assert L.nb200_pool2d(ctypes.byref(huge), None, None, None) == -1
     assert L.nb200_pool2d(ctypes.byref(good), None, None, None) == -1                    # null tensors
     empty = lib.PoolDesc(0, 3, 8, 8, 4, 4, 2, 2, 0, 0, lib.POOL_MAX, lib.NCHW)
     assert L.nb200_pool2d(ctypes.byref(empty), None, None, None) == 0
