@@ -277,6 +277,122 @@ namespace nb200
             }
         }
 
+        // ------------------------------------------------------------ input gradient, two dx rows per thread
+        // Same arithmetic for the common geometry (pad 1, aligned, W % 4 == 0, even H): a thread owns the 4-pixel quads of TWO
+        // consecutive dx rows, so the 4 dy rows it loads per filter serve 216 FMAs instead of 3 rows serving 108 -- a third less
+        // L2->L1 traffic per output (every dy row used to be fetched by the blocks of three dx rows).
+        template <int C>
+        __global__ void __launch_bounds__(kSmallThreads)
+        smallc_dgrad2_kernel(SmallGeo g, const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ bias, int act,
+                             float alpha, float* __restrict__ dx)
+        {
+            constexpr int T = C * 9;
+            constexpr int TP = (T + 3) & ~3;
+            extern __shared__ float sw[];         // [K][TP], taps flipped: sw[k][(c*3+a)*3+b] = w[k][c][2-a][2-b]
+            for (int i = threadIdx.x; i < g.K * TP; i += kSmallThreads)
+            {
+                const int k = i / TP, t = i - k * TP;
+                float v = 0.f;
+                if (t < T)
+                {
+                    const int c = t / 9, a = (t % 9) / 3, b = t % 3;
+                    v = w[(k * C + c) * 9 + (2 - a) * 3 + (2 - b)];
+                }
+                sw[i] = v;
+            }
+            __syncthreads();
+
+            const int quadsPerRow = g.W >> 2, H2 = g.H >> 1;
+            const long long quads = (long long)g.N * H2 * quadsPerRow;
+            const long long q = (long long)blockIdx.x * kSmallThreads + threadIdx.x;
+            if (q >= quads)
+                return;
+            const int qw = (int)(q % quadsPerRow);
+            const int h = 2 * (int)((q / quadsPerRow) % H2);
+            const int n = (int)(q / ((long long)quadsPerRow * H2));
+            const int w0 = qw * 4;
+
+            float acc[2][C][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        acc[i][c][j] = 0.f;
+
+            const long long plane = (long long)g.Ho * g.Wo;
+            const float* rp[4];
+            bool rowOk[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+            {
+                const int oh = h - 1 + r;
+                rowOk[r] = oh >= 0 && oh < g.Ho;
+                rp[r] = dy + (long long)n * g.K * plane + (long long)(rowOk[r] ? oh : 0) * g.Wo + w0;
+            }
+            const bool leftOk = w0 > 0, rightOk = w0 + 4 < g.Wo;
+            for (int k = 0; k < g.K; ++k)
+            {
+                float win[4][6];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                {
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float l = 0.f, rr = 0.f;
+                    if (rowOk[r])
+                    {
+                        f = __ldcs((const float4*)rp[r]);
+                        if (leftOk) l = __ldg(rp[r] - 1);
+                        if (rightOk) rr = __ldg(rp[r] + 4);
+                    }
+                    win[r][0] = l; win[r][1] = f.x; win[r][2] = f.y; win[r][3] = f.z; win[r][4] = f.w; win[r][5] = rr;
+                    rp[r] += plane;
+                }
+                float wk[TP];
+                const float4* wp = (const float4*)(sw + k * TP);
+#pragma unroll
+                for (int i = 0; i < TP / 4; ++i)
+                {
+                    const float4 f = wp[i];
+                    wk[4 * i] = f.x; wk[4 * i + 1] = f.y; wk[4 * i + 2] = f.z; wk[4 * i + 3] = f.w;
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b)
+                        {
+                            const float wv = wk[(c * 3 + a) * 3 + b];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    acc[i][c][j] = fmaf(win[i + a][b + j], wv, acc[i][c][j]);
+                        }
+            }
+
+            if (bias != nullptr || act != NB200_ACT_IDENTITY)
+            {
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                {
+                    const float b = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            acc[i][c][j] = apply_activation(act, alpha, acc[i][c][j] + b);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    *(float4*)(dx + (((long long)n * C + c) * g.H + h + i) * g.W + w0) = make_float4(acc[i][c][0], acc[i][c][1], acc[i][c][2], acc[i][c][3]);
+        }
+
         // ------------------------------------------------------------ input gradient, filters split over the warps of a block
         // Same arithmetic as smallc_dgrad_kernel for grids that would leave most of the chip idle (few pixels, many filters:
         // the forward of a few-filter output layer, e.g. DCGAN's 128 -> 3 at 32x32): all 8 warps of a block work on the SAME 32
@@ -709,6 +825,24 @@ namespace nb200
         const SmallGeo g = small_geo(d, dy, dx, nullptr);
         const long long quads = (long long)d.N * d.H * ((d.W + 3) / 4);
         const size_t smem = (size_t)d.K * ((d.C * 9 + 3) & ~3) * 4;
+        {
+            // two dx rows per thread where the geometry allows it and the halved grid still fills the chip
+            static const char* env2 = getenv("NB200_SMALLC_DGRAD2"); // 0 disables (profiling)
+            const long long quads2 = (long long)d.N * (d.H / 2) * (d.W / 4);
+            if (g.aligned && d.padX == 1 && (d.W & 3) == 0 && d.W == d.Wo && d.H == d.Ho && (d.H & 1) == 0 && ceil_div(quads2, kSmallThreads) >= 148 &&
+                !(env2 && env2[0] == '0'))
+            {
+#define CALL(CC)                                                                                                              \
+                if (smem > 48 * 1024)                                                                                          \
+                    NB200_CUDA_TRY(cudaFuncSetAttribute(smallc_dgrad2_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                smallc_dgrad2_kernel<CC><<<ceil_div(quads2, kSmallThreads), kSmallThreads, smem, st>>>(g, dy, w, bias, act, alpha, dx);
+                SMALLC_DISPATCH(CALL)
+#undef CALL
+                NB200_CUDA_TRY(cudaGetLastError());
+                count_launch();
+                return NB200_OK;
+            }
+        }
         // less than one block per SM and enough filters to share out: split the filters over the warps of a block instead
         // (DCGAN 128 -> 3 @32x32 batch 128, 128 blocks: 0.089 -> 0.070 ms; at 256 blocks -- VGG 64 -> 3 @512x512 batch 1 -- the
         // split is slower, 0.067 vs 0.050 ms, because every block reloads the filters)

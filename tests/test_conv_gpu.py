@@ -64,6 +64,7 @@ TC_CASES = [
     (0, 1, 64, 30, 30, 64, 3, 3, 1, 1, 1),     # W % 4 != 0 -> TMA stride rule fails, must fall back
     (0, 2, 3, 64, 64, 64, 3, 3, 1, 1, 1),      # first-layer (small-channel) kernels: VGG block1_conv1 geometry
     (0, 4, 1, 28, 28, 16, 3, 3, 1, 1, 1),      # conv autoencoder enc conv1 (config 1)
+    (0, 2, 3, 512, 512, 16, 3, 3, 1, 1, 1),    # first layer at full resolution: input gradient with two dx rows per thread (>= 148 blocks)
     (0, 2, 3, 30, 27, 10, 3, 3, 1, 1, 1),      # small-channel, ragged width (scalar paths)
     (0, 2, 4, 20, 24, 12, 3, 3, 1, 2, 2),      # small-channel, full padding
     (0, 2, 2, 20, 24, 12, 3, 3, 1, 0, 0),      # small-channel, valid padding
