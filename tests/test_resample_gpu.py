@@ -112,3 +112,40 @@ def test_full_size_round_trips():
     assert int((dx != 0).sum()) == dy.numel()                                    # one receiver per window
     assert torch.equal(dx.view(8, 64, 256, 2, 256, 2).sum(dim=(3, 5)), dy)      # and it receives dy itself
     assert torch.equal((dx != 0) * r, (dx != 0) * pooled.repeat_interleave(2, 2).repeat_interleave(2, 3))   # at the maximum
+
+
+def test_against_committed_reference_outputs():
+    """CUDA kernels vs the outputs of the reference's own compiled loops (tests/golden/ref_neighbour_cases.npz), bit for bit."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_neighbours as G
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_neighbour_cases.npz"))
+    op = TensorOpB200()
+    for case in G.POOL_CASES:
+        name, fmt, N, C, H, W, f, st, p = case
+        for mode, tag in ((O.MAX_POOL, "max"), (O.AVG_POOL, "avg")):
+            x = G.pool_input(case, mode)
+            ref_y = golden["pool.%s.%s.y" % (name, tag)]
+            y = torch.full(ref_y.shape, float("nan"), device="cuda"); dx = torch.full(x.shape, float("nan"), device="cuda")
+            xd = dev(x)
+            op.Pool2D(xd, f, st, mode, p, p, fmt, y)
+            op.Pool2DGradient(y, xd, dev(synth.uniform(22, ref_y.shape)), f, st, mode, p, p, fmt, dx)
+            assert np.array_equal(y.cpu().numpy(), ref_y), (name, tag)
+            assert np.array_equal(dx.cpu().numpy(), golden["pool.%s.%s.dx" % (name, tag)]), (name, tag)
+    for name, shape, s in G.UP_CASES:
+        ref_y = golden["up.%s.y" % name]
+        y = torch.full(ref_y.shape, float("nan"), device="cuda"); dx = torch.full(shape, float("nan"), device="cuda")
+        op.UpSample2D(dev(synth.uniform(23, shape)), s, y)
+        op.UpSample2DGradient(dev(synth.uniform(24, ref_y.shape)), s, dx)
+        assert np.array_equal(y.cpu().numpy(), ref_y) and np.array_equal(dx.cpu().numpy(), golden["up.%s.dx" % name]), name
+    for name, shape, l, r, t, b, v in G.PAD_CASES:
+        ref_y = golden["pad.%s.y" % name]
+        y = torch.full(ref_y.shape, float("nan"), device="cuda")
+        op.ConstantPad2D(dev(synth.uniform(25, shape)), l, r, t, b, v, y)
+        assert np.array_equal(y.cpu().numpy(), ref_y), name
+    for act in (O.IDENTITY, O.SIGMOID, O.RELU, O.TANH, O.ELU, O.LEAKY_RELU):
+        yv, dy = G.act_inputs(act)
+        dz = torch.full(dy.shape, float("nan"), device="cuda")
+        op.ActivationGradient(act, 0.2, dev(yv), dev(dy), dz)
+        assert np.array_equal(dz.cpu().numpy(), golden["actgrad.%d.dz" % act]), act

@@ -61,3 +61,34 @@ def test_upsample_and_pad_restatements_equal_compiled_reference():
         assert np.array_equal(O.upsample2d_gradient(dy, s), O.ref_upsample2d_gradient(dy, s))
     for (l, r, t, b, v) in [(1, 1, 1, 1, 0.0), (0, 3, 2, 0, -1.5), (2, 0, 0, 1, 7.0)]:
         assert np.array_equal(O.constant_pad2d(x, l, r, t, b, v), O.ref_constant_pad2d(x, l, r, t, b, v))
+
+
+# ---- committed outputs of the reference itself (tests/golden/make_golden_neighbours.py): pins the restatement on boxes without
+# /root/reference, bit for bit
+import os  # noqa: E402
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_golden_neighbours as G  # noqa: E402
+
+GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_neighbour_cases.npz"))
+
+
+def test_restatement_equals_committed_reference_outputs():
+    for case in G.POOL_CASES:
+        name, fmt, N, C, H, W, f, st, p = case
+        for mode, tag in ((O.MAX_POOL, "max"), (O.AVG_POOL, "avg")):
+            x = G.pool_input(case, mode)
+            y = O.pool2d(x, f, st, mode, p, p, fmt)
+            assert np.array_equal(y, GOLDEN["pool.%s.%s.y" % (name, tag)])
+            dy = synth.uniform(22, y.shape)
+            assert np.array_equal(O.pool2d_gradient(y, x, dy, f, st, mode, p, p, fmt), GOLDEN["pool.%s.%s.dx" % (name, tag)])
+    for name, shape, s in G.UP_CASES:
+        y = O.upsample2d(synth.uniform(23, shape), s)
+        assert np.array_equal(y, GOLDEN["up.%s.y" % name])
+        assert np.array_equal(O.upsample2d_gradient(synth.uniform(24, y.shape), s), GOLDEN["up.%s.dx" % name])
+    for name, shape, l, r, t, b, v in G.PAD_CASES:
+        assert np.array_equal(O.constant_pad2d(synth.uniform(25, shape), l, r, t, b, v), GOLDEN["pad.%s.y" % name])
+    for act in (O.IDENTITY, O.SIGMOID, O.RELU, O.TANH, O.ELU, O.LEAKY_RELU):
+        y, dy = G.act_inputs(act)
+        assert np.array_equal(O.activation_gradient(act, 0.2, y, dy), GOLDEN["actgrad.%d.dz" % act])
