@@ -168,3 +168,32 @@ def test_workspace_sizes_cover_every_kernel_of_an_op(L):
     d0 = _desc(8, 3, 512, 512, 64, 3, 3, 1, 1, 1)
     assert L.nb200_conv2d_workspace_bytes(lib.OP_KERNELS_GRADIENT, ctypes.byref(d0)) >= 148 * 128 * 32 * 4
     assert L.nb200_conv2d_workspace_bytes(lib.OP_FORWARD, ctypes.byref(d0)) == 0
+
+
+def test_workspace_sizes_of_the_gathered_and_small_families(L):
+    """Host-side plans added for the GAN configs: channel splits keep their partials behind the repacked filters, the kernel
+    gradient of odd-sized maps carries a pitched copy of dy, few-filter layers hold the transposed + rotated filters."""
+    L.nb200_conv2d_workspace_bytes.restype = ctypes.c_size_t
+    ws = lambda op, d: L.nb200_conv2d_workspace_bytes(op, ctypes.byref(d))
+    # pix2pix G dec2: 1024 -> 512 on 4x4 maps, batch 8: one pixel tile -> BN 64, 8 channel splits
+    d = _desc(8, 1024, 4, 4, 512, 3, 3, 1, 1, 1)
+    repack = 9 * 512 * 1024 * 4
+    out = 8 * 512 * 4 * 4 * 4
+    assert ws(lib.OP_FORWARD, d) >= repack + 8 * out
+    assert ws(lib.OP_INPUT_GRADIENT, d) >= repack + 2 * (8 * 1024 * 4 * 4 * 4)
+    # a grid that already fills the chip keeps the plain layout (no partials)
+    big = _desc(128, 128, 32, 32, 128, 4, 4, 2, 1, 1)
+    assert ws(lib.OP_FORWARD, big) == (16 * 128 * 128 * 4 + 255) // 256 * 256
+    # PatchGAN 256 -> 512 on 31x31 maps: split-K partials + dy pitched from 961 to 964 floats per plane
+    pg = _desc(8, 256, 34, 34, 512, 4, 4, 1, 0, 0)
+    assert ws(lib.OP_KERNELS_GRADIENT, pg) >= 16 * 512 * 256 * 4 + 8 * 512 * 964 * 4
+    # 1x1 maps (U-Net bottleneck): planes pitched to 4 floats
+    bn = _desc(8, 512, 2, 2, 512, 3, 3, 2, 1, 1)
+    assert ws(lib.OP_KERNELS_GRADIENT, bn) >= 9 * 512 * 512 * 4 + 8 * 512 * 4 * 4
+    # few-filter layer: forward / input gradient hold w' (C x K x 9); the kernel gradient adds dw' and the small-channel partials
+    fk = _desc(8, 128, 256, 256, 3, 3, 3, 1, 1, 1)
+    assert ws(lib.OP_FORWARD, fk) == ws(lib.OP_INPUT_GRADIENT, fk) == (128 * 3 * 9 * 4 + 255) // 256 * 256
+    assert ws(lib.OP_KERNELS_GRADIENT, fk) > ws(lib.OP_FORWARD, fk)
+    # strided few-channel kernel gradient: one partial per slice
+    sg = _desc(8, 3, 256, 256, 64, 3, 3, 2, 1, 1)
+    assert ws(lib.OP_KERNELS_GRADIENT, sg) % (64 * 27 * 4) == 0 and ws(lib.OP_KERNELS_GRADIENT, sg) >= 64 * 27 * 4
