@@ -442,3 +442,129 @@ API void oracle_constant_pad2d(int planes, int H, int W, int left, int right, in
         y[((size_t)p * Ho + h) * Wo + w] = v;
     }
 }
+
+
+/* ---- batch normalisation ----
+ * Follows TensorOpCpu::BatchNormalizationTrain / BatchNormalizationGradient / BatchNormalization,
+ * Neuro/src/Tensors/TensorOpCpu.cpp:1392-1480, 1371-1389. The reference writes them with Tensor operators; every operator is a
+ * loop of TensorOpCpu.cpp:28-75 (Add: alpha*a + beta*b), :136-183 (Mul: alpha*a*beta*b), :186-196 (Mul by scalar),
+ * :285-299 + :327-351 (Sum: zero, then += walking the tensor n, d, h, w), :354-376 (Mean: Sum, then times 1/count -- Tensor::Div(float)
+ * is Mul(1/v), Tensor.cpp:554-557), :379-389 (Pow through double ::pow), :433-442 (Sqrt), :472-481 (Inverse). The statements below
+ * apply those loops in the same order with the same intermediate roundings, so results are bit-identical to the compiled
+ * reference (tests/test_oracle.py).
+ *
+ * One layout serves the three EBatchNormMode values. A tensor is viewed as x[n][g][s], n < Nn, g < G, s < S; statistics are taken
+ * per group g over (n, s); gamma/beta/mean/variance hold G values:
+ *   Spatial        (axis _013Axes, m = W*H*N):  Nn = N, G = C,     S = H*W
+ *   PerActivation  (axis BatchAxis, m = N):     Nn = N, G = W*H*C, S = 1
+ *   Instance       (axis _01Axes,  m = W*H):    Nn = 1, G = C*N,   S = H*W   (gamma is Shape(1,1,C,N) there) */
+static inline size_t bi(int G, int S, int n, int g, int s) { return ((size_t)n * G + g) * S + s; }
+
+API void oracle_batch_norm_train(int Nn, int G, int S, const float* x, const float* gamma, const float* beta, float momentum, float epsilon,
+                                 float* runningMean, float* runningVar, float* saveMean, float* saveInvVar, float* y)
+{
+    const float m = (float)((unsigned)S * (unsigned)Nn);
+    if (m == 1)
+    {
+        memcpy(y, x, sizeof(float) * (size_t)Nn * G * S); /* "cannot normalize single values so just copy input to output" */
+        return;
+    }
+    const float invm = 1 / m;
+    for (int g = 0; g < G; ++g)
+    {
+        float sum = 0.f;
+        for (int n = 0; n < Nn; ++n)
+            for (int s = 0; s < S; ++s)
+                sum += x[bi(G, S, n, g, s)];
+        const float mean = sum * invm;
+        saveMean[g] = mean;
+        float sq = 0.f;
+        for (int n = 0; n < Nn; ++n)
+            for (int s = 0; s < S; ++s)
+            {
+                const float xmu = 1.f * x[bi(G, S, n, g, s)] + -1.f * mean;
+                sq += (float)pow((double)xmu, (double)2.f);
+            }
+        const float var = sq * invm;
+        const float inv = 1.f / sqrtf(var + epsilon);
+        saveInvVar[g] = inv;
+        for (int n = 0; n < Nn; ++n)
+            for (int s = 0; s < S; ++s)
+            {
+                const float xmu = 1.f * x[bi(G, S, n, g, s)] + -1.f * mean;
+                const float xnorm = 1.f * xmu * 1.f * inv;
+                y[bi(G, S, n, g, s)] = 1.f * (1.f * xnorm * 1.f * gamma[g]) + 1.f * beta[g];
+            }
+        if (runningMean)
+            runningMean[g] = (1 - momentum) * runningMean[g] + momentum * mean;
+        if (runningVar)
+        {
+            const float temp = var * (m / (m - 1)); /* "according to the original BN paper" */
+            runningVar[g] = (1 - momentum) * runningVar[g] + momentum * temp;
+        }
+    }
+}
+
+/* Inference form, TensorOpCpu.cpp:1371-1389 with running statistics. */
+API void oracle_batch_norm(int Nn, int G, int S, const float* x, const float* gamma, const float* beta, float epsilon,
+                           const float* runningMean, const float* runningVar, float* y)
+{
+    for (int g = 0; g < G; ++g)
+    {
+        const float f = 1.f / sqrtf(runningVar[g] + epsilon);
+        for (int n = 0; n < Nn; ++n)
+            for (int s = 0; s < S; ++s)
+            {
+                const float xmu = 1.f * x[bi(G, S, n, g, s)] + -1.f * runningMean[g];
+                const float xnorm = 1.f * xmu * 1.f * f;
+                y[bi(G, S, n, g, s)] = 1.f * (1.f * xnorm * 1.f * gamma[g]) + 1.f * beta[g];
+            }
+    }
+}
+
+API void oracle_batch_norm_gradient(int Nn, int G, int S, const float* x, const float* gamma, const float* dy, const float* savedMean,
+                                    const float* savedInvVar, float* dgamma, float* dbeta, float* dx)
+{
+    const float m = (float)((unsigned)S * (unsigned)Nn);
+    if (m == 1)
+    {
+        memcpy(dx, dy, sizeof(float) * (size_t)Nn * G * S);
+        memset(dgamma, 0, sizeof(float) * G);
+        memset(dbeta, 0, sizeof(float) * G);
+        return;
+    }
+    const float invm = 1 / m;
+    for (int g = 0; g < G; ++g)
+    {
+        const float mean = savedMean[g], inv = savedInvVar[g], ninv = -inv;
+        float sumA = 0.f, sumB = 0.f, sumC = 0.f, sumG = 0.f, sumD = 0.f;
+        for (int n = 0; n < Nn; ++n)
+            for (int s = 0; s < S; ++s)
+            {
+                const size_t i = bi(G, S, n, g, s);
+                const float xmu = 1.f * x[i] + -1.f * mean;
+                const float xnorm = 1.f * xmu * 1.f * inv;
+                const float dxn = 1.f * dy[i] * 1.f * gamma[g];
+                sumA += 1.f * dxn * 1.f * xmu;
+                sumB += 1.f * dxn * 1.f * ninv;
+                sumC += xmu * -2.f;
+                sumG += 1.f * dy[i] * 1.f * xnorm;
+                sumD += dy[i];
+            }
+        const float dVar = 1.f * (sumA * -.5f) * 1.f * (float)pow((double)inv, (double)3.f);
+        const float dMu = 1.f * sumB + 1.f * (1.f * dVar * 1.f * (sumC * invm));
+        const float dMuM = dMu * invm;
+        for (int n = 0; n < Nn; ++n)
+            for (int s = 0; s < S; ++s)
+            {
+                const size_t i = bi(G, S, n, g, s);
+                const float xmu = 1.f * x[i] + -1.f * mean;
+                const float dxn = 1.f * dy[i] * 1.f * gamma[g];
+                const float a = 1.f * dxn * 1.f * inv;
+                const float b = ((1.f * dVar * 1.f * xmu) * 2.f) * invm;
+                dx[i] = 1.f * (1.f * a + 1.f * b) + 1.f * dMuM;
+            }
+        dgamma[g] = sumG;
+        dbeta[g] = sumD;
+    }
+}

@@ -175,6 +175,45 @@ def sgd_step(p, g, lr):
     lib().oracle_sgd_step(_fp(p), _fp(g), ctypes.c_size_t(p.size), ctypes.c_float(lr))
 
 
+# EBatchNormMode, Neuro/include/Types.h
+PER_ACTIVATION, SPATIAL, INSTANCE = 0, 1, 2
+
+
+def bn_layout(mode, shape):
+    """(Nn, G, S) view of an NCHW array for the three normalisation modes (see conv_oracle.c)."""
+    N, C, H, W = shape
+    if mode == SPATIAL:
+        return N, C, H * W
+    if mode == PER_ACTIVATION:
+        return N, C * H * W, 1
+    return 1, N * C, H * W
+
+
+def batch_norm_train(mode, x, gamma, beta, momentum, eps, running_mean=None, running_var=None):
+    """Returns (y, save_mean, save_inv_var); running_mean / running_var (flat, G values) are updated in place."""
+    Nn, G, S = bn_layout(mode, x.shape)
+    y = np.empty_like(x); sm = np.zeros(G, np.float32); sv = np.zeros(G, np.float32)
+    lib().oracle_batch_norm_train(Nn, G, S, _fp(x), _fp(gamma), _fp(beta), ctypes.c_float(momentum), ctypes.c_float(eps),
+                                  _fp(running_mean) if running_mean is not None else None,
+                                  _fp(running_var) if running_var is not None else None, _fp(sm), _fp(sv), _fp(y))
+    return y, sm, sv
+
+
+def batch_norm(mode, x, gamma, beta, eps, running_mean, running_var):
+    Nn, G, S = bn_layout(mode, x.shape)
+    y = np.empty_like(x)
+    lib().oracle_batch_norm(Nn, G, S, _fp(x), _fp(gamma), _fp(beta), ctypes.c_float(eps), _fp(running_mean), _fp(running_var), _fp(y))
+    return y
+
+
+def batch_norm_gradient(mode, x, gamma, dy, save_mean, save_inv_var):
+    """Returns (dx, dgamma, dbeta)."""
+    Nn, G, S = bn_layout(mode, x.shape)
+    dx = np.empty_like(x); dg = np.zeros(G, np.float32); db = np.zeros(G, np.float32)
+    lib().oracle_batch_norm_gradient(Nn, G, S, _fp(x), _fp(gamma), _fp(dy), _fp(save_mean), _fp(save_inv_var), _fp(dg), _fp(db), _fp(dx))
+    return dx, dg, db
+
+
 MAX_POOL, AVG_POOL = 0, 1
 
 
@@ -316,3 +355,48 @@ def ref_constant_pad2d(x, left, right, top, bottom, value):
     y = np.empty((N, C, H + top + bottom, W + left + right), np.float32)
     ref().neuro_ref_constant_pad2d(_fp(x), _shape4(NCHW, x), left, right, top, bottom, ctypes.c_float(value), _fp(y), _shape4(NCHW, y))
     return y
+
+
+def ref_adam_step(p, g, m, v, lr, beta1, beta2, eps):
+    """TensorOpCpu::AdamStep itself (TensorOpCpu.cpp:987-1003), in place on p, m, v."""
+    ref().neuro_ref_adam_step(_fp(p), _fp(g), _fp(m), _fp(v), ctypes.c_uint32(p.size), ctypes.c_float(lr), ctypes.c_float(beta1),
+                              ctypes.c_float(beta2), ctypes.c_float(eps))
+
+
+def ref_sgd_step(p, g, lr):
+    ref().neuro_ref_sgd_step(_fp(p), _fp(g), ctypes.c_uint32(p.size), ctypes.c_float(lr))
+
+
+def _bn_param_dims(mode, shape):
+    """Reference Shape of gamma / beta / statistics for an NCHW input (BatchNormalization.cpp Build; InstanceNormalize op)."""
+    N, C, H, W = shape
+    if mode == SPATIAL:
+        return (ctypes.c_uint32 * 4)(1, 1, C, 1)
+    if mode == PER_ACTIVATION:
+        return (ctypes.c_uint32 * 4)(W, H, C, 1)
+    return (ctypes.c_uint32 * 4)(1, 1, C, N)
+
+
+def ref_batch_norm_train(mode, x, gamma, beta, momentum, eps, running_mean=None, running_var=None):
+    G = gamma.size
+    y = np.empty_like(x); sm = np.zeros(G, np.float32); sv = np.zeros(G, np.float32)
+    ref().neuro_ref_batch_norm_train(int(mode), _fp(x), _shape4(NCHW, x), _fp(gamma), _fp(beta), _bn_param_dims(mode, x.shape),
+                                     ctypes.c_float(momentum), ctypes.c_float(eps),
+                                     _fp(running_mean) if running_mean is not None else None,
+                                     _fp(running_var) if running_var is not None else None, _fp(sm), _fp(sv), _fp(y))
+    return y, sm, sv
+
+
+def ref_batch_norm(mode, x, gamma, beta, eps, running_mean, running_var):
+    y = np.empty_like(x)
+    ref().neuro_ref_batch_norm(int(mode), _fp(x), _shape4(NCHW, x), _fp(gamma), _fp(beta), _bn_param_dims(mode, x.shape), ctypes.c_float(eps),
+                               _fp(running_mean), _fp(running_var), _fp(y))
+    return y
+
+
+def ref_batch_norm_gradient(mode, x, gamma, eps, dy, save_mean, save_inv_var):
+    G = gamma.size
+    dx = np.empty_like(x); dg = np.zeros(G, np.float32); db = np.zeros(G, np.float32)
+    ref().neuro_ref_batch_norm_gradient(int(mode), _fp(x), _shape4(NCHW, x), _fp(gamma), _bn_param_dims(mode, x.shape), ctypes.c_float(eps),
+                                        _fp(dy), _fp(save_mean), _fp(save_inv_var), _fp(dg), _fp(db), 1, _fp(dx))
+    return dx, dg, db

@@ -12,6 +12,12 @@
 //   TensorOpCpu::Conv2DKernelsGradient  Neuro/src/Tensors/TensorOpCpu.cpp:1129
 //   TensorOpCpuMt::{same three}         Neuro/src/Tensors/TensorOpCpuMt.cpp:173,220,278
 //   TensorOpCpu::{Sigmoid,Tanh,ReLU,Elu,LeakyReLU}Gradient   Neuro/src/Tensors/TensorOpCpu.cpp:813-864
+//   TensorOpCpu::AdamStep / SgdStep     Neuro/src/Tensors/TensorOpCpu.cpp:987-1009
+//   TensorOpCpu::BatchNormalization{,Train,Gradient}          Neuro/src/Tensors/TensorOpCpu.cpp:1371-1480
+// The last two groups are written in terms of Tensor arithmetic (Add/Sub/Mul/Div/Map/Sum/Mean/Pow/Sqrt, operators);
+// in the reference those are one-line forwards `Op()->X(...)` (Tensor.cpp:489-975, 2720-2808) whose loops -- including
+// all broadcasting rules -- live in TensorOpCpu.cpp. The forwards below do the same, so every number is still produced
+// by the reference's own compiled loops.
 #include <cstdlib>
 #include <cstring>
 #include <omp.h>
@@ -98,6 +104,131 @@ namespace Neuro
                              d < 0 || d >= (int)Depth() || n < 0 || n > (int)Batch();
         return outside ? def : Get(w, h, d, n);
     }
+
+    // ---- value semantics (deep host copy, as Storage.cpp:51-81 does for host-resident tensors) ----
+    Storage::Storage(const Storage& other)
+        : m_Type(other.m_Type), m_AllocSize(other.m_AllocSize), m_Size(other.m_Size), m_Name(other.m_Name)
+    {
+        if (other.m_DataPtr)
+        {
+            AllocateOnHost();
+            memcpy(m_DataPtr, other.m_DataPtr, sizeof(float) * m_Size);
+        }
+    }
+
+    Storage::Storage(Storage&& other) { *this = std::move(other); }
+
+    Storage& Storage::operator=(const Storage& other)
+    {
+        if (this == &other)
+            return *this;
+        free(m_DataPtr);
+        m_DataPtr = nullptr;
+        m_DataLocation = None;
+        m_Type = other.m_Type; m_AllocSize = other.m_AllocSize; m_Size = other.m_Size; m_Name = other.m_Name;
+        if (other.m_DataPtr)
+        {
+            AllocateOnHost();
+            memcpy(m_DataPtr, other.m_DataPtr, sizeof(float) * m_Size);
+        }
+        return *this;
+    }
+
+    Storage& Storage::operator=(Storage&& other)
+    {
+        if (this == &other)
+            return *this;
+        free(m_DataPtr);
+        m_DataPtr = other.m_DataPtr; other.m_DataPtr = nullptr;
+        m_Type = other.m_Type; m_AllocSize = other.m_AllocSize; m_Size = other.m_Size; m_Name = other.m_Name;
+        m_DataLocation = other.m_DataLocation; other.m_DataLocation = None;
+        return *this;
+    }
+
+    Tensor::Tensor(const Tensor& t) : m_Op(nullptr), m_Shape(t.m_Shape), m_Storage(t.m_Storage), m_Name(t.m_Name) {}
+    Tensor::Tensor(Tensor&& t) : m_Op(nullptr), m_Shape(t.m_Shape), m_Storage(std::move(t.m_Storage)), m_Name(t.m_Name) {}
+    Tensor& Tensor::operator=(const Tensor& t)
+    {
+        if (this != &t) { m_Shape = t.m_Shape; m_Storage = t.m_Storage; m_Name = t.m_Name; }
+        return *this;
+    }
+    Tensor& Tensor::operator=(Tensor&& t)
+    {
+        if (this != &t) { m_Shape = t.m_Shape; m_Storage = std::move(t.m_Storage); m_Name = t.m_Name; }
+        return *this;
+    }
+
+    // full-tensor copy (tau = 0 branch of Tensor.cpp:2096-2116)
+    void Tensor::CopyTo(Tensor& target, float) const
+    {
+        memcpy(target.Values(), Values(), sizeof(float) * m_Shape.Length);
+    }
+
+    // ---- arithmetic forwards: Tensor::X -> the single-thread op's own loop ----
+    namespace
+    {
+        alignas(16) char g_OpMem[64];
+        const TensorOpCpu* RefOp() { return reinterpret_cast<const TensorOpCpu*>(g_OpMem); }
+        Shape Broadcast(const Tensor& a, const Tensor& b)
+        {
+            return Shape(max(a.Width(), b.Width()), max(a.Height(), b.Height()), max(a.Depth(), b.Depth()), max(a.Batch(), b.Batch()));
+        }
+        Shape Reduced(const Tensor& t, EAxis axis)
+        {
+            const bool w = axis == GlobalAxis || axis == WidthAxis || axis == _01Axes || axis == _012Axes || axis == _013Axes;
+            const bool h = axis == GlobalAxis || axis == HeightAxis || axis == _01Axes || axis == _012Axes || axis == _013Axes || axis == _123Axes;
+            const bool d = axis == GlobalAxis || axis == DepthAxis || axis == _012Axes || axis == _123Axes;
+            const bool n = axis == GlobalAxis || axis == BatchAxis || axis == _013Axes || axis == _123Axes;
+            return Shape(w ? 1 : t.Width(), h ? 1 : t.Height(), d ? 1 : t.Depth(), n ? 1 : t.Batch());
+        }
+    }
+
+    void Tensor::MulElem(const Tensor& t, Tensor& result) const { RefOp()->TensorOpCpu::Mul(1.f, *this, 1.f, t, result); }
+    Tensor Tensor::MulElem(const Tensor& t) const { Tensor r(Broadcast(*this, t)); MulElem(t, r); return r; }
+    void Tensor::Mul(float v, Tensor& result) const { RefOp()->TensorOpCpu::Mul(*this, v, result); }
+    Tensor Tensor::Mul(float v) const { Tensor r(m_Shape); Mul(v, r); return r; }
+    void Tensor::Div(const Tensor& t, Tensor& result) const { RefOp()->TensorOpCpu::Div(1.f, *this, 1.f, t, result); }
+    Tensor Tensor::Div(const Tensor& t) const { Tensor r(m_Shape); Div(t, r); return r; }
+    void Tensor::Div(float v, Tensor& result) const { Mul(1 / v, result); }
+    Tensor Tensor::Div(float v) const { Tensor r(m_Shape); Div(v, r); return r; }
+    void Tensor::Add(float alpha, float beta, const Tensor& t, Tensor& result) const { RefOp()->TensorOpCpu::Add(alpha, *this, beta, t, result); }
+    void Tensor::Add(const Tensor& t, Tensor& result) const { Add(1, 1, t, result); }
+    Tensor Tensor::Add(const Tensor& t) const { Tensor r(Broadcast(*this, t)); Add(t, r); return r; }
+    void Tensor::Add(float v, Tensor& result) const { RefOp()->TensorOpCpu::Add(*this, v, result); }
+    Tensor Tensor::Add(float v) const { Tensor r(m_Shape); Add(v, r); return r; }
+    // TensorOpCpu::Sub is `Add(1, t1, -1, t2, output)` through the vtable (TensorOpCpu.cpp:78-81); the glue object has none, so that one line is applied here
+    void Tensor::Sub(const Tensor& t, Tensor& result) const { RefOp()->TensorOpCpu::Add(1, *this, -1, t, result); }
+    Tensor Tensor::Sub(const Tensor& t) const { Tensor r(Broadcast(*this, t)); Sub(t, r); return r; }
+    void Tensor::Negated(Tensor& result) const { RefOp()->TensorOpCpu::Negate(*this, result); }
+    Tensor Tensor::Negated() const { Tensor r(m_Shape); Negated(r); return r; }
+    void Tensor::Inversed(float alpha, Tensor& result) const { RefOp()->TensorOpCpu::Inverse(alpha, *this, result); }
+    Tensor Tensor::Inversed(float alpha) const { Tensor r(m_Shape); Inversed(alpha, r); return r; }
+    void Tensor::Pow(float power, Tensor& result) const { RefOp()->TensorOpCpu::Pow(*this, power, result); }
+    Tensor Tensor::Pow(float power) const { Tensor r(m_Shape); Pow(power, r); return r; }
+    void Tensor::Sqrt(Tensor& output) const { RefOp()->TensorOpCpu::Sqrt(*this, output); }
+    Tensor Tensor::Sqrt() const { Tensor r(m_Shape); Sqrt(r); return r; }
+    void Tensor::Map(const function<float(float)>& func, Tensor& result) const { RefOp()->TensorOpCpu::Map(func, *this, result); }
+    Tensor Tensor::Map(const function<float(float)>& func) const { Tensor r(m_Shape); Map(func, r); return r; }
+    void Tensor::Sum(EAxis axis, Tensor& output) const { RefOp()->TensorOpCpu::Sum(*this, axis, output); }
+    Tensor Tensor::Sum(EAxis axis) const { Tensor r(Reduced(*this, axis)); Sum(axis, r); return r; }
+    void Tensor::Mean(EAxis axis, Tensor& output) const { RefOp()->TensorOpCpu::Mean(*this, axis, output); }
+    Tensor Tensor::Mean(EAxis axis) const { Tensor r(Reduced(*this, axis)); Mean(axis, r); return r; }
+
+    // free operators, Tensor.cpp:2720-2808
+    Tensor operator*(const Tensor& t1, const Tensor& t2) { return t1.MulElem(t2); }
+    Tensor operator*(const Tensor& t, float v) { return t.Mul(v); }
+    Tensor operator/(const Tensor& t1, const Tensor& t2) { return t1.Div(t2); }
+    Tensor operator/(const Tensor& t, float v) { return t.Div(v); }
+    Tensor operator/(float v, const Tensor& t) { return t.Inversed(v); }
+    Tensor operator+(const Tensor& t1, const Tensor& t2) { return t1.Add(t2); }
+    Tensor operator+(const Tensor& t, float v) { return t.Add(v); }
+    Tensor operator-(const Tensor& t1, const Tensor& t2) { return t1.Sub(t2); }
+    Tensor operator-(const Tensor& t) { return t.Negated(); }
+    Tensor pow(const Tensor& t, float p) { return t.Pow(p); }
+    Tensor sqr(const Tensor& t) { return t.Pow(2); }
+    Tensor sqrt(const Tensor& t) { return t.Sqrt(); }
+    Tensor sum(const Tensor& t, EAxis axis) { return t.Sum(axis); }
+    Tensor mean(const Tensor& t, EAxis axis) { return t.Mean(axis); }
 }
 
 using namespace Neuro;
@@ -232,4 +363,64 @@ REF_API void neuro_ref_constant_pad2d(const float* x, const uint32_t* xDims, uin
     Load(tx, x);
     OpSt()->TensorOpCpu::ConstantPad2D(tx, left, right, top, bottom, value, ty);
     Store(ty, y);
+}
+
+// ---- optimiser updates (TensorOpCpu.cpp:987-1009); all four tensors are flat Shape(count) ----
+REF_API void neuro_ref_adam_step(float* param, const float* grad, float* m, float* v, uint32_t count, float lr, float beta1, float beta2, float epsilon)
+{
+    const Shape flat(count);
+    Tensor tp(flat), tg(flat), tm(flat), tv(flat);
+    Load(tp, param); Load(tg, grad); Load(tm, m); Load(tv, v);
+    OpSt()->TensorOpCpu::AdamStep(tp, tg, tm, tv, lr, beta1, beta2, epsilon);
+    Store(tp, param); Store(tm, m); Store(tv, v);
+}
+
+REF_API void neuro_ref_sgd_step(float* param, const float* grad, uint32_t count, float lr)
+{
+    const Shape flat(count);
+    Tensor tp(flat), tg(flat);
+    Load(tp, param); Load(tg, grad);
+    OpSt()->TensorOpCpu::SgdStep(tp, tg, lr);
+    Store(tp, param);
+}
+
+// ---- batch normalisation (TensorOpCpu.cpp:1371-1480). mode follows EBatchNormMode (Types.h): 0 PerActivation, 1 Spatial, 2 Instance.
+// xDims = Shape of input/output/gradients, pDims = Shape of gamma/beta/mean/variance tensors. running* may be NULL. ----
+REF_API void neuro_ref_batch_norm_train(int mode, const float* x, const uint32_t* xDims, const float* gamma, const float* beta, const uint32_t* pDims,
+                                        float momentum, float epsilon, float* runningMean, float* runningVar, float* saveMean, float* saveInvVar, float* y)
+{
+    Tensor tx(MakeShape(xDims)), tg(MakeShape(pDims)), tb(MakeShape(pDims)), trm(MakeShape(pDims)), trv(MakeShape(pDims)), tsm(MakeShape(pDims)),
+        tsv(MakeShape(pDims)), ty(MakeShape(xDims));
+    Load(tx, x); Load(tg, gamma); Load(tb, beta);
+    if (runningMean) Load(trm, runningMean);
+    if (runningVar) Load(trv, runningVar);
+    tsm.Zero(); tsv.Zero();
+    OpSt()->TensorOpCpu::BatchNormalizationTrain(tx, (EBatchNormMode)mode, tg, tb, momentum, epsilon, runningMean ? &trm : nullptr,
+                                                 runningVar ? &trv : nullptr, tsm, tsv, ty);
+    if (runningMean) Store(trm, runningMean);
+    if (runningVar) Store(trv, runningVar);
+    Store(tsm, saveMean); Store(tsv, saveInvVar); Store(ty, y);
+}
+
+REF_API void neuro_ref_batch_norm(int mode, const float* x, const uint32_t* xDims, const float* gamma, const float* beta, const uint32_t* pDims,
+                                  float epsilon, const float* runningMean, const float* runningVar, float* y)
+{
+    Tensor tx(MakeShape(xDims)), tg(MakeShape(pDims)), tb(MakeShape(pDims)), trm(MakeShape(pDims)), trv(MakeShape(pDims)), ty(MakeShape(xDims));
+    Load(tx, x); Load(tg, gamma); Load(tb, beta);
+    if (runningMean) Load(trm, runningMean);
+    if (runningVar) Load(trv, runningVar);
+    OpSt()->TensorOpCpu::BatchNormalization(tx, (EBatchNormMode)mode, tg, tb, epsilon, runningMean ? &trm : nullptr, runningVar ? &trv : nullptr, ty);
+    Store(ty, y);
+}
+
+REF_API void neuro_ref_batch_norm_gradient(int mode, const float* x, const uint32_t* xDims, const float* gamma, const uint32_t* pDims, float epsilon,
+                                           const float* dy, const float* savedMean, const float* savedInvVar, float* dgamma, float* dbeta, int trainable,
+                                           float* dx)
+{
+    Tensor tx(MakeShape(xDims)), tg(MakeShape(pDims)), tdy(MakeShape(xDims)), tsm(MakeShape(pDims)), tsv(MakeShape(pDims)), tdg(MakeShape(pDims)),
+        tdb(MakeShape(pDims)), tdx(MakeShape(xDims));
+    Load(tx, x); Load(tg, gamma); Load(tdy, dy); Load(tsm, savedMean); Load(tsv, savedInvVar);
+    tdg.Zero(); tdb.Zero(); tdx.Zero();
+    OpSt()->TensorOpCpu::BatchNormalizationGradient(tx, (EBatchNormMode)mode, tg, epsilon, tdy, tsm, tsv, tdg, tdb, trainable != 0, tdx);
+    Store(tdg, dgamma); Store(tdb, dbeta); Store(tdx, dx);
 }
