@@ -198,6 +198,64 @@ NB200_API int nb200_adam_step(float* param, const float* grad, float* m, float* 
                               float grad_scale, float lr, float beta1, float beta2, float epsilon, void* stream);
 NB200_API int nb200_sgd_step(float* param, const float* grad, size_t count, float grad_scale, float lr, void* stream);
 
+/* ---- batch normalisation around the convolutions; HBM-bound ----
+ * EBatchNormMode, Neuro/include/Types.h:70-75 (same numbering). x is NCHW (N,C,H,W); statistics have G values:
+ * PerActivation G = C*H*W (over N), Spatial G = C (over N,H,W), Instance G = N*C (over H,W). */
+enum { NB200_BN_PER_ACTIVATION = 0, NB200_BN_SPATIAL = 1, NB200_BN_INSTANCE = 2 };
+typedef struct nb200_bn_desc
+{
+    int32_t N, C, H, W;
+    int32_t mode; /* NB200_BN_* */
+} nb200_bn_desc;
+
+/* Number of statistics (G) for this problem, and the device scratch every call below may use. */
+NB200_API int32_t nb200_batch_norm_groups(const nb200_bn_desc* d);
+NB200_API size_t nb200_batch_norm_workspace_bytes(const nb200_bn_desc* d);
+
+/* y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta. Replaces TensorOpCpu::BatchNormalization
+ * (TensorOpCpu.h:55, TensorOpCpu.cpp:1371-1389). */
+NB200_API int nb200_batch_norm(const nb200_bn_desc* d, const float* x, const float* gamma, const float* beta, float epsilon,
+                               const float* running_mean, const float* running_var, float* y, void* stream);
+
+/* Training forward. Replaces TensorOpCpu::BatchNormalizationTrain (TensorOpCpu.h:56, TensorOpCpu.cpp:1392-1434):
+ * save_mean = mean(x), save_inv_var = 1/sqrt(var + eps) (biased variance), y = (x - mean) * inv * gamma + beta,
+ * running_mean = (1-momentum)*running_mean + momentum*mean, running_var likewise with var*m/(m-1); running_* may be
+ * NULL. One element per group (m == 1): y = x and nothing else is written, as in the reference. */
+NB200_API int nb200_batch_norm_train(const nb200_bn_desc* d, const float* x, const float* gamma, const float* beta,
+                                     float momentum, float epsilon, float* running_mean, float* running_var,
+                                     float* save_mean, float* save_inv_var, float* y, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+
+/* Gradient. Replaces TensorOpCpu::BatchNormalizationGradient (TensorOpCpu.h:57, TensorOpCpu.cpp:1437-1480; the
+ * reference ignores `trainable` and `epsilon`, so they are not parameters). dgamma / dbeta may be NULL. */
+NB200_API int nb200_batch_norm_gradient(const nb200_bn_desc* d, const float* x, const float* gamma, const float* dy,
+                                        const float* save_mean, const float* save_inv_var, float* dgamma, float* dbeta,
+                                        float* dx, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same two ops for batch-sharded replicas (data-parallel Fit: every replica must normalise with the statistics
+ * of the GLOBAL batch or the loss curve differs from the single-device run). The host inserts the exchange:
+ *   forward : nb200_batch_norm_moments(x) -> moments[G][2] = (mean, sum of squared deviations) of the local shard;
+ *             all-gather them (2*G floats per replica, rank order) -> all_moments[replicas][G][2];
+ *             nb200_batch_norm_train_from_moments(all_moments, replicas, ...) combines them in rank order (Chan's
+ *             formula; every replica derives bit-identical statistics) and normalises the local shard.
+ *   backward: nb200_batch_norm_gradient_sums(x, dy, save_mean) -> sums[G][3] = (sum dy, sum dy*(x-mean), sum (x-mean));
+ *             all-reduce(sum) a COPY -> global_sums;  nb200_batch_norm_gradient_from_sums(global_sums, local_sums, ...):
+ *             dx uses the global sums and m = replicas * local elements per group; dgamma / dbeta are the LOCAL
+ *             partial sums (they are reduced with the other parameter gradients).
+ * All shards must have the same extent. replicas == 1 with all_moments = moments reproduces the single-device ops. */
+NB200_API int nb200_batch_norm_moments(const nb200_bn_desc* d, const float* x, float* moments, void* workspace,
+                                       size_t workspace_bytes, void* stream);
+NB200_API int nb200_batch_norm_train_from_moments(const nb200_bn_desc* d, const float* all_moments, int32_t replicas,
+                                                  const float* x, const float* gamma, const float* beta, float momentum,
+                                                  float epsilon, float* running_mean, float* running_var, float* save_mean,
+                                                  float* save_inv_var, float* y, void* stream);
+NB200_API int nb200_batch_norm_gradient_sums(const nb200_bn_desc* d, const float* x, const float* dy, const float* save_mean,
+                                             float* sums, void* workspace, size_t workspace_bytes, void* stream);
+NB200_API int nb200_batch_norm_gradient_from_sums(const nb200_bn_desc* d, int32_t replicas, const float* global_sums,
+                                                  const float* local_sums, const float* x, const float* gamma,
+                                                  const float* dy, const float* save_mean, const float* save_inv_var,
+                                                  float* dgamma, float* dbeta, float* dx, void* stream);
+
 /* Host-buffer variants (pageable or pinned host memory in, host memory out): stage through device
  * buffers owned by the library on `stream`, run the op, copy the result back and wait for it. This is
  * what a caller holding host-resident Tensors (reference residency protocol, Storage.cpp:534-604)

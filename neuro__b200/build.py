@@ -9,9 +9,7 @@ OUT = os.path.join(HERE, "libneuro_b200.so")
 OBJ = os.path.join(HERE, "_obj")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["api.cu", "conv_direct.cu", "conv_smallc.cu", "conv_tc.cu", "elementwise.cu", "resample.cu"]
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math=false" if False else "-Xptxas", "-v"]
+SOURCES = ["api.cu", "batchnorm.cu", "conv_direct.cu", "conv_smallc.cu", "conv_tc.cu", "elementwise.cu", "resample.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 

@@ -1,4 +1,5 @@
 // C ABI (include/neuro_b200.h): validation, kernel-family dispatch, host-buffer staging.
+#include <initializer_list>
 #include <stdarg.h>
 #include <string.h>
 
@@ -54,6 +55,21 @@ namespace nb200
             return NB200_OK;
         }
 
+        // a*b*c*e <= 2^32-1 (Neuro::Shape::Length is uint32_t, Shape.h) without overflowing the intermediate products:
+        // every factor is a non-negative int32, so each partial product is checked before the next multiply
+        bool fits_u32(long long a, long long b, long long c, long long e)
+        {
+            const long long lim = 0xFFFFFFFFll;
+            long long v = a;
+            for (long long f : {b, c, e})
+            {
+                if (f != 0 && v > lim / f)
+                    return false;
+                v *= f;
+            }
+            return v <= lim;
+        }
+
         int validate(const nb200_conv_desc* d, int op)
         {
             if (!d)
@@ -66,8 +82,7 @@ namespace nb200
                 return fail(NB200_E_INVALID, "unknown data format %d", d->fmt);
             if (d->math < NB200_MATH_TF32 || d->math > NB200_MATH_FP32)
                 return fail(NB200_E_INVALID, "unknown math mode %d", d->math);
-            const long long lim = 0xFFFFFFFFll; // Neuro::Shape::Length is uint32_t (Shape.h)
-            if ((long long)d->N * d->C * d->H * d->W > lim || (long long)d->N * d->K * d->Ho * d->Wo > lim || (long long)d->K * d->C * d->R * d->S > lim)
+            if (!fits_u32(d->N, d->C, d->H, d->W) || !fits_u32(d->N, d->K, d->Ho, d->Wo) || !fits_u32(d->K, d->C, d->R, d->S))
                 return fail(NB200_E_INVALID, "tensor exceeds 2^32-1 elements");
             if (op == NB200_OP_FORWARD && d->N > 0 && d->K > 0)
             {
@@ -77,6 +92,15 @@ namespace nb200
                 const int ho = (d->H + 2 * d->padY - d->R) / d->stride + 1, wo = (d->W + 2 * d->padX - d->S) / d->stride + 1;
                 if (ho != d->Ho || wo != d->Wo)
                     return fail(NB200_E_INVALID, "output extent %dx%d does not match GetConvOutputShape %dx%d", d->Ho, d->Wo, ho, wo);
+            }
+            if ((op == NB200_OP_INPUT_GRADIENT || op == NB200_OP_KERNELS_GRADIENT) && d->N > 0 && d->K > 0 && d->Ho > 0 && d->Wo > 0)
+            {
+                // The gradient ops take (H, W) and (Ho, Wo) from two caller tensors (transposed convolution and ragged strides
+                // need that freedom), but every gradient element must come from a tap position of the forward op: the last
+                // output row / column may not start beyond what GetConvOutputShape allows for this input extent.
+                if ((long long)(d->Ho - 1) * d->stride + d->R - 2ll * d->padY > d->H || (long long)(d->Wo - 1) * d->stride + d->S - 2ll * d->padX > d->W)
+                    return fail(NB200_E_INVALID, "gradient extent %dx%d exceeds the output of a %dx%d input (filter %dx%d stride %d pad %d,%d)",
+                                d->Ho, d->Wo, d->H, d->W, d->R, d->S, d->stride, d->padY, d->padX);
             }
             return NB200_OK;
         }
@@ -332,6 +356,8 @@ extern "C"
     {
         if (!d || d->N < 0 || d->K < 0 || d->Ho < 0 || d->Wo < 0 || (d->fmt != NB200_NCHW && d->fmt != NB200_NHWC))
             return fail(NB200_E_INVALID, "bad descriptor");
+        if (!fits_u32(d->N, d->K, d->Ho, d->Wo))
+            return fail(NB200_E_INVALID, "tensor exceeds 2^32-1 elements");
         if (d->K == 0)
             return NB200_OK;
         if (!db || (!dy && (long long)d->N * d->Ho * d->Wo > 0))
@@ -355,6 +381,8 @@ extern "C"
             return fail(NB200_E_INVALID, "bad descriptor");
         if (act < NB200_ACT_IDENTITY || act > NB200_ACT_LEAKY_RELU)
             return fail(NB200_E_INVALID, "activation %d has no gradient here", act);
+        if (!fits_u32(d->N, d->K, d->Ho, d->Wo))
+            return fail(NB200_E_INVALID, "tensor exceeds 2^32-1 elements");
         const long long n = (long long)d->N * d->K * d->Ho * d->Wo;
         if (n > 0 && (!y || !dy || !dz))
             return fail(NB200_E_INVALID, "null tensor pointer");
@@ -439,6 +467,150 @@ extern "C"
         int rc = require_device();
         if (rc) return rc;
         return sgd_step(param, grad, count, grad_scale, lr, (cudaStream_t)stream);
+    }
+
+    // ---- batch normalisation (batchnorm.cu) ----
+
+    int32_t nb200_batch_norm_groups(const nb200_bn_desc* d) { return bn_check(d) ? 0 : bn_groups(*d); }
+    size_t nb200_batch_norm_workspace_bytes(const nb200_bn_desc* d) { return bn_check(d) ? 0 : bn_workspace_bytes(*d); }
+
+    int nb200_batch_norm(const nb200_bn_desc* d, const float* x, const float* gamma, const float* beta, float epsilon,
+                         const float* running_mean, const float* running_var, float* y, void* stream)
+    {
+        int rc = bn_check(d);
+        if (rc) return rc;
+        if ((long long)bn_groups(*d) * bn_group_elements(*d) == 0)
+            return NB200_OK;
+        if (!x || !gamma || !beta || !running_mean || !running_var || !y)
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        if ((rc = require_device())) return rc;
+        return bn_apply(*d, true, x, gamma, beta, running_mean, running_var, epsilon, y, (cudaStream_t)stream);
+    }
+
+    int nb200_batch_norm_moments(const nb200_bn_desc* d, const float* x, float* moments, void* workspace, size_t workspace_bytes,
+                                 void* stream)
+    {
+        int rc = bn_check(d);
+        if (rc) return rc;
+        if ((long long)bn_groups(*d) * bn_group_elements(*d) == 0)
+            return NB200_OK;
+        if (!x || !moments)
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        if ((rc = require_device())) return rc;
+        return bn_moments(*d, x, moments, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
+
+    int nb200_batch_norm_train_from_moments(const nb200_bn_desc* d, const float* all_moments, int32_t replicas, const float* x,
+                                            const float* gamma, const float* beta, float momentum, float epsilon, float* running_mean,
+                                            float* running_var, float* save_mean, float* save_inv_var, float* y, void* stream)
+    {
+        int rc = bn_check(d);
+        if (rc) return rc;
+        if (replicas < 1)
+            return fail(NB200_E_INVALID, "replicas must be >= 1");
+        const long long total = (long long)bn_groups(*d) * bn_group_elements(*d);
+        if (total == 0)
+            return NB200_OK;
+        if (!x || !y || !gamma || !beta)
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        if ((rc = require_device())) return rc;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (bn_group_elements(*d) * replicas == 1)
+        {
+            // "cannot normalize single values so just copy input to output" (TensorOpCpu.cpp:1412-1416)
+            if (y != x)
+                NB200_CUDA_TRY(cudaMemcpyAsync(y, x, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            return NB200_OK;
+        }
+        if (!all_moments || !save_mean || !save_inv_var)
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        if ((rc = bn_finalize(*d, all_moments, replicas, momentum, epsilon, running_mean, running_var, save_mean, save_inv_var, st))) return rc;
+        return bn_apply(*d, false, x, gamma, beta, save_mean, save_inv_var, epsilon, y, st);
+    }
+
+    int nb200_batch_norm_train(const nb200_bn_desc* d, const float* x, const float* gamma, const float* beta, float momentum, float epsilon,
+                               float* running_mean, float* running_var, float* save_mean, float* save_inv_var, float* y, void* workspace,
+                               size_t workspace_bytes, void* stream)
+    {
+        int rc = bn_check(d);
+        if (rc) return rc;
+        const long long total = (long long)bn_groups(*d) * bn_group_elements(*d);
+        if (total == 0)
+            return NB200_OK;
+        if (bn_group_elements(*d) > 1)
+        {
+            // the local moments live at the tail of the workspace (2 of the 3 floats per group reserved there)
+            if (!workspace || workspace_bytes < bn_workspace_bytes(*d))
+                return fail(NB200_E_WORKSPACE, "batch norm needs %zu workspace bytes, got %zu", bn_workspace_bytes(*d), workspace_bytes);
+            float* moments = (float*)((uint8_t*)workspace + bn_workspace_bytes(*d)) - (size_t)bn_groups(*d) * 3;
+            if ((rc = nb200_batch_norm_moments(d, x, moments, workspace, workspace_bytes, stream))) return rc;
+            return nb200_batch_norm_train_from_moments(d, moments, 1, x, gamma, beta, momentum, epsilon, running_mean, running_var, save_mean,
+                                                       save_inv_var, y, stream);
+        }
+        return nb200_batch_norm_train_from_moments(d, nullptr, 1, x, gamma, beta, momentum, epsilon, running_mean, running_var, save_mean,
+                                                   save_inv_var, y, stream);
+    }
+
+    int nb200_batch_norm_gradient_sums(const nb200_bn_desc* d, const float* x, const float* dy, const float* save_mean, float* sums,
+                                       void* workspace, size_t workspace_bytes, void* stream)
+    {
+        int rc = bn_check(d);
+        if (rc) return rc;
+        if ((long long)bn_groups(*d) * bn_group_elements(*d) == 0)
+            return NB200_OK;
+        if (!x || !dy || !save_mean || !sums)
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        if ((rc = require_device())) return rc;
+        return bn_gradient_sums(*d, x, dy, save_mean, sums, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
+
+    int nb200_batch_norm_gradient_from_sums(const nb200_bn_desc* d, int32_t replicas, const float* global_sums, const float* local_sums,
+                                            const float* x, const float* gamma, const float* dy, const float* save_mean,
+                                            const float* save_inv_var, float* dgamma, float* dbeta, float* dx, void* stream)
+    {
+        int rc = bn_check(d);
+        if (rc) return rc;
+        if (replicas < 1)
+            return fail(NB200_E_INVALID, "replicas must be >= 1");
+        const int G = bn_groups(*d);
+        const long long total = (long long)G * bn_group_elements(*d);
+        if (total == 0)
+            return NB200_OK;
+        if (!dy || !dx)
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        if ((rc = require_device())) return rc;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (bn_group_elements(*d) * replicas == 1)
+        {
+            // m == 1: the gradient passes through, the parameter gradients are zero (TensorOpCpu.cpp:1458-1463)
+            if (dx != dy)
+                NB200_CUDA_TRY(cudaMemcpyAsync(dx, dy, (size_t)total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            if (dgamma) NB200_CUDA_TRY(cudaMemsetAsync(dgamma, 0, (size_t)G * sizeof(float), st));
+            if (dbeta) NB200_CUDA_TRY(cudaMemsetAsync(dbeta, 0, (size_t)G * sizeof(float), st));
+            return NB200_OK;
+        }
+        if (!x || !gamma || !save_mean || !save_inv_var || !global_sums || !local_sums)
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        return bn_gradient_apply(*d, replicas, x, gamma, dy, save_mean, save_inv_var, global_sums, local_sums, dgamma, dbeta, dx, st);
+    }
+
+    int nb200_batch_norm_gradient(const nb200_bn_desc* d, const float* x, const float* gamma, const float* dy, const float* save_mean,
+                                  const float* save_inv_var, float* dgamma, float* dbeta, float* dx, void* workspace, size_t workspace_bytes,
+                                  void* stream)
+    {
+        int rc = bn_check(d);
+        if (rc) return rc;
+        if ((long long)bn_groups(*d) * bn_group_elements(*d) == 0)
+            return NB200_OK;
+        float* sums = nullptr;
+        if (bn_group_elements(*d) > 1)
+        {
+            if (!workspace || workspace_bytes < bn_workspace_bytes(*d))
+                return fail(NB200_E_WORKSPACE, "batch norm needs %zu workspace bytes, got %zu", bn_workspace_bytes(*d), workspace_bytes);
+            sums = (float*)((uint8_t*)workspace + bn_workspace_bytes(*d)) - (size_t)bn_groups(*d) * 3;
+            if ((rc = nb200_batch_norm_gradient_sums(d, x, dy, save_mean, sums, workspace, workspace_bytes, stream))) return rc;
+        }
+        return nb200_batch_norm_gradient_from_sums(d, 1, sums, sums, x, gamma, dy, save_mean, save_inv_var, dgamma, dbeta, dx, stream);
     }
 
     // ---- host-buffer variants ----

@@ -136,4 +136,20 @@ namespace nb200
     int adam_step(float* p, const float* g, float* m, float* v, size_t n, float gs, float lr, float b1, float b2, float eps,
                   cudaStream_t st);
     int sgd_step(float* p, const float* g, size_t n, float gs, float lr, cudaStream_t st);
+
+    // batchnorm.cu -- statistics are split from the normalisation so that replicas can exchange them (2*G / 3*G floats)
+    int bn_check(const nb200_bn_desc* d);
+    int bn_groups(const nb200_bn_desc& d);
+    long long bn_group_elements(const nb200_bn_desc& d);
+    size_t bn_workspace_bytes(const nb200_bn_desc& d);
+    int bn_moments(const nb200_bn_desc& d, const float* x, float* moments, void* ws, size_t wsBytes, cudaStream_t st);
+    int bn_finalize(const nb200_bn_desc& d, const float* allMoments, int replicas, float momentum, float epsilon, float* runningMean,
+                    float* runningVar, float* saveMean, float* saveInvVar, cudaStream_t st);
+    int bn_apply(const nb200_bn_desc& d, bool inference, const float* x, const float* gamma, const float* beta, const float* mean,
+                 const float* invOrVar, float epsilon, float* y, cudaStream_t st);
+    int bn_gradient_sums(const nb200_bn_desc& d, const float* x, const float* dy, const float* saveMean, float* sums, void* ws, size_t wsBytes,
+                         cudaStream_t st);
+    int bn_gradient_apply(const nb200_bn_desc& d, int replicas, const float* x, const float* gamma, const float* dy, const float* saveMean,
+                          const float* saveInvVar, const float* globalSums, const float* localSums, float* dgamma, float* dbeta, float* dx,
+                          cudaStream_t st);
 }

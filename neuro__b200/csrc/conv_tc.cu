@@ -2917,6 +2917,43 @@ namespace nb200
 
         inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+        // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) property of a kernel, so the one-time
+        // opt-in is keyed by the device ordinal: a process that drives several GPUs (one host thread per device) opts in on
+        // each of them. The flag is only ever set after a successful call and the call is idempotent, so two host threads
+        // racing on the same device at worst both make it.
+        constexpr int kMaxDevices = 64;
+        struct DeviceOnce { unsigned char done[kMaxDevices]; };
+
+        template <typename Kernel>
+        int opt_in_smem(DeviceOnce& once, Kernel kernel, int bytes)
+        {
+            int dev = 0;
+            NB200_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev >= 0 && dev < kMaxDevices && __atomic_load_n(&once.done[dev], __ATOMIC_ACQUIRE))
+                return NB200_OK;
+            NB200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            if (dev >= 0 && dev < kMaxDevices)
+                __atomic_store_n(&once.done[dev], (unsigned char)1, __ATOMIC_RELEASE);
+            return NB200_OK;
+        }
+
+        // SM count of the current device (persistent grids are sized from it), cached per device ordinal.
+        int device_sms(int* out)
+        {
+            static int cache[kMaxDevices];
+            int dev = 0;
+            NB200_CUDA_TRY(cudaGetDevice(&dev));
+            int v = (dev >= 0 && dev < kMaxDevices) ? __atomic_load_n(&cache[dev], __ATOMIC_RELAXED) : 0;
+            if (!v)
+            {
+                NB200_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+                if (dev >= 0 && dev < kMaxDevices)
+                    __atomic_store_n(&cache[dev], v, __ATOMIC_RELAXED);
+            }
+            *out = v;
+            return NB200_OK;
+        }
+
         int pick_bn(int K)
         {
             // Shared-memory traffic per MMA cycle falls with the tile's N (the converted A tile is reused across more
@@ -3022,19 +3059,17 @@ namespace nb200
 
         size_t repack_bytes(const FwdShape& f)
         {
-            return (size_t)f.R * f.S * f.Kout * round_up(f.Cin, kBlockC) * sizeof(float) * (f.x3 ? 2 : 1);
+            // 256-byte aligned: what follows in the workspace (channel-split partials) wants the alignment, and the launcher
+            // and nb200_conv2d_workspace_bytes must agree on ONE number (odd R*S*Kout*Cp/32 is only a multiple of 128)
+            return ((size_t)f.R * f.S * f.Kout * round_up(f.Cin, kBlockC) * sizeof(float) * (f.x3 ? 2 : 1) + 255) & ~(size_t)255;
         }
 
         template <int BN, bool X3>
         int launch_fprop(const FwdShape& f, const Plan& pl, const CUtensorMap& mapX, const CUtensorMap& mapW, const FpropParams& p,
                          const float* bias, float* out, cudaStream_t st)
         {
-            static bool attrSet = false;
-            if (!attrSet)
-            {
-                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1));
-                attrSet = true;
-            }
+            static DeviceOnce attrSet{};
+            if (const int rcAttr = opt_in_smem(attrSet, tc_fprop_kernel<BN, X3>, kSmemBudget1)) return rcAttr;
             const long long tiles = (long long)p.tilesK * p.tilesW * p.tilesH * f.N * p.splits;
             if (tiles > 0x3FFFFFFFll)
                 return fail(NB200_E_UNSUPPORTED, "too many tiles");
@@ -3052,23 +3087,15 @@ namespace nb200
             {
                 if constexpr (BN <= 128 && !X3)
                 {
-                    static bool attrSetM = false;
-                    if (!attrSetM)
-                    {
-                        NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop_m256_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1));
-                        attrSetM = true;
-                    }
+                    static DeviceOnce attrSetM{};
+                    if (const int rcAttr = opt_in_smem(attrSetM, tc_fprop_m256_kernel<BN>, kSmemBudget1)) return rcAttr;
                     tc_fprop_m256_kernel<BN><<<(unsigned)tiles, kFpropThreads, pl.smemBytes, st>>>(mapX, mapW, pd, bias, out);
                 }
             }
             else if (pl.pair && !X3)
             {
-                static bool attrSet2 = false;
-                if (!attrSet2)
-                {
-                    NB200_CUDA_TRY(cudaFuncSetAttribute(tc_fprop2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, BN > 128 ? kSmemBudget1 : kSmemBudget2));
-                    attrSet2 = true;
-                }
+                static DeviceOnce attrSet2{};
+                if (const int rcAttr = opt_in_smem(attrSet2, tc_fprop2_kernel<BN>, BN > 128 ? kSmemBudget1 : kSmemBudget2)) return rcAttr;
                 cudaLaunchConfig_t cfg{};
                 cfg.gridDim = dim3((unsigned)(2 * tiles));
                 cfg.blockDim = dim3(kFpropThreads);
@@ -3181,19 +3208,10 @@ namespace nb200
                 int rc = make_map(&mapW, wr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
                 if (rc) return rc;
             }
-            static bool attrSet = false;
-            if (!attrSet)
-            {
-                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_rowtap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget1));
-                attrSet = true;
-            }
-            static int smCount = 0;
-            if (!smCount)
-            {
-                int dev = 0;
-                NB200_CUDA_TRY(cudaGetDevice(&dev));
-                NB200_CUDA_TRY(cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, dev));
-            }
+            static DeviceOnce attrSet{};
+            if (const int rcAttr = opt_in_smem(attrSet, tc_rowtap_kernel, kSmemBudget1)) return rcAttr;
+            int smCount = 0;
+            if (const int rcSm = device_sms(&smCount)) return rcSm;
             const unsigned grid = (unsigned)(tiles < smCount ? tiles : smCount);
             tc_rowtap_kernel<<<grid, kRtThreads, smemBytes, st>>>(mapX, mapW, p, bias, out);
             NB200_CUDA_TRY(cudaGetLastError());
@@ -3320,12 +3338,8 @@ namespace nb200
         template <int BN>
         int launch_gather(const CUtensorMap& mapW, const GatherBatch& b, int bStages, const float* in, const float* bias, float* out, cudaStream_t st)
         {
-            static bool attrSet = false;
-            if (!attrSet)
-            {
-                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_gather_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, BN > 128 ? kSmemBudget1 : kSmemBudget2));
-                attrSet = true;
-            }
+            static DeviceOnce attrSet{};
+            if (const int rcAttr = opt_in_smem(attrSet, tc_gather_kernel<BN>, BN > 128 ? kSmemBudget1 : kSmemBudget2)) return rcAttr;
             const long long tiles = b.tileStart[b.count];
             const size_t smemBytes = 1024 + 512 + (size_t)bStages * BN * kBlockC * 4;
             tc_gather_kernel<BN><<<(unsigned)tiles, kFpropThreads, smemBytes, st>>>(mapW, b, in, bias, out);
@@ -3508,12 +3522,8 @@ namespace nb200
         template <int BN, bool PACK, int OFF0>
         int launch_wgrad_t(const WgradPlan& pl, const CUtensorMap& mapX, const CUtensorMap& mapDy, const WgradParams& p, float* ws, cudaStream_t st)
         {
-            static bool attrSet = false;
-            if (!attrSet)
-            {
-                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<BN, PACK, OFF0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-                attrSet = true;
-            }
+            static DeviceOnce attrSet{};
+            if (const int rcAttr = opt_in_smem(attrSet, tc_wgrad_kernel<BN, PACK, OFF0>, 220 * 1024)) return rcAttr;
             const long long ctas = (long long)p.splits * p.tilesK * p.tilesC * p.R;
             tc_wgrad_kernel<BN, PACK, OFF0><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapX, mapDy, p, ws);
             NB200_CUDA_TRY(cudaGetLastError());
@@ -3708,12 +3718,8 @@ namespace nb200
         template <int BN>
         int launch_wgather(const WgatherPlan& pl, const CUtensorMap& mapDy, const WgatherParams& p, const float* x, float* ws, cudaStream_t st)
         {
-            static bool attrSet = false;
-            if (!attrSet)
-            {
-                NB200_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_gather_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-                attrSet = true;
-            }
+            static DeviceOnce attrSet{};
+            if (const int rcAttr = opt_in_smem(attrSet, tc_wgrad_gather_kernel<BN>, 220 * 1024)) return rcAttr;
             const long long ctas = (long long)p.splits * p.tilesK * p.tilesC * p.groups;
             tc_wgrad_gather_kernel<BN><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapDy, p, x, ws);
             NB200_CUDA_TRY(cudaGetLastError());
@@ -3821,12 +3827,8 @@ namespace nb200
             int rc = make_map(&mapDy, dy, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
             if (rc) return rc;
         }
-        static bool attrSet = false;
-        if (!attrSet)
-        {
-            NB200_CUDA_TRY(cudaFuncSetAttribute(tc_smallc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            attrSet = true;
-        }
+        static DeviceOnce attrSet{};
+        if (const int rcAttr = opt_in_smem(attrSet, tc_smallc_wgrad_kernel, 220 * 1024)) return rcAttr;
         const int splits = sc_splits(d);
         tc_smallc_wgrad_kernel<<<(unsigned)(splits * p.tilesK), kScThreads, smemBytes, st>>>(mapX, mapDy, p, (float*)ws);
         NB200_CUDA_TRY(cudaGetLastError());
@@ -3957,12 +3959,8 @@ namespace nb200
             int rc = make_map(&mapDy, dy, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
             if (rc) return rc;
         }
-        static bool attrSet = false;
-        if (!attrSet)
-        {
-            NB200_CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_rowfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            attrSet = true;
-        }
+        static DeviceOnce attrSet{};
+        if (const int rcAttr = opt_in_smem(attrSet, tc_wgrad_rowfold_kernel, 220 * 1024)) return rcAttr;
         p.stageBytes = (uint32_t)((d.R * kRfDyBytes + kRfXBytes + 1023) & ~1023);
         p.stages = (int)((200 * 1024) / p.stageBytes);
         if (p.stages > 8) p.stages = 8;

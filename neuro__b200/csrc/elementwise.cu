@@ -200,12 +200,14 @@ namespace nb200
             const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
             if (i >= n)
                 return;
-            const float gi = gs * g[i];
-            const float mi = b1 * m[i] + (1.f - b1) * gi;
-            const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+            // every step rounded separately (no FMA contraction) in the reference's operation order, so that with gs == 1 the
+            // update is bit-identical to the reference's compiled loop (tests/test_conv_gpu.py)
+            const float gi = __fmul_rn(gs, g[i]);
+            const float mi = __fadd_rn(__fmul_rn(b1, m[i]), __fmul_rn(1.f - b1, gi));
+            const float vi = __fadd_rn(__fmul_rn(v[i], b2), __fmul_rn(__fmul_rn(1.f - b2, gi), gi));
             m[i] = mi;
             v[i] = vi;
-            p[i] = p[i] - mi / (sqrtf(vi) + eps) * lr;
+            p[i] = __fsub_rn(p[i], __fmul_rn(__fdiv_rn(mi, __fadd_rn(__fsqrt_rn(vi), eps)), lr));
         }
 
         // TensorOpCpu::SgdStep (TensorOpCpu.cpp:1006-1009)
@@ -213,7 +215,7 @@ namespace nb200
         {
             const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
             if (i < n)
-                p[i] = p[i] - lr * (gs * g[i]);
+                p[i] = __fadd_rn(p[i], __fmul_rn(-lr, __fmul_rn(gs, g[i]))); // Tensor::Add(1, -lr, gradient): 1*p + (-lr)*g
         }
     }
 

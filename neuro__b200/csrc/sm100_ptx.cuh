@@ -127,13 +127,19 @@ namespace nb200
 
         // Bounded wait: a protocol bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.
         // The bound is a poll count (no clock reads in the loop): each poll sleeps up to the hint, or returns within
-        // ~100 cycles if the hardware ignores it, so 2^20 polls is >= ~50 ms (hint ignored) and <= ~20 s (every poll sleeping the full hint).
+        // ~100 cycles if the hardware ignores it, so 2^26 polls is >= ~3.5 s of pure spinning -- far beyond anything a
+        // legitimate wait sees even under time-slicing, MPS or profiler replay (a trap poisons the context, so the bound
+        // must only ever fire on a genuine deadlock); -DNB200_MBAR_MAX_POLLS=... overrides it for bring-up.
+#ifndef NB200_MBAR_MAX_POLLS
+#define NB200_MBAR_MAX_POLLS (1u << 26)
+#endif
+        constexpr uint32_t kMbarMaxPolls = NB200_MBAR_MAX_POLLS;
         __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         {
             uint32_t polls = 0;
             while (!mbar_try_wait(bar, parity))
             {
-                if (++polls > (1u << 20))
+                if (++polls > kMbarMaxPolls)
                 {
                     printf("nb200: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
                     __trap();
@@ -171,7 +177,7 @@ namespace nb200
             uint32_t polls = 0;
             while (!mbar_try_wait(bar, parity))
             {
-                if (++polls > (1u << 20))
+                if (++polls > kMbarMaxPolls)
                 {
                     printf("nb200: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
                     __trap();

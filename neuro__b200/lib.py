@@ -23,6 +23,9 @@ EXPORTS = [
     "nb200_conv2d_bias_activation_gradient_workspace_bytes", "nb200_conv2d_bias_activation_gradient",
     "nb200_conv2d_prepare_filters", "nb200_conv2d_forward_prepared", "nb200_conv2d_input_gradient_prepared",
     "nb200_pool2d", "nb200_pool2d_gradient", "nb200_upsample2d", "nb200_upsample2d_gradient", "nb200_constant_pad2d",
+    "nb200_batch_norm_groups", "nb200_batch_norm_workspace_bytes", "nb200_batch_norm", "nb200_batch_norm_train",
+    "nb200_batch_norm_gradient", "nb200_batch_norm_moments", "nb200_batch_norm_train_from_moments",
+    "nb200_batch_norm_gradient_sums", "nb200_batch_norm_gradient_from_sums",
 ]
 
 
@@ -47,6 +50,14 @@ POOL_MAX, POOL_AVG = 0, 1
 class PoolDesc(ctypes.Structure):
     """struct nb200_pool_desc"""
     _fields_ = [(n, ctypes.c_int32) for n in ("N", "C", "H", "W", "Ho", "Wo", "filter", "stride", "padX", "padY", "mode", "fmt")]
+
+
+BN_PER_ACTIVATION, BN_SPATIAL, BN_INSTANCE = 0, 1, 2
+
+
+class BnDesc(ctypes.Structure):
+    """struct nb200_bn_desc"""
+    _fields_ = [(n, ctypes.c_int32) for n in ("N", "C", "H", "W", "mode")]
 
 
 class NeuroB200Error(RuntimeError):
@@ -98,6 +109,16 @@ def load():
     L.nb200_upsample2d.argtypes = [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
     L.nb200_upsample2d_gradient.argtypes = [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
     L.nb200_constant_pad2d.argtypes = [c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p]
+    bp = ctypes.POINTER(BnDesc)
+    L.nb200_batch_norm_groups.argtypes = [bp]; L.nb200_batch_norm_groups.restype = c_i
+    L.nb200_batch_norm_workspace_bytes.argtypes = [bp]; L.nb200_batch_norm_workspace_bytes.restype = c_sz
+    L.nb200_batch_norm.argtypes = [bp, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_p]
+    L.nb200_batch_norm_train.argtypes = [bp, c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]
+    L.nb200_batch_norm_gradient.argtypes = [bp, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]
+    L.nb200_batch_norm_moments.argtypes = [bp, c_p, c_p, c_p, c_sz, c_p]
+    L.nb200_batch_norm_train_from_moments.argtypes = [bp, c_p, c_i, c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p]
+    L.nb200_batch_norm_gradient_sums.argtypes = [bp, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]
+    L.nb200_batch_norm_gradient_from_sums.argtypes = [bp, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]
     _lib = L
     return L
 

@@ -80,6 +80,7 @@ class TensorOpB200:
     def __init__(self, math=lib.MATH_TF32):
         self.math = math
         self._ws = None
+        self._bnws = None
         self._L = lib.load()
 
     # -- helpers
@@ -219,6 +220,59 @@ class TensorOpB200:
         N, C, H, W = input.shape
         assert tuple(output.shape) == (N, C, H + top + bottom, W + left + right)   # Tensor.cpp:1502
         check(self._L.nb200_constant_pad2d(N, C, H, W, left, right, top, bottom, value, _ptr(input), _ptr(output), _stream()))
+
+    # -- batch normalisation (TensorOpCpu.h:55-57); gamma / beta / statistics are flat tensors of G values
+    def _bn(self, input, mode):
+        N, C, H, W = input.shape
+        d = lib.BnDesc(N, C, H, W, mode)
+        need = self._L.nb200_batch_norm_workspace_bytes(ctypes.byref(d))
+        if self._bnws is None or self._bnws.numel() < need:
+            self._bnws = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
+        return d, ctypes.c_void_p(self._bnws.data_ptr()), need
+
+    def BatchNormalization(self, input, mode, gamma, beta, epsilon, runningMean, runningVar, output):
+        d, _, _ = self._bn(input, mode)
+        check(self._L.nb200_batch_norm(ctypes.byref(d), _ptr(input), _ptr(gamma), _ptr(beta), epsilon, _ptr(runningMean),
+                                       _ptr(runningVar), _ptr(output), _stream()))
+
+    def BatchNormalizationTrain(self, input, mode, gamma, beta, momentum, epsilon, runningMean, runningVar, saveMean,
+                                saveInvVariance, output):
+        d, ws, n = self._bn(input, mode)
+        check(self._L.nb200_batch_norm_train(ctypes.byref(d), _ptr(input), _ptr(gamma), _ptr(beta), momentum, epsilon,
+                                             _ptr(runningMean), _ptr(runningVar), _ptr(saveMean), _ptr(saveInvVariance),
+                                             _ptr(output), ws, n, _stream()))
+
+    def BatchNormalizationGradient(self, input, mode, gamma, epsilon, outputGradient, savedMean, savedInvVariance,
+                                   gammaGradient, betaGradient, trainable, inputGradient):
+        """`epsilon` and `trainable` are accepted for signature parity; the reference ignores both (TensorOpCpu.cpp:1437-1480)."""
+        d, ws, n = self._bn(input, mode)
+        check(self._L.nb200_batch_norm_gradient(ctypes.byref(d), _ptr(input), _ptr(gamma), _ptr(outputGradient), _ptr(savedMean),
+                                                _ptr(savedInvVariance), _ptr(gammaGradient), _ptr(betaGradient),
+                                                _ptr(inputGradient), ws, n, _stream()))
+
+    # the same ops split around the replicas' exchange (include/neuro_b200.h: nb200_batch_norm_moments ...)
+    def BatchNormalizationMoments(self, input, mode, moments):
+        d, ws, n = self._bn(input, mode)
+        check(self._L.nb200_batch_norm_moments(ctypes.byref(d), _ptr(input), _ptr(moments), ws, n, _stream()))
+
+    def BatchNormalizationTrainFromMoments(self, allMoments, replicas, input, mode, gamma, beta, momentum, epsilon, runningMean,
+                                           runningVar, saveMean, saveInvVariance, output):
+        d, _, _ = self._bn(input, mode)
+        check(self._L.nb200_batch_norm_train_from_moments(ctypes.byref(d), _ptr(allMoments), replicas, _ptr(input), _ptr(gamma),
+                                                          _ptr(beta), momentum, epsilon, _ptr(runningMean), _ptr(runningVar),
+                                                          _ptr(saveMean), _ptr(saveInvVariance), _ptr(output), _stream()))
+
+    def BatchNormalizationGradientSums(self, input, mode, outputGradient, savedMean, sums):
+        d, ws, n = self._bn(input, mode)
+        check(self._L.nb200_batch_norm_gradient_sums(ctypes.byref(d), _ptr(input), _ptr(outputGradient), _ptr(savedMean), _ptr(sums),
+                                                     ws, n, _stream()))
+
+    def BatchNormalizationGradientFromSums(self, replicas, globalSums, localSums, input, mode, gamma, outputGradient, savedMean,
+                                           savedInvVariance, gammaGradient, betaGradient, inputGradient):
+        d, _, _ = self._bn(input, mode)
+        check(self._L.nb200_batch_norm_gradient_from_sums(ctypes.byref(d), replicas, _ptr(globalSums), _ptr(localSums), _ptr(input),
+                                                          _ptr(gamma), _ptr(outputGradient), _ptr(savedMean), _ptr(savedInvVariance),
+                                                          _ptr(gammaGradient), _ptr(betaGradient), _ptr(inputGradient), _stream()))
 
     # -- optimiser tail (TensorOpCpu.h:75-76)
     def AdamStep(self, parameter, gradient, mGrad, vGrad, lr, beta1, beta2, epsilon, gradScale=1.0):

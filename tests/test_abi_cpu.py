@@ -197,3 +197,63 @@ def test_workspace_sizes_of_the_gathered_and_small_families(L):
     # strided few-channel kernel gradient: one partial per slice
     sg = _desc(8, 3, 256, 256, 64, 3, 3, 2, 1, 1)
     assert ws(lib.OP_KERNELS_GRADIENT, sg) % (64 * 27 * 4) == 0 and ws(lib.OP_KERNELS_GRADIENT, sg) >= 64 * 27 * 4
+
+
+def test_workspace_bytes_is_what_the_launcher_demands_for_odd_filter_counts(L):
+    """R*S*Kout*Cp*4 is only a multiple of 128 for odd K (or odd C in the input gradient); the launcher rounds to 256.
+    Both now go through ONE rounded number: a 1x1 / 3x3 conv to 9 or 21 classes reports a 256-byte multiple."""
+    L.nb200_conv2d_workspace_bytes.restype = ctypes.c_size_t
+    for (C, K, F, p) in [(16, 9, 3, 1), (16, 21, 1, 0), (32, 33, 3, 1), (96, 9, 3, 1)]:
+        d = _desc(8, C, 32, 32, K, F, F, 1, p, p)
+        assert L.nb200_conv2d_kernel_name(lib.OP_FORWARD, ctypes.byref(d)) == b"tcgen05_fprop"
+        need = F * F * K * ((C + 31) // 32 * 32) * 4
+        got = L.nb200_conv2d_workspace_bytes(lib.OP_FORWARD, ctypes.byref(d))
+        assert got % 256 == 0 and got >= (need + 255) // 256 * 256
+    d = _desc(8, 9, 32, 32, 16, 3, 3, 1, 1, 1)       # input gradient: the repacked rows are the C = 9 channels
+    assert L.nb200_conv2d_kernel_name(lib.OP_INPUT_GRADIENT, ctypes.byref(d)) == b"tcgen05_dgrad"
+    assert L.nb200_conv2d_workspace_bytes(lib.OP_INPUT_GRADIENT, ctypes.byref(d)) % 256 == 0
+
+
+def test_gradient_ops_validate_their_extents(L):
+    """(Ho, Wo) of the gradient ops used to flow unchecked into tensor maps. A gradient larger than the forward op
+    can produce for this input is rejected; transposed-conv and ragged-stride extents (smaller or equal) stay valid; products of
+    large extents are checked without overflowing."""
+    p = ctypes.c_void_p(16)
+    ok = lib.ConvDesc(0, 8, 10, 10, 8, 4, 4, 4, 4, 2, 1, 1, lib.NCHW, lib.MATH_FP32)          # empty batch: validation only
+    assert L.nb200_conv2d_input_gradient(ctypes.byref(ok), None, None, None, None, 0, None) == 0
+    ragged = lib.ConvDesc(2, 8, 11, 11, 8, 4, 4, 4, 4, 2, 0, 0, lib.NCHW, lib.MATH_FP32)      # (11-4)//2+1 = 4: last row/col of dx untouched
+    too_big = lib.ConvDesc(2, 8, 10, 10, 8, 3, 3, 11, 10, 1, 1, 1, lib.NCHW, lib.MATH_FP32)   # Ho = 11 > 10
+    assert L.nb200_conv2d_input_gradient(ctypes.byref(too_big), p, p, p, None, 0, None) == -1
+    assert b"exceeds the output" in L.nb200_last_error()
+    assert L.nb200_conv2d_kernels_gradient(ctypes.byref(too_big), p, p, p, None, None, 0, None) == -1
+    import torch
+    if not torch.cuda.is_available():
+        assert L.nb200_conv2d_input_gradient(ctypes.byref(ragged), p, p, p, None, 0, None) == -2   # valid: reaches the device check
+    # 46341^2 * 2 overflows int32 products and 65536^2 * 65536 overflows int64 if multiplied blindly
+    huge = lib.ConvDesc(65536, 65536, 65536, 65536, 1, 1, 1, 65536, 65536, 1, 0, 0, lib.NCHW, lib.MATH_FP32)
+    assert L.nb200_conv2d_forward(ctypes.byref(huge), p, p, None, 0, 0.0, p, None, 0, None) == -1
+    assert b"2^32-1" in L.nb200_last_error()
+    hb = lib.ConvDesc(2 ** 31 - 1, 0, 0, 0, 2 ** 31 - 1, 1, 1, 2 ** 31 - 1, 2 ** 31 - 1, 1, 0, 0, lib.NCHW, lib.MATH_FP32)
+    assert L.nb200_conv2d_bias_gradient(ctypes.byref(hb), p, p, None) == -1
+
+
+def test_batch_norm_entry_points_are_host_validated(L):
+    """EBatchNormMode layouts (G statistics), workspace, argument checks, and no CPU fallback."""
+    g = lambda N, C, H, W, mode: L.nb200_batch_norm_groups(ctypes.byref(lib.BnDesc(N, C, H, W, mode)))
+    assert g(6, 5, 4, 3, lib.BN_SPATIAL) == 5 and g(6, 5, 4, 3, lib.BN_PER_ACTIVATION) == 60 and g(6, 5, 4, 3, lib.BN_INSTANCE) == 30
+    d = lib.BnDesc(8, 64, 128, 128, lib.BN_SPATIAL)
+    # 131072 elements per channel = 32 blocks of 4096; 3 floats per block + one row of per-channel sums
+    assert L.nb200_batch_norm_workspace_bytes(ctypes.byref(d)) == (64 * 32 * 3 + 64 * 3) * 4
+    bad = lib.BnDesc(8, 64, 128, 128, 5)
+    p = ctypes.c_void_p(16)
+    assert L.nb200_batch_norm_train(ctypes.byref(bad), p, p, p, 0.9, 1e-3, None, None, p, p, p, p, 1 << 20, None) == -1
+    assert L.nb200_batch_norm_train(ctypes.byref(d), None, p, p, 0.9, 1e-3, None, None, p, p, p, p, 1 << 20, None) == -1
+    assert L.nb200_batch_norm_train(ctypes.byref(d), p, p, p, 0.9, 1e-3, None, None, p, p, p, p, 16, None) == -4     # workspace too small
+    assert L.nb200_batch_norm_train_from_moments(ctypes.byref(d), p, 0, p, p, p, 0.9, 1e-3, None, None, p, p, p, None) == -1
+    empty = lib.BnDesc(0, 64, 8, 8, lib.BN_SPATIAL)
+    assert L.nb200_batch_norm_train(ctypes.byref(empty), None, None, None, 0.9, 1e-3, None, None, None, None, None, None, 0, None) == 0
+    import torch
+    if not torch.cuda.is_available():
+        assert L.nb200_batch_norm_train(ctypes.byref(d), p, p, p, 0.9, 1e-3, None, None, p, p, p, p, 1 << 20, None) == -2
+        assert L.nb200_batch_norm_gradient(ctypes.byref(d), p, p, p, p, p, p, p, p, p, 1 << 20, None) == -2
+        assert L.nb200_batch_norm(ctypes.byref(d), p, p, p, 1e-3, p, p, p, None) == -2

@@ -232,21 +232,51 @@ def test_full_size_layer_adjoint_identities(math):
 
 
 def test_optimizer_steps_match_reference_formulas():
+    """nb200_adam_step / nb200_sgd_step vs TensorOpCpu::AdamStep / SgdStep (TensorOpCpu.cpp:987-1009). The oracle restatement is
+    pinned bit for bit to the compiled reference and to committed reference outputs (tests/test_optim_bn_oracle.py); the CUDA
+    kernels round every step separately in the same order, so three consecutive updates are BIT-IDENTICAL."""
     n = 100003
-    p = synth.uniform(1, (n,)); g = synth.uniform(2, (n,)); m = synth.uniform(3, (n,), 0, 0.1); v = synth.uniform(4, (n,), 0, 0.1)
+    p = synth.uniform(1, (n,)); m = synth.uniform(3, (n,), 0, 0.1); v = synth.uniform(4, (n,), 0, 0.1)
     pr, mr, vr = p.copy(), m.copy(), v.copy()
-    O.adam_step(pr, g, mr, vr, 0.01, 0.9, 0.999, 1e-8)
     pd, md, vd = dev(p), dev(m), dev(v)
     op = TensorOpB200()
-    op.AdamStep(pd, dev(g), md, vd, 0.01, 0.9, 0.999, 1e-8)
-    assert np.abs(pd.cpu().numpy() - pr).max() <= 1e-6 and np.abs(md.cpu().numpy() - mr).max() <= 1e-7
-    assert np.abs(vd.cpu().numpy() - vr).max() <= 1e-7
+    for step in range(1, 4):
+        g = synth.uniform(20 + step, (n,))
+        lr_t = float(np.float32(1e-3 * np.sqrt(1 - 0.999 ** step) / (1 - 0.9 ** step)))   # Adam.cpp:90
+        O.adam_step(pr, g, mr, vr, lr_t, 0.9, 0.999, 1e-8)
+        op.AdamStep(pd, dev(g), md, vd, lr_t, 0.9, 0.999, 1e-8)
+        assert np.array_equal(pd.cpu().numpy(), pr) and np.array_equal(md.cpu().numpy(), mr) and np.array_equal(vd.cpu().numpy(), vr)
+    g = synth.uniform(2, (n,))
     qr = p.copy(); O.sgd_step(qr, g, 0.05)
     qd = dev(p); op.SgdStep(qd, dev(g), 0.05)
-    assert np.abs(qd.cpu().numpy() - qr).max() <= 2.5e-7
-    # grad_scale folds the 1/replicas of an all-reduced sum
+    assert np.array_equal(qd.cpu().numpy(), qr)
+    # grad_scale folds the 1/replicas of an all-reduced sum (a power of two scales exactly)
     qd2 = dev(p); op.SgdStep(qd2, dev(g * 4), 0.05, gradScale=0.25)
-    assert np.abs(qd2.cpu().numpy() - qr).max() <= 1e-6
+    assert np.array_equal(qd2.cpu().numpy(), qr)
+    pd2, md2, vd2 = dev(p), dev(m), dev(v)
+    pr2, mr2, vr2 = p.copy(), m.copy(), v.copy()
+    O.adam_step(pr2, g, mr2, vr2, 0.01, 0.9, 0.999, 1e-8)
+    op.AdamStep(pd2, dev(g * 8), md2, vd2, 0.01, 0.9, 0.999, 1e-8, gradScale=0.125)
+    assert np.array_equal(pd2.cpu().numpy(), pr2)
+
+
+def test_optimizer_steps_match_committed_reference_outputs():
+    """The same kernels against OUTPUTS OF THE REFERENCE ITSELF (tests/golden/ref_optim_bn_cases.npz, written by the reference's
+    AdamStep / SgdStep compiled into oracle/_ref; generator tests/golden/make_golden_optim_bn.py) -- bit for bit."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_optim_bn as G
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_optim_bn_cases.npz"))
+    p, m, v, grads = G.adam_inputs()
+    pd, md, vd = dev(p), dev(m), dev(v)
+    op = TensorOpB200()
+    for i, g in enumerate(grads):
+        op.AdamStep(pd, dev(g), md, vd, G.ADAM_HYPER["lr"], G.ADAM_HYPER["beta1"], G.ADAM_HYPER["beta2"], G.ADAM_HYPER["eps"])
+        assert np.array_equal(pd.cpu().numpy(), golden["adam.%d.p" % i]) and np.array_equal(md.cpu().numpy(), golden["adam.%d.m" % i])
+        assert np.array_equal(vd.cpu().numpy(), golden["adam.%d.v" % i])
+    qd = dev(synth.uniform(41, (G.ADAM_COUNT,)))
+    op.SgdStep(qd, dev(grads[0]), G.SGD_LR)
+    assert np.array_equal(qd.cpu().numpy(), golden["sgd.p"])
 
 
 def test_host_buffer_entry_points():
