@@ -119,6 +119,10 @@ TC_CASES = [
     # channel-split forward / input gradient (few tiles, many channels: batch-1 style transfer on the deep layers)
     (0, 1, 256, 32, 32, 128, 3, 3, 1, 1, 1),   # 8 tiles x 4 channel splits (forward), 16 tiles x 2 splits (input gradient)
     (0, 1, 160, 32, 64, 96, 3, 3, 1, 1, 1),    # 5 channel blocks: uneven split 3 + 2
+    # odd filter / channel counts on the halo-tile path: the repacked filters are only a multiple of 128 bytes
+    (0, 2, 16, 32, 32, 9, 3, 3, 1, 1, 1),      # 9 filters (forward repack 9*9*32*4 bytes), 9-row input-gradient tiles
+    (0, 2, 32, 32, 32, 21, 1, 1, 1, 0, 0),     # 1x1 conv to 21 classes
+    (0, 2, 9, 32, 32, 16, 3, 3, 1, 1, 1),      # 9 channels: the input gradient's repacked rows
 ]
 
 
@@ -393,3 +397,65 @@ def test_full_size_gan_layers_adjoint_identities(cfg):
     patch = xp[:, :, oh * st:oh * st + F, ow * st:ow * st + F]
     ref = np.einsum("ncrs,kcrs->nk", patch, w.astype(np.float64))
     assert np.abs(y[:, :, oh, ow] - ref).max() <= 2e-3 * np.abs(ref).max()
+
+
+# ---- parity AT THE SIZES bench.py RUNS: the longest reductions of the benchmarked configuration ----
+BENCH_SIZE = [  # (name, N, C, H, W, K): VGG16 batch 8, 3x3 s1 p1
+    ("vgg_block1_conv2", 8, 64, 512, 512, 64),     # kernel-gradient reduction N*Ho*Wo = 2 097 152 (tc_wgrad_rowfold_kernel, tc_rowtap_kernel)
+    ("vgg_block2_conv1", 8, 64, 256, 256, 128),    # 524 288 (rowfold kernel gradient, BN = 128 forward, row-tap input gradient)
+    ("vgg_block1_conv1", 8, 3, 512, 512, 64),      # 2 097 152 (tc_smallc_wgrad_kernel, small-channel forward / input gradient)
+    ("vgg_block3_conv1", 8, 128, 128, 128, 256),   # 131 072 (tc_wgrad_kernel)
+]
+
+
+@pytest.mark.parametrize("math", [lib.MATH_TF32, lib.MATH_3XTF32], ids=["tf32", "3xtf32"])
+@pytest.mark.parametrize("cfg", BENCH_SIZE, ids=[c[0] for c in BENCH_SIZE])
+def test_bench_size_layers_against_the_oracle(cfg, math):
+    """The GPU runs the FULL layer exactly as bench.py does; the oracle (fp64 restatement of TensorOpCpu.cpp:1012-1184) checks
+      * the kernel gradient on a filter x channel subset: dw[k, c] depends only on dy[:, k] and x[:, c], so the oracle is given
+        those planes alone -- same 2.1 M-term reduction per element, a few hundred MFLOP instead of 155 GFLOP;
+      * forward and input gradient on row bands that include the top and bottom padding rows and an image boundary.
+    Bounds: TF32 2e-3, 3xTF32 1e-5 max-normalised (BASELINE.json north_star), normalised by the full tensor's maximum."""
+    _, N, C, H, W, K = cfg
+    F, st, p = 3, 1, 1
+    x, w, dy = make_inputs(lib.NCHW, N, C, H, W, K, F, F, st, p, p, glorot=True)
+    y, dx, dw = run_all_three(TensorOpB200(math), lib.NCHW, x, w, dy, st, p, p)
+    tol = TOL[math]
+    ks = [0, K // 2 + 1, K - 1]
+    cs = sorted(set([0, C // 2, C - 1]))
+    xs = np.ascontiguousarray(x[:, cs]); dys = np.ascontiguousarray(dy[:, ks])
+    dw64 = O.conv2d_kernels_gradient(xs, dys, st, p, p, (F, F), f64=True)
+    got = dw[np.ix_(ks, cs)]
+    assert float(np.abs(got.astype(np.float64) - dw64).max()) <= tol * float(np.abs(dw64).max())
+    # forward bands: rows [0, 4) (top padding), [H-4, H) (bottom padding) of the first and last image
+    for n in (0, N - 1):
+        for (r0, r1, pt, pb) in ((0, 4, 1, 0), (H - 4, H, 0, 1)):
+            lo, hi = max(0, r0 - 1), min(H, r1 + 1)
+            xb = np.pad(x[n:n + 1, :, lo:hi, :], ((0, 0), (0, 0), (pt, pb), (0, 0)))
+            band = O.conv2d(np.ascontiguousarray(xb), w, 1, 1, 0, f64=True)
+            assert band.shape[2] == r1 - r0
+            assert float(np.abs(y[n:n + 1, :, r0:r1, :].astype(np.float64) - band).max()) <= tol * float(np.abs(band).max())
+            # input gradient of the same rows: dx rows [r0, r1) see dy rows [r0-1, r1+1)
+            dyb = np.pad(dy[n:n + 1, :, lo:hi, :], ((0, 0), (0, 0), (pt, pb), (0, 0)))
+            full = O.conv2d_input_gradient(np.ascontiguousarray(dyb), w, 1, 1, 1, (dyb.shape[2], W), f64=True)
+            ref = full[:, :, 1:1 + (r1 - r0), :]
+            assert float(np.abs(dx[n:n + 1, :, r0:r1, :].astype(np.float64) - ref).max()) <= tol * float(np.abs(full).max())
+
+
+def test_full_layer_element_for_element_with_the_compiled_reference():
+    """One whole BASELINE layer (VGG16 block5: 512 -> 512 @ 32x32, 4.8 GFLOP per op) against the REFERENCE'S OWN
+    TensorOpCpuMt ops (oracle/_ref, compiled unmodified from the reference sources) -- every element of y, dx and dw."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built")
+    N, C, H, W, K, F, st, p = 1, 512, 32, 32, 512, 3, 1, 1
+    x, w, dy = make_inputs(lib.NCHW, N, C, H, W, K, F, F, st, p, p, glorot=True)
+    O.ref_set_threads(0)
+    yr = O.ref_conv2d(x, w, st, p, p, mt=True)
+    dxr = O.ref_conv2d_input_gradient(dy, w, st, p, p, (H, W), mt=True)
+    dwr = O.ref_conv2d_kernels_gradient(x, dy, st, p, p, (F, F), mt=True)
+    for math in (lib.MATH_TF32, lib.MATH_3XTF32):
+        y, dx, dw = run_all_three(TensorOpB200(math), lib.NCHW, x, w, dy, st, p, p)
+        tol = TOL[math]
+        assert max_norm_err(y, yr) <= tol and max_norm_err(dx, dxr) <= tol
+        # the reference's fp32 running sum over 1024 pixels is itself ~1e-6 off; the 3xTF32 bound still holds against it
+        assert max_norm_err(dw, dwr) <= tol
