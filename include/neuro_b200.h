@@ -140,6 +140,14 @@ NB200_API int nb200_conv2d_bias_activation_gradient(const nb200_conv_desc* d, in
                                                     const float* dy, float* dz, float* db, void* workspace,
                                                     size_t workspace_bytes, void* stream);
 
+/* y = act(x + bias[k]) over an (N,K,Ho,Wo) tensor in d->fmt (only those fields of the descriptor are read); bias may be
+ * NULL, y may alias x. One pass for the bias AddOp (Neuro/src/ComputationalGraph/Operations/AddOp.cpp:38-50) and the
+ * Activation layer's forward (Tensor::Activation -> TensorOpCpu.cpp:807-864) of layers whose convolution cannot carry
+ * them in its epilogue -- a BatchNormalization sits between the conv and the activation in the GAN / pix2pix stacks
+ * (Neuro.Examples/src/DeepConvGAN.cpp:3-43, Pix2Pix.cpp:4-109). Its gradient is nb200_conv2d_bias_activation_gradient. */
+NB200_API int nb200_bias_activation(const nb200_conv_desc* d, const float* x, const float* bias, int32_t act, float alpha,
+                                    float* y, void* stream);
+
 /* Filters that do not change between calls (inference; style transfer runs forward and input gradient against frozen
  * VGG weights, Neuro.Examples/include/NeuralStyleTransfer.h). The tensor-core kernels read the filters from a repacked
  * TF32 copy at the head of the workspace; nb200_conv2d_forward / _input_gradient rebuild it on every call because the

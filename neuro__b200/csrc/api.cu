@@ -397,6 +397,23 @@ extern "C"
         return bias_activation_gradient(*d, act, alpha, y, dy, dz, db, workspace, workspace_bytes, (cudaStream_t)stream);
     }
 
+    int nb200_bias_activation(const nb200_conv_desc* d, const float* x, const float* bias, int32_t act, float alpha, float* y, void* stream)
+    {
+        if (!d || d->N < 0 || d->K < 0 || d->Ho < 0 || d->Wo < 0 || (d->fmt != NB200_NCHW && d->fmt != NB200_NHWC))
+            return fail(NB200_E_INVALID, "bad descriptor");
+        if (act < NB200_ACT_IDENTITY || act > NB200_ACT_LEAKY_RELU)
+            return fail(NB200_E_INVALID, "activation %d is not elementwise", act);
+        if (!fits_u32(d->N, d->K, d->Ho, d->Wo))
+            return fail(NB200_E_INVALID, "tensor exceeds 2^32-1 elements");
+        if ((long long)d->N * d->K * d->Ho * d->Wo == 0)
+            return NB200_OK;
+        if (!x || !y)
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        int rc = require_device();
+        if (rc) return rc;
+        return bias_activation(*d, x, bias, act, alpha, y, (cudaStream_t)stream);
+    }
+
     namespace
     {
         struct FilterModeScope

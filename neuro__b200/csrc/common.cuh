@@ -133,6 +133,8 @@ namespace nb200
     size_t bias_activation_gradient_workspace(const nb200_conv_desc& d);
     int bias_activation_gradient(const nb200_conv_desc& d, int act, float alpha, const float* y, const float* dy, float* dz, float* db,
                                  void* ws, size_t wsBytes, cudaStream_t st);
+    // y = act(x + bias): bias add + activation forward as one pass (layers whose conv epilogue cannot carry them)
+    int bias_activation(const nb200_conv_desc& d, const float* x, const float* bias, int act, float alpha, float* y, cudaStream_t st);
     int adam_step(float* p, const float* g, float* m, float* v, size_t n, float gs, float lr, float b1, float b2, float eps,
                   cudaStream_t st);
     int sgd_step(float* p, const float* g, size_t n, float gs, float lr, cudaStream_t st);

@@ -193,6 +193,49 @@ namespace nb200
             return NB200_OK;
         }
 
+        // y = act(x + bias[k]): the bias AddOp (Operations/AddOp.cpp:38-50) and the Activation layer's forward
+        // (TensorOpCpu.cpp:807-864) in one pass, for convolutions whose epilogue cannot carry them (a BatchNormalization sits
+        // between the convolution and its activation in the GAN / pix2pix stacks). Bound: HBM, 8 bytes per element.
+        template <bool VEC>
+        __global__ void bias_activation_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y, long long n,
+                                               int K, int HW, int nchw, int act, float alpha)
+        {
+            const long long stride = (long long)gridDim.x * blockDim.x;
+            if (VEC)
+            {
+                for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i * 4 < n; i += stride)
+                {
+                    float4 q = __ldcs(reinterpret_cast<const float4*>(x) + i);
+                    if (bias)
+                    {
+                        if (nchw)
+                        {
+                            const float b = __ldg(bias + (int)(((i * 4) / HW) % K)); // HW % 4 == 0: one channel per float4
+                            q.x += b; q.y += b; q.z += b; q.w += b;
+                        }
+                        else
+                        {
+                            const int k = (int)((i * 4) % K);                          // K % 4 == 0
+                            q.x += __ldg(bias + k); q.y += __ldg(bias + k + 1); q.z += __ldg(bias + k + 2); q.w += __ldg(bias + k + 3);
+                        }
+                    }
+                    q.x = apply_activation(act, alpha, q.x); q.y = apply_activation(act, alpha, q.y);
+                    q.z = apply_activation(act, alpha, q.z); q.w = apply_activation(act, alpha, q.w);
+                    reinterpret_cast<float4*>(y)[i] = q;
+                }
+            }
+            else
+            {
+                for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+                {
+                    float v = x[i];
+                    if (bias)
+                        v += __ldg(bias + (nchw ? (int)((i / HW) % K) : (int)(i % K)));
+                    y[i] = apply_activation(act, alpha, v);
+                }
+            }
+        }
+
         // TensorOpCpu::AdamStep (TensorOpCpu.cpp:987-1003) with the gradient pre-scale folded in.
         __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                          float* __restrict__ v, size_t n, float gs, float lr, float b1, float b2, float eps)
@@ -252,6 +295,26 @@ namespace nb200
         case NB200_ACT_LEAKY_RELU: return launch_act_bias_gradient<NB200_ACT_LEAKY_RELU>(d, alpha, y, dy, dz, db, partial, st);
         default: return launch_act_bias_gradient<NB200_ACT_IDENTITY>(d, alpha, y, dy, dz, db, partial, st);
         }
+    }
+
+    int bias_activation(const nb200_conv_desc& d, const float* x, const float* bias, int act, float alpha, float* y, cudaStream_t st)
+    {
+        const int HW = d.Ho * d.Wo;
+        const long long n = (long long)d.N * d.K * HW;
+        if (n == 0)
+            return NB200_OK;
+        const int nchw = d.fmt == NB200_NCHW;
+        const bool vec = ((nchw ? HW : d.K) % 4 == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
+        const long long work = vec ? n / 4 : n;
+        const long long blocks = (work + 255) / 256;
+        const unsigned grid = (unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks);
+        if (vec)
+            bias_activation_kernel<true><<<grid, 256, 0, st>>>(x, bias, y, n, d.K, HW, nchw, act, alpha);
+        else
+            bias_activation_kernel<false><<<grid, 256, 0, st>>>(x, bias, y, n, d.K, HW, nchw, act, alpha);
+        NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        return NB200_OK;
     }
 
     int adam_step(float* p, const float* g, float* m, float* v, size_t n, float gs, float lr, float b1, float b2, float eps,

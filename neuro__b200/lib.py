@@ -23,7 +23,7 @@ EXPORTS = [
     "nb200_conv2d_bias_activation_gradient_workspace_bytes", "nb200_conv2d_bias_activation_gradient",
     "nb200_conv2d_prepare_filters", "nb200_conv2d_forward_prepared", "nb200_conv2d_input_gradient_prepared",
     "nb200_pool2d", "nb200_pool2d_gradient", "nb200_upsample2d", "nb200_upsample2d_gradient", "nb200_constant_pad2d",
-    "nb200_batch_norm_groups", "nb200_batch_norm_workspace_bytes", "nb200_batch_norm", "nb200_batch_norm_train",
+    "nb200_bias_activation", "nb200_batch_norm_groups", "nb200_batch_norm_workspace_bytes", "nb200_batch_norm", "nb200_batch_norm_train",
     "nb200_batch_norm_gradient", "nb200_batch_norm_moments", "nb200_batch_norm_train_from_moments",
     "nb200_batch_norm_gradient_sums", "nb200_batch_norm_gradient_from_sums",
 ]
@@ -100,6 +100,7 @@ def load():
     L.nb200_conv2d_bias_activation_gradient_workspace_bytes.argtypes = [dp]
     L.nb200_conv2d_bias_activation_gradient_workspace_bytes.restype = c_sz
     L.nb200_conv2d_bias_activation_gradient.argtypes = [dp, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]
+    L.nb200_bias_activation.argtypes = [dp, c_p, c_p, c_i, c_f, c_p, c_p]
     L.nb200_conv2d_prepare_filters.argtypes = [c_i, dp, c_p, c_p, c_sz, c_p]
     L.nb200_conv2d_forward_prepared.argtypes = L.nb200_conv2d_forward.argtypes
     L.nb200_conv2d_input_gradient_prepared.argtypes = L.nb200_conv2d_input_gradient.argtypes

@@ -156,6 +156,13 @@ class TensorOpB200:
                                                             _ptr(outputGradient), _ptr(activationInputGradient),
                                                             _ptr(biasGradient), ws, need, _stream()))
 
+    def BiasActivation(self, input, bias, activation, activationAlpha, output, dataFormat=NCHW):
+        """output = act(input + bias): AddOp (AddOp.cpp:38-50) + Tensor::Activation (TensorOpCpu.cpp:807-864) in one pass;
+        bias may be None, output may be input."""
+        N, K, Ho, Wo = _act_extent(dataFormat, input)
+        d = ConvDesc(N, 0, 0, 0, K, 1, 1, Ho, Wo, 1, 0, 0, dataFormat, self.math)
+        check(self._L.nb200_bias_activation(ctypes.byref(d), _ptr(input), _ptr(bias), activation, activationAlpha, _ptr(output), _stream()))
+
     def Conv2DBiasGradient(self, gradient, biasGradient, dataFormat=NCHW):
         N, K, Ho, Wo = _act_extent(dataFormat, gradient)
         d = ConvDesc(N, 0, 0, 0, K, 1, 1, Ho, Wo, 1, 0, 0, dataFormat, self.math)

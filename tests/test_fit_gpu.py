@@ -71,3 +71,48 @@ def test_strided_stack_loss_curve_tracks_reference(math, tol):
     assert rel.max() <= tol, (losses, ref_losses)
     assert ref_losses[-1] < ref_losses[0]
     assert np.abs(params - ref_params).max() <= (5e-3 if math == lib.MATH_TF32 else 1e-5)
+
+
+# DeepConvGAN-like stack (Neuro.Examples/src/DeepConvGAN.cpp:3-43; BASELINE configs[1]): strided convolutions with a
+# BatchNormalization between conv(+bias) and LeakyReLU, up-sampling + convolution and a transposed convolution on the generator
+# side, max pooling -- every layer kind ConvStackTrainer knows, through the CUDA kernels.
+from neuro__b200.fit import PoolSpec, UpSampleSpec  # noqa: E402
+
+BN_LAYERS = [ConvLayerSpec(16, 3, 2, 1, lib.ACT_LEAKY_RELU, 0.2, batch_norm=True),            # 1x28x28 -> 16x14x14
+             ConvLayerSpec(32, 3, 1, 1, lib.ACT_RELU, batch_norm=True),                       # 32x14x14
+             PoolSpec(2, 2, 0, lib.POOL_MAX),                                                  # 32x7x7
+             UpSampleSpec(2),                                                                  # 32x14x14
+             ConvLayerSpec(16, 4, 2, 1, lib.ACT_RELU, batch_norm=True, transposed=True),       # 16x28x28
+             ConvLayerSpec(1, 3, 1, 1, lib.ACT_TANH)]                                          # 1x28x28
+BN_IN = (1, 28, 28)
+
+
+def _run_bn(op, device, use_graph=False):
+    tr = ConvStackTrainer(op, BN_IN, BN_LAYERS, device, optimizer="adam", lr=0.002, use_graph=use_graph)
+    assert tr.out_shape == (1, 28, 28)
+    x = torch.from_numpy(synth.uniform(synth.SEED_X, (16,) + BN_IN))
+    t = torch.from_numpy(synth.uniform(synth.SEED_DY, (16,) + tr.out_shape, -0.5, 0.5))
+    losses = tr.fit(x, t, 8, epochs=4)
+    return losses, tr.params.detach().cpu().numpy(), [v["rvar"].cpu().numpy() for v in tr.views if v and "rvar" in v]
+
+
+@pytest.mark.parametrize("math,tol", [(lib.MATH_TF32, 5e-3), (lib.MATH_FP32, 2e-4)], ids=["tf32", "fp32"])
+def test_batch_norm_gan_stack_loss_curve_tracks_reference(math, tol):
+    ref_losses, ref_params, ref_rvar = _run_bn(OracleOp(), torch.device("cpu"))
+    losses, params, rvar = _run_bn(TensorOpB200(math), torch.device("cuda", 0))
+    rel = np.abs(np.array(losses) - np.array(ref_losses)) / np.abs(np.array(ref_losses))
+    assert rel.max() <= tol, (losses, ref_losses)
+    assert ref_losses[-1] < ref_losses[0]
+    for a, b in zip(rvar, ref_rvar):   # running statistics follow the reference's update rule
+        assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max())
+
+
+def test_cuda_graph_step_is_the_eager_step():
+    """use_graph=True replays forward + backward as one CUDA graph over the static buffers: same kernels, same order, so the
+    loss curve and the parameters are bit-identical to issuing the calls one by one."""
+    eager = _run_bn(TensorOpB200(lib.MATH_TF32), torch.device("cuda", 0), use_graph=False)
+    graph = _run_bn(TensorOpB200(lib.MATH_TF32), torch.device("cuda", 0), use_graph=True)
+    assert eager[0] == graph[0]
+    assert np.array_equal(eager[1], graph[1])
+    # running statistics: the graph path advanced them three extra times during warm-up / capture (documented in fit.py)
+    assert all(np.isfinite(a).all() for a in graph[2])
