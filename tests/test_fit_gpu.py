@@ -103,8 +103,11 @@ def test_batch_norm_gan_stack_loss_curve_tracks_reference(math, tol):
     rel = np.abs(np.array(losses) - np.array(ref_losses)) / np.abs(np.array(ref_losses))
     assert rel.max() <= tol, (losses, ref_losses)
     assert ref_losses[-1] < ref_losses[0]
-    for a, b in zip(rvar, ref_rvar):   # running statistics follow the reference's update rule
-        assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max())
+    # running statistics follow the reference's update rule; with momentum 0.99 they are essentially the LAST step's batch variance,
+    # i.e. a function of parameters that 8 Adam steps (1/sqrt(v) amplifies TF32-sized gradient differences, see above) moved apart
+    rtol = 3e-2 if math == lib.MATH_TF32 else 1e-3
+    for a, b in zip(rvar, ref_rvar):
+        assert np.abs(a - b).max() <= rtol * max(1.0, np.abs(b).max())
 
 
 def test_cuda_graph_step_is_the_eager_step():
