@@ -1606,6 +1606,7 @@ namespace nb200
             float* partial;
             long long partialStride;
             short iyAdd[32], ixAdd[32], wtap[32];
+            int dbgFlags; // NB200_GATHER_DEBUG ablations (profiling only): 1 no gather loads, 2 no output stores, 4 empty body, 8 no TMEM either
         };
 
         // Several pixel lists served by ONE launch: the stride^2 parity classes of a strided input gradient (transposed
@@ -1660,7 +1661,8 @@ namespace nb200
                 ptx::mbar_init(accBar, 1);
                 ptx::fence_mbar_init();
             }
-            if (warp == 1)
+            const int dbgFlags = p.dbgFlags;
+            if (warp == 1 && !(dbgFlags & 8))
                 ptx::tmem_alloc(tmemSlot, kTmemCols);
             ptx::tc_fence_before_sync();
             __syncthreads();
@@ -1669,7 +1671,11 @@ namespace nb200
             const uint32_t tmemA = tmemAcc + BN;
             const int iters = p.ntaps * max(cbEnd - cbBegin, 0);
 
-            if (warp == 0)
+            if (dbgFlags & 12)
+            {
+                // profiling: launch + prologue + teardown only
+            }
+            else if (warp == 0)
             {
                 if (lane == 0)
                 {
@@ -1734,7 +1740,7 @@ namespace nb200
                 {
                     const int cbRel = it / p.ntaps, t = it - cbRel * p.ntaps;
                     const int iy = a * p.iyMul + p.iyAdd[t], ix = b * p.ixMul + p.ixAdd[t];
-                    const bool ok = pixOk && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                    const bool ok = pixOk && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && !(dbgFlags & 1);
                     const int cbase = (cbBegin + cbRel) * kBlockC;
                     uint32_t v[kBlockC];
                     if (ok)
@@ -1785,7 +1791,7 @@ namespace nb200
 
                 // ----- epilogue -----
                 const int oy = a * p.oyMul + p.oyAdd, ox = b * p.oxMul + p.oxAdd;
-                const bool outOk = pixOk && oy < p.Ho && ox < p.Wo;
+                const bool outOk = pixOk && oy < p.Ho && ox < p.Wo && !(dbgFlags & 2);
                 const long long oplane = (long long)p.Ho * p.Wo;
                 const bool raw = p.splits > 1; // partial sums: no bias, no activation
                 float* op = (raw ? p.partial + split * p.partialStride : out) + n * p.K * oplane + (long long)oy * p.Wo + ox;
@@ -1832,7 +1838,7 @@ namespace nb200
 
             ptx::tc_fence_before_sync();
             __syncthreads();
-            if (warp == 1)
+            if (warp == 1 && !(dbgFlags & 8))
             {
                 ptx::tc_fence_after_sync();
                 ptx::tmem_dealloc(tmemAcc, kTmemCols);
@@ -3542,6 +3548,12 @@ namespace nb200
     }
 
 
+    static int gather_debug_flags()
+    {
+        static const char* env = getenv("NB200_GATHER_DEBUG");
+        return env ? atoi(env) : 0;
+    }
+
     // ---- gather kernel entry points ----
     bool tc_gather_forward_supported(const nb200_conv_desc& d) { return gather_ok(d); }
     bool tc_gather_input_gradient_supported(const nb200_conv_desc& d) { return gather_ok(d); }
@@ -3577,6 +3589,7 @@ namespace nb200
         p.PH = d.Ho; p.PW = d.Wo; p.oyMul = 1; p.oyAdd = 0; p.oxMul = 1; p.oxAdd = 0; p.iyMul = d.stride; p.ixMul = d.stride;
         p.totalPix = (long long)d.N * d.Ho * d.Wo;
         p.tilesK = ceil_div(d.K, BN); p.bStages = bStages; p.act = act; p.alpha = alpha;
+        p.dbgFlags = gather_debug_flags();
         for (int r = 0; r < d.R; ++r)
             for (int s2 = 0; s2 < d.S; ++s2)
             {
@@ -3615,6 +3628,7 @@ namespace nb200
                 p.oyMul = st2; p.oyAdd = ph; p.oxMul = st2; p.oxAdd = pw; p.iyMul = 1; p.ixMul = 1;
                 p.totalPix = (long long)d.N * p.PH * p.PW;
                 p.tilesK = ceil_div(d.C, BN); p.bStages = bStages; p.act = NB200_ACT_IDENTITY; p.alpha = 0.f;
+                p.dbgFlags = gather_debug_flags();
                 int nt = 0;
                 // taps that reach this parity class: (ph + padY - r) divisible by the stride (and likewise in x)
                 for (int r = 0; r < d.R; ++r)

@@ -4,8 +4,10 @@ Times forward, input gradient and kernel gradient of synthetic layers whose ITER
 varies while the grid stays the same, replayed as a CUDA graph of 20 calls (GPU time only). A straight-line fit over the
 iteration count separates launch + prologue + epilogue (intercept) from the per-iteration chain (slope).
 
-  python tools/floor_probe.py
+  python tools/floor_probe.py            # the table
+  NB200_GATHER_DEBUG=<flags> python tools/floor_probe.py ablate
 """
+import os
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -50,22 +52,35 @@ def probe(tag, N, C, H, K, F, st, p):
           (tag, iters, d.flops() / 1e9, op.kernel_name(0, d), t[0] * 1e3, op.kernel_name(1, d), t[1] * 1e3, op.kernel_name(2, d), t[2] * 1e3), flush=True)
 
 
-# empty-kernel floor of a graph node on this box
-a = torch.zeros(1024, device="cuda")
-print("graph node floor (torch fill_ of 4 KB): %.1f us" % (graph_ms(lambda: a.fill_(1.0)) * 1e3))
-# gathered kernel, fixed grid (M = 128*4*4 = 2048 pixels = 16 tiles), growing reduction
-for C in (32, 64, 128, 256, 512):
-    probe("gather s2 @8 N128 C%d K128 3x3" % C, 128, C, 8, 128, 3, 2, 1)
-for C in (32, 128, 512):
-    probe("gather s2 @8 N128 C%d K128 1x1" % C, 128, C, 8, 128, 1, 2, 0)
-# gathered kernel, a full wave (M = 128*16*16 = 32768 pixels = 256 tiles)
-for C in (32, 128, 512):
-    probe("gather s2 @32 N128 C%d K128 3x3" % C, 128, C, 32, 128, 3, 2, 1)
-# halo-tile kernel at batch 1 (style transfer): 64x64 map = 32 tiles per filter tile
-for C in (32, 128, 512):
-    probe("halo s1 @64 N1 C%d K256 3x3" % C, 1, C, 64, 256, 3, 1, 1)
-for C in (32, 128, 512):
-    probe("halo s1 @64 N1 C%d K256 1x1" % C, 1, C, 64, 256, 1, 1, 0)
-# halo-tile kernel, full waves
-for C in (32, 128, 512):
-    probe("halo s1 @128 N4 C%d K256 3x3" % C, 4, C, 128, 256, 3, 1, 1)
+def run_table(which):
+    # empty-kernel floor of a graph node on this box
+    a = torch.zeros(1024, device="cuda")
+    print("graph node floor (torch fill_ of 4 KB): %.1f us" % (graph_ms(lambda: a.fill_(1.0)) * 1e3))
+    if which == "ablate":
+        # attribute the gathered kernel's fixed cost: run once per NB200_GATHER_DEBUG value (read once per process):
+        # 0 full | 1 no gather loads | 2 no output stores | 3 neither | 4 empty body (launch + barrier init + TMEM alloc/free) | 12 no TMEM either
+        print("NB200_GATHER_DEBUG=%s" % os.environ.get("NB200_GATHER_DEBUG", "0"))
+        probe("gather s2 @8 N128 C32 K128 1x1", 128, 32, 8, 128, 1, 2, 0)
+        probe("gather s2 @8 N128 C128 K128 3x3", 128, 128, 8, 128, 3, 2, 1)
+        probe("gather s2 @32 N128 C128 K128 3x3", 128, 128, 32, 128, 3, 2, 1)
+        return
+    # gathered kernel, fixed grid (M = 128*4*4 = 2048 pixels = 16 tiles), growing reduction
+    for C in (32, 64, 128, 256, 512):
+        probe("gather s2 @8 N128 C%d K128 3x3" % C, 128, C, 8, 128, 3, 2, 1)
+    for C in (32, 128, 512):
+        probe("gather s2 @8 N128 C%d K128 1x1" % C, 128, C, 8, 128, 1, 2, 0)
+    # gathered kernel, a full wave (M = 128*16*16 = 32768 pixels = 256 tiles)
+    for C in (32, 128, 512):
+        probe("gather s2 @32 N128 C%d K128 3x3" % C, 128, C, 32, 128, 3, 2, 1)
+    # halo-tile kernel at batch 1 (style transfer): 64x64 map = 32 tiles per filter tile
+    for C in (32, 128, 512):
+        probe("halo s1 @64 N1 C%d K256 3x3" % C, 1, C, 64, 256, 3, 1, 1)
+    for C in (32, 128, 512):
+        probe("halo s1 @64 N1 C%d K256 1x1" % C, 1, C, 64, 256, 1, 1, 0)
+    # halo-tile kernel, full waves
+    for C in (32, 128, 512):
+        probe("halo s1 @128 N4 C%d K256 3x3" % C, 4, C, 128, 256, 3, 1, 1)
+
+
+if __name__ == "__main__":
+    run_table(sys.argv[1] if len(sys.argv) > 1 else "all")
