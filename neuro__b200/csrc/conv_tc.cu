@@ -1591,6 +1591,7 @@ namespace nb200
         struct GatherParams
         {
             int Cblocks, ntaps;
+            int ntapsA;                     // class pair (tc_gather_kernel<BN, true>): taps [0, ntapsA) feed the first accumulator
             int C, H, W;                    // gathered tensor: channels, rows, cols
             int K, Ho, Wo;                  // produced tensor: channels, rows, cols
             int PH, PW;                     // pixel list extent per image
@@ -1606,6 +1607,7 @@ namespace nb200
             float* partial;
             long long partialStride;
             short iyAdd[32], ixAdd[32], wtap[32];
+            int smemSlack; // bytes the launch reserved for aligning the dynamic shared memory base to 1 KB
             int dbgFlags; // NB200_GATHER_DEBUG ablations (profiling only): 1 no gather loads, 2 no output stores, 4 empty body, 8 no TMEM either
         };
 
@@ -1619,24 +1621,84 @@ namespace nb200
             GatherParams cls[kGatherMaxClasses];
         };
 
-        template <int BN>
-        __global__ void __launch_bounds__(kFpropThreads, (BN > 128 ? 1 : 2))
+        // float2 variant of store_chunk for a class PAIR (see tc_gather_kernel): v0 / v1 are the two horizontally adjacent
+        // output pixels (2b, 2b + 1) of this thread, so 32 lanes write 256 contiguous bytes per channel -- whole sectors,
+        // where the two classes launched separately each wrote every other float of every sector.
+        template <int ACT>
+        __device__ __forceinline__ void store_chunk2_t(float* yp, long long strideK, int kBase, int K, float biasLane, int act, float alpha,
+                                                       bool pixelOk, const uint32_t (&v0)[32], const uint32_t (&v1)[32])
+        {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+            {
+                const float b = __shfl_sync(0xffffffffu, biasLane, j);
+                if (pixelOk && kBase + j < K)
+                {
+                    float2 f = make_float2(__uint_as_float(v0[j]) + b, __uint_as_float(v1[j]) + b);
+                    if constexpr (ACT == NB200_ACT_RELU) { f.x = f.x > 0.f ? f.x : 0.f; f.y = f.y > 0.f ? f.y : 0.f; }
+                    else if constexpr (ACT == NB200_ACT_LEAKY_RELU) { f.x = f.x >= 0.f ? f.x : alpha * f.x; f.y = f.y >= 0.f ? f.y : alpha * f.y; }
+                    else if constexpr (ACT != NB200_ACT_IDENTITY) { f.x = apply_activation(act, alpha, f.x); f.y = apply_activation(act, alpha, f.y); }
+                    *reinterpret_cast<float2*>(yp + (long long)(kBase + j) * strideK) = f;
+                }
+            }
+        }
+
+        __device__ __forceinline__ void store_chunk2(float* yp, long long strideK, int kBase, int K, const float* __restrict__ bias, int lane,
+                                                     int act, float alpha, bool pixelOk, const uint32_t (&v0)[32], const uint32_t (&v1)[32])
+        {
+            const float bl = (bias && kBase + lane < K) ? __ldg(bias + kBase + lane) : 0.f;
+            switch (act)
+            {
+            case NB200_ACT_IDENTITY: store_chunk2_t<NB200_ACT_IDENTITY>(yp, strideK, kBase, K, bl, act, alpha, pixelOk, v0, v1); break;
+            case NB200_ACT_RELU: store_chunk2_t<NB200_ACT_RELU>(yp, strideK, kBase, K, bl, act, alpha, pixelOk, v0, v1); break;
+            case NB200_ACT_LEAKY_RELU: store_chunk2_t<NB200_ACT_LEAKY_RELU>(yp, strideK, kBase, K, bl, act, alpha, pixelOk, v0, v1); break;
+            default: store_chunk2_t<-1>(yp, strideK, kBase, K, bl, act, alpha, pixelOk, v0, v1); break;
+            }
+        }
+
+        // (A version that staged the gathers through per-thread cp.async FIFOs in shared memory -- 2-4 iterations in flight per
+        // converter group instead of one -- was parity-clean but no faster: the gathers are bound by L1 wavefronts / LSU issue,
+        // not by latency, and the read-back doubled the LSU work: 42.6 vs 44.2 us on a 36-iteration full-wave layer, and 33.9
+        // vs 17.3 us with loads and stores ablated; profiles/r2_gather_ablate.txt.)
+        template <int BN, bool PAIR>
+        struct GatherCfg
+        {
+            static constexpr bool kOnePerSm = BN > 128 || PAIR;
+            static constexpr uint32_t kTmemCols = (BN > 128 || PAIR) ? 512 : 256;
+            static constexpr int kAStages = kOnePerSm ? (PAIR && BN > 64 ? 4 : 8) : 4;
+            static_assert((PAIR ? 2 : 1) * BN + kAStages * kBlockC <= (int)kTmemCols, "TMEM budget");
+        };
+
+        // PAIR: the CTA computes TWO pixel classes of a stride-2 input gradient (transposed convolution) for the same 128 list
+        // entries -- output columns 2b and 2b + 1 of row 2a + ph -- one after the other into two accumulators (taps [0, ntapsA)
+        // belong to the first class) and its epilogue interleaves them.
+        template <int BN, bool PAIR>
+        __global__ void __launch_bounds__(kFpropThreads, (GatherCfg<BN, PAIR>::kOnePerSm ? 1 : 2))
         tc_gather_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ GatherBatch batch, const float* __restrict__ in,
                          const float* __restrict__ bias, float* __restrict__ out)
         {
+            using Cfg = GatherCfg<BN, PAIR>;
             int cls = 0;
             while (cls + 1 < batch.count && (int)blockIdx.x >= batch.tileStart[cls + 1])
                 ++cls;
             const GatherParams& p = batch.cls[cls];
             const int bid = (int)blockIdx.x - batch.tileStart[cls];
             constexpr uint32_t kBBytes = BN * kBlockC * 4;
-            constexpr int kAStages = a_stages(BN);
-            constexpr uint32_t kTmemCols = BN > 128 ? 512 : 256;
+            constexpr int kAStages = Cfg::kAStages;
+            constexpr uint32_t kTmemCols = Cfg::kTmemCols;
 
             extern __shared__ uint8_t smemRaw[];
             uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
             uint8_t* bRing = smem;
             uint64_t* bars = (uint64_t*)(smem + p.bStages * kBBytes);
+            if ((uint32_t)(smem - smemRaw) > (uint32_t)p.smemSlack)
+            {
+                // two CTAs per SM leave no room for a full kilobyte of alignment slack (gather_smem): the launch relies on the
+                // dynamic shared memory window starting (nearly) 1 KB aligned, which holds for a kernel without static shared memory
+                if (threadIdx.x == 0)
+                    printf("nb200: tc_gather_kernel shared memory base misaligned by %u bytes (slack %d)\n", (uint32_t)(smem - smemRaw), p.smemSlack);
+                __trap();
+            }
             uint64_t* bFull = bars;
             uint64_t* bEmpty = bFull + 8;
             uint64_t* aFull = bEmpty + 8;
@@ -1648,10 +1710,11 @@ namespace nb200
             const int lane = threadIdx.x & 31;
             const int split = bid % p.splits;
             const int kt = (bid / p.splits) % p.tilesK;
-            const long long tile = bid / (p.splits * p.tilesK);
+            const int tile = bid / (p.splits * p.tilesK);
             const int k0 = kt * BN;
             const int cbBegin = split * p.cbPer;
             const int cbEnd = min(p.Cblocks, cbBegin + p.cbPer);
+            const int dbgFlags = p.dbgFlags;
 
             if (warp == 0 && lane == 0)
             {
@@ -1661,15 +1724,16 @@ namespace nb200
                 ptx::mbar_init(accBar, 1);
                 ptx::fence_mbar_init();
             }
-            const int dbgFlags = p.dbgFlags;
             if (warp == 1 && !(dbgFlags & 8))
                 ptx::tmem_alloc(tmemSlot, kTmemCols);
             ptx::tc_fence_before_sync();
             __syncthreads();
             ptx::tc_fence_after_sync();
             const uint32_t tmemAcc = *tmemSlot;
-            const uint32_t tmemA = tmemAcc + BN;
-            const int iters = p.ntaps * max(cbEnd - cbBegin, 0);
+            const uint32_t tmemA = tmemAcc + (PAIR ? 2 : 1) * BN;
+            const int nCb = max(cbEnd - cbBegin, 0);
+            const int iters = p.ntaps * nCb;
+            const int ntapsA = PAIR ? p.ntapsA : p.ntaps;
 
             if (dbgFlags & 12)
             {
@@ -1695,24 +1759,30 @@ namespace nb200
             {
                 constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, 0, 0);
                 const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(bRing), 16, 1024);
-                int as = 0, bs = 0;
+                int as = 0, bs = 0, t = 0;
                 uint32_t aph = 0, bph = 0;
+                bool first0 = true, first1 = true;   // the first MMA into an accumulator overwrites it
                 for (int it = 0; it < iters; ++it)
                 {
                     ptx::mbar_wait(&bFull[bs], bph);
                     ptx::mbar_wait(&aFull[as], aph);
                     ptx::tc_fence_after_sync();
+                    const bool second = PAIR && t >= ntapsA;
+                    const bool fresh = second ? first1 : first0;
                     if (ptx::elect_one())
                     {
                         const uint64_t db = descB0 + (uint64_t)((bs * kBBytes) >> 4);
                         const uint32_t ta = tmemA + as * kBlockC;
+                        const uint32_t acc = tmemAcc + (second ? BN : 0);
 #pragma unroll
                         for (int kk = 0; kk < kBlockC / 8; ++kk)
-                            ptx::mma_tf32_ts(tmemAcc, ta + kk * 8, db + kk * 2, idesc, (it | kk) != 0);
+                            ptx::mma_tf32_ts(acc, ta + kk * 8, db + kk * 2, idesc, !(fresh && kk == 0));
                         ptx::mma_commit(&aEmpty[as]);
                         ptx::mma_commit(&bEmpty[bs]);
                     }
                     __syncwarp();
+                    if (second) first1 = false; else first0 = false;
+                    if (++t == p.ntaps) t = 0;
                     if (++as == kAStages) { as = 0; aph ^= 1; }
                     if (++bs == p.bStages) { bs = 0; bph ^= 1; }
                 }
@@ -1725,14 +1795,14 @@ namespace nb200
                 const int q = warp & 3;
                 const int g = (warp - kFirstConvWarp) >> 2;
                 const uint32_t laneSel = (uint32_t)(q * 32) << 16;
-                // this thread's entry of the pixel list
-                const long long pix = tile * 128 + q * 32 + lane;
-                const bool pixOk = pix < p.totalPix;
-                const int b = (int)(pix % p.PW);
-                const int a = (int)((pix / p.PW) % p.PH);
-                const long long n = pix / ((long long)p.PW * p.PH);
+                // this thread's entry of the pixel list (32-bit arithmetic: lists beyond 2^31 entries are rejected on the host)
+                const int pix = tile * 128 + q * 32 + lane;
+                const bool pixOk = pix < (int)p.totalPix;
+                const int b = pix % p.PW;
+                const int a = (pix / p.PW) % p.PH;
+                const int n = pix / (p.PW * p.PH);
                 const long long plane = (long long)p.H * p.W;
-                const float* inN = in + n * p.C * plane;
+                const float* inN = in + (long long)n * p.C * plane;
 
                 bool pending = false;
                 int pendStage = 0;
@@ -1794,44 +1864,42 @@ namespace nb200
                 const bool outOk = pixOk && oy < p.Ho && ox < p.Wo && !(dbgFlags & 2);
                 const long long oplane = (long long)p.Ho * p.Wo;
                 const bool raw = p.splits > 1; // partial sums: no bias, no activation
-                float* op = (raw ? p.partial + split * p.partialStride : out) + n * p.K * oplane + (long long)oy * p.Wo + ox;
+                float* op = (raw ? p.partial + split * p.partialStride : out) + (long long)n * p.K * oplane + (long long)oy * p.Wo + ox;
+                const float* eb = raw ? nullptr : bias;
+                const int eact = raw ? NB200_ACT_IDENTITY : p.act;
                 ptx::mbar_wait(accBar, 0);
                 ptx::tc_fence_after_sync();
+                const bool have0 = nCb > 0 && ntapsA > 0, have1 = PAIR && nCb > 0 && p.ntaps > ntapsA;
 #pragma unroll 1
                 for (int c0 = g * 32; c0 < BN; c0 += 32 * kConvGroups)
                 {
                     if (k0 + c0 >= p.K)
                         break;
                     uint32_t v[32];
-                    if (iters > 0)
-                    {
+                    if (have0)
                         ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + c0, v);
-                        ptx::tmem_ld_wait();
-                    }
                     else
                     {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = 0u; // a pixel class no tap reaches (e.g. 1x1 filters, stride 2)
                     }
-                    if (outOk)
+                    if constexpr (PAIR)
                     {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
+                        uint32_t v1[32];
+                        if (have1)
+                            ptx::tmem_ld_32x32b_x32(tmemAcc + BN + laneSel + c0, v1);
+                        else
                         {
-                            const int k = k0 + c0 + j;
-                            if (k < p.K)
-                            {
-                                float f = __uint_as_float(v[j]);
-                                if (raw)
-                                {
-                                    op[k * oplane] = f;
-                                    continue;
-                                }
-                                if (bias)
-                                    f += __ldg(bias + k);
-                                op[k * oplane] = apply_activation(p.act, p.alpha, f);
-                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v1[j] = 0u;
                         }
+                        ptx::tmem_ld_wait();
+                        store_chunk2(op, oplane, k0 + c0, p.K, eb, lane, eact, p.alpha, outOk, v, v1);
+                    }
+                    else
+                    {
+                        ptx::tmem_ld_wait();
+                        store_chunk(op, oplane, k0 + c0, p.K, eb, lane, eact, p.alpha, outOk, v);
                     }
                 }
             }
@@ -3341,14 +3409,29 @@ namespace nb200
 
 
         // ---------------------------------------------------------------- gather kernel, host side
-        template <int BN>
-        int launch_gather(const CUtensorMap& mapW, const GatherBatch& b, int bStages, const float* in, const float* bias, float* out, cudaStream_t st)
+        // Shared memory of tc_gather_kernel<BN, PAIR>: filter ring + barriers (+ 1 KB to align the ring).
+        struct GatherSmem { int bStages, slack; size_t bytes; int maxBytes; };
+        GatherSmem gather_smem(int BN, bool pair)
         {
+            const bool onePerSm = BN > 128 || pair;
+            const long long cap = onePerSm ? kSmemBudget1 : kSmemBudget2;
+            GatherSmem g{};
+            g.slack = 1024;
+            g.maxBytes = (int)cap;
+            long long bs = (cap - g.slack - 512) / ((long long)BN * kBlockC * 4);
+            g.bStages = (int)(bs > 8 ? 8 : bs);
+            g.bytes = (size_t)(g.slack + 512 + (long long)g.bStages * BN * kBlockC * 4);
+            return g;
+        }
+
+        template <int BN, bool PAIR>
+        int launch_gather(const CUtensorMap& mapW, const GatherBatch& b, const float* in, const float* bias, float* out, cudaStream_t st)
+        {
+            const GatherSmem sm = gather_smem(BN, PAIR);
             static DeviceOnce attrSet{};
-            if (const int rcAttr = opt_in_smem(attrSet, tc_gather_kernel<BN>, BN > 128 ? kSmemBudget1 : kSmemBudget2)) return rcAttr;
+            if (const int rcAttr = opt_in_smem(attrSet, tc_gather_kernel<BN, PAIR>, sm.maxBytes)) return rcAttr;
             const long long tiles = b.tileStart[b.count];
-            const size_t smemBytes = 1024 + 512 + (size_t)bStages * BN * kBlockC * 4;
-            tc_gather_kernel<BN><<<(unsigned)tiles, kFpropThreads, smemBytes, st>>>(mapW, b, in, bias, out);
+            tc_gather_kernel<BN, PAIR><<<(unsigned)tiles, kFpropThreads, sm.bytes, st>>>(mapW, b, in, bias, out);
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             return NB200_OK;
@@ -3361,6 +3444,7 @@ namespace nb200
         struct GatherPlan
         {
             int BN, splits, cbPer, Cblocks;
+            bool pair; // stride-2 input gradient: the two column-parity classes of a row class share a CTA (whole-sector stores)
             long long outElems;
             size_t repackBytes, wsBytes;
         };
@@ -3371,8 +3455,15 @@ namespace nb200
             const bool fwd = op == NB200_OP_FORWARD;
             const int Kout = fwd ? d.K : d.C, Cin = fwd ? d.C : d.K;
             long long tilesM = 0;
+            {
+                static const char* pairEnv = getenv("NB200_GATHER_PAIR"); // 0 disables (profiling)
+                pl.pair = !fwd && d.stride == 2 && d.W % 2 == 0 && d.W >= 2 && !(pairEnv && pairEnv[0] == '0');
+            }
             if (fwd)
                 tilesM = ((long long)d.N * d.Ho * d.Wo + 127) / 128;
+            else if (pl.pair)
+                for (int ph = 0; ph < 2 && ph < d.H; ++ph)
+                    tilesM += ((long long)d.N * ((d.H - ph + 1) / 2) * (d.W / 2) + 127) / 128;
             else
                 for (int ph = 0; ph < d.stride && ph < d.H; ++ph)
                     for (int pw = 0; pw < d.stride && pw < d.W; ++pw)
@@ -3380,6 +3471,8 @@ namespace nb200
             const int Cp = round_up(Cin, kBlockC);
             pl.Cblocks = Cp / kBlockC;
             pl.BN = pick_bn(Kout);
+            if (pl.pair && pl.BN > 128)
+                pl.BN = 128; // two accumulators + the A ring in 512 TMEM columns
             pl.splits = 1;
             static const char* env = getenv("NB200_GATHER_SPLIT"); // 0 disables (profiling)
             if (!(env && env[0] == '0'))
@@ -3424,9 +3517,7 @@ namespace nb200
             cuuint32_t box[3] = {kBlockC, (cuuint32_t)*BN, 1};
             int rc = make_map(mapW, ws, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
             if (rc) return rc;
-            const long long budget = (*BN > 128 ? kSmemBudget1 : kSmemBudget2) - 1536;
-            int bs = (int)(budget / ((long long)*BN * kBlockC * 4));
-            *bStages = bs > 8 ? 8 : bs;
+            *bStages = gather_smem(*BN, pl.pair).bStages;
             *Cblocks = Cp / kBlockC;
             return NB200_OK;
         }
@@ -3443,29 +3534,31 @@ namespace nb200
         bool gather_batch_add(GatherBatch& b, const GatherParams& p)
         {
             const long long tiles = (p.totalPix + 127) / 128 * p.tilesK * p.splits;
-            if (b.count == kGatherMaxClasses || (long long)b.tileStart[b.count] + tiles > 0x3FFFFFFFll)
-                return false;
+            if (b.count == kGatherMaxClasses || (long long)b.tileStart[b.count] + tiles > 0x3FFFFFFFll || p.totalPix > 0x7FFF0000ll)
+                return false; // (the kernel indexes its pixel list with 32-bit integers)
             b.cls[b.count] = p;
             b.tileStart[b.count + 1] = b.tileStart[b.count] + (int)tiles;
             ++b.count;
             return true;
         }
 
-        int dispatch_gather(int BN, const CUtensorMap& mapW, const GatherBatch& b, int bStages, const float* in, const float* bias, float* out, cudaStream_t st)
+        int dispatch_gather(int BN, bool pair, const CUtensorMap& mapW, const GatherBatch& b, const float* in, const float* bias, float* out, cudaStream_t st)
         {
             if (b.count == 0 || b.tileStart[b.count] == 0)
                 return NB200_OK;
-            return BN == 64 ? launch_gather<64>(mapW, b, bStages, in, bias, out, st)
-                 : BN == 128 ? launch_gather<128>(mapW, b, bStages, in, bias, out, st)
-                             : launch_gather<256>(mapW, b, bStages, in, bias, out, st);
+            if (pair)
+                return BN == 64 ? launch_gather<64, true>(mapW, b, in, bias, out, st) : launch_gather<128, true>(mapW, b, in, bias, out, st);
+            return BN == 64 ? launch_gather<64, false>(mapW, b, in, bias, out, st)
+                 : BN == 128 ? launch_gather<128, false>(mapW, b, in, bias, out, st)
+                             : launch_gather<256, false>(mapW, b, in, bias, out, st);
         }
 
-        int dispatch_gather(int BN, const CUtensorMap& mapW, const GatherParams& p, int bStages, const float* in, const float* bias, float* out, cudaStream_t st)
+        int dispatch_gather(int BN, const CUtensorMap& mapW, const GatherParams& p, const float* in, const float* bias, float* out, cudaStream_t st)
         {
             GatherBatch b{};
             if (!gather_batch_add(b, p))
                 return fail(NB200_E_UNSUPPORTED, "too many tiles");
-            return dispatch_gather(BN, mapW, b, bStages, in, bias, out, st);
+            return dispatch_gather(BN, false, mapW, b, in, bias, out, st);
         }
 
         FwdShape fwd_shape(const nb200_conv_desc& d)
@@ -3590,13 +3683,15 @@ namespace nb200
         p.totalPix = (long long)d.N * d.Ho * d.Wo;
         p.tilesK = ceil_div(d.K, BN); p.bStages = bStages; p.act = act; p.alpha = alpha;
         p.dbgFlags = gather_debug_flags();
+        p.smemSlack = gather_smem(BN, false).slack;
+        p.ntapsA = d.R * d.S;
         for (int r = 0; r < d.R; ++r)
             for (int s2 = 0; s2 < d.S; ++s2)
             {
                 const int t = r * d.S + s2;
                 p.iyAdd[t] = (short)(r - d.padY); p.ixAdd[t] = (short)(s2 - d.padX); p.wtap[t] = (short)t;
             }
-        rc = dispatch_gather(BN, mapW, p, bStages, x, bias, y, st);
+        rc = dispatch_gather(BN, mapW, p, x, bias, y, st);
         if (rc) return rc;
         return gather_split_reduce(pl, ws, bias, act, alpha, y, (long long)d.Ho * d.Wo, d.K, st);
     }
@@ -3615,8 +3710,28 @@ namespace nb200
         static const char* batchEnv = getenv("NB200_GATHER_BATCH");
         const bool batched = !(batchEnv && batchEnv[0] == '0');
         GatherBatch batch{};
+        // taps that reach parity class (ph, pw): (ph + padY - r) divisible by the stride (and likewise in x); appended to p
+        auto add_taps = [&](GatherParams& p, int ph, int pw) {
+            int nt = p.ntaps;
+            for (int r = 0; r < d.R; ++r)
+            {
+                const int ty = ph + d.padY - r;
+                if (((ty % st2) + st2) % st2 != 0) continue;
+                for (int s2 = 0; s2 < d.S; ++s2)
+                {
+                    const int tx = pw + d.padX - s2;
+                    if (((tx % st2) + st2) % st2 != 0) continue;
+                    // exact division (ty, tx may be negative)
+                    p.iyAdd[nt] = (short)(ty >= 0 ? ty / st2 : -((-ty) / st2));
+                    p.ixAdd[nt] = (short)(tx >= 0 ? tx / st2 : -((-tx) / st2));
+                    p.wtap[nt] = (short)(r * d.S + s2);
+                    ++nt;
+                }
+            }
+            p.ntaps = nt;
+        };
         for (int ph = 0; ph < st2; ++ph)
-            for (int pw = 0; pw < st2; ++pw)
+            for (int pw = 0; pw < (pl.pair ? 1 : st2); ++pw)
             {
                 if (ph >= d.H || pw >= d.W)
                     continue;
@@ -3624,39 +3739,26 @@ namespace nb200
                 p.Cblocks = Cblocks;
                 p.splits = pl.splits; p.cbPer = pl.cbPer; p.partial = (float*)((uint8_t*)ws + pl.repackBytes); p.partialStride = pl.outElems;
                 p.C = d.K; p.H = d.Ho; p.W = d.Wo; p.K = d.C; p.Ho = d.H; p.Wo = d.W;
-                p.PH = (d.H - ph + st2 - 1) / st2; p.PW = (d.W - pw + st2 - 1) / st2;
+                p.PH = (d.H - ph + st2 - 1) / st2; p.PW = pl.pair ? d.W / 2 : (d.W - pw + st2 - 1) / st2;
                 p.oyMul = st2; p.oyAdd = ph; p.oxMul = st2; p.oxAdd = pw; p.iyMul = 1; p.ixMul = 1;
                 p.totalPix = (long long)d.N * p.PH * p.PW;
                 p.tilesK = ceil_div(d.C, BN); p.bStages = bStages; p.act = NB200_ACT_IDENTITY; p.alpha = 0.f;
                 p.dbgFlags = gather_debug_flags();
-                int nt = 0;
-                // taps that reach this parity class: (ph + padY - r) divisible by the stride (and likewise in x)
-                for (int r = 0; r < d.R; ++r)
-                {
-                    const int ty = ph + d.padY - r;
-                    if (((ty % st2) + st2) % st2 != 0) continue;
-                    for (int s2 = 0; s2 < d.S; ++s2)
-                    {
-                        const int tx = pw + d.padX - s2;
-                        if (((tx % st2) + st2) % st2 != 0) continue;
-                        // exact division (ty, tx may be negative)
-                        p.iyAdd[nt] = (short)(ty >= 0 ? ty / st2 : -((-ty) / st2));
-                        p.ixAdd[nt] = (short)(tx >= 0 ? tx / st2 : -((-tx) / st2));
-                        p.wtap[nt] = (short)(r * d.S + s2);
-                        ++nt;
-                    }
-                }
-                p.ntaps = nt;
+                p.smemSlack = gather_smem(BN, pl.pair).slack;
+                add_taps(p, ph, pw);
+                p.ntapsA = p.ntaps;
+                if (pl.pair)
+                    add_taps(p, ph, 1); // the class of output columns 2b + 1, into the second accumulator
                 if (batched && gather_batch_add(batch, p))
                     continue;
                 // batch full (stride > 3) or batching disabled: flush what is queued, then start over with this class
-                rc = dispatch_gather(BN, mapW, batch, bStages, dy, nullptr, dx, st);
+                rc = dispatch_gather(BN, pl.pair, mapW, batch, dy, nullptr, dx, st);
                 if (rc) return rc;
                 batch = GatherBatch{};
                 if (!gather_batch_add(batch, p))
                     return fail(NB200_E_UNSUPPORTED, "too many tiles");
             }
-        rc = dispatch_gather(BN, mapW, batch, bStages, dy, nullptr, dx, st);
+        rc = dispatch_gather(BN, pl.pair, mapW, batch, dy, nullptr, dx, st);
         if (rc) return rc;
         return gather_split_reduce(pl, ws, nullptr, NB200_ACT_IDENTITY, 0.f, dx, (long long)d.H * d.W, d.C, st);
     }

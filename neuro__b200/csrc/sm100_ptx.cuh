@@ -48,6 +48,23 @@ namespace nb200
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
         }
 
+        // Ampere-style asynchronous 4-byte gather copies (LDGSTS): global -> shared without holding a register while the load
+        // is in flight. srcBytes = 0 reads nothing and writes zeros (padding taps, ragged channels); `src` must still be a
+        // valid address. Completion is tracked per thread in commit groups.
+        __device__ __forceinline__ void cp_async_4(uint32_t smemDst, const void* src, uint32_t srcBytes)
+        {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smemDst), "l"(src), "r"(srcBytes) : "memory");
+        }
+        __device__ __forceinline__ void cp_async_commit()
+        {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        template <int N>
+        __device__ __forceinline__ void cp_async_wait()
+        {
+            asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+        }
+
         __device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d)
         {
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
