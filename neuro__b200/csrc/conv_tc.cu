@@ -1592,6 +1592,7 @@ namespace nb200
         {
             int Cblocks, ntaps;
             int ntapsA;                     // class pair (tc_gather_kernel<BN, true>): taps [0, ntapsA) feed the first accumulator
+            int tapsAll;                    // R * S of the filter (3xTF32: the lo parts start at this tap index of the repacked tensor)
             int C, H, W;                    // gathered tensor: channels, rows, cols
             int K, Ho, Wo;                  // produced tensor: channels, rows, cols
             int PH, PW;                     // pixel list extent per image
@@ -1660,31 +1661,38 @@ namespace nb200
         // converter group instead of one -- was parity-clean but no faster: the gathers are bound by L1 wavefronts / LSU issue,
         // not by latency, and the read-back doubled the LSU work: 42.6 vs 44.2 us on a 36-iteration full-wave layer, and 33.9
         // vs 17.3 us with loads and stores ablated; profiles/r2_gather_ablate.txt.)
-        template <int BN, bool PAIR>
+        template <int BN, bool PAIR, bool X3>
         struct GatherCfg
         {
-            static constexpr bool kOnePerSm = BN > 128 || PAIR;
-            static constexpr uint32_t kTmemCols = (BN > 128 || PAIR) ? 512 : 256;
-            static constexpr int kAStages = kOnePerSm ? (PAIR && BN > 64 ? 4 : 8) : 4;
-            static_assert((PAIR ? 2 : 1) * BN + kAStages * kBlockC <= (int)kTmemCols, "TMEM budget");
+            static_assert(!(PAIR && X3), "3xTF32 drains ONE accumulator per channel block");
+            static_assert(!X3 || BN <= 128, "3xTF32 keeps the running sums of BN / 2 filters in registers");
+            static constexpr bool kOnePerSm = BN > 128 || PAIR || X3;
+            static constexpr uint32_t kTmemCols = kOnePerSm ? 512 : 256;
+            static constexpr int kACols = X3 ? 2 * kBlockC : kBlockC;       // [hi | lo] A tiles
+            static constexpr int kAStages = X3 ? 4 : kOnePerSm ? (PAIR && BN > 64 ? 4 : 8) : 4;
+            static_assert((PAIR ? 2 : 1) * BN + kAStages * kACols <= (int)kTmemCols, "TMEM budget");
         };
 
         // PAIR: the CTA computes TWO pixel classes of a stride-2 input gradient (transposed convolution) for the same 128 list
         // entries -- output columns 2b and 2b + 1 of row 2a + ph -- one after the other into two accumulators (taps [0, ntapsA)
         // belong to the first class) and its epilogue interleaves them.
-        template <int BN, bool PAIR>
-        __global__ void __launch_bounds__(kFpropThreads, (GatherCfg<BN, PAIR>::kOnePerSm ? 1 : 2))
+        // X3 (NB200_MATH_3XTF32): operands split into hi + lo TF32 parts (filters in the repack, activations here), three MMAs per
+        // K slice, and the accumulation chain cut per channel block exactly as in tc_fprop_kernel<BN, true>.
+        template <int BN, bool PAIR, bool X3>
+        __global__ void __launch_bounds__(kFpropThreads, (GatherCfg<BN, PAIR, X3>::kOnePerSm ? 1 : 2))
         tc_gather_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ GatherBatch batch, const float* __restrict__ in,
                          const float* __restrict__ bias, float* __restrict__ out)
         {
-            using Cfg = GatherCfg<BN, PAIR>;
+            using Cfg = GatherCfg<BN, PAIR, X3>;
             int cls = 0;
             while (cls + 1 < batch.count && (int)blockIdx.x >= batch.tileStart[cls + 1])
                 ++cls;
             const GatherParams& p = batch.cls[cls];
             const int bid = (int)blockIdx.x - batch.tileStart[cls];
-            constexpr uint32_t kBBytes = BN * kBlockC * 4;
+            constexpr uint32_t kBTile = BN * kBlockC * 4;
+            constexpr uint32_t kBBytes = kBTile * (X3 ? 2 : 1);
             constexpr int kAStages = Cfg::kAStages;
+            constexpr int kACols = Cfg::kACols;
             constexpr uint32_t kTmemCols = Cfg::kTmemCols;
 
             extern __shared__ uint8_t smemRaw[];
@@ -1704,7 +1712,8 @@ namespace nb200
             uint64_t* aFull = bEmpty + 8;
             uint64_t* aEmpty = aFull + kAStagesMax;
             uint64_t* accBar = aEmpty + kAStagesMax;
-            uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
+            uint64_t* accFree = accBar + 1;    // 3xTF32 only: the accumulator has been drained into registers
+            uint32_t* tmemSlot = (uint32_t*)(accFree + 1);
 
             const int warp = threadIdx.x >> 5;
             const int lane = threadIdx.x & 31;
@@ -1722,6 +1731,7 @@ namespace nb200
                 for (int s = 0; s < p.bStages; ++s) { ptx::mbar_init(&bFull[s], 1); ptx::mbar_init(&bEmpty[s], 1); }
                 for (int s = 0; s < kAStages; ++s) { ptx::mbar_init(&aFull[s], kTileH); ptx::mbar_init(&aEmpty[s], 1); }
                 ptx::mbar_init(accBar, 1);
+                ptx::mbar_init(accFree, kTileH * kConvGroups);
                 ptx::fence_mbar_init();
             }
             if (warp == 1 && !(dbgFlags & 8))
@@ -1751,6 +1761,8 @@ namespace nb200
                             ptx::mbar_wait(&bEmpty[bs], bph ^ 1);
                             ptx::mbar_arrive_expect_tx(&bFull[bs], kBBytes);
                             ptx::tma_load_3d(bRing + bs * kBBytes, &mapW, &bFull[bs], cb * kBlockC, k0, p.wtap[t]);
+                            if (X3) // lo parts live behind the hi parts in the repacked tensor (tap index + all taps of the filter)
+                                ptx::tma_load_3d(bRing + bs * kBBytes + kBTile, &mapW, &bFull[bs], cb * kBlockC, k0, p.tapsAll + p.wtap[t]);
                             if (++bs == p.bStages) { bs = 0; bph ^= 1; }
                         }
                 }
@@ -1759,34 +1771,45 @@ namespace nb200
             {
                 constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, 0, 0);
                 const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(bRing), 16, 1024);
-                int as = 0, bs = 0, t = 0;
+                int as = 0, bs = 0, t = 0, cbc = 0;
                 uint32_t aph = 0, bph = 0;
                 bool first0 = true, first1 = true;   // the first MMA into an accumulator overwrites it
                 for (int it = 0; it < iters; ++it)
                 {
                     ptx::mbar_wait(&bFull[bs], bph);
                     ptx::mbar_wait(&aFull[as], aph);
+                    if (X3 && t == 0 && cbc > 0)
+                        ptx::mbar_wait(accFree, (uint32_t)(cbc - 1) & 1); // the previous block's partial sums are in registers
                     ptx::tc_fence_after_sync();
                     const bool second = PAIR && t >= ntapsA;
-                    const bool fresh = second ? first1 : first0;
+                    const bool fresh = X3 ? t == 0 : second ? first1 : first0;
                     if (ptx::elect_one())
                     {
                         const uint64_t db = descB0 + (uint64_t)((bs * kBBytes) >> 4);
-                        const uint32_t ta = tmemA + as * kBlockC;
+                        const uint32_t ta = tmemA + as * kACols;
                         const uint32_t acc = tmemAcc + (second ? BN : 0);
 #pragma unroll
                         for (int kk = 0; kk < kBlockC / 8; ++kk)
-                            ptx::mma_tf32_ts(acc, ta + kk * 8, db + kk * 2, idesc, !(fresh && kk == 0));
+                        {
+                            ptx::mma_tf32_ts(acc, ta + kk * 8, db + kk * 2, idesc, !(fresh && kk == 0));                       // hi * hi
+                            if (X3)
+                            {
+                                ptx::mma_tf32_ts(acc, ta + kk * 8, db + (kBTile >> 4) + kk * 2, idesc, 1);                     // hi * lo
+                                ptx::mma_tf32_ts(acc, ta + kBlockC + kk * 8, db + kk * 2, idesc, 1);                           // lo * hi
+                            }
+                        }
                         ptx::mma_commit(&aEmpty[as]);
                         ptx::mma_commit(&bEmpty[bs]);
+                        if (X3 && t == p.ntaps - 1)
+                            ptx::mma_commit(accBar); // this channel block's partial accumulator is complete
                     }
                     __syncwarp();
                     if (second) first1 = false; else first0 = false;
-                    if (++t == p.ntaps) t = 0;
+                    if (++t == p.ntaps) { t = 0; ++cbc; }
                     if (++as == kAStages) { as = 0; aph ^= 1; }
                     if (++bs == p.bStages) { bs = 0; bph ^= 1; }
                 }
-                if (ptx::elect_one())
+                if (!X3 && ptx::elect_one())
                     ptx::mma_commit(accBar);
                 __syncwarp();
             }
@@ -1806,35 +1829,18 @@ namespace nb200
 
                 bool pending = false;
                 int pendStage = 0;
-                for (int it = g; it < iters; it += kConvGroups)
+                // 3xTF32: running sums of this warp's filter chunks (see tc_fprop_kernel)
+                constexpr int kOwnChunks = X3 ? (BN / (32 * kConvGroups)) : 1;
+                float racc[kOwnChunks][32];
+                if (X3)
                 {
-                    const int cbRel = it / p.ntaps, t = it - cbRel * p.ntaps;
-                    const int iy = a * p.iyMul + p.iyAdd[t], ix = b * p.ixMul + p.ixAdd[t];
-                    const bool ok = pixOk && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && !(dbgFlags & 1);
-                    const int cbase = (cbBegin + cbRel) * kBlockC;
-                    uint32_t v[kBlockC];
-                    if (ok)
-                    {
-                        const float* src = inN + cbase * plane + (long long)iy * p.W + ix;
-                        if (cbase + kBlockC <= p.C)
-                        {
 #pragma unroll
-                            for (int c = 0; c < kBlockC; ++c)
-                                v[c] = ptx::tf32_round_bits(__float_as_uint(__ldg(src + c * plane)));
-                        }
-                        else
-                        {
+                    for (int ch = 0; ch < kOwnChunks; ++ch)
 #pragma unroll
-                            for (int c = 0; c < kBlockC; ++c)
-                                v[c] = cbase + c < p.C ? ptx::tf32_round_bits(__float_as_uint(__ldg(src + c * plane))) : 0u;
-                        }
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int c = 0; c < kBlockC; ++c)
-                            v[c] = 0u;
-                    }
+                        for (int j = 0; j < 32; ++j)
+                            racc[ch][j] = 0.f;
+                }
+                auto publish = [&]() {
                     if (pending)
                     {
                         ptx::tmem_st_wait();
@@ -1842,22 +1848,86 @@ namespace nb200
                         __syncwarp();
                         if (lane == 0)
                             ptx::mbar_arrive(&aFull[pendStage]);
+                        pending = false;
                     }
-                    const int as = it & (kAStages - 1);
-                    ptx::mbar_wait(&aEmpty[as], ((uint32_t)(it / kAStages) & 1) ^ 1);
-                    ptx::tc_fence_after_sync();
-                    ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kBlockC, v);
-                    pending = true;
-                    pendStage = as;
-                }
-                if (pending)
+                };
+                int it = 0;
+                for (int cbRel = 0; cbRel < nCb; ++cbRel)
                 {
-                    ptx::tmem_st_wait();
-                    ptx::tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0)
-                        ptx::mbar_arrive(&aFull[pendStage]);
+                    const int cbase = (cbBegin + cbRel) * kBlockC;
+                    for (int t = 0; t < p.ntaps; ++t, ++it)
+                    {
+                        if ((it & 1) != g)
+                            continue;
+                        const int iy = a * p.iyMul + p.iyAdd[t], ix = b * p.ixMul + p.ixAdd[t];
+                        const bool ok = pixOk && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && !(dbgFlags & 1);
+                        uint32_t v[kBlockC];
+                        if (ok)
+                        {
+                            const float* src = inN + cbase * plane + (long long)iy * p.W + ix;
+                            if (cbase + kBlockC <= p.C)
+                            {
+#pragma unroll
+                                for (int c = 0; c < kBlockC; ++c)
+                                    v[c] = ptx::tf32_round_bits(__float_as_uint(__ldg(src + c * plane)));
+                            }
+                            else
+                            {
+#pragma unroll
+                                for (int c = 0; c < kBlockC; ++c)
+                                    v[c] = cbase + c < p.C ? ptx::tf32_round_bits(__float_as_uint(__ldg(src + c * plane))) : 0x1000u;
+                            }
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int c = 0; c < kBlockC; ++c)
+                                v[c] = 0x1000u; // tf32_round_bits(0): the tensor core reads the upper 19 bits only
+                        }
+                        uint32_t vlo[kBlockC]; // only live in the 3xTF32 instantiation
+                        if (X3)
+                        {
+#pragma unroll
+                            for (int c = 0; c < kBlockC; ++c)
+                            {
+                                const float full = __uint_as_float(v[c] - 0x1000u);           // undo the rounding add: the raw fp32 value
+                                const uint32_t hi = v[c] & 0xFFFFE000u;                         // exactly what the tensor core will read
+                                vlo[c] = ptx::tf32_round_bits(__float_as_uint(full - __uint_as_float(hi)));
+                                v[c] = hi;
+                            }
+                        }
+                        publish();
+                        const int as = it & (kAStages - 1);
+                        ptx::mbar_wait(&aEmpty[as], ((uint32_t)(it / kAStages) & 1) ^ 1);
+                        ptx::tc_fence_after_sync();
+                        ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kACols, v);
+                        if (X3)
+                            ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kACols + kBlockC, vlo);
+                        pending = true;
+                        pendStage = as;
+                    }
+                    if (X3 && p.ntaps > 0)
+                    {
+                        publish(); // the MMAs of this block cannot finish before its last A tile is published
+                        ptx::mbar_wait(accBar, (uint32_t)cbRel & 1);
+                        ptx::tc_fence_after_sync();
+#pragma unroll
+                        for (int ch = 0; ch < kOwnChunks; ++ch)
+                        {
+                            uint32_t pv[32];
+                            ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + (g + ch * kConvGroups) * 32, pv);
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                racc[ch][j] += __uint_as_float(pv[j]);
+                        }
+                        ptx::tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0)
+                            ptx::mbar_arrive(accFree);
+                    }
                 }
+                publish();
 
                 // ----- epilogue -----
                 const int oy = a * p.oyMul + p.oyAdd, ox = b * p.oxMul + p.oxAdd;
@@ -1867,9 +1937,29 @@ namespace nb200
                 float* op = (raw ? p.partial + split * p.partialStride : out) + (long long)n * p.K * oplane + (long long)oy * p.Wo + ox;
                 const float* eb = raw ? nullptr : bias;
                 const int eact = raw ? NB200_ACT_IDENTITY : p.act;
-                ptx::mbar_wait(accBar, 0);
-                ptx::tc_fence_after_sync();
+                if (!X3)
+                {
+                    ptx::mbar_wait(accBar, 0);
+                    ptx::tc_fence_after_sync();
+                }
                 const bool have0 = nCb > 0 && ntapsA > 0, have1 = PAIR && nCb > 0 && p.ntaps > ntapsA;
+                if constexpr (X3)
+                {
+#pragma unroll
+                    for (int ch = 0; ch < kOwnChunks; ++ch)
+                    {
+                        const int c0 = (g + ch * kConvGroups) * 32;
+                        if (k0 + c0 < p.K)
+                        {
+                            uint32_t v[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                v[j] = __float_as_uint(racc[ch][j]);
+                            store_chunk(op, oplane, k0 + c0, p.K, eb, lane, eact, p.alpha, outOk, v);
+                        }
+                    }
+                }
+                else
 #pragma unroll 1
                 for (int c0 = g * 32; c0 < BN; c0 += 32 * kConvGroups)
                 {
@@ -2497,13 +2587,24 @@ namespace nb200
 
         constexpr int kWgScratchFloats = 32 * 33;
 
-        template <int BN>
+        // X3 (NB200_MATH_3XTF32): one tap per CTA; A = [hi | lo] x windows (split by the converters, as in the forward kernels),
+        // B = dy as TMA lands it (the tensor core reads its upper 19 bits = hi) plus a lo tile = tf32(dy - hi) that the
+        // converter warps write behind it in the same swizzled layout; D += hi*hi + hi*lo + lo*hi. The tensor core's fp32
+        // accumulator truncates on every add -- a bias that grows with the chain length, and a kernel gradient's chain is
+        // thousands of MMAs long -- so the chain is cut every kWgX3Segment steps: the accumulator is drained from TMEM and
+        // added, round-to-nearest, into registers (96 accumulations per segment, like the 108 of a 3x3 channel block in
+        // tc_fprop_kernel<BN, true>).
+        constexpr int kWgX3Segment = 8;
+
+        template <int BN, bool X3>
         __global__ void __launch_bounds__(kThreads, 1)
         tc_wgrad_gather_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ WgatherParams p, const float* __restrict__ x,
                                float* __restrict__ ws)
         {
-            constexpr uint32_t kBBytes = BN * 32 * 4;
+            constexpr uint32_t kBTile = BN * 32 * 4;
+            constexpr uint32_t kBBytes = kBTile * (X3 ? 2 : 1);
             constexpr uint32_t kTmemCols = 512;
+            constexpr int kACols = X3 ? 64 : 32;
 
             extern __shared__ uint8_t smemRaw[];
             uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
@@ -2514,7 +2615,9 @@ namespace nb200
             uint64_t* aFull = empty + 8;
             uint64_t* aEmpty = aFull + kWgAStages;
             uint64_t* accBar = aEmpty + kWgAStages;
-            uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
+            uint64_t* accFree = accBar + 1;     // X3: the accumulator has been drained into registers
+            uint64_t* loFull = accFree + 1;     // X3 [stages]: the lo tile of a dy stage has been written
+            uint32_t* tmemSlot = (uint32_t*)(loFull + 8);
 
             const int warp = threadIdx.x >> 5;
             const int lane = threadIdx.x & 31;
@@ -2526,7 +2629,7 @@ namespace nb200
             const int grp = t;
             const int c0 = ct * 128, k0 = kt * BN;
             const int tap0 = grp * p.tapsPerGroup;
-            const int ntap = min(p.tapsPerGroup, p.ntaps - tap0);
+            const int ntap = X3 ? 1 : min(p.tapsPerGroup, p.ntaps - tap0);
             const long long chunkBegin = split * p.chunksPerSplit;
             const long long chunkEnd = min(chunkBegin + p.chunksPerSplit, p.chunks);
             const int steps = (int)max(chunkEnd - chunkBegin, 0ll);
@@ -2535,9 +2638,10 @@ namespace nb200
             if (warp == 0 && lane == 0)
             {
                 ptx::prefetch_tensormap(&mapDy);
-                for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+                for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); ptx::mbar_init(&loFull[s], 8); }
                 for (int s = 0; s < kWgAStages; ++s) { ptx::mbar_init(&aFull[s], kTileH); ptx::mbar_init(&aEmpty[s], 1); }
                 ptx::mbar_init(accBar, 1);
+                ptx::mbar_init(accFree, 8);
                 ptx::fence_mbar_init();
             }
             if (warp == 1)
@@ -2546,7 +2650,7 @@ namespace nb200
             __syncthreads();
             ptx::tc_fence_after_sync();
             const uint32_t tmemAcc = *tmemSlot;
-            const uint32_t tmemA = tmemAcc + kTmemCols - kWgAStages * 32;
+            const uint32_t tmemA = tmemAcc + kTmemCols - kWgAStages * kACols;
 
             if (warp == 0)
             {
@@ -2559,7 +2663,7 @@ namespace nb200
                         const long long img0 = ch / p.chunksPerImg * imgsPerChunk; // first image of the chunk
                         const int hw0 = (int)(ch % p.chunksPerImg) * p.PXI;
                         ptx::mbar_wait(&empty[st], ph ^ 1);
-                        ptx::mbar_arrive_expect_tx(&full[st], kBBytes);
+                        ptx::mbar_arrive_expect_tx(&full[st], kBTile);
                         // dy viewed as (Ho*Wo, K, N): box {PXI, BN, 32/PXI}; images / filters past the end read as 0
                         ptx::tma_load_3d(smem + st * kBBytes, &mapDy, &full[st], hw0, k0, (int)img0);
                         if (++st == p.stages) { st = 0; ph ^= 1; }
@@ -2576,6 +2680,12 @@ namespace nb200
                 for (int it = 0; it < steps; ++it)
                 {
                     ptx::mbar_wait(&full[st], ph);
+                    if (X3)
+                    {
+                        ptx::mbar_wait(&loFull[st], ph);
+                        if (it > 0 && it % kWgX3Segment == 0)
+                            ptx::mbar_wait(accFree, (uint32_t)(it / kWgX3Segment - 1) & 1); // the previous segment is in registers
+                    }
                     const uint32_t stageOff = st * kBBytes;
                     for (int tp = 0; tp < ntap; ++tp)
                     {
@@ -2583,24 +2693,32 @@ namespace nb200
                         ptx::tc_fence_after_sync();
                         if (ptx::elect_one())
                         {
-                            const uint32_t ta = tmemA + as * 32;
+                            const uint32_t ta = tmemA + as * kACols;
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)
                             {
                                 // reduction elements kk*8 .. kk*8+7: sub-tile (kk*8)/PXI, byte offset ((kk*8)%PXI)*4 inside the row
                                 const uint32_t off = stageOff + ((kk * 8) / p.PXI) * subTile + (((kk * 8) % p.PXI) << 2);
-                                ptx::mma_tf32_ts(tmemAcc + tp * BN, ta + kk * 8, descB0 + (uint64_t)(off >> 4), idesc, (it | kk) != 0);
+                                const uint32_t accumulate = X3 ? ((it % kWgX3Segment) | kk) != 0 : (it | kk) != 0;
+                                ptx::mma_tf32_ts(tmemAcc + tp * BN, ta + kk * 8, descB0 + (uint64_t)(off >> 4), idesc, accumulate);          // hi * hi
+                                if (X3)
+                                {
+                                    ptx::mma_tf32_ts(tmemAcc, ta + kk * 8, descB0 + (uint64_t)((off + kBTile) >> 4), idesc, 1);              // hi * lo
+                                    ptx::mma_tf32_ts(tmemAcc, ta + 32 + kk * 8, descB0 + (uint64_t)(off >> 4), idesc, 1);                    // lo * hi
+                                }
                             }
                             ptx::mma_commit(&aEmpty[as]);
                             if (tp == ntap - 1)
                                 ptx::mma_commit(&empty[st]);
+                            if (X3 && ((it + 1) % kWgX3Segment == 0 || it == steps - 1))
+                                ptx::mma_commit(accBar); // this segment's partial accumulator is complete
                         }
                         __syncwarp();
                         if (++as == kWgAStages) { as = 0; aph ^= 1; }
                     }
                     if (++st == p.stages) { st = 0; ph ^= 1; }
                 }
-                if (ptx::elect_one())
+                if (!X3 && ptx::elect_one())
                     ptx::mma_commit(accBar);
                 __syncwarp();
             }
@@ -2616,9 +2734,80 @@ namespace nb200
                 bool pending = false;
                 int pendStage = 0;
                 const long long nTiles = (long long)steps * ntap;
-                for (long long j = g; j < nTiles; j += 2)
+                constexpr int kOwnChunks = X3 ? BN / 64 : 1;
+                float racc[kOwnChunks][32];
+                if (X3)
+                {
+#pragma unroll
+                    for (int ch = 0; ch < kOwnChunks; ++ch)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            racc[ch][j] = 0.f;
+                }
+                auto publish = [&]() {
+                    if (pending)
+                    {
+                        ptx::tmem_st_wait();
+                        ptx::tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0)
+                            ptx::mbar_arrive(&aFull[pendStage]);
+                        pending = false;
+                    }
+                };
+                // X3: every converter warp writes its share of the lo tile of EVERY dy stage (all 8 warps, both groups)
+                int loStage = 0;
+                uint32_t loPhase = 0;
+                auto write_lo = [&]() {
+                    ptx::mbar_wait(&full[loStage], loPhase);
+                    const uint32_t* hiT = (const uint32_t*)(smem + loStage * kBBytes);
+                    uint32_t* loT = (uint32_t*)(smem + loStage * kBBytes + kBTile);
+                    const int w8 = warp - 2;
+#pragma unroll 4
+                    for (int i = w8 * 32 + lane; i < (int)(kBTile / 4); i += 256)
+                    {
+                        const uint32_t raw = hiT[i];
+                        const uint32_t hi = raw & 0xFFFFE000u;   // what the tensor core reads of the raw fp32 value
+                        loT[i] = ptx::tf32_round_bits(__float_as_uint(__uint_as_float(raw) - __uint_as_float(hi)));
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the MMA's async proxy
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(&loFull[loStage]);
+                    if (++loStage == p.stages) { loStage = 0; loPhase ^= 1; }
+                };
+                auto drain = [&](int seg) {
+                    publish();
+                    ptx::mbar_wait(accBar, (uint32_t)seg & 1);
+                    ptx::tc_fence_after_sync();
+#pragma unroll
+                    for (int ch = 0; ch < kOwnChunks; ++ch)
+                    {
+                        uint32_t pv[32];
+                        ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + (g + 2 * ch) * 32, pv);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            racc[ch][j] += __uint_as_float(pv[j]);
+                    }
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(accFree);
+                };
+                for (long long j = X3 ? 0 : g; j < nTiles; j += X3 ? 1 : 2)
                 {
                     const int it = (int)(j / ntap), tp = (int)(j - (long long)it * ntap);
+                    if (X3)
+                    {
+                        write_lo();               // step `it`'s dy stage (ntap == 1: j == it); the empty barrier orders stage reuse
+                        if ((it & 1) != g)
+                        {
+                            if ((it + 1) % kWgX3Segment == 0 || it == steps - 1)
+                                drain(it / kWgX3Segment);
+                            continue;
+                        }
+                    }
                     const int tap = tap0 + tp;
                     const int r = tap / p.S, s = tap - r * p.S;
                     // lane = pixel of the chunk
@@ -2641,33 +2830,38 @@ namespace nb200
                     for (int i = 0; i < 32; ++i)
                         v[i] = ptx::tf32_round_bits(__float_as_uint(myScratch[lane * 33 + i])); // lane = channel, i = pixel
                     __syncwarp();
-                    if (pending)
+                    uint32_t vlo[32]; // only live in the 3xTF32 instantiation
+                    if (X3)
                     {
-                        ptx::tmem_st_wait();
-                        ptx::tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0)
-                            ptx::mbar_arrive(&aFull[pendStage]);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                        {
+                            const float fullv = __uint_as_float(v[i] - 0x1000u);
+                            const uint32_t hi = v[i] & 0xFFFFE000u;
+                            vlo[i] = ptx::tf32_round_bits(__float_as_uint(fullv - __uint_as_float(hi)));
+                            v[i] = hi;
+                        }
                     }
+                    publish();
                     const int as = (int)(j & (kWgAStages - 1));
                     ptx::mbar_wait(&aEmpty[as], ((uint32_t)(j / kWgAStages) & 1) ^ 1);
                     ptx::tc_fence_after_sync();
-                    ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * 32, v);
+                    ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kACols, v);
+                    if (X3)
+                        ptx::tmem_st_32x32b_x32(tmemA + laneSel + as * kACols + 32, vlo);
                     pending = true;
                     pendStage = as;
+                    if (X3 && ((it + 1) % kWgX3Segment == 0 || it == steps - 1))
+                        drain(it / kWgX3Segment);
                 }
-                if (pending)
-                {
-                    ptx::tmem_st_wait();
-                    ptx::tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0)
-                        ptx::mbar_arrive(&aFull[pendStage]);
-                }
+                publish();
 
                 // ----- epilogue: partial[split][tap][k][c] -----
-                ptx::mbar_wait(accBar, 0);
-                ptx::tc_fence_after_sync();
+                if (!X3)
+                {
+                    ptx::mbar_wait(accBar, 0);
+                    ptx::tc_fence_after_sync();
+                }
                 const int c = c0 + q * 32 + lane;
                 for (int tp = 0; tp < ntap; ++tp)
                 {
@@ -2678,7 +2872,17 @@ namespace nb200
                         if (k0 + j0 >= p.K)
                             break;
                         uint32_t v[32];
-                        if (steps > 0)
+                        if (X3)
+                        {
+#pragma unroll
+                            for (int ch = 0; ch < kOwnChunks; ++ch)
+                                if (j0 == (g + 2 * ch) * 32)
+                                {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(racc[ch][j]);
+                                }
+                        }
+                        else if (steps > 0)
                         {
                             ptx::tmem_ld_32x32b_x32(tmemAcc + laneSel + tp * BN + j0, v);
                             ptx::tmem_ld_wait();
@@ -3411,27 +3615,28 @@ namespace nb200
         // ---------------------------------------------------------------- gather kernel, host side
         // Shared memory of tc_gather_kernel<BN, PAIR>: filter ring + barriers (+ 1 KB to align the ring).
         struct GatherSmem { int bStages, slack; size_t bytes; int maxBytes; };
-        GatherSmem gather_smem(int BN, bool pair)
+        GatherSmem gather_smem(int BN, bool pair, bool x3)
         {
-            const bool onePerSm = BN > 128 || pair;
+            const bool onePerSm = BN > 128 || pair || x3;
             const long long cap = onePerSm ? kSmemBudget1 : kSmemBudget2;
+            const long long stage = (long long)BN * kBlockC * 4 * (x3 ? 2 : 1);
             GatherSmem g{};
             g.slack = 1024;
             g.maxBytes = (int)cap;
-            long long bs = (cap - g.slack - 512) / ((long long)BN * kBlockC * 4);
+            long long bs = (cap - g.slack - 512) / stage;
             g.bStages = (int)(bs > 8 ? 8 : bs);
-            g.bytes = (size_t)(g.slack + 512 + (long long)g.bStages * BN * kBlockC * 4);
+            g.bytes = (size_t)(g.slack + 512 + g.bStages * stage);
             return g;
         }
 
-        template <int BN, bool PAIR>
+        template <int BN, bool PAIR, bool X3>
         int launch_gather(const CUtensorMap& mapW, const GatherBatch& b, const float* in, const float* bias, float* out, cudaStream_t st)
         {
-            const GatherSmem sm = gather_smem(BN, PAIR);
+            const GatherSmem sm = gather_smem(BN, PAIR, X3);
             static DeviceOnce attrSet{};
-            if (const int rcAttr = opt_in_smem(attrSet, tc_gather_kernel<BN, PAIR>, sm.maxBytes)) return rcAttr;
+            if (const int rcAttr = opt_in_smem(attrSet, tc_gather_kernel<BN, PAIR, X3>, sm.maxBytes)) return rcAttr;
             const long long tiles = b.tileStart[b.count];
-            tc_gather_kernel<BN, PAIR><<<(unsigned)tiles, kFpropThreads, sm.bytes, st>>>(mapW, b, in, bias, out);
+            tc_gather_kernel<BN, PAIR, X3><<<(unsigned)tiles, kFpropThreads, sm.bytes, st>>>(mapW, b, in, bias, out);
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             return NB200_OK;
@@ -3444,6 +3649,7 @@ namespace nb200
         struct GatherPlan
         {
             int BN, splits, cbPer, Cblocks;
+            bool x3;   // NB200_MATH_3XTF32: hi + lo operand tiles, one CTA per SM, BN <= 128
             bool pair; // stride-2 input gradient: the two column-parity classes of a row class share a CTA (whole-sector stores)
             long long outElems;
             size_t repackBytes, wsBytes;
@@ -3457,7 +3663,8 @@ namespace nb200
             long long tilesM = 0;
             {
                 static const char* pairEnv = getenv("NB200_GATHER_PAIR"); // 0 disables (profiling)
-                pl.pair = !fwd && d.stride == 2 && d.W % 2 == 0 && d.W >= 2 && !(pairEnv && pairEnv[0] == '0');
+                pl.x3 = d.math == NB200_MATH_3XTF32;
+                pl.pair = !fwd && !pl.x3 && d.stride == 2 && d.W % 2 == 0 && d.W >= 2 && !(pairEnv && pairEnv[0] == '0');
             }
             if (fwd)
                 tilesM = ((long long)d.N * d.Ho * d.Wo + 127) / 128;
@@ -3471,8 +3678,8 @@ namespace nb200
             const int Cp = round_up(Cin, kBlockC);
             pl.Cblocks = Cp / kBlockC;
             pl.BN = pick_bn(Kout);
-            if (pl.pair && pl.BN > 128)
-                pl.BN = 128; // two accumulators + the A ring in 512 TMEM columns
+            if ((pl.pair || pl.x3) && pl.BN > 128)
+                pl.BN = 128; // two accumulators (or [hi | lo] A tiles) + the A ring in 512 TMEM columns
             pl.splits = 1;
             static const char* env = getenv("NB200_GATHER_SPLIT"); // 0 disables (profiling)
             if (!(env && env[0] == '0'))
@@ -3492,7 +3699,7 @@ namespace nb200
             pl.cbPer = ceil_div(pl.Cblocks, pl.splits);
             pl.splits = ceil_div(pl.Cblocks, pl.cbPer);
             pl.outElems = fwd ? (long long)d.N * d.K * d.Ho * d.Wo : (long long)d.N * d.C * d.H * d.W;
-            pl.repackBytes = ((size_t)d.R * d.S * Kout * Cp * sizeof(float) + 255) & ~(size_t)255;
+            pl.repackBytes = ((size_t)d.R * d.S * Kout * Cp * sizeof(float) * (pl.x3 ? 2 : 1) + 255) & ~(size_t)255;
             pl.wsBytes = pl.repackBytes + (pl.splits > 1 ? (size_t)pl.splits * pl.outElems * sizeof(float) : 0);
             return pl;
         }
@@ -3508,16 +3715,16 @@ namespace nb200
             if ((uintptr_t)ws & 15)
                 return fail(NB200_E_INVALID, "workspace must be 16-byte aligned for TMA");
             {
-                const int rc = launch_repack(w, (float*)ws, wK, wC, R, S, Kout, Cp, repackMode, 0, st);
+                const int rc = launch_repack(w, (float*)ws, wK, wC, R, S, Kout, Cp, repackMode, pl.x3 ? 1 : 0, st);
                 if (rc) return rc;
             }
             *BN = pl.BN;
-            cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)Kout, (cuuint64_t)(R * S)};
+            cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)Kout, (cuuint64_t)(R * S * (pl.x3 ? 2 : 1))};
             cuuint64_t strides[2] = {(cuuint64_t)Cp * 4, (cuuint64_t)Cp * Kout * 4};
             cuuint32_t box[3] = {kBlockC, (cuuint32_t)*BN, 1};
             int rc = make_map(mapW, ws, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
             if (rc) return rc;
-            *bStages = gather_smem(*BN, pl.pair).bStages;
+            *bStages = gather_smem(*BN, pl.pair, pl.x3).bStages;
             *Cblocks = Cp / kBlockC;
             return NB200_OK;
         }
@@ -3526,7 +3733,7 @@ namespace nb200
         {
             // C or K below 8 (first / last layers of the GAN configs) run with zero-padded operand tiles: wasteful for the
             // tensor core, irrelevant in time (these layers are bound by the gather), and far faster than CUDA-core loops.
-            return d.fmt == NB200_NCHW && d.math == NB200_MATH_TF32 && d.C >= 1 && d.K >= 1 && d.R * d.S <= 32 && d.N >= 1 &&
+            return d.fmt == NB200_NCHW && (d.math == NB200_MATH_TF32 || d.math == NB200_MATH_3XTF32) && d.C >= 1 && d.K >= 1 && d.R * d.S <= 32 && d.N >= 1 &&
                    d.H >= 1 && d.W >= 1 && d.Ho >= 1 && d.Wo >= 1 && d.R <= 127 && d.S <= 127 && d.padX <= 127 && d.padY <= 127;
         }
 
@@ -3542,23 +3749,25 @@ namespace nb200
             return true;
         }
 
-        int dispatch_gather(int BN, bool pair, const CUtensorMap& mapW, const GatherBatch& b, const float* in, const float* bias, float* out, cudaStream_t st)
+        int dispatch_gather(int BN, bool pair, bool x3, const CUtensorMap& mapW, const GatherBatch& b, const float* in, const float* bias, float* out, cudaStream_t st)
         {
             if (b.count == 0 || b.tileStart[b.count] == 0)
                 return NB200_OK;
+            if (x3)
+                return BN == 64 ? launch_gather<64, false, true>(mapW, b, in, bias, out, st) : launch_gather<128, false, true>(mapW, b, in, bias, out, st);
             if (pair)
-                return BN == 64 ? launch_gather<64, true>(mapW, b, in, bias, out, st) : launch_gather<128, true>(mapW, b, in, bias, out, st);
-            return BN == 64 ? launch_gather<64, false>(mapW, b, in, bias, out, st)
-                 : BN == 128 ? launch_gather<128, false>(mapW, b, in, bias, out, st)
-                             : launch_gather<256, false>(mapW, b, in, bias, out, st);
+                return BN == 64 ? launch_gather<64, true, false>(mapW, b, in, bias, out, st) : launch_gather<128, true, false>(mapW, b, in, bias, out, st);
+            return BN == 64 ? launch_gather<64, false, false>(mapW, b, in, bias, out, st)
+                 : BN == 128 ? launch_gather<128, false, false>(mapW, b, in, bias, out, st)
+                             : launch_gather<256, false, false>(mapW, b, in, bias, out, st);
         }
 
-        int dispatch_gather(int BN, const CUtensorMap& mapW, const GatherParams& p, const float* in, const float* bias, float* out, cudaStream_t st)
+        int dispatch_gather(int BN, bool x3, const CUtensorMap& mapW, const GatherParams& p, const float* in, const float* bias, float* out, cudaStream_t st)
         {
             GatherBatch b{};
             if (!gather_batch_add(b, p))
                 return fail(NB200_E_UNSUPPORTED, "too many tiles");
-            return dispatch_gather(BN, false, mapW, b, in, bias, out, st);
+            return dispatch_gather(BN, false, x3, mapW, b, in, bias, out, st);
         }
 
         FwdShape fwd_shape(const nb200_conv_desc& d)
@@ -3683,15 +3892,15 @@ namespace nb200
         p.totalPix = (long long)d.N * d.Ho * d.Wo;
         p.tilesK = ceil_div(d.K, BN); p.bStages = bStages; p.act = act; p.alpha = alpha;
         p.dbgFlags = gather_debug_flags();
-        p.smemSlack = gather_smem(BN, false).slack;
-        p.ntapsA = d.R * d.S;
+        p.smemSlack = gather_smem(BN, false, pl.x3).slack;
+        p.ntapsA = d.R * d.S; p.tapsAll = d.R * d.S;
         for (int r = 0; r < d.R; ++r)
             for (int s2 = 0; s2 < d.S; ++s2)
             {
                 const int t = r * d.S + s2;
                 p.iyAdd[t] = (short)(r - d.padY); p.ixAdd[t] = (short)(s2 - d.padX); p.wtap[t] = (short)t;
             }
-        rc = dispatch_gather(BN, mapW, p, x, bias, y, st);
+        rc = dispatch_gather(BN, pl.x3, mapW, p, x, bias, y, st);
         if (rc) return rc;
         return gather_split_reduce(pl, ws, bias, act, alpha, y, (long long)d.Ho * d.Wo, d.K, st);
     }
@@ -3744,7 +3953,8 @@ namespace nb200
                 p.totalPix = (long long)d.N * p.PH * p.PW;
                 p.tilesK = ceil_div(d.C, BN); p.bStages = bStages; p.act = NB200_ACT_IDENTITY; p.alpha = 0.f;
                 p.dbgFlags = gather_debug_flags();
-                p.smemSlack = gather_smem(BN, pl.pair).slack;
+                p.smemSlack = gather_smem(BN, pl.pair, pl.x3).slack;
+                p.tapsAll = d.R * d.S;
                 add_taps(p, ph, pw);
                 p.ntapsA = p.ntaps;
                 if (pl.pair)
@@ -3752,13 +3962,13 @@ namespace nb200
                 if (batched && gather_batch_add(batch, p))
                     continue;
                 // batch full (stride > 3) or batching disabled: flush what is queued, then start over with this class
-                rc = dispatch_gather(BN, pl.pair, mapW, batch, dy, nullptr, dx, st);
+                rc = dispatch_gather(BN, pl.pair, pl.x3, mapW, batch, dy, nullptr, dx, st);
                 if (rc) return rc;
                 batch = GatherBatch{};
                 if (!gather_batch_add(batch, p))
                     return fail(NB200_E_UNSUPPORTED, "too many tiles");
             }
-        rc = dispatch_gather(BN, pl.pair, mapW, batch, dy, nullptr, dx, st);
+        rc = dispatch_gather(BN, pl.pair, pl.x3, mapW, batch, dy, nullptr, dx, st);
         if (rc) return rc;
         return gather_split_reduce(pl, ws, nullptr, NB200_ACT_IDENTITY, 0.f, dx, (long long)d.H * d.W, d.C, st);
     }
@@ -3798,7 +4008,8 @@ namespace nb200
             // is first copied into the workspace with its planes pitched to a multiple of 4 floats.
             pl.PXI = hw > 16 ? 32 : hw > 8 ? 16 : 8;
             pl.hwPad = round_up(hw, 4);
-            pl.ok = d.fmt == NB200_NCHW && d.math == NB200_MATH_TF32 && hw >= 1 &&
+            const bool x3 = d.math == NB200_MATH_3XTF32;
+            pl.ok = d.fmt == NB200_NCHW && (d.math == NB200_MATH_TF32 || x3) && hw >= 1 &&
                     d.R * d.S <= 32 && d.C >= 1 && d.K >= 1 && d.N >= 1 && d.H >= 1 && d.W >= 1;
             {
                 // tiny channel counts fill a sliver of the 128 x BN tile; below this K*C the CUDA-core kernel is used instead
@@ -3813,6 +4024,7 @@ namespace nb200
             const int ntaps = d.R * d.S;
             pl.tapsPerGroup = 384 / pl.BN; // accumulator columns (512 - 128 for the A ring) / BN
             if (pl.tapsPerGroup > ntaps) pl.tapsPerGroup = ntaps;
+            if (x3) pl.tapsPerGroup = 1; // one accumulator per CTA: its running sums live in registers between segments
             pl.groups = ceil_div(ntaps, pl.tapsPerGroup);
             pl.tilesC = ceil_div(d.C, 128);
             pl.tilesK = ceil_div(d.K, pl.BN);
@@ -3824,20 +4036,20 @@ namespace nb200
             if (splits > pl.chunks) splits = pl.chunks;
             pl.chunksPerSplit = (pl.chunks + splits - 1) / splits;
             pl.splits = (int)((pl.chunks + pl.chunksPerSplit - 1) / pl.chunksPerSplit);
-            pl.stages = 6;
-            pl.smemBytes = 1024 + 512 + (size_t)pl.stages * pl.BN * 128 + 8 * kWgScratchFloats * sizeof(float);
+            pl.stages = x3 ? 5 : 6;     // 3xTF32 stages carry a hi and a lo tile
+            pl.smemBytes = 1024 + 512 + (size_t)pl.stages * pl.BN * 128 * (x3 ? 2 : 1) + 8 * kWgScratchFloats * sizeof(float);
             pl.partialBytes = ((size_t)pl.splits * ntaps * d.K * d.C * sizeof(float) + 255) & ~(size_t)255;
             pl.wsBytes = pl.partialBytes + (pl.hwPad != hw ? (size_t)d.N * d.K * pl.hwPad * sizeof(float) : 0);
             return pl;
         }
 
-        template <int BN>
+        template <int BN, bool X3>
         int launch_wgather(const WgatherPlan& pl, const CUtensorMap& mapDy, const WgatherParams& p, const float* x, float* ws, cudaStream_t st)
         {
             static DeviceOnce attrSet{};
-            if (const int rcAttr = opt_in_smem(attrSet, tc_wgrad_gather_kernel<BN>, 220 * 1024)) return rcAttr;
+            if (const int rcAttr = opt_in_smem(attrSet, tc_wgrad_gather_kernel<BN, X3>, 220 * 1024)) return rcAttr;
             const long long ctas = (long long)p.splits * p.tilesK * p.tilesC * p.groups;
-            tc_wgrad_gather_kernel<BN><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapDy, p, x, ws);
+            tc_wgrad_gather_kernel<BN, X3><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapDy, p, x, ws);
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             return NB200_OK;
@@ -3883,7 +4095,9 @@ namespace nb200
         p.tilesC = pl.tilesC; p.tilesK = pl.tilesK; p.groups = pl.groups; p.tapsPerGroup = pl.tapsPerGroup; p.ntaps = d.R * d.S;
         p.splits = pl.splits; p.chunksPerSplit = pl.chunksPerSplit; p.stages = pl.stages;
         p.rowBytes = (uint32_t)pl.PXI * 4; p.layoutType = pl.PXI == 32 ? 2u : pl.PXI == 16 ? 4u : 6u;
-        int rc = pl.BN == 64 ? launch_wgather<64>(pl, mapDy, p, x, (float*)ws, st) : launch_wgather<128>(pl, mapDy, p, x, (float*)ws, st);
+        const bool x3 = d.math == NB200_MATH_3XTF32;
+        int rc = x3 ? (pl.BN == 64 ? launch_wgather<64, true>(pl, mapDy, p, x, (float*)ws, st) : launch_wgather<128, true>(pl, mapDy, p, x, (float*)ws, st))
+                    : (pl.BN == 64 ? launch_wgather<64, false>(pl, mapDy, p, x, (float*)ws, st) : launch_wgather<128, false>(pl, mapDy, p, x, (float*)ws, st));
         if (rc) return rc;
         return launch_wgrad_reduce((const float*)ws, dw, d.K, d.C, d.R * d.S, pl.splits, st);
     }

@@ -144,11 +144,12 @@ namespace nb200
 
         // Bounded wait: a protocol bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.
         // The bound is a poll count (no clock reads in the loop): each poll sleeps up to the hint, or returns within
-        // ~100 cycles if the hardware ignores it, so 2^26 polls is >= ~3.5 s of pure spinning -- far beyond anything a
-        // legitimate wait sees even under time-slicing, MPS or profiler replay (a trap poisons the context, so the bound
-        // must only ever fire on a genuine deadlock); -DNB200_MBAR_MAX_POLLS=... overrides it for bring-up.
+        // ~100 cycles if the hardware ignores it, so 2^22 polls is >= ~0.2 s of pure spinning and, as measured on
+        // B200 where a poll sleeps ~3.7 us, ~15 s -- far beyond anything a legitimate wait sees even under time-slicing, MPS
+        // or profiler replay (a trap poisons the context, so the bound must only ever fire on a genuine deadlock);
+        // -DNB200_MBAR_MAX_POLLS=... overrides it.
 #ifndef NB200_MBAR_MAX_POLLS
-#define NB200_MBAR_MAX_POLLS (1u << 26)
+#define NB200_MBAR_MAX_POLLS (1u << 22)
 #endif
         constexpr uint32_t kMbarMaxPolls = NB200_MBAR_MAX_POLLS;
         __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)

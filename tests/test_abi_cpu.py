@@ -148,9 +148,13 @@ def test_kernel_dispatch_is_host_logic(L):
     assert names(_desc(128, 128, 32, 32, 3, 3, 3, 1, 1, 1)) == ["smallk_fprop", "smallk_dgrad", "tcgen05_smallk_wgrad"]
     assert names(_desc(8, 128, 256, 256, 3, 3, 3, 1, 1, 1)) == ["smallk_fprop", "smallk_dgrad", "tcgen05_smallk_wgrad"]
     assert names(_desc(256, 16, 28, 28, 1, 3, 3, 1, 1, 1))[:2] == ["smallk_fprop", "smallk_dgrad"]
-    # 3xTF32: forward / input gradient stay on tensor cores (no row-tap), kernel gradient on fp32 CUDA cores
+    # 3xTF32: all three ops on tensor cores -- forward / input gradient on the halo-tile kernel (no row-tap), the kernel gradient on
+    # the gathered kernel (one tap per CTA, accumulation chain cut every 8 steps); strided / small-map layers on the gathered kernels
     n3 = names(_desc(8, 64, 512, 512, 64, 3, 3, 1, 1, 1, math=lib.MATH_3XTF32))
-    assert n3[0] == "tcgen05_fprop" and n3[1] == "tcgen05_dgrad" and n3[2] == "direct_wgrad"
+    assert n3 == ["tcgen05_fprop", "tcgen05_dgrad", "tcgen05_gather_wgrad"]
+    for shape in [(128, 64, 32, 32, 128, 3, 3, 2, 1, 1), (128, 128, 8, 8, 256, 4, 4, 2, 1, 1), (8, 256, 34, 34, 512, 4, 4, 1, 0, 0), (8, 512, 512 // 16, 512 // 16, 512, 3, 3, 1, 1, 1)]:
+        n3 = names(_desc(*shape, math=lib.MATH_3XTF32))
+        assert all(n.startswith("tcgen05_") for n in n3), (shape, n3)
     # fp32 math and NHWC never touch the tensor-core families
     assert all(n.startswith("direct_") for n in names(_desc(8, 64, 64, 64, 64, 3, 3, 1, 1, 1, math=lib.MATH_FP32)))
     assert all(n.startswith("direct_") for n in names(_desc(8, 64, 64, 64, 64, 3, 3, 1, 1, 1, fmt=lib.NHWC)))
