@@ -186,6 +186,20 @@ NB200_API int nb200_pool2d(const nb200_pool_desc* d, const float* x, float* y, v
  * overlapping windows add in (oh, ow) order. dx is overwritten (the reference zeroes it first). y, x may be NULL for avg. */
 NB200_API int nb200_pool2d_gradient(const nb200_pool_desc* d, const float* y, const float* x, const float* dy, float* dx,
                                     void* stream);
+/* Backward of "fused convolution layer -> 2x2 max pooling" (every VGG block boundary) in ONE pass over HBM:
+ *   dz = act'(x) * Pool2DGradient(y, x, dy)      -- TensorOpCpu::Pool2DGradient (TensorOpCpu.cpp:1249-1338), then the
+ *   db[c] = sum_{n,h,w} dz                           ActivationGradient + Conv2DBiasGradient of the layer that produced x
+ *                                                    (Conv2dBiasActivationOp.cpp:47-60; x is that layer's activation output)
+ * bit-identical to nb200_pool2d_gradient followed by nb200_conv2d_bias_activation_gradient, at 2.5 instead of 5.5 tensor
+ * passes. Max pooling 2x2 stride 2 without padding, NCHW, H % 2 == 0, W % 8 == 0, 16-byte aligned tensors; anything else
+ * returns NB200_E_UNSUPPORTED (nb200_pool2d_gradient_activation_supported tells) and the caller issues the two calls.
+ * db may be NULL (then no workspace is needed). */
+NB200_API int32_t nb200_pool2d_gradient_activation_supported(const nb200_pool_desc* d);
+NB200_API size_t nb200_pool2d_gradient_activation_workspace_bytes(const nb200_pool_desc* d);
+NB200_API int nb200_pool2d_gradient_activation(const nb200_pool_desc* d, int32_t act, float alpha, const float* y, const float* x,
+                                               const float* dy, float* dz, float* db, void* workspace, size_t workspace_bytes,
+                                               void* stream);
+
 /* y[n,c,oh,ow] = x[n,c,oh/scale,ow/scale]; (N,C,H,W) = INPUT extent, NCHW planes. Replaces TensorOpCpu::UpSample2D
  * (TensorOpCpu.h:53, TensorOpCpu.cpp:1340-1354). */
 NB200_API int nb200_upsample2d(int32_t N, int32_t C, int32_t H, int32_t W, int32_t scale, const float* x, float* y, void* stream);

@@ -133,6 +133,11 @@ namespace nb200
     size_t bias_activation_gradient_workspace(const nb200_conv_desc& d);
     int bias_activation_gradient(const nb200_conv_desc& d, int act, float alpha, const float* y, const float* dy, float* dz, float* db,
                                  void* ws, size_t wsBytes, cudaStream_t st);
+    // dz = act'(x) * maxpool2x2_gradient(y, x, dy), db = sum dz: backward of "fused conv layer -> 2x2 max pooling" in one pass
+    bool pool_act_bias_supported(const nb200_pool_desc& d);
+    size_t pool_act_bias_workspace(const nb200_pool_desc& d);
+    int pool_act_bias_gradient(const nb200_pool_desc& d, int act, float alpha, const float* y, const float* x, const float* dy, float* dz, float* db,
+                               void* ws, size_t wsBytes, cudaStream_t st);
     // y = act(x + bias): bias add + activation forward as one pass (layers whose conv epilogue cannot carry them)
     int bias_activation(const nb200_conv_desc& d, const float* x, const float* bias, int act, float alpha, float* y, cudaStream_t st);
     int adam_step(float* p, const float* g, float* m, float* v, size_t n, float gs, float lr, float b1, float b2, float eps,

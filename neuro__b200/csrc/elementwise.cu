@@ -150,6 +150,75 @@ namespace nb200
                 db[k] = acc;
         }
 
+        // first-match rule of the reference's max-pool gradient on one 2x2 window (scan order e00, e01, e10, e11;
+        // TensorOpCpu.cpp:1249-1338), then the activation gradient through the window's own values (they ARE the activation's
+        // output) -- every step rounded as the two separate reference passes round it
+        template <int ACT>
+        __device__ __forceinline__ float pool_act_window(float e00, float e01, float e10, float e11, float m, float g, float alpha, float& d00,
+                                                         float& d01, float& d10, float& d11)
+        {
+            const bool m0 = e00 == m, m1 = !m0 && e01 == m, m2 = !m0 && !m1 && e10 == m, m3 = !m0 && !m1 && !m2 && e11 == m;
+            d00 = activation_gradient<ACT>(e00, m0 ? g : 0.f, alpha); d01 = activation_gradient<ACT>(e01, m1 ? g : 0.f, alpha);
+            d10 = activation_gradient<ACT>(e10, m2 ? g : 0.f, alpha); d11 = activation_gradient<ACT>(e11, m3 ? g : 0.f, alpha);
+            return (d00 + d01) + (d10 + d11);
+        }
+
+        constexpr int kPgSeg = 2048; // float4 groups of the POOLED plane per block: 8 per thread, 32 K elements of dz
+
+        // Pool2DGradient (2x2 max, stride 2) + ActivationGradient + first half of Conv2DBiasGradient in one pass: the backward of
+        // "fused conv layer -> max pooling" (every VGG block boundary). Block (seg, k, n) owns float4 groups [seg*kPgSeg, ...) of
+        // pooled plane (n, k); x = the pooling input = the convolution's activation output.
+        template <int ACT>
+        __global__ void __launch_bounds__(kAgThreads)
+        pool2x2_gradient_act_bias_kernel(const float4* __restrict__ y, const float4* __restrict__ x, const float4* __restrict__ dy, float4* __restrict__ dz,
+                                         float* __restrict__ partial, unsigned H, unsigned W4, unsigned Ho, unsigned Wo4, int segs, float alpha)
+        {
+            const int seg = blockIdx.x, k = blockIdx.y, n = blockIdx.z;
+            const unsigned plane = (unsigned)n * gridDim.y + k;
+            const unsigned quadsPerPlane = Ho * Wo4;
+            const unsigned lo = seg * kPgSeg, hi = min(quadsPerPlane, lo + kPgSeg);
+            float acc = 0.f;
+            for (unsigned i = lo + threadIdx.x; i < hi; i += kAgThreads)
+            {
+                const unsigned ow4 = i % Wo4, oh = i / Wo4;
+                const size_t q = (size_t)plane * quadsPerPlane + i;
+                const size_t r0 = ((size_t)plane * H + 2 * oh) * W4 + 2 * ow4;
+                const float4 g = __ldcs(dy + q), m = __ldcs(y + q);
+                const float4 a0 = __ldcs(x + r0), a1 = __ldcs(x + r0 + 1), b0 = __ldcs(x + r0 + W4), b1 = __ldcs(x + r0 + W4 + 1);
+                float4 t0, t1, u0, u1; // dz rows 2*oh (t) and 2*oh+1 (u), two float4 each
+                acc += pool_act_window<ACT>(a0.x, a0.y, b0.x, b0.y, m.x, g.x, alpha, t0.x, t0.y, u0.x, u0.y);
+                acc += pool_act_window<ACT>(a0.z, a0.w, b0.z, b0.w, m.y, g.y, alpha, t0.z, t0.w, u0.z, u0.w);
+                acc += pool_act_window<ACT>(a1.x, a1.y, b1.x, b1.y, m.z, g.z, alpha, t1.x, t1.y, u1.x, u1.y);
+                acc += pool_act_window<ACT>(a1.z, a1.w, b1.z, b1.w, m.w, g.w, alpha, t1.z, t1.w, u1.z, u1.w);
+                dz[r0] = t0; dz[r0 + 1] = t1; dz[r0 + W4] = u0; dz[r0 + W4 + 1] = u1;
+            }
+            if (partial)
+            {
+                const float v = block_sum_256(acc);
+                if (threadIdx.x == 0)
+                    partial[(long long)k * gridDim.z * segs + (long long)n * segs + seg] = v;
+            }
+        }
+
+        template <int ACT>
+        int launch_pool_act_bias(const nb200_pool_desc& d, float alpha, const float* y, const float* x, const float* dy, float* dz, float* db,
+                                 float* partial, cudaStream_t st)
+        {
+            const int segs = ceil_div((long long)d.Ho * d.Wo / 4, kPgSeg);
+            const dim3 grid((unsigned)segs, (unsigned)d.C, (unsigned)d.N);
+            pool2x2_gradient_act_bias_kernel<ACT><<<grid, kAgThreads, 0, st>>>((const float4*)y, (const float4*)x, (const float4*)dy, (float4*)dz,
+                                                                              db ? partial : nullptr, d.H, d.W / 4, d.Ho, d.Wo / 4, segs, alpha);
+            NB200_CUDA_TRY(cudaGetLastError());
+            count_launch();
+            if (db)
+            {
+                bias_partial_reduce_kernel<<<ceil_div(d.C, 8), 256, 0, st>>>(partial, db, d.C, d.N * segs);
+                NB200_CUDA_TRY(cudaGetLastError());
+                count_launch();
+            }
+            return NB200_OK;
+        }
+
         // any layout, no reduction (NHWC callers: the channel of an element is not a block-uniform)
         template <int ACT>
         __global__ void act_gradient_flat_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dz,
@@ -294,6 +363,34 @@ namespace nb200
         case NB200_ACT_ELU: return launch_act_bias_gradient<NB200_ACT_ELU>(d, alpha, y, dy, dz, db, partial, st);
         case NB200_ACT_LEAKY_RELU: return launch_act_bias_gradient<NB200_ACT_LEAKY_RELU>(d, alpha, y, dy, dz, db, partial, st);
         default: return launch_act_bias_gradient<NB200_ACT_IDENTITY>(d, alpha, y, dy, dz, db, partial, st);
+        }
+    }
+
+    bool pool_act_bias_supported(const nb200_pool_desc& d)
+    {
+        return d.fmt == NB200_NCHW && d.mode == NB200_POOL_MAX && d.filter == 2 && d.stride == 2 && d.padX == 0 && d.padY == 0 && d.H % 2 == 0 &&
+               d.W % 8 == 0 && d.Ho == d.H / 2 && d.Wo == d.W / 2 && d.C <= 65535 && d.N <= 65535;
+    }
+
+    size_t pool_act_bias_workspace(const nb200_pool_desc& d)
+    {
+        return (size_t)d.C * d.N * ceil_div((long long)d.Ho * d.Wo / 4, kPgSeg) * sizeof(float);
+    }
+
+    int pool_act_bias_gradient(const nb200_pool_desc& d, int act, float alpha, const float* y, const float* x, const float* dy, float* dz, float* db,
+                               void* ws, size_t wsBytes, cudaStream_t st)
+    {
+        if (db && (!ws || wsBytes < pool_act_bias_workspace(d)))
+            return fail(NB200_E_WORKSPACE, "pool + activation gradient needs %zu workspace bytes, got %zu", pool_act_bias_workspace(d), wsBytes);
+        float* partial = (float*)ws;
+        switch (act)
+        {
+        case NB200_ACT_SIGMOID: return launch_pool_act_bias<NB200_ACT_SIGMOID>(d, alpha, y, x, dy, dz, db, partial, st);
+        case NB200_ACT_RELU: return launch_pool_act_bias<NB200_ACT_RELU>(d, alpha, y, x, dy, dz, db, partial, st);
+        case NB200_ACT_TANH: return launch_pool_act_bias<NB200_ACT_TANH>(d, alpha, y, x, dy, dz, db, partial, st);
+        case NB200_ACT_ELU: return launch_pool_act_bias<NB200_ACT_ELU>(d, alpha, y, x, dy, dz, db, partial, st);
+        case NB200_ACT_LEAKY_RELU: return launch_pool_act_bias<NB200_ACT_LEAKY_RELU>(d, alpha, y, x, dy, dz, db, partial, st);
+        default: return launch_pool_act_bias<NB200_ACT_IDENTITY>(d, alpha, y, x, dy, dz, db, partial, st);
         }
     }
 

@@ -409,6 +409,40 @@ extern "C"
         return NB200_OK;
     }
 
+    int32_t nb200_pool2d_gradient_activation_supported(const nb200_pool_desc* d)
+    {
+        return check_pool(d) == NB200_OK && pool_act_bias_supported(*d) ? 1 : 0;
+    }
+
+    size_t nb200_pool2d_gradient_activation_workspace_bytes(const nb200_pool_desc* d)
+    {
+        return nb200_pool2d_gradient_activation_supported(d) ? pool_act_bias_workspace(*d) : 0;
+    }
+
+    int nb200_pool2d_gradient_activation(const nb200_pool_desc* d, int32_t act, float alpha, const float* y, const float* x, const float* dy,
+                                         float* dz, float* db, void* workspace, size_t workspace_bytes, void* stream)
+    {
+        int rc = check_pool(d);
+        if (rc) return rc;
+        if (act < NB200_ACT_IDENTITY || act > NB200_ACT_LEAKY_RELU)
+            return fail(NB200_E_INVALID, "activation %d has no gradient here", act);
+        if (!pool_act_bias_supported(*d) || ((((uintptr_t)y | (uintptr_t)x | (uintptr_t)dy | (uintptr_t)dz) & 15) != 0))
+            return fail(NB200_E_UNSUPPORTED, "fused pool + activation gradient takes 2x2 stride-2 max pooling of aligned NCHW tensors only");
+        if ((long long)d->N * d->C * d->H * d->W == 0)
+        {
+            if (db && d->C > 0)
+            {
+                if ((rc = device_ok())) return rc;
+                NB200_CUDA_TRY(cudaMemsetAsync(db, 0, d->C * sizeof(float), (cudaStream_t)stream));
+            }
+            return NB200_OK;
+        }
+        if (!y || !x || !dy || !dz)
+            return fail(NB200_E_INVALID, "null tensor pointer");
+        if ((rc = device_ok())) return rc;
+        return pool_act_bias_gradient(*d, act, alpha, y, x, dy, dz, db, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
+
     int nb200_upsample2d(int32_t N, int32_t C, int32_t H, int32_t W, int32_t scale, const float* x, float* y, void* stream)
     {
         if (N < 0 || C < 0 || H < 0 || W < 0 || scale < 1) return fail(NB200_E_INVALID, "up-sampling extents out of range");

@@ -228,6 +228,7 @@ class ConvStackTrainer:
         op = self.op
         works = []
         pending = {b[2]: b for b in self.buckets}
+        fused_act = set()   # conv layers whose activation / bias gradient was produced by the pooling layer above them
         for i in reversed(range(len(self.layers))):
             l, v = self.layers[i], self.views[i]
             xin, y, dy = self.acts[i], self.acts[i + 1], self.dact[i]
@@ -235,7 +236,14 @@ class ConvStackTrainer:
             dx = (self.dact[i - 1] if i > 0 else self.dx_in) if need_dx else None
             self._tag(i)
             if isinstance(l, PoolSpec):
-                if need_dx:
+                prev = self.layers[i - 1] if i > 0 else None
+                if (isinstance(prev, ConvLayerSpec) and not prev.batch_norm and hasattr(op, "Pool2DGradientActivation")
+                        and op.Pool2DGradientActivationSupported(xin, l.filter_size, l.stride, l.mode, l.padding, l.padding, NCHW, y)):
+                    # "fused conv layer -> max pooling": pooling gradient, the conv's activation gradient and its bias gradient in one pass
+                    op.Pool2DGradientActivation(y, xin, dy, l.filter_size, l.stride, l.mode, l.padding, l.padding, NCHW, prev.activation, prev.alpha,
+                                                self.dpre[i - 1], self.views[i - 1]["db"] if weight_gradients else None)
+                    fused_act.add(i - 1)
+                elif need_dx:
                     op.Pool2DGradient(y, xin, dy, l.filter_size, l.stride, l.mode, l.padding, l.padding, NCHW, dx)
                 continue
             if isinstance(l, UpSampleSpec):
@@ -259,7 +267,7 @@ class ConvStackTrainer:
                                                   v["dgamma"], v["dbeta"], True, dz)
                 if weight_gradients:
                     op.Conv2DBiasGradient(dz, v["db"])
-            else:
+            elif i not in fused_act:
                 # backward of Conv2dBiasActivationOp (Conv2dBiasActivationOp.cpp:47-60): activation gradient and bias gradient
                 # in one pass over the output gradient, then kernel gradient and input gradient of the result
                 op.Conv2DBiasActivationGradient(y, dy, l.activation, l.alpha, dz, v["db"] if weight_gradients else None)

@@ -118,7 +118,10 @@ struct Replica
                 flopsPerStep += 3 * 2.0 * batch * L.K * L.Ho * L.Wo * C * s.filter * s.filter;
             }
             else
+            {
                 L.pd = nb200_pool_desc{batch, C, H, W, L.Ho, L.Wo, s.filter, s.stride, s.pad, s.pad, NB200_POOL_MAX, NB200_NCHW};
+                const size_t b = nb200_pool2d_gradient_activation_workspace_bytes(&L.pd); if (b > wsBytes) wsBytes = b;
+            }
             const size_t n = (size_t)batch * L.K * L.Ho * L.Wo;
             CK(cudaMalloc(&L.y, n * 4)); CK(cudaMalloc(&L.dy, n * 4));
             if (!s.pool) CK(cudaMalloc(&L.dz, n * 4));
@@ -181,13 +184,26 @@ struct Replica
         const size_t nOut = (size_t)batch * outCount;
         CK(cudaMemcpyAsync(last.dy, last.y, nOut * 4, cudaMemcpyDeviceToDevice, st));
         NB(nb200_sgd_step(last.dy, target, nOut, 1.f, 1.f, st));
+        std::vector<char> fused(layers.size(), 0);
         for (int i = (int)layers.size() - 1; i >= 0; --i)
         {
             Layer& L = layers[i];
             const float* xin = i ? layers[i - 1].y : x;
             float* dxo = i ? layers[i - 1].dy : dx;
-            if (L.s.pool) { NB(nb200_pool2d_gradient(&L.pd, L.y, xin, L.dy, dxo, st)); continue; }
-            NB(nb200_conv2d_bias_activation_gradient(&L.cd, L.s.act, L.s.alpha, L.y, L.dy, L.dz, grads + L.bOff, ws, wsBytes, st));
+            if (L.s.pool)
+            {
+                if (i > 0 && !layers[i - 1].s.pool && nb200_pool2d_gradient_activation_supported(&L.pd))
+                {   // "fused conv layer -> max pooling": pooling, activation and bias gradients in one pass
+                    Layer& P = layers[i - 1];
+                    NB(nb200_pool2d_gradient_activation(&L.pd, P.s.act, P.s.alpha, L.y, xin, L.dy, P.dz, grads + P.bOff, ws, wsBytes, st));
+                    fused[i - 1] = true;
+                }
+                else
+                    NB(nb200_pool2d_gradient(&L.pd, L.y, xin, L.dy, dxo, st));
+                continue;
+            }
+            if (!fused[i])
+                NB(nb200_conv2d_bias_activation_gradient(&L.cd, L.s.act, L.s.alpha, L.y, L.dy, L.dz, grads + L.bOff, ws, wsBytes, st));
             NB(nb200_conv2d_kernels_gradient(&L.cd, xin, L.dz, grads + L.wOff, nullptr, ws, wsBytes, st));
             if (world > 1)
                 for (Bucket& b : buckets)

@@ -23,7 +23,8 @@ EXPORTS = [
     "nb200_conv2d_bias_activation_gradient_workspace_bytes", "nb200_conv2d_bias_activation_gradient",
     "nb200_conv2d_prepare_filters", "nb200_conv2d_forward_prepared", "nb200_conv2d_input_gradient_prepared",
     "nb200_pool2d", "nb200_pool2d_gradient", "nb200_upsample2d", "nb200_upsample2d_gradient", "nb200_constant_pad2d",
-    "nb200_bias_activation", "nb200_batch_norm_groups", "nb200_batch_norm_workspace_bytes", "nb200_batch_norm", "nb200_batch_norm_train",
+    "nb200_bias_activation", "nb200_pool2d_gradient_activation_supported", "nb200_pool2d_gradient_activation_workspace_bytes",
+    "nb200_pool2d_gradient_activation", "nb200_batch_norm_groups", "nb200_batch_norm_workspace_bytes", "nb200_batch_norm", "nb200_batch_norm_train",
     "nb200_batch_norm_gradient", "nb200_batch_norm_moments", "nb200_batch_norm_train_from_moments",
     "nb200_batch_norm_gradient_sums", "nb200_batch_norm_gradient_from_sums",
 ]
@@ -107,6 +108,9 @@ def load():
     pp = ctypes.POINTER(PoolDesc)
     L.nb200_pool2d.argtypes = [pp, c_p, c_p, c_p]
     L.nb200_pool2d_gradient.argtypes = [pp, c_p, c_p, c_p, c_p, c_p]
+    L.nb200_pool2d_gradient_activation_supported.argtypes = [pp]; L.nb200_pool2d_gradient_activation_supported.restype = c_i
+    L.nb200_pool2d_gradient_activation_workspace_bytes.argtypes = [pp]; L.nb200_pool2d_gradient_activation_workspace_bytes.restype = c_sz
+    L.nb200_pool2d_gradient_activation.argtypes = [pp, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]
     L.nb200_upsample2d.argtypes = [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
     L.nb200_upsample2d_gradient.argtypes = [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]
     L.nb200_constant_pad2d.argtypes = [c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p]

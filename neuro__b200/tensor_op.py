@@ -213,6 +213,24 @@ class TensorOpB200:
         d = self._pool_desc(input, filterSize, stride, type, paddingX, paddingY, dataFormat, output)
         check(self._L.nb200_pool2d_gradient(ctypes.byref(d), _ptr(output), _ptr(input), _ptr(outputGradient), _ptr(inputGradient), _stream()))
 
+    def Pool2DGradientActivationSupported(self, input, filterSize, stride, type, paddingX, paddingY, dataFormat, output):
+        d = self._pool_desc(input, filterSize, stride, type, paddingX, paddingY, dataFormat, output)
+        return bool(self._L.nb200_pool2d_gradient_activation_supported(ctypes.byref(d))) and input.data_ptr() % 16 == 0 and output.data_ptr() % 16 == 0
+
+    def Pool2DGradientActivation(self, output, input, outputGradient, filterSize, stride, type, paddingX, paddingY, dataFormat, activation,
+                                 activationAlpha, activationInputGradient, biasGradient=None):
+        """Pool2DGradient followed by the ActivationGradient (+ Conv2DBiasGradient) of the fused conv layer that produced `input`, in
+        one pass: activationInputGradient = act'(input) * poolGradient, biasGradient = its sum over N,H,W."""
+        d = self._pool_desc(input, filterSize, stride, type, paddingX, paddingY, dataFormat, output)
+        need = self._L.nb200_pool2d_gradient_activation_workspace_bytes(ctypes.byref(d)) if biasGradient is not None else 0
+        ws = None
+        if need:
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+            ws = ctypes.c_void_p(self._ws.data_ptr())
+        check(self._L.nb200_pool2d_gradient_activation(ctypes.byref(d), activation, activationAlpha, _ptr(output), _ptr(input), _ptr(outputGradient),
+                                                       _ptr(activationInputGradient), _ptr(biasGradient), ws, need, _stream()))
+
     def UpSample2D(self, input, scaleFactor, output):
         N, C, H, W = input.shape
         assert tuple(output.shape) == (N, C, H * scaleFactor, W * scaleFactor)   # Tensor.cpp:1859

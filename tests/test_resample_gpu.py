@@ -149,3 +149,36 @@ def test_against_committed_reference_outputs():
         dz = torch.full(dy.shape, float("nan"), device="cuda")
         op.ActivationGradient(act, 0.2, dev(yv), dev(dy), dz)
         assert np.array_equal(dz.cpu().numpy(), golden["actgrad.%d.dz" % act]), act
+
+
+@pytest.mark.parametrize("act", [lib.ACT_RELU, lib.ACT_LEAKY_RELU, lib.ACT_TANH, lib.ACT_SIGMOID, lib.ACT_ELU, lib.ACT_IDENTITY])
+def test_fused_pool_activation_bias_gradient_is_the_two_reference_passes(act):
+    """nb200_pool2d_gradient_activation = Pool2DGradient (TensorOpCpu.cpp:1249-1338) followed by ActivationGradient + Conv2DBiasGradient
+    (Conv2dBiasActivationOp.cpp:47-60) in one pass: dz BIT-IDENTICAL to the oracle's two passes (ties inside windows included), db within
+    fp32 summation order."""
+    rng = np.random.RandomState(17 + act)
+    op = TensorOpB200()
+    for (N, C, H, W) in [(2, 5, 8, 16), (3, 4, 36, 40), (1, 3, 128, 256)]:
+        z = rng.uniform(-1, 1, (N, C, H, W)).astype(np.float32)
+        z[:, :, ::3, ::5] = np.float32(0.25); z[:, :, 1::3, 1::5] = np.float32(0.25)     # ties inside windows
+        x = np.maximum(z, 0) if act == lib.ACT_RELU else (np.tanh(z) if act == lib.ACT_TANH else z)   # "activation outputs"
+        x = np.ascontiguousarray(x, np.float32)
+        y = O.pool2d(x, 2, 2, lib.POOL_MAX)
+        dy = rng.uniform(-1, 1, y.shape).astype(np.float32)
+        dx_ref = O.pool2d_gradient(y, x, dy, 2, 2, lib.POOL_MAX)
+        dz_ref = O.activation_gradient(act, 0.2, x, dx_ref)
+        db_ref = dz_ref.astype(np.float64).sum(axis=(0, 2, 3))
+        xd, yd, dyd = dev(x), dev(y), dev(dy)
+        assert op.Pool2DGradientActivationSupported(xd, 2, 2, lib.POOL_MAX, 0, 0, lib.NCHW, yd)
+        dz = torch.full(x.shape, float("nan"), device="cuda"); db = torch.full((C,), float("nan"), device="cuda")
+        op.Pool2DGradientActivation(yd, xd, dyd, 2, 2, lib.POOL_MAX, 0, 0, lib.NCHW, act, 0.2, dz, db)
+        assert np.array_equal(dz.cpu().numpy(), dz_ref)
+        assert np.abs(db.cpu().numpy() - db_ref).max() <= 1e-5 * max(1.0, np.abs(db_ref).max())
+        # and it is what the two separate CUDA calls produce
+        dx2 = torch.empty_like(dz); dz2 = torch.empty_like(dz)
+        op.Pool2DGradient(yd, xd, dyd, 2, 2, lib.POOL_MAX, 0, 0, lib.NCHW, dx2)
+        op.Conv2DBiasActivationGradient(xd, dx2, act, 0.2, dz2, None)
+        assert torch.equal(dz, dz2)
+    # shapes outside the fast path are refused, not silently mishandled
+    xd = dev(np.zeros((1, 2, 9, 12), np.float32)); yd = dev(np.zeros((1, 2, 4, 6), np.float32))
+    assert not op.Pool2DGradientActivationSupported(xd, 2, 2, lib.POOL_MAX, 0, 0, lib.NCHW, yd)
