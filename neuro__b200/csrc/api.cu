@@ -10,6 +10,12 @@ namespace nb200
     static thread_local char g_err[512] = "";
     static unsigned long long g_launches = 0;
 
+    bool pdl_enabled()
+    {
+        static const bool on = !(getenv("NB200_PDL") && getenv("NB200_PDL")[0] == '0');
+        return on;
+    }
+
     void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
     void set_error(const char* fmt, ...)

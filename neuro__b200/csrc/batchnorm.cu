@@ -116,6 +116,8 @@ namespace nb200
         __global__ void __launch_bounds__(kBnThreads)
         bn_moments_partial_kernel(const float* __restrict__ x, float* __restrict__ partial, int G, int S, long long m, int chunks)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             __shared__ float red[kBnThreads / 32];
             const int g = blockIdx.x, b = blockIdx.y;
             const long long j0 = (long long)b * kBnChunk;
@@ -161,6 +163,8 @@ namespace nb200
         __global__ void bn_moments_combine_kernel(const float* __restrict__ partial, int G, int parts, float cntFull, float cntLast,
                                                   float* __restrict__ moments)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
             const int lane = threadIdx.x & 31;
             if (g >= G) return;
@@ -195,6 +199,8 @@ namespace nb200
                                            float* __restrict__ runningMean, float* __restrict__ runningVar, float* __restrict__ saveMean,
                                            float* __restrict__ saveInvVar)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const int g = blockIdx.x * blockDim.x + threadIdx.x;
             if (g >= G) return;
             float n = 0.f, mean = 0.f, M2 = 0.f;
@@ -216,6 +222,8 @@ namespace nb200
         bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                         const float* __restrict__ invOrVar, float epsilon, float* __restrict__ y, long long total, int G, int S)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const long long stride = (long long)gridDim.x * blockDim.x;
             if (VEC)
             {
@@ -250,6 +258,8 @@ namespace nb200
         bn_gradient_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean, float* __restrict__ partial,
                                    int G, int S, long long m, int chunks)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             __shared__ float red[kBnThreads / 32];
             const int g = blockIdx.x, b = blockIdx.y;
             const long long j0 = (long long)b * kBnChunk;
@@ -297,6 +307,8 @@ namespace nb200
         // sums[g*3 + {0,1,2}] = the three sums of group g (warp per group, interleaved sequential adds + fixed tree)
         __global__ void bn_gradient_combine_kernel(const float* __restrict__ partial, int G, int parts, float* __restrict__ sums)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
             const int lane = threadIdx.x & 31;
             if (g >= G) return;
@@ -322,6 +334,8 @@ namespace nb200
         bn_gradient_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma, const float* __restrict__ mean,
                                  const float* __restrict__ inv, const float* __restrict__ sums, float m, float* __restrict__ dx, long long total, int G, int S)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const long long stride = (long long)gridDim.x * blockDim.x;
             const float invm = 1.f / m;
             for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i * (VEC ? 4 : 1) < total; i += stride)
@@ -350,6 +364,8 @@ namespace nb200
         __global__ void bn_param_gradient_kernel(const float* __restrict__ localSums, const float* __restrict__ inv, int G, float* __restrict__ dgamma,
                                                  float* __restrict__ dbeta)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const int g = blockIdx.x * blockDim.x + threadIdx.x;
             if (g >= G) return;
             if (dgamma) dgamma[g] = __ldg(inv + g) * localSums[3 * g + 1];
@@ -399,12 +415,12 @@ namespace nb200
         if (l.chunks > 65535)
             return fail(NB200_E_UNSUPPORTED, "more than 65535 x 4096 elements per normalisation group");
         if (l.vec && !((uintptr_t)x & 15))
-            bn_moments_partial_kernel<true><<<grid, kBnThreads, 0, st>>>(x, partial, l.G, l.S, l.m, l.chunks);
+            NB200_CUDA_TRY(launch_kernel(bn_moments_partial_kernel<true>, dim3(grid), dim3(kBnThreads), 0, st, x, partial, l.G, l.S, l.m, l.chunks));
         else
-            bn_moments_partial_kernel<false><<<grid, kBnThreads, 0, st>>>(x, partial, l.G, l.S, l.m, l.chunks);
+            NB200_CUDA_TRY(launch_kernel(bn_moments_partial_kernel<false>, dim3(grid), dim3(kBnThreads), 0, st, x, partial, l.G, l.S, l.m, l.chunks));
         NB200_CUDA_TRY(cudaGetLastError());
         const long long last = l.m - (long long)(l.chunks - 1) * kBnChunk;
-        bn_moments_combine_kernel<<<(unsigned)((l.G + 7) / 8), 256, 0, st>>>(partial, l.G, l.chunks, (float)kBnChunk, (float)last, moments);
+        NB200_CUDA_TRY(launch_kernel(bn_moments_combine_kernel, dim3((unsigned)((l.G + 7) / 8)), dim3(256), 0, st, partial, l.G, l.chunks, (float)kBnChunk, (float)last, moments));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch(2);
         return NB200_OK;
@@ -415,8 +431,7 @@ namespace nb200
     {
         const BnLayout l = bn_layout(d);
         if (l.G == 0) return NB200_OK;
-        bn_finalize_kernel<<<(unsigned)((l.G + 127) / 128), 128, 0, st>>>(allMoments, replicas, l.G, (float)l.m, momentum, epsilon, runningMean, runningVar,
-                                                                          saveMean, saveInvVar);
+        NB200_CUDA_TRY(launch_kernel(bn_finalize_kernel, dim3((unsigned)((l.G + 127) / 128)), dim3(128), 0, st, allMoments, replicas, l.G, (float)l.m, momentum, epsilon, runningMean, runningVar, saveMean, saveInvVar));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -432,13 +447,13 @@ namespace nb200
         const unsigned grid = grid_for(vec ? total / 4 : total, kBnThreads);
         if (vec)
         {
-            if (inference) bn_apply_kernel<true, true><<<grid, kBnThreads, 0, st>>>(x, gamma, beta, mean, invOrVar, epsilon, y, total, l.G, l.S);
-            else bn_apply_kernel<true, false><<<grid, kBnThreads, 0, st>>>(x, gamma, beta, mean, invOrVar, epsilon, y, total, l.G, l.S);
+            if (inference) NB200_CUDA_TRY(launch_kernel(bn_apply_kernel<true, true>, dim3(grid), dim3(kBnThreads), 0, st, x, gamma, beta, mean, invOrVar, epsilon, y, total, l.G, l.S));
+            else NB200_CUDA_TRY(launch_kernel(bn_apply_kernel<true, false>, dim3(grid), dim3(kBnThreads), 0, st, x, gamma, beta, mean, invOrVar, epsilon, y, total, l.G, l.S));
         }
         else
         {
-            if (inference) bn_apply_kernel<false, true><<<grid, kBnThreads, 0, st>>>(x, gamma, beta, mean, invOrVar, epsilon, y, total, l.G, l.S);
-            else bn_apply_kernel<false, false><<<grid, kBnThreads, 0, st>>>(x, gamma, beta, mean, invOrVar, epsilon, y, total, l.G, l.S);
+            if (inference) NB200_CUDA_TRY(launch_kernel(bn_apply_kernel<false, true>, dim3(grid), dim3(kBnThreads), 0, st, x, gamma, beta, mean, invOrVar, epsilon, y, total, l.G, l.S));
+            else NB200_CUDA_TRY(launch_kernel(bn_apply_kernel<false, false>, dim3(grid), dim3(kBnThreads), 0, st, x, gamma, beta, mean, invOrVar, epsilon, y, total, l.G, l.S));
         }
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
@@ -457,11 +472,11 @@ namespace nb200
         float* partial = (float*)ws;
         const dim3 grid((unsigned)l.G, (unsigned)l.chunks);
         if (l.vec && !(((uintptr_t)x | (uintptr_t)dy) & 15))
-            bn_gradient_partial_kernel<true><<<grid, kBnThreads, 0, st>>>(x, dy, saveMean, partial, l.G, l.S, l.m, l.chunks);
+            NB200_CUDA_TRY(launch_kernel(bn_gradient_partial_kernel<true>, dim3(grid), dim3(kBnThreads), 0, st, x, dy, saveMean, partial, l.G, l.S, l.m, l.chunks));
         else
-            bn_gradient_partial_kernel<false><<<grid, kBnThreads, 0, st>>>(x, dy, saveMean, partial, l.G, l.S, l.m, l.chunks);
+            NB200_CUDA_TRY(launch_kernel(bn_gradient_partial_kernel<false>, dim3(grid), dim3(kBnThreads), 0, st, x, dy, saveMean, partial, l.G, l.S, l.m, l.chunks));
         NB200_CUDA_TRY(cudaGetLastError());
-        bn_gradient_combine_kernel<<<(unsigned)((l.G + 7) / 8), 256, 0, st>>>(partial, l.G, l.chunks, sums);
+        NB200_CUDA_TRY(launch_kernel(bn_gradient_combine_kernel, dim3((unsigned)((l.G + 7) / 8)), dim3(256), 0, st, partial, l.G, l.chunks, sums));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch(2);
         return NB200_OK;
@@ -478,14 +493,14 @@ namespace nb200
         const bool vec = l.vec && !(((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15);
         const unsigned grid = grid_for(vec ? total / 4 : total, kBnThreads);
         if (vec)
-            bn_gradient_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(x, dy, gamma, saveMean, saveInvVar, globalSums, m, dx, total, l.G, l.S);
+            NB200_CUDA_TRY(launch_kernel(bn_gradient_apply_kernel<true>, dim3(grid), dim3(kBnThreads), 0, st, x, dy, gamma, saveMean, saveInvVar, globalSums, m, dx, total, l.G, l.S));
         else
-            bn_gradient_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(x, dy, gamma, saveMean, saveInvVar, globalSums, m, dx, total, l.G, l.S);
+            NB200_CUDA_TRY(launch_kernel(bn_gradient_apply_kernel<false>, dim3(grid), dim3(kBnThreads), 0, st, x, dy, gamma, saveMean, saveInvVar, globalSums, m, dx, total, l.G, l.S));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         if (dgamma || dbeta)
         {
-            bn_param_gradient_kernel<<<(unsigned)((l.G + 127) / 128), 128, 0, st>>>(localSums, saveInvVar, l.G, dgamma, dbeta);
+            NB200_CUDA_TRY(launch_kernel(bn_param_gradient_kernel, dim3((unsigned)((l.G + 127) / 128)), dim3(128), 0, st, localSums, saveInvVar, l.G, dgamma, dbeta));
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
         }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/neuro_b200.h"
 
@@ -21,6 +22,39 @@ namespace nb200
         if (_e != cudaSuccess)                                                                    \
             return nb200::fail(NB200_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
+
+    namespace ptx
+    {
+        // Programmatic dependent launch (launch attribute cudaLaunchAttributeProgrammaticStreamSerialization, launch_kernel below): the NEXT kernel of the stream may start its CTAs -- and run everything up to its own pdl_wait() --
+        // once every CTA of this grid has executed pdl_launch_dependents() (or exited); pdl_wait() blocks until the previous
+        // grid has completed and its memory is visible. Kernels call both right after their prologue (barrier init, TMEM
+        // allocation, tensor-map prefetch), which therefore overlaps the previous kernel's tail; without the launch attribute
+        // both instructions are no-ops.
+        __device__ __forceinline__ void pdl_launch_dependents()
+        {
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        }
+        __device__ __forceinline__ void pdl_wait()
+        {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+        }
+    }
+
+    // Launch with programmatic stream serialisation (see ptx::pdl_wait above). ONLY for kernels that execute pdl_wait()
+    // before their first global-memory access; every other kernel keeps the <<< >>> launch and with it full stream order.
+    // NB200_PDL=0 disables the attribute (then the device-side instructions are no-ops).
+    bool pdl_enabled();
+    template <typename... KArgs, typename... Args>
+    cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smemBytes, cudaStream_t st, Args&&... args)
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smemBytes; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    }
 
     // Element strides of an activation tensor in either data format, so one kernel body serves
     // NCHW and NHWC (Neuro::Shape semantics, Neuro/src/Tensors/Shape.cpp:11-22).

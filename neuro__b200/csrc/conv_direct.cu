@@ -39,6 +39,8 @@ namespace nb200
         direct_fprop_kernel(Geo g, const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                             int act, float alpha, float* __restrict__ y)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const long long pixels = (long long)g.N * g.Ho * g.Wo;
             const long long p = (long long)blockIdx.x * kPixelsPerBlock + threadIdx.x;
             if (p >= pixels)
@@ -94,6 +96,8 @@ namespace nb200
         __global__ void __launch_bounds__(kPixelsPerBlock)
         direct_dgrad_kernel(Geo g, const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const long long pixels = (long long)g.N * g.H * g.W;
             const long long p = (long long)blockIdx.x * kPixelsPerBlock + threadIdx.x;
             if (p >= pixels)
@@ -160,6 +164,8 @@ namespace nb200
         direct_wgrad_kernel(Geo g, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ out,
                             int slices)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const int k = blockIdx.x, c = blockIdx.y, slice = blockIdx.z;
             const int taps = g.R * g.S;
             const long long pixels = (long long)g.N * g.Ho * g.Wo;
@@ -225,6 +231,8 @@ namespace nb200
 
         __global__ void reduce_slices_kernel(const float* __restrict__ part, float* __restrict__ out, long long count, int slices)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
             if (i >= count)
                 return;
@@ -256,7 +264,7 @@ namespace nb200
         if (pixels == 0 || d.K == 0)
             return NB200_OK;
         dim3 grid(ceil_div(pixels, kPixelsPerBlock), ceil_div(d.K, kFiltersPerThread));
-        direct_fprop_kernel<<<grid, kPixelsPerBlock, 0, st>>>(g, x, w, bias, act, alpha, y);
+        NB200_CUDA_TRY(launch_kernel(direct_fprop_kernel, dim3(grid), dim3(kPixelsPerBlock), 0, st, g, x, w, bias, act, alpha, y));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -269,7 +277,7 @@ namespace nb200
         if (pixels == 0 || d.C == 0)
             return NB200_OK;
         dim3 grid(ceil_div(pixels, kPixelsPerBlock), ceil_div(d.C, kFiltersPerThread));
-        direct_dgrad_kernel<<<grid, kPixelsPerBlock, 0, st>>>(g, dy, w, dx);
+        NB200_CUDA_TRY(launch_kernel(direct_dgrad_kernel, dim3(grid), dim3(kPixelsPerBlock), 0, st, g, dy, w, dx));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -300,12 +308,12 @@ namespace nb200
             return fail(NB200_E_WORKSPACE, "direct wgrad needs %zu workspace bytes, got %zu", (size_t)slices * count * sizeof(float), wsBytes);
         float* out = slices > 1 ? (float*)ws : dw;
         dim3 grid(d.K, d.C, slices);
-        direct_wgrad_kernel<<<grid, kWgradThreads, 0, st>>>(g, x, dy, out, slices);
+        NB200_CUDA_TRY(launch_kernel(direct_wgrad_kernel, dim3(grid), dim3(kWgradThreads), 0, st, g, x, dy, out, slices));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         if (slices > 1)
         {
-            reduce_slices_kernel<<<ceil_div(count, 256), 256, 0, st>>>((const float*)ws, dw, count, slices);
+            NB200_CUDA_TRY(launch_kernel(reduce_slices_kernel, dim3(ceil_div(count, 256)), dim3(256), 0, st, (const float*)ws, dw, count, slices));
             NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         }

@@ -43,6 +43,8 @@ namespace nb200
         smallc_fprop_kernel(SmallGeo g, const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                             int act, float alpha, float* __restrict__ y)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             constexpr int T = C * 9;              // taps per filter
             constexpr int TP = (T + 3) & ~3;      // padded to a multiple of 4 for LDS.128
             extern __shared__ float sw[];         // [K][TP]
@@ -130,6 +132,8 @@ namespace nb200
         smallc_dgrad_kernel(SmallGeo g, const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ bias, int act,
                             float alpha, float* __restrict__ dx)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             constexpr int T = C * 9;
             constexpr int TP = (T + 3) & ~3;
             extern __shared__ float sw[];         // [K][TP], taps flipped: sw[k][(c*3+a)*3+b] = w[k][c][2-a][2-b]
@@ -286,6 +290,8 @@ namespace nb200
         smallc_dgrad2_kernel(SmallGeo g, const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ bias, int act,
                              float alpha, float* __restrict__ dx)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             constexpr int T = C * 9;
             constexpr int TP = (T + 3) & ~3;
             extern __shared__ float sw[];         // [K][TP], taps flipped: sw[k][(c*3+a)*3+b] = w[k][c][2-a][2-b]
@@ -403,6 +409,8 @@ namespace nb200
         smallc_dgrad_ksplit_kernel(SmallGeo g, const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ bias, int act,
                             float alpha, float* __restrict__ dx)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             constexpr int T = C * 9;
             constexpr int TP = (T + 3) & ~3;
             extern __shared__ float sw[];         // [K][TP], taps flipped: sw[k][(c*3+a)*3+b] = w[k][c][2-a][2-b]
@@ -554,6 +562,8 @@ namespace nb200
         smallc_wgrad_kernel(SmallGeo g, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part,
                             int rowsPerSlice)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             constexpr int T = C * 9;
             const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
             const int k = blockIdx.x * 8 + warp;
@@ -644,6 +654,8 @@ namespace nb200
 
         __global__ void smallc_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int count, int slices)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const int i = blockIdx.x * blockDim.x + threadIdx.x;
             if (i >= count)
                 return;
@@ -668,6 +680,8 @@ namespace nb200
         __global__ void __launch_bounds__(kSmallThreads)
         strided_wgrad_kernel(StridedGeo g, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part, int pixPerSlice)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             constexpr int T = C * F * F;
             const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
             const int kBase = (blockIdx.x * 8 + warp) * KPW;
@@ -745,6 +759,8 @@ namespace nb200
         // out[b][a][2-r][2-s] = in[a][b][r][s]: filters transposed and rotated by 180 degrees (3x3 taps: index t -> 8 - t)
         __global__ void swap_filters_kernel(const float* __restrict__ in, float* __restrict__ out, int A, int B)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const int i = blockIdx.x * blockDim.x + threadIdx.x;
             if (i >= A * B * 9)
                 return;
@@ -800,7 +816,7 @@ namespace nb200
         {                                                                                                                      \
             if (smem > 48 * 1024)                                                                                              \
                 NB200_CUDA_TRY(cudaFuncSetAttribute(smallc_fprop_kernel<CC, AA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            smallc_fprop_kernel<CC, AA><<<ceil_div(quads, kSmallThreads), kSmallThreads, smem, st>>>(g, x, w, bias, act, alpha, y); \
+            NB200_CUDA_TRY(launch_kernel(smallc_fprop_kernel<CC, AA>, dim3(ceil_div(quads, kSmallThreads)), dim3(kSmallThreads), smem, st, g, x, w, bias, act, alpha, y)); \
         }
 #define CALL(CC)                                                                                                              \
         if (act == NB200_ACT_IDENTITY) CALL_ACT(CC, NB200_ACT_IDENTITY)                                                        \
@@ -835,7 +851,7 @@ namespace nb200
 #define CALL(CC)                                                                                                              \
                 if (smem > 48 * 1024)                                                                                          \
                     NB200_CUDA_TRY(cudaFuncSetAttribute(smallc_dgrad2_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                smallc_dgrad2_kernel<CC><<<ceil_div(quads2, kSmallThreads), kSmallThreads, smem, st>>>(g, dy, w, bias, act, alpha, dx);
+                NB200_CUDA_TRY(launch_kernel(smallc_dgrad2_kernel<CC>, dim3(ceil_div(quads2, kSmallThreads)), dim3(kSmallThreads), smem, st, g, dy, w, bias, act, alpha, dx));
                 SMALLC_DISPATCH(CALL)
 #undef CALL
                 NB200_CUDA_TRY(cudaGetLastError());
@@ -853,7 +869,7 @@ namespace nb200
 #define CALL(CC)                                                                                                              \
             if (smem2 > 48 * 1024)                                                                                              \
                 NB200_CUDA_TRY(cudaFuncSetAttribute(smallc_dgrad_ksplit_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
-            smallc_dgrad_ksplit_kernel<CC><<<ceil_div(quads, 32), kSmallThreads, smem2, st>>>(g, dy, w, bias, act, alpha, dx);
+            NB200_CUDA_TRY(launch_kernel(smallc_dgrad_ksplit_kernel<CC>, dim3(ceil_div(quads, 32)), dim3(kSmallThreads), smem2, st, g, dy, w, bias, act, alpha, dx));
             SMALLC_DISPATCH(CALL)
 #undef CALL
             NB200_CUDA_TRY(cudaGetLastError());
@@ -863,7 +879,7 @@ namespace nb200
 #define CALL(CC)                                                                                                              \
         if (smem > 48 * 1024)                                                                                                  \
             NB200_CUDA_TRY(cudaFuncSetAttribute(smallc_dgrad_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        smallc_dgrad_kernel<CC><<<ceil_div(quads, kSmallThreads), kSmallThreads, smem, st>>>(g, dy, w, bias, act, alpha, dx);
+        NB200_CUDA_TRY(launch_kernel(smallc_dgrad_kernel<CC>, dim3(ceil_div(quads, kSmallThreads)), dim3(kSmallThreads), smem, st, g, dy, w, bias, act, alpha, dx));
         SMALLC_DISPATCH(CALL)
 #undef CALL
         NB200_CUDA_TRY(cudaGetLastError());
@@ -881,13 +897,13 @@ namespace nb200
             return fail(NB200_E_WORKSPACE, "small-channel kernel gradient needs %zu workspace bytes, got %zu", need, wsBytes);
         const int rowsPerSlice = ceil_div(d.N * d.Ho, slices);
         dim3 grid(ceil_div(d.K, 8), slices);
-#define CALL(CC) smallc_wgrad_kernel<CC><<<grid, kSmallThreads, 0, st>>>(g, x, dy, (float*)ws, rowsPerSlice);
+#define CALL(CC) NB200_CUDA_TRY(launch_kernel(smallc_wgrad_kernel<CC>, dim3(grid), dim3(kSmallThreads), 0, st, g, x, dy, (float*)ws, rowsPerSlice));
         SMALLC_DISPATCH(CALL)
 #undef CALL
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         const int count = d.K * d.C * 9;
-        smallc_reduce_kernel<<<ceil_div(count, 256), 256, 0, st>>>((const float*)ws, dw, count, slices);
+        NB200_CUDA_TRY(launch_kernel(smallc_reduce_kernel, dim3(ceil_div(count, 256)), dim3(256), 0, st, (const float*)ws, dw, count, slices));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -918,7 +934,7 @@ namespace nb200
 
     int smallc_swap_filters(const float* in, float* out, int A, int B, cudaStream_t st)
     {
-        swap_filters_kernel<<<ceil_div((long long)A * B * 9, 256), 256, 0, st>>>(in, out, A, B);
+        NB200_CUDA_TRY(launch_kernel(swap_filters_kernel, dim3(ceil_div((long long)A * B * 9, 256)), dim3(256), 0, st, in, out, A, B));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -951,7 +967,7 @@ namespace nb200
         {                                                                                                                      \
             constexpr int kpw = strided_kpw(CC, FF);                                                                           \
             dim3 grid(ceil_div(d.K, 8 * kpw), slices);                                                                         \
-            strided_wgrad_kernel<CC, FF, kpw><<<grid, kSmallThreads, 0, st>>>(g, x, dy, (float*)ws, rowsPerSlice);            \
+            NB200_CUDA_TRY(launch_kernel(strided_wgrad_kernel<CC, FF, kpw>, dim3(grid), dim3(kSmallThreads), 0, st, g, x, dy, (float*)ws, rowsPerSlice));            \
         }
         if (d.R == 3)
         {
@@ -965,7 +981,7 @@ namespace nb200
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         const int count = d.K * d.C * d.R * d.S;
-        smallc_reduce_kernel<<<ceil_div(count, 256), 256, 0, st>>>((const float*)ws, dw, count, slices);
+        NB200_CUDA_TRY(launch_kernel(smallc_reduce_kernel, dim3(ceil_div(count, 256)), dim3(256), 0, st, (const float*)ws, dw, count, slices));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;

@@ -126,6 +126,8 @@ namespace nb200
         __global__ void repack_filters_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int C, int R, int S,
                                               int outRows, int outCp, int mode, int x3)
         {
+            ptx::pdl_launch_dependents();
+            ptx::pdl_wait();
             const long long total = (long long)R * S * outRows * outCp;
             for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
             {
@@ -185,6 +187,8 @@ namespace nb200
         // mode 0: out[tap][k][c] = w[k][c][tap]. Block = (32-channel tile, filter k): reads 32*taps contiguous floats.
         __global__ void repack_fwd_tiled_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int C, int taps, int outCp, int x3)
         {
+            ptx::pdl_launch_dependents();
+            ptx::pdl_wait();
             extern __shared__ float tile[]; // [32 channels][taps]
             const int k = blockIdx.y, c0 = blockIdx.x * 32;
             const int n = 32 * taps;
@@ -206,6 +210,8 @@ namespace nb200
         __global__ void repack_dgrad_tiled_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int C, int R, int S, int outRows,
                                                   int outCp, int flip, int x3)
         {
+            ptx::pdl_launch_dependents();
+            ptx::pdl_wait();
             extern __shared__ float tile[]; // [32 filters][8 * taps + 1]
             const int taps = R * S, run = 8 * taps, pitch = run + 1;
             const int c0 = blockIdx.x * 8, k0 = blockIdx.y * 32;
@@ -232,6 +238,8 @@ namespace nb200
         // along c, one contiguous run of 32*taps floats written (the element-wise reduce wrote with a stride of `taps` floats).
         __global__ void wgrad_reduce_tiled_kernel(const float* __restrict__ ws, float* __restrict__ dw, int K, int C, int taps, int splits)
         {
+            ptx::pdl_launch_dependents();
+            ptx::pdl_wait();
             extern __shared__ float tile[]; // [32 channels][taps]
             const int k = blockIdx.y, c0 = blockIdx.x * 32;
             const int n = 32 * taps;
@@ -351,6 +359,8 @@ namespace nb200
             ptx::tc_fence_before_sync();
             __syncthreads();
             ptx::tc_fence_after_sync();
+            ptx::pdl_launch_dependents(); // the next kernel's prologue may overlap this kernel (sm100_ptx.cuh)
+            ptx::pdl_wait();              // nothing below runs before the previous kernel's memory is visible
             const uint32_t tmemAcc = *tmemSlot;
             const uint32_t tmemA = tmemAcc + BN;
             // 32-bit shared addresses of the barrier arrays, computed once (see sm100_ptx.cuh)
@@ -723,6 +733,8 @@ namespace nb200
             ptx::tc_fence_before_sync();
             __syncthreads();
             ptx::tc_fence_after_sync();
+            ptx::pdl_launch_dependents(); // the next kernel's prologue may overlap this kernel (sm100_ptx.cuh)
+            ptx::pdl_wait();              // nothing below runs before the previous kernel's memory is visible
             const uint32_t tmemAcc = *tmemSlot;            // D0 at +0, D1 at +BN
             const uint32_t tmemA = tmemAcc + 2 * BN;       // half h, stage s at +(h * kHalfStages + s) * 32
 
@@ -1052,6 +1064,8 @@ namespace nb200
             ptx::tc_fence_before_sync();
             __syncthreads();
             ptx::tc_fence_after_sync();
+            ptx::pdl_launch_dependents();
+            ptx::pdl_wait();
             const uint32_t tmemBase = *tmemSlot;
             const uint32_t bFull32 = ptx::smem_u32(bFull), bEmpty32 = ptx::smem_u32(bEmpty), xFull32 = ptx::smem_u32(xFull),
                            xEmpty32 = ptx::smem_u32(xEmpty), aFull32 = ptx::smem_u32(aFull), aEmpty32 = ptx::smem_u32(aEmpty),
@@ -1310,6 +1324,8 @@ namespace nb200
         __global__ void repack_rowtap_kernel(const float* __restrict__ w, float* __restrict__ out, int K, int C, int R, int S, int ktiles,
                                              int outCp, int mode)
         {
+            ptx::pdl_launch_dependents();
+            ptx::pdl_wait();
             const int rowsPerR = ktiles * S * kRtBNK;
             const long long total = (long long)R * rowsPerR * outCp;
             for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
@@ -1739,6 +1755,8 @@ namespace nb200
             ptx::tc_fence_before_sync();
             __syncthreads();
             ptx::tc_fence_after_sync();
+            ptx::pdl_launch_dependents(); // the next kernel's prologue may overlap this kernel (sm100_ptx.cuh)
+            ptx::pdl_wait();              // nothing below runs before the previous kernel's memory is visible
             const uint32_t tmemAcc = *tmemSlot;
             const uint32_t tmemA = tmemAcc + (PAIR ? 2 : 1) * BN;
             const int nCb = max(cbEnd - cbBegin, 0);
@@ -2085,6 +2103,8 @@ namespace nb200
             ptx::tc_fence_before_sync();
             __syncthreads();
             ptx::tc_fence_after_sync();
+            ptx::pdl_launch_dependents(); // the next kernel's prologue may overlap this kernel (sm100_ptx.cuh)
+            ptx::pdl_wait();              // nothing below runs before the previous kernel's memory is visible
             const uint32_t tmemAcc = *tmemSlot;
             const uint32_t tmemA = tmemAcc + kTmemCols - kWgAStages * 32;
 
@@ -2365,6 +2385,8 @@ namespace nb200
             ptx::tc_fence_before_sync();
             __syncthreads();
             ptx::tc_fence_after_sync();
+            ptx::pdl_launch_dependents(); // the next kernel's prologue may overlap this kernel (sm100_ptx.cuh)
+            ptx::pdl_wait();              // nothing below runs before the previous kernel's memory is visible
             const uint32_t tmemAcc = *tmemSlot;
             const uint32_t tmemA = tmemAcc + 512 - 4 * 32;
             const uint32_t full32 = ptx::smem_u32(full), empty32 = ptx::smem_u32(empty), aFull32 = ptx::smem_u32(aFull),
@@ -2649,6 +2671,8 @@ namespace nb200
             ptx::tc_fence_before_sync();
             __syncthreads();
             ptx::tc_fence_after_sync();
+            ptx::pdl_launch_dependents(); // the next kernel's prologue may overlap this kernel (sm100_ptx.cuh)
+            ptx::pdl_wait();              // nothing below runs before the previous kernel's memory is visible
             const uint32_t tmemAcc = *tmemSlot;
             const uint32_t tmemA = tmemAcc + kTmemCols - kWgAStages * kACols;
 
@@ -2915,6 +2939,8 @@ namespace nb200
         // dw[k][c][tap] = sum over splits of partial[split][tap][k][c]
         __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int K, int C, int taps, int splits)
         {
+            ptx::pdl_launch_dependents();
+            ptx::pdl_wait();
             const long long total = (long long)K * C * taps;
             const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
             if (i >= total)
@@ -2997,6 +3023,8 @@ namespace nb200
             ptx::tc_fence_before_sync();
             __syncthreads();
             ptx::tc_fence_after_sync();
+            ptx::pdl_launch_dependents(); // the next kernel's prologue may overlap this kernel (sm100_ptx.cuh)
+            ptx::pdl_wait();              // nothing below runs before the previous kernel's memory is visible
             const uint32_t tmemAcc = *tmemSlot;
             const uint32_t full32 = ptx::smem_u32(full), empty32 = ptx::smem_u32(empty), bFull32 = ptx::smem_u32(bFull),
                            bEmpty32 = ptx::smem_u32(bEmpty), accBar32 = ptx::smem_u32(accBar);
@@ -3134,6 +3162,8 @@ namespace nb200
         // dw[k][j] = sum over splits of partial[split][k / 128][k % 128][j]   (j = (c, r, s) is already the KCRS order)
         __global__ void smallc_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int K, int J, int Jpad, int tilesK, int splits)
         {
+            ptx::pdl_launch_dependents();
+            ptx::pdl_wait();
             const int i = blockIdx.x * blockDim.x + threadIdx.x;
             if (i >= K * J)
                 return;
@@ -3150,6 +3180,8 @@ namespace nb200
         __global__ void fprop_split_reduce_kernel(const float* __restrict__ partial, long long stride, int splits, const float* __restrict__ bias,
                                                   int act, float alpha, float* __restrict__ y, long long total, long long plane, int K)
         {
+            ptx::pdl_launch_dependents();
+            ptx::pdl_wait();
             for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
             {
                 float acc = 0.f;
@@ -3367,7 +3399,7 @@ namespace nb200
                 {
                     static DeviceOnce attrSetM{};
                     if (const int rcAttr = opt_in_smem(attrSetM, tc_fprop_m256_kernel<BN>, kSmemBudget1)) return rcAttr;
-                    tc_fprop_m256_kernel<BN><<<(unsigned)tiles, kFpropThreads, pl.smemBytes, st>>>(mapX, mapW, pd, bias, out);
+                    NB200_CUDA_TRY(launch_kernel(tc_fprop_m256_kernel<BN>, dim3((unsigned)tiles), dim3(kFpropThreads), pl.smemBytes, st, mapX, mapW, pd, bias, out));
                 }
             }
             else if (pl.pair && !X3)
@@ -3386,7 +3418,7 @@ namespace nb200
                 NB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_fprop2_kernel<BN>, mapX, mapW, pd, bias, out));
             }
             else
-                tc_fprop_kernel<BN, X3><<<(unsigned)tiles, kFpropThreads, pl.smemBytes, st>>>(mapX, mapW, pd, bias, out);
+                NB200_CUDA_TRY(launch_kernel(tc_fprop_kernel<BN, X3>, dim3((unsigned)tiles), dim3(kFpropThreads), pl.smemBytes, st, mapX, mapW, pd, bias, out));
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             if (debugWaits)
@@ -3441,7 +3473,7 @@ namespace nb200
             {
                 const long long total = (long long)f.R * rowsPerR * Cp;
                 const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-                repack_rowtap_kernel<<<blocks, 256, 0, st>>>(w, wr, wK, wC, f.R, f.S, ktiles, Cp, repackMode);
+                NB200_CUDA_TRY(launch_kernel(repack_rowtap_kernel, dim3(blocks), dim3(256), 0, st, w, wr, wK, wC, f.R, f.S, ktiles, Cp, repackMode));
                 NB200_CUDA_TRY(cudaGetLastError());
                 count_launch();
             }
@@ -3491,7 +3523,7 @@ namespace nb200
             int smCount = 0;
             if (const int rcSm = device_sms(&smCount)) return rcSm;
             const unsigned grid = (unsigned)(tiles < smCount ? tiles : smCount);
-            tc_rowtap_kernel<<<grid, kRtThreads, smemBytes, st>>>(mapX, mapW, p, bias, out);
+            NB200_CUDA_TRY(launch_kernel(tc_rowtap_kernel, dim3(grid), dim3(kRtThreads), smemBytes, st, mapX, mapW, p, bias, out));
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             return NB200_OK;
@@ -3508,19 +3540,19 @@ namespace nb200
                 if (mode == 0)
                 {
                     dim3 grid((unsigned)(outCp / 32), (unsigned)wK);
-                    repack_fwd_tiled_kernel<<<grid, 288, 32 * taps * sizeof(float), st>>>(w, out, wK, wC, taps, outCp, x3);
+                    NB200_CUDA_TRY(launch_kernel(repack_fwd_tiled_kernel, dim3(grid), dim3(288), 32 * taps * sizeof(float), st, w, out, wK, wC, taps, outCp, x3));
                 }
                 else
                 {
                     dim3 grid((unsigned)ceil_div(outRows, 8), (unsigned)(outCp / 32));
-                    repack_dgrad_tiled_kernel<<<grid, 256, 32 * (8 * taps + 1) * sizeof(float), st>>>(w, out, wK, wC, R, S, outRows, outCp, mode == 1, x3);
+                    NB200_CUDA_TRY(launch_kernel(repack_dgrad_tiled_kernel, dim3(grid), dim3(256), 32 * (8 * taps + 1) * sizeof(float), st, w, out, wK, wC, R, S, outRows, outCp, mode == 1, x3));
                 }
             }
             else
             {
                 const long long total = (long long)taps * outRows * outCp;
                 const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-                repack_filters_kernel<<<blocks, 256, 0, st>>>(w, out, wK, wC, R, S, outRows, outCp, mode, x3);
+                NB200_CUDA_TRY(launch_kernel(repack_filters_kernel, dim3(blocks), dim3(256), 0, st, w, out, wK, wC, R, S, outRows, outCp, mode, x3));
             }
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
@@ -3532,12 +3564,12 @@ namespace nb200
             if (taps <= 32)
             {
                 dim3 grid((unsigned)ceil_div(C, 32), (unsigned)K);
-                wgrad_reduce_tiled_kernel<<<grid, 288, 32 * taps * sizeof(float), st>>>(ws, dw, K, C, taps, splits);
+                NB200_CUDA_TRY(launch_kernel(wgrad_reduce_tiled_kernel, dim3(grid), dim3(288), 32 * taps * sizeof(float), st, ws, dw, K, C, taps, splits));
             }
             else
             {
                 const long long total = (long long)K * C * taps;
-                wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(ws, dw, K, C, taps, splits);
+                NB200_CUDA_TRY(launch_kernel(wgrad_reduce_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, st, ws, dw, K, C, taps, splits));
             }
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
@@ -3605,7 +3637,7 @@ namespace nb200
             if (rc || pl.splits == 1)
                 return rc;
             const int blocks = (int)((outElems + 255) / 256 > 148 * 8 ? 148 * 8 : (outElems + 255) / 256);
-            fprop_split_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, outElems, pl.splits, bias, act, alpha, out, outElems, p.yStrideK, f.Kout);
+            NB200_CUDA_TRY(launch_kernel(fprop_split_reduce_kernel, dim3(blocks), dim3(256), 0, st, p.partial, outElems, pl.splits, bias, act, alpha, out, outElems, p.yStrideK, f.Kout));
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             return NB200_OK;
@@ -3636,7 +3668,7 @@ namespace nb200
             static DeviceOnce attrSet{};
             if (const int rcAttr = opt_in_smem(attrSet, tc_gather_kernel<BN, PAIR, X3>, sm.maxBytes)) return rcAttr;
             const long long tiles = b.tileStart[b.count];
-            tc_gather_kernel<BN, PAIR, X3><<<(unsigned)tiles, kFpropThreads, sm.bytes, st>>>(mapW, b, in, bias, out);
+            NB200_CUDA_TRY(launch_kernel(tc_gather_kernel<BN, PAIR, X3>, dim3((unsigned)tiles), dim3(kFpropThreads), sm.bytes, st, mapW, b, in, bias, out));
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             return NB200_OK;
@@ -3833,7 +3865,7 @@ namespace nb200
             static DeviceOnce attrSet{};
             if (const int rcAttr = opt_in_smem(attrSet, tc_wgrad_kernel<BN, PACK, OFF0>, 220 * 1024)) return rcAttr;
             const long long ctas = (long long)p.splits * p.tilesK * p.tilesC * p.R;
-            tc_wgrad_kernel<BN, PACK, OFF0><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapX, mapDy, p, ws);
+            NB200_CUDA_TRY(launch_kernel(tc_wgrad_kernel<BN, PACK, OFF0>, dim3((unsigned)ctas), dim3(kThreads), pl.smemBytes, st, mapX, mapDy, p, ws));
             NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
             return NB200_OK;
@@ -3869,7 +3901,7 @@ namespace nb200
             return NB200_OK;
         const float* partial = (const float*)((const uint8_t*)ws + pl.repackBytes);
         const int blocks = (int)((pl.outElems + 255) / 256 > 148 * 8 ? 148 * 8 : (pl.outElems + 255) / 256);
-        fprop_split_reduce_kernel<<<blocks, 256, 0, st>>>(partial, pl.outElems, pl.splits, bias, act, alpha, out, pl.outElems, plane, Kout);
+        NB200_CUDA_TRY(launch_kernel(fprop_split_reduce_kernel, dim3(blocks), dim3(256), 0, st, partial, pl.outElems, pl.splits, bias, act, alpha, out, pl.outElems, plane, Kout));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -3989,6 +4021,8 @@ namespace nb200
         // dst[plane][0 .. hwPad) = src[plane][0 .. hw), tail zero: gives dy planes the 16-byte pitch TMA requires
         __global__ void pitch_planes_kernel(const float* __restrict__ src, float* __restrict__ dst, long long planes, int hw, int hwPad)
         {
+            ptx::pdl_launch_dependents();
+            ptx::pdl_wait();
             const long long total = planes * hwPad;
             for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
             {
@@ -4049,7 +4083,7 @@ namespace nb200
             static DeviceOnce attrSet{};
             if (const int rcAttr = opt_in_smem(attrSet, tc_wgrad_gather_kernel<BN, X3>, 220 * 1024)) return rcAttr;
             const long long ctas = (long long)p.splits * p.tilesK * p.tilesC * p.groups;
-            tc_wgrad_gather_kernel<BN, X3><<<(unsigned)ctas, kThreads, pl.smemBytes, st>>>(mapDy, p, x, ws);
+            NB200_CUDA_TRY(launch_kernel(tc_wgrad_gather_kernel<BN, X3>, dim3((unsigned)ctas), dim3(kThreads), pl.smemBytes, st, mapDy, p, x, ws));
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             return NB200_OK;
@@ -4074,7 +4108,7 @@ namespace nb200
             float* pitched = (float*)((uint8_t*)ws + pl.partialBytes);
             const long long total = (long long)d.N * d.K * pl.hwPad;
             const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-            pitch_planes_kernel<<<blocks, 256, 0, st>>>(dy, pitched, (long long)d.N * d.K, hw, pl.hwPad);
+            NB200_CUDA_TRY(launch_kernel(pitch_planes_kernel, dim3(blocks), dim3(256), 0, st, dy, pitched, (long long)d.N * d.K, hw, pl.hwPad));
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             dy = pitched;
@@ -4160,10 +4194,10 @@ namespace nb200
         static DeviceOnce attrSet{};
         if (const int rcAttr = opt_in_smem(attrSet, tc_smallc_wgrad_kernel, 220 * 1024)) return rcAttr;
         const int splits = sc_splits(d);
-        tc_smallc_wgrad_kernel<<<(unsigned)(splits * p.tilesK), kScThreads, smemBytes, st>>>(mapX, mapDy, p, (float*)ws);
+        NB200_CUDA_TRY(launch_kernel(tc_smallc_wgrad_kernel, dim3((unsigned)(splits * p.tilesK)), dim3(kScThreads), smemBytes, st, mapX, mapDy, p, (float*)ws));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
-        smallc_wgrad_reduce_kernel<<<ceil_div((long long)d.K * p.J, 256), 256, 0, st>>>((const float*)ws, dw, d.K, p.J, p.Jpad, p.tilesK, splits);
+        NB200_CUDA_TRY(launch_kernel(smallc_wgrad_reduce_kernel, dim3(ceil_div((long long)d.K * p.J, 256)), dim3(256), 0, st, (const float*)ws, dw, d.K, p.J, p.Jpad, p.tilesK, splits));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -4295,7 +4329,7 @@ namespace nb200
         p.stages = (int)((200 * 1024) / p.stageBytes);
         if (p.stages > 8) p.stages = 8;
         const size_t smemBytes = 1024 + (size_t)p.stages * p.stageBytes + 512;
-        tc_wgrad_rowfold_kernel<<<(unsigned)(p.splits * p.tilesK), kThreads, smemBytes, st>>>(mapX, mapDy, p, (float*)ws);
+        NB200_CUDA_TRY(launch_kernel(tc_wgrad_rowfold_kernel, dim3((unsigned)(p.splits * p.tilesK)), dim3(kThreads), smemBytes, st, mapX, mapDy, p, (float*)ws));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return launch_wgrad_reduce((const float*)ws, dw, d.K, d.C, d.R * d.S, p.splits, st);

@@ -13,6 +13,8 @@ namespace nb200
         __global__ void __launch_bounds__(kReduceThreads)
         bias_gradient_kernel(const float* __restrict__ dy, float* __restrict__ db, int N, int K, int HW, ActStrides ys, int nchw)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const int k = blockIdx.x;
             float acc = 0.f;
             if (nchw)
@@ -94,6 +96,8 @@ namespace nb200
         act_bias_gradient_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dz,
                                  float* __restrict__ partial, int HW, int K, int segs, float alpha)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const int seg = blockIdx.x, k = blockIdx.y, n = blockIdx.z;
             const long long base = ((long long)n * K + k) * HW;
             const int lo = seg * kAgSeg;
@@ -136,6 +140,8 @@ namespace nb200
         // db[k] = partials of channel k added in index order by one warp (fixed order => deterministic)
         __global__ void bias_partial_reduce_kernel(const float* __restrict__ partial, float* __restrict__ db, int K, int per)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const int k = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
             if (k >= K)
                 return;
@@ -173,6 +179,8 @@ namespace nb200
         pool2x2_gradient_act_bias_kernel(const float4* __restrict__ y, const float4* __restrict__ x, const float4* __restrict__ dy, float4* __restrict__ dz,
                                          float* __restrict__ partial, unsigned H, unsigned W4, unsigned Ho, unsigned Wo4, int segs, float alpha)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const int seg = blockIdx.x, k = blockIdx.y, n = blockIdx.z;
             const unsigned plane = (unsigned)n * gridDim.y + k;
             const unsigned quadsPerPlane = Ho * Wo4;
@@ -206,13 +214,12 @@ namespace nb200
         {
             const int segs = ceil_div((long long)d.Ho * d.Wo / 4, kPgSeg);
             const dim3 grid((unsigned)segs, (unsigned)d.C, (unsigned)d.N);
-            pool2x2_gradient_act_bias_kernel<ACT><<<grid, kAgThreads, 0, st>>>((const float4*)y, (const float4*)x, (const float4*)dy, (float4*)dz,
-                                                                              db ? partial : nullptr, d.H, d.W / 4, d.Ho, d.Wo / 4, segs, alpha);
+            NB200_CUDA_TRY(launch_kernel(pool2x2_gradient_act_bias_kernel<ACT>, dim3(grid), dim3(kAgThreads), 0, st, (const float4*)y, (const float4*)x, (const float4*)dy, (float4*)dz, db ? partial : nullptr, d.H, d.W / 4, d.Ho, d.Wo / 4, segs, alpha));
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             if (db)
             {
-                bias_partial_reduce_kernel<<<ceil_div(d.C, 8), 256, 0, st>>>(partial, db, d.C, d.N * segs);
+                NB200_CUDA_TRY(launch_kernel(bias_partial_reduce_kernel, dim3(ceil_div(d.C, 8)), dim3(256), 0, st, partial, db, d.C, d.N * segs));
                 NB200_CUDA_TRY(cudaGetLastError());
                 count_launch();
             }
@@ -224,6 +231,8 @@ namespace nb200
         __global__ void act_gradient_flat_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dz,
                                                  long long n, float alpha)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
                 dz[i] = activation_gradient<ACT>(y[i], dy[i], alpha);
         }
@@ -237,7 +246,7 @@ namespace nb200
             {
                 const long long n = (long long)d.N * d.K * HW;
                 const long long blocks = (n + 255) / 256;
-                act_gradient_flat_kernel<ACT><<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, st>>>(y, dy, dz, n, alpha);
+                NB200_CUDA_TRY(launch_kernel(act_gradient_flat_kernel<ACT>, dim3((unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks)), dim3(256), 0, st, y, dy, dz, n, alpha));
                 NB200_CUDA_TRY(cudaGetLastError());
                 count_launch();
                 return db ? bias_gradient(d, dz, db, st) : NB200_OK;
@@ -248,14 +257,14 @@ namespace nb200
             const dim3 grid((unsigned)segs, (unsigned)d.K, (unsigned)d.N);
             const bool vec = HW % 4 == 0 && (((uintptr_t)y | (uintptr_t)dy | (uintptr_t)dz) & 15) == 0;
             if (vec)
-                act_bias_gradient_kernel<ACT, true><<<grid, kAgThreads, 0, st>>>(y, dy, dz, db ? partial : nullptr, HW, d.K, segs, alpha);
+                NB200_CUDA_TRY(launch_kernel(act_bias_gradient_kernel<ACT, true>, dim3(grid), dim3(kAgThreads), 0, st, y, dy, dz, db ? partial : nullptr, HW, d.K, segs, alpha));
             else
-                act_bias_gradient_kernel<ACT, false><<<grid, kAgThreads, 0, st>>>(y, dy, dz, db ? partial : nullptr, HW, d.K, segs, alpha);
+                NB200_CUDA_TRY(launch_kernel(act_bias_gradient_kernel<ACT, false>, dim3(grid), dim3(kAgThreads), 0, st, y, dy, dz, db ? partial : nullptr, HW, d.K, segs, alpha));
             NB200_CUDA_TRY(cudaGetLastError());
             count_launch();
             if (db)
             {
-                bias_partial_reduce_kernel<<<ceil_div(d.K, 8), 256, 0, st>>>(partial, db, d.K, d.N * segs);
+                NB200_CUDA_TRY(launch_kernel(bias_partial_reduce_kernel, dim3(ceil_div(d.K, 8)), dim3(256), 0, st, partial, db, d.K, d.N * segs));
                 NB200_CUDA_TRY(cudaGetLastError());
                 count_launch();
             }
@@ -269,6 +278,8 @@ namespace nb200
         __global__ void bias_activation_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y, long long n,
                                                int K, int HW, int nchw, int act, float alpha)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const long long stride = (long long)gridDim.x * blockDim.x;
             if (VEC)
             {
@@ -309,6 +320,8 @@ namespace nb200
         __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                          float* __restrict__ v, size_t n, float gs, float lr, float b1, float b2, float eps)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
             if (i >= n)
                 return;
@@ -325,6 +338,8 @@ namespace nb200
         // TensorOpCpu::SgdStep (TensorOpCpu.cpp:1006-1009)
         __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, size_t n, float gs, float lr)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
             if (i < n)
                 p[i] = __fadd_rn(p[i], __fmul_rn(-lr, __fmul_rn(gs, g[i]))); // Tensor::Add(1, -lr, gradient): 1*p + (-lr)*g
@@ -336,7 +351,7 @@ namespace nb200
         if (d.K == 0)
             return NB200_OK;
         const ActStrides ys = act_strides(d.fmt, d.K, d.Ho, d.Wo);
-        bias_gradient_kernel<<<d.K, kReduceThreads, 0, st>>>(dy, db, d.N, d.K, d.Ho * d.Wo, ys, d.fmt == NB200_NCHW);
+        NB200_CUDA_TRY(launch_kernel(bias_gradient_kernel, dim3(d.K), dim3(kReduceThreads), 0, st, dy, db, d.N, d.K, d.Ho * d.Wo, ys, d.fmt == NB200_NCHW));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -406,9 +421,9 @@ namespace nb200
         const long long blocks = (work + 255) / 256;
         const unsigned grid = (unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks);
         if (vec)
-            bias_activation_kernel<true><<<grid, 256, 0, st>>>(x, bias, y, n, d.K, HW, nchw, act, alpha);
+            NB200_CUDA_TRY(launch_kernel(bias_activation_kernel<true>, dim3(grid), dim3(256), 0, st, x, bias, y, n, d.K, HW, nchw, act, alpha));
         else
-            bias_activation_kernel<false><<<grid, 256, 0, st>>>(x, bias, y, n, d.K, HW, nchw, act, alpha);
+            NB200_CUDA_TRY(launch_kernel(bias_activation_kernel<false>, dim3(grid), dim3(256), 0, st, x, bias, y, n, d.K, HW, nchw, act, alpha));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -419,7 +434,7 @@ namespace nb200
     {
         if (n == 0)
             return NB200_OK;
-        adam_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, m, v, n, gs, lr, b1, b2, eps);
+        NB200_CUDA_TRY(launch_kernel(adam_step_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, p, g, m, v, n, gs, lr, b1, b2, eps));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -429,7 +444,7 @@ namespace nb200
     {
         if (n == 0)
             return NB200_OK;
-        sgd_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, n, gs, lr);
+        NB200_CUDA_TRY(launch_kernel(sgd_step_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, p, g, n, gs, lr));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;

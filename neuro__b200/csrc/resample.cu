@@ -52,6 +52,8 @@ namespace nb200
         template <bool MAX>
         __global__ void __launch_bounds__(kThreads) pool2d_kernel(const float* __restrict__ x, float* __restrict__ y, Geo g, long long total)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             for (long long i64 = (long long)blockIdx.x * kThreads + threadIdx.x; i64 < total; i64 += (long long)gridDim.x * kThreads)
             {
                 const unsigned i = (unsigned)i64;
@@ -79,6 +81,8 @@ namespace nb200
         __global__ void __launch_bounds__(kThreads)
         pool2x2_kernel(const float4* __restrict__ x, float4* __restrict__ y, unsigned H, unsigned W4, unsigned Ho, unsigned Wo4, long long quads)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             for (long long q64 = (long long)blockIdx.x * kThreads + threadIdx.x; q64 < quads; q64 += (long long)gridDim.x * kThreads)
             {
                 const unsigned q = (unsigned)q64;
@@ -117,6 +121,8 @@ namespace nb200
         pool2x2_gradient_kernel(const float4* __restrict__ y, const float4* __restrict__ x, const float4* __restrict__ dy, float4* __restrict__ dx,
                                 unsigned H, unsigned W4, unsigned Ho, unsigned Wo4, long long quads)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             for (long long q64 = (long long)blockIdx.x * kThreads + threadIdx.x; q64 < quads; q64 += (long long)gridDim.x * kThreads)
             {
                 const unsigned q = (unsigned)q64;
@@ -152,6 +158,8 @@ namespace nb200
         pool2d_gradient_kernel(const float* __restrict__ y, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, Geo g,
                                long long total)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             for (long long i64 = (long long)blockIdx.x * kThreads + threadIdx.x; i64 < total; i64 += (long long)gridDim.x * kThreads)
             {
                 const unsigned i = (unsigned)i64;
@@ -213,6 +221,8 @@ namespace nb200
         __global__ void __launch_bounds__(kThreads)
         upsample2d_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned H, unsigned W, unsigned s, long long groups)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const unsigned Wo = W * s, Ho = H * s, WoG = Wo / VEC;
             for (long long i64 = (long long)blockIdx.x * kThreads + threadIdx.x; i64 < groups; i64 += (long long)gridDim.x * kThreads)
             {
@@ -236,6 +246,8 @@ namespace nb200
         __global__ void __launch_bounds__(kThreads)
         upsample2d_gradient_kernel(const float* __restrict__ dy, float* __restrict__ dx, unsigned H, unsigned W, unsigned s, long long total)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const unsigned Wo = W * s;
             for (long long i64 = (long long)blockIdx.x * kThreads + threadIdx.x; i64 < total; i64 += (long long)gridDim.x * kThreads)
             {
@@ -255,6 +267,8 @@ namespace nb200
         __global__ void __launch_bounds__(kThreads)
         upsample2x_gradient_kernel(const float4* __restrict__ dy, float2* __restrict__ dx, unsigned H, unsigned W2, long long pairs)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             for (long long i64 = (long long)blockIdx.x * kThreads + threadIdx.x; i64 < pairs; i64 += (long long)gridDim.x * kThreads)
             {
                 const unsigned i = (unsigned)i64;
@@ -274,6 +288,8 @@ namespace nb200
         constant_pad2d_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int left, int top, unsigned Ho, unsigned Wo, float value,
                               long long groups)
         {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
             const unsigned WoG = Wo / VEC;
             for (long long i64 = (long long)blockIdx.x * kThreads + threadIdx.x; i64 < groups; i64 += (long long)gridDim.x * kThreads)
             {
@@ -368,14 +384,14 @@ extern "C"
         {
             const long long quads = total / 4;
             if (d->mode == NB200_POOL_MAX)
-                pool2x2_kernel<true><<<grid_for(quads), kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, d->H, d->W / 4, d->Ho, d->Wo / 4, quads);
+                NB200_CUDA_TRY(launch_kernel(pool2x2_kernel<true>, dim3(grid_for(quads)), dim3(kThreads), 0, (cudaStream_t)stream, (const float4*)x, (float4*)y, d->H, d->W / 4, d->Ho, d->Wo / 4, quads));
             else
-                pool2x2_kernel<false><<<grid_for(quads), kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, d->H, d->W / 4, d->Ho, d->Wo / 4, quads);
+                NB200_CUDA_TRY(launch_kernel(pool2x2_kernel<false>, dim3(grid_for(quads)), dim3(kThreads), 0, (cudaStream_t)stream, (const float4*)x, (float4*)y, d->H, d->W / 4, d->Ho, d->Wo / 4, quads));
         }
         else if (d->mode == NB200_POOL_MAX)
-            pool2d_kernel<true><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(x, y, g, total);
+            NB200_CUDA_TRY(launch_kernel(pool2d_kernel<true>, dim3(grid_for(total)), dim3(kThreads), 0, (cudaStream_t)stream, x, y, g, total));
         else
-            pool2d_kernel<false><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(x, y, g, total);
+            NB200_CUDA_TRY(launch_kernel(pool2d_kernel<false>, dim3(grid_for(total)), dim3(kThreads), 0, (cudaStream_t)stream, x, y, g, total));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -394,16 +410,14 @@ extern "C"
         {
             const long long quads = (long long)d->N * d->C * d->Ho * d->Wo / 4;
             if (d->mode == NB200_POOL_MAX)
-                pool2x2_gradient_kernel<true><<<grid_for(quads), kThreads, 0, (cudaStream_t)stream>>>((const float4*)y, (const float4*)x, (const float4*)dy, (float4*)dx,
-                                                                                                       d->H, d->W / 4, d->Ho, d->Wo / 4, quads);
+                NB200_CUDA_TRY(launch_kernel(pool2x2_gradient_kernel<true>, dim3(grid_for(quads)), dim3(kThreads), 0, (cudaStream_t)stream, (const float4*)y, (const float4*)x, (const float4*)dy, (float4*)dx, d->H, d->W / 4, d->Ho, d->Wo / 4, quads));
             else
-                pool2x2_gradient_kernel<false><<<grid_for(quads), kThreads, 0, (cudaStream_t)stream>>>(nullptr, nullptr, (const float4*)dy, (float4*)dx,
-                                                                                                        d->H, d->W / 4, d->Ho, d->Wo / 4, quads);
+                NB200_CUDA_TRY(launch_kernel(pool2x2_gradient_kernel<false>, dim3(grid_for(quads)), dim3(kThreads), 0, (cudaStream_t)stream, nullptr, nullptr, (const float4*)dy, (float4*)dx, d->H, d->W / 4, d->Ho, d->Wo / 4, quads));
         }
         else if (d->mode == NB200_POOL_MAX)
-            pool2d_gradient_kernel<true><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(y, x, dy, dx, g, total);
+            NB200_CUDA_TRY(launch_kernel(pool2d_gradient_kernel<true>, dim3(grid_for(total)), dim3(kThreads), 0, (cudaStream_t)stream, y, x, dy, dx, g, total));
         else
-            pool2d_gradient_kernel<false><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(y, x, dy, dx, g, total);
+            NB200_CUDA_TRY(launch_kernel(pool2d_gradient_kernel<false>, dim3(grid_for(total)), dim3(kThreads), 0, (cudaStream_t)stream, y, x, dy, dx, g, total));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -453,9 +467,9 @@ extern "C"
         int rc = device_ok();
         if (rc) return rc;
         if ((W * scale) % 4 == 0 && ((uintptr_t)y & 15) == 0)
-            upsample2d_kernel<4><<<grid_for(total / 4), kThreads, 0, (cudaStream_t)stream>>>(x, y, H, W, scale, total / 4);
+            NB200_CUDA_TRY(launch_kernel(upsample2d_kernel<4>, dim3(grid_for(total / 4)), dim3(kThreads), 0, (cudaStream_t)stream, x, y, H, W, scale, total / 4));
         else
-            upsample2d_kernel<1><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(x, y, H, W, scale, total);
+            NB200_CUDA_TRY(launch_kernel(upsample2d_kernel<1>, dim3(grid_for(total)), dim3(kThreads), 0, (cudaStream_t)stream, x, y, H, W, scale, total));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -471,9 +485,9 @@ extern "C"
         int rc = device_ok();
         if (rc) return rc;
         if (scale == 2 && W % 2 == 0 && (((uintptr_t)dy & 15) | ((uintptr_t)dx & 7)) == 0)
-            upsample2x_gradient_kernel<<<grid_for(total / 2), kThreads, 0, (cudaStream_t)stream>>>((const float4*)dy, (float2*)dx, H, W / 2, total / 2);
+            NB200_CUDA_TRY(launch_kernel(upsample2x_gradient_kernel, dim3(grid_for(total / 2)), dim3(kThreads), 0, (cudaStream_t)stream, (const float4*)dy, (float2*)dx, H, W / 2, total / 2));
         else
-            upsample2d_gradient_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(dy, dx, H, W, scale, total);
+            NB200_CUDA_TRY(launch_kernel(upsample2d_gradient_kernel, dim3(grid_for(total)), dim3(kThreads), 0, (cudaStream_t)stream, dy, dx, H, W, scale, total));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
@@ -491,9 +505,9 @@ extern "C"
         int rc = device_ok();
         if (rc) return rc;
         if (Wo % 4 == 0 && ((uintptr_t)y & 15) == 0)
-            constant_pad2d_kernel<4><<<grid_for(total / 4), kThreads, 0, (cudaStream_t)stream>>>(x, y, H, W, left, top, Ho, Wo, value, total / 4);
+            NB200_CUDA_TRY(launch_kernel(constant_pad2d_kernel<4>, dim3(grid_for(total / 4)), dim3(kThreads), 0, (cudaStream_t)stream, x, y, H, W, left, top, Ho, Wo, value, total / 4));
         else
-            constant_pad2d_kernel<1><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(x, y, H, W, left, top, Ho, Wo, value, total);
+            NB200_CUDA_TRY(launch_kernel(constant_pad2d_kernel<1>, dim3(grid_for(total)), dim3(kThreads), 0, (cudaStream_t)stream, x, y, H, W, left, top, Ho, Wo, value, total));
         NB200_CUDA_TRY(cudaGetLastError());
         count_launch();
         return NB200_OK;
