@@ -266,7 +266,9 @@ def init_dist():
         # The exchange is 59 MB per ~10 ms step: bandwidth is irrelevant, but every NCCL CTA takes an SM away from the
         # one-CTA-per-SM persistent convolution grids it runs under (+12 % on the input gradient at N = 8).
         os.environ.setdefault("NCCL_MAX_CTAS", "4")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a rank that fails alone must not leave the others hanging for NCCL's default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     return rank, world, local
 
 
@@ -407,7 +409,8 @@ def run_ours(args):
 
     e2e_run(2); barrier()
     s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(3, min(timed_steps, int(math.ceil(MIN_TIMED_SECONDS / est))))
+    # (from the max-over-ranks step time: every rank must run the same number of steps -- they contain collectives)
+    e2e_steps = max(3, min(timed_steps, int(math.ceil(MIN_TIMED_SECONDS / (ms * 1e-3)))))
     s0.record()
     e2e_run(e2e_steps)
     s1.record()

@@ -121,7 +121,7 @@ namespace nb200
             }
         }
 
-        enum Family { kDirect, kTc, kSmallC, kGather, kSmallK, kStrided };
+        enum Family { kDirect, kTc, kSmallC, kGather, kSmallK, kStrided, kSmallCGather };
 
         inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
         inline size_t smallk_filter_bytes(const nb200_conv_desc& d) { return align256((size_t)d.K * d.C * 9 * sizeof(float)); }
@@ -174,6 +174,8 @@ namespace nb200
                 return kSmallC; // fp32 CUDA cores, HBM-bound: serves every math mode
             if (smallk_supported(d))
                 return kSmallK; // few filters: the same kernels with x and y exchanged
+            if (op == NB200_OP_KERNELS_GRADIENT && tc_smallc_wgrad_gather_supported(d))
+                return kSmallCGather; // few channels, any stride / filter: dy streamed through an SS-form tcgen05 GEMM, HBM-bound
             if (op == NB200_OP_KERNELS_GRADIENT && strided_wgrad_supported(d))
                 return kStrided; // stride 2, 1-6 channels: HBM-bound, fp32 CUDA cores (forward / input gradient stay gathered)
             if (d.math == NB200_MATH_FP32)
@@ -251,6 +253,8 @@ extern "C"
             return op != NB200_OP_KERNELS_GRADIENT ? 0 : tc_smallc_wgrad_supported(*d) ? tc_smallc_wgrad_workspace(*d) : smallc_wgrad_workspace(*d);
         if (f == kSmallK)
             return smallk_workspace(op, *d);
+        if (f == kSmallCGather)
+            return tc_smallc_wgrad_gather_workspace(*d);
         if (f == kStrided)
             return strided_wgrad_workspace(*d);
         if (f == kGather)
@@ -263,6 +267,8 @@ extern "C"
         if (!d || validate(d, -1) != NB200_OK)
             return "invalid";
         const Family f = pick(op, *d);
+        if (f == kSmallCGather)
+            return "tcgen05_smallc_gather_wgrad";
         if (f == kStrided)
             return "strided_smallc_wgrad";
         if (f == kSmallK)
@@ -351,6 +357,8 @@ extern "C"
                                                  : smallc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         if (f == kSmallK)
             return smallk_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
+        if (f == kSmallCGather)
+            return tc_smallc_gather_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         if (f == kStrided)
             return strided_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
         if (f == kGather)

@@ -133,6 +133,10 @@ namespace nb200
     bool tc_smallc_wgrad_supported(const nb200_conv_desc& d);
     size_t tc_smallc_wgrad_workspace(const nb200_conv_desc& d);
     int tc_smallc_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st);
+    // the same GEMM for strided / larger-filter first layers (C*R*S <= 96), im2col rows gathered from global memory
+    bool tc_smallc_wgrad_gather_supported(const nb200_conv_desc& d);
+    size_t tc_smallc_wgrad_gather_workspace(const nb200_conv_desc& d);
+    int tc_smallc_gather_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st);
     bool tc_uses_rowfold(const nb200_conv_desc& d);        // kernel gradient takes tc_wgrad_rowfold_kernel
     bool tc_uses_rowtap(int op, const nb200_conv_desc& d); // forward / stride-1 input gradient take tc_rowtap_kernel
     int tc_forward(const nb200_conv_desc& d, const float* x, const float* w, const float* bias, int act, float alpha, float* y,

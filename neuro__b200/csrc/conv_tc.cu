@@ -3159,6 +3159,202 @@ namespace nb200
             }
         }
 
+        // ---------------------------------------------------------------- kernel gradient, few input channels, ANY stride / filter
+        // The same GEMM with the roles swapped (D[128 filters][N = round16(C*R*S)] += dy tile * im2col rows) for the first layers
+        // the kernel above cannot take: strided convolutions (pix2pix enc1, DCGAN D conv1: 3 channels, 3x3, stride 2), 4x4
+        // filters with 6 channels on an input whose width is not a multiple of 4 (PatchGAN d1 on the 259 x 259 padded pair: TMA
+        // cannot address x there), any padding. dy arrives by TMA exactly as above (SS-form A operand); the im2col rows are
+        // gathered by the converter warps STRAIGHT from global memory / L1 (lane = output pixel, one 4-byte load per (c, r, s);
+        // every x element is reused by up to R*S/stride^2 rows and stays in L1), rounded to TF32 and written as the swizzled
+        // K-major B tile. C*R*S <= 96 columns of TMEM. Bound: HBM in principle (4*(C*stride^2 + K) bytes per output pixel),
+        // the converters' LSU issue in practice.
+        constexpr int kSgBBytes = 96 * 128;      // im2col tile: Jpad <= 96 rows of 128 bytes (12 KB, 1 KB aligned)
+        constexpr int kSgTmemCols = 128;
+
+        struct SgWgradParams
+        {
+            int C, K, J, Jpad, R, S, stride, padX, padY;
+            int N, H, W, Ho, Wo, segs;
+            int stages, tilesK;
+            long long steps;            // N * Ho * segs
+        };
+
+        __global__ void __launch_bounds__(kScThreads, 1)
+        tc_smallc_wgrad_gather_kernel(const __grid_constant__ CUtensorMap mapDy, SgWgradParams p, const float* __restrict__ x, float* __restrict__ ws)
+        {
+            extern __shared__ uint8_t smemRaw[];
+            uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+            uint8_t* bRing = smem + p.stages * kScABytes;
+            uint64_t* bars = (uint64_t*)(bRing + kScBStages * kSgBBytes);
+            uint64_t* full = bars;               // [stages <= 8] TMA landed
+            uint64_t* empty = full + 8;          // [stages] MMA done with dy
+            uint64_t* bFull = empty + 8;         // [4]
+            uint64_t* bEmpty = bFull + 4;        // [4]
+            uint64_t* accBar = bEmpty + 4;
+            uint32_t* tmemSlot = (uint32_t*)(accBar + 1);
+
+            const int warp = threadIdx.x >> 5;
+            const int lane = threadIdx.x & 31;
+            const int kt = blockIdx.x % p.tilesK;
+            const int split = blockIdx.x / p.tilesK;
+            const int splits = gridDim.x / p.tilesK;
+            const long long per = (p.steps + splits - 1) / splits;
+            const long long begin = (long long)split * per;
+            const long long end = begin + per < p.steps ? begin + per : p.steps;
+            const int steps = end > begin ? (int)(end - begin) : 0;
+
+            if (warp == 0 && lane == 0)
+            {
+                ptx::prefetch_tensormap(&mapDy);
+                for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+                for (int s = 0; s < kScBStages; ++s) { ptx::mbar_init(&bFull[s], 1); ptx::mbar_init(&bEmpty[s], 1); }
+                ptx::mbar_init(accBar, 1);
+                ptx::fence_mbar_init();
+            }
+            if (warp == 1)
+                ptx::tmem_alloc(tmemSlot, kSgTmemCols);
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            ptx::tc_fence_after_sync();
+            ptx::pdl_launch_dependents();
+            ptx::pdl_wait();
+            const uint32_t tmemAcc = *tmemSlot;
+            const uint32_t full32 = ptx::smem_u32(full), empty32 = ptx::smem_u32(empty), bFull32 = ptx::smem_u32(bFull),
+                           bEmpty32 = ptx::smem_u32(bEmpty), accBar32 = ptx::smem_u32(accBar);
+
+            if (warp == 0)
+            {
+                if (lane == 0)
+                {
+                    int st = 0;
+                    uint32_t ph = 0;
+                    long long g = begin;
+                    int seg = (int)(g % p.segs);
+                    long long row = g / p.segs;
+                    int oh = (int)(row % p.Ho), n = (int)(row / p.Ho);
+                    for (int it = 0; it < steps; ++it)
+                    {
+                        ptx::mbar_wait(empty32 + 8u * st, ph ^ 1);
+                        ptx::mbar_arrive_expect_tx(full32 + 8u * st, kScABytes);
+                        // dy viewed as (Wo, K, Ho, N): [128 filters][32 pixels], rows past K / columns past Wo read as zeros
+                        ptx::tma_load_4d(smem + st * kScABytes, &mapDy, &full[st], seg * 32, kt * 128, oh, n);
+                        if (++st == p.stages) { st = 0; ph ^= 1; }
+                        if (++seg == p.segs) { seg = 0; if (++oh == p.Ho) { oh = 0; ++n; } }
+                    }
+                }
+            }
+            else if (warp == 1)
+            {
+                const uint32_t idesc = ptx::idesc_tf32(128, p.Jpad, 0, 0);
+                const uint64_t descA0 = ptx::smem_desc_sw128(ptx::smem_u32(smem), 16, 1024);
+                const uint64_t descB0 = ptx::smem_desc_sw128(ptx::smem_u32(bRing), 16, 1024);
+                int st = 0;
+                uint32_t ph = 0;
+                for (int it = 0; it < steps; ++it)
+                {
+                    const uint32_t bs = it & (kScBStages - 1);
+                    ptx::mbar_wait(full32 + 8u * st, ph);
+                    ptx::mbar_wait(bFull32 + 8u * bs, (it / kScBStages) & 1);
+                    ptx::tc_fence_after_sync();
+                    if (ptx::elect_one())
+                    {
+                        const uint64_t da = descA0 + (uint64_t)((st * kScABytes) >> 4);
+                        const uint64_t db = descB0 + (uint64_t)((bs * kSgBBytes) >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            ptx::mma_tf32_ss(tmemAcc, da + kk * 2, db + kk * 2, idesc, (it | kk) != 0);
+                        ptx::mma_commit(bEmpty32 + 8u * bs);
+                        ptx::mma_commit(empty32 + 8u * st);
+                    }
+                    __syncwarp();
+                    if (++st == p.stages) { st = 0; ph ^= 1; }
+                }
+                if (ptx::elect_one())
+                    ptx::mma_commit(accBar32);
+                __syncwarp();
+            }
+            else
+            {
+                // ===== converters: lane = output pixel of the step; row j = (c, r, s) of the im2col tile =====
+                const int cw = warp - 2;                       // also this warp's B stage
+                const uint32_t bTile = ptx::smem_u32(bRing) + cw * kSgBBytes;
+                // swizzled position of pixel `lane` in row j: 16-byte chunk (lane / 4) ^ (j % 8)
+                const uint32_t laneLo = (uint32_t)(lane & 3) * 4, laneChunk = (uint32_t)(lane >> 2);
+                if (steps > 0)
+                {
+                    // rows J .. Jpad-1 stay zero for the whole kernel (no other writer touches them)
+                    for (int j = p.J; j < p.Jpad; ++j)
+                        ptx::sts_b32(bTile + j * 128 + ((laneChunk ^ (uint32_t)(j & 7)) << 4) + laneLo, 0u);
+                }
+                const long long plane = (long long)p.H * p.W;
+                for (int it = cw; it < steps; it += kScBStages)
+                {
+                    const long long g = begin + it;
+                    const int seg = (int)(g % p.segs);
+                    const long long row = g / p.segs;
+                    const int oh = (int)(row % p.Ho), n = (int)(row / p.Ho);
+                    const int ow = seg * 32 + lane;
+                    const int iy0 = oh * p.stride - p.padY, ix0 = ow * p.stride - p.padX;
+                    const bool pixOk = ow < p.Wo;
+                    ptx::mbar_wait(bEmpty32 + 8u * cw, ((uint32_t)(it / kScBStages) & 1) ^ 1);
+                    const float* xn = x + (long long)n * p.C * plane;
+                    int j = 0;
+                    for (int c = 0; c < p.C; ++c)
+                        for (int r = 0; r < p.R; ++r)
+                        {
+                            const int iy = iy0 + r;
+                            const bool rowOk = pixOk && iy >= 0 && iy < p.H;
+                            const float* xr = xn + c * plane + (long long)iy * p.W;
+                            for (int s = 0; s < p.S; ++s, ++j)
+                            {
+                                const int ix = ix0 + s;
+                                const float f = (rowOk && ix >= 0 && ix < p.W) ? __ldg(xr + ix) : 0.f;
+                                ptx::sts_b32(bTile + j * 128 + ((laneChunk ^ (uint32_t)(j & 7)) << 4) + laneLo, ptx::tf32_round_bits(__float_as_uint(f)));
+                            }
+                        }
+                    // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0)
+                        ptx::mbar_arrive(bFull32 + 8u * cw);
+                }
+
+                // ----- epilogue: partial[split][kt][filter][Jpad] -----
+                const int q = warp & 3;
+                ptx::mbar_wait(accBar32, 0);
+                ptx::tc_fence_after_sync();
+                float* dst = ws + (((long long)split * p.tilesK + kt) * 128 + q * 32 + lane) * p.Jpad;
+                for (int j0 = 0; j0 < p.Jpad; j0 += 8)
+                {
+                    uint32_t v[8];
+                    if (steps > 0)
+                    {
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                                     : "r"(tmemAcc + ((uint32_t)(q * 32) << 16) + j0)
+                                     : "memory");
+                        ptx::tmem_ld_wait();
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        dst[j0 + j] = __uint_as_float(v[j]);
+                }
+            }
+
+            ptx::tc_fence_before_sync();
+            __syncthreads();
+            if (warp == 1)
+            {
+                ptx::tc_fence_after_sync();
+                ptx::tmem_dealloc(tmemAcc, kSgTmemCols);
+            }
+        }
+
         // dw[k][j] = sum over splits of partial[split][k / 128][k % 128][j]   (j = (c, r, s) is already the KCRS order)
         __global__ void smallc_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int K, int J, int Jpad, int tilesK, int splits)
         {
@@ -4199,6 +4395,65 @@ namespace nb200
         count_launch();
         NB200_CUDA_TRY(launch_kernel(smallc_wgrad_reduce_kernel, dim3(ceil_div((long long)d.K * p.J, 256)), dim3(256), 0, st, (const float*)ws, dw, d.K, p.J, p.Jpad, p.tilesK, splits));
         NB200_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        return NB200_OK;
+    }
+
+    // ---- small-channel kernel gradient, any stride / filter size (tc_smallc_wgrad_gather_kernel) ----
+    bool tc_smallc_wgrad_gather_supported(const nb200_conv_desc& d)
+    {
+        static const char* env = getenv("NB200_SMALLC_WGRAD_GATHER"); // 0 disables (profiling)
+        if (env && env[0] == '0')
+            return false;
+        return d.math == NB200_MATH_TF32 && d.fmt == NB200_NCHW && d.C >= 1 && d.C <= 8 && d.R >= 1 && d.S >= 1 && d.C * d.R * d.S <= 96 &&
+               d.stride >= 1 && d.stride <= 4 && d.Wo % 4 == 0 && d.K >= 8 && d.N >= 1 && d.H >= 1 && d.W >= 1 && d.Ho >= 1 &&
+               (long long)d.N * d.Ho * d.Wo >= 16 * 1024 && !tc_smallc_wgrad_supported(d);
+    }
+
+    static int sg_splits(const nb200_conv_desc& d)
+    {
+        const int tilesK = ceil_div(d.K, 128);
+        const long long steps = (long long)d.N * d.Ho * ceil_div(d.Wo, 32);
+        long long splits = 148 / tilesK;
+        if (splits < 1) splits = 1;
+        if (splits > steps) splits = steps > 0 ? steps : 1;
+        return (int)splits;
+    }
+
+    size_t tc_smallc_wgrad_gather_workspace(const nb200_conv_desc& d)
+    {
+        const int Jpad = round_up(d.C * d.R * d.S, 16);
+        return (size_t)sg_splits(d) * ceil_div(d.K, 128) * 128 * Jpad * sizeof(float);
+    }
+
+    int tc_smallc_gather_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes, cudaStream_t st)
+    {
+        const size_t need = tc_smallc_wgrad_gather_workspace(d);
+        if (wsBytes < need || !ws)
+            return fail(NB200_E_WORKSPACE, "kernel gradient needs %zu workspace bytes, got %zu", need, wsBytes);
+        if ((uintptr_t)dy & 15)
+            return fail(NB200_E_INVALID, "tensor base addresses must be 16-byte aligned for TMA");
+        SgWgradParams p;
+        p.C = d.C; p.K = d.K; p.J = d.C * d.R * d.S; p.Jpad = round_up(p.J, 16); p.R = d.R; p.S = d.S; p.stride = d.stride; p.padX = d.padX; p.padY = d.padY;
+        p.N = d.N; p.H = d.H; p.W = d.W; p.Ho = d.Ho; p.Wo = d.Wo; p.segs = ceil_div(d.Wo, 32);
+        p.tilesK = ceil_div(d.K, 128);
+        p.steps = (long long)d.N * d.Ho * p.segs;
+        p.stages = 8;
+        const size_t smemBytes = 1024 + (size_t)p.stages * kScABytes + kScBStages * kSgBBytes + 512;
+        CUtensorMap mapDy;
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)d.Wo, (cuuint64_t)d.K, (cuuint64_t)d.Ho, (cuuint64_t)d.N};
+            cuuint64_t strides[3] = {(cuuint64_t)d.Ho * d.Wo * 4, (cuuint64_t)d.Wo * 4, (cuuint64_t)d.K * d.Ho * d.Wo * 4};
+            cuuint32_t box[4] = {32, 128, 1, 1};
+            int rc = make_map(&mapDy, dy, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (rc) return rc;
+        }
+        static DeviceOnce attrSet{};
+        if (const int rcAttr = opt_in_smem(attrSet, tc_smallc_wgrad_gather_kernel, 220 * 1024)) return rcAttr;
+        const int splits = sg_splits(d);
+        NB200_CUDA_TRY(launch_kernel(tc_smallc_wgrad_gather_kernel, dim3((unsigned)(splits * p.tilesK)), dim3(kScThreads), smemBytes, st, mapDy, p, x, (float*)ws));
+        count_launch();
+        NB200_CUDA_TRY(launch_kernel(smallc_wgrad_reduce_kernel, dim3(ceil_div((long long)d.K * p.J, 256)), dim3(256), 0, st, (const float*)ws, dw, d.K, p.J, p.Jpad, p.tilesK, splits));
         count_launch();
         return NB200_OK;
     }

@@ -140,10 +140,14 @@ def test_kernel_dispatch_is_host_logic(L):
     assert names(_desc(8, 256, 34, 34, 512, 4, 4, 1, 0, 0))[2] == "tcgen05_gather_wgrad"
     assert names(_desc(8, 512, 4, 4, 512, 3, 3, 2, 1, 1))[2] == "tcgen05_gather_wgrad"
     assert names(_desc(8, 512, 2, 2, 512, 3, 3, 2, 1, 1))[2] == "tcgen05_gather_wgrad"
-    # stride-2 first layers with 3 / 6 channels (pix2pix enc1, PatchGAN d1, DCGAN D conv1): HBM-bound kernel gradient off the GEMM path
-    assert names(_desc(8, 3, 256, 256, 64, 3, 3, 2, 1, 1)) == ["tcgen05_gather_fprop", "tcgen05_gather_dgrad", "strided_smallc_wgrad"]
-    assert names(_desc(8, 6, 259, 259, 64, 4, 4, 2, 0, 0))[2] == "tcgen05_gather_wgrad"   # 96 running sums per filter: measured slower there
-    assert names(_desc(128, 3, 32, 32, 64, 3, 3, 2, 1, 1))[2] == "strided_smallc_wgrad"
+    # stride-2 first layers with 3 / 6 channels (pix2pix enc1, PatchGAN d1, DCGAN D conv1): HBM-bound kernel gradient as an SS-form
+    # tcgen05 GEMM over the dy stream with the im2col rows gathered from global memory (C*R*S <= 96; >= 16K output pixels) ...
+    assert names(_desc(8, 3, 256, 256, 64, 3, 3, 2, 1, 1)) == ["tcgen05_gather_fprop", "tcgen05_gather_dgrad", "tcgen05_smallc_gather_wgrad"]
+    assert names(_desc(8, 6, 259, 259, 64, 4, 4, 2, 0, 0))[2] == "tcgen05_smallc_gather_wgrad"   # x width 259: no TMA on x needed
+    assert names(_desc(128, 3, 32, 32, 64, 3, 3, 2, 1, 1))[2] == "tcgen05_smallc_gather_wgrad"
+    # ... and on small problems (or other math modes) the CUDA-core strided kernel
+    assert names(_desc(2, 3, 32, 32, 64, 3, 3, 2, 1, 1))[2] == "strided_smallc_wgrad"
+    assert names(_desc(8, 3, 256, 256, 64, 3, 3, 2, 1, 1, math=lib.MATH_FP32))[2] == "strided_smallc_wgrad"
     # few-filter output convolutions (DCGAN G out, pix2pix last, autoencoder dec3): small-channel kernels with x and y exchanged
     assert names(_desc(128, 128, 32, 32, 3, 3, 3, 1, 1, 1)) == ["smallk_fprop", "smallk_dgrad", "tcgen05_smallk_wgrad"]
     assert names(_desc(8, 128, 256, 256, 3, 3, 3, 1, 1, 1)) == ["smallk_fprop", "smallk_dgrad", "tcgen05_smallk_wgrad"]
@@ -198,9 +202,13 @@ def test_workspace_sizes_of_the_gathered_and_small_families(L):
     fk = _desc(8, 128, 256, 256, 3, 3, 3, 1, 1, 1)
     assert ws(lib.OP_FORWARD, fk) == ws(lib.OP_INPUT_GRADIENT, fk) == (128 * 3 * 9 * 4 + 255) // 256 * 256
     assert ws(lib.OP_KERNELS_GRADIENT, fk) > ws(lib.OP_FORWARD, fk)
-    # strided few-channel kernel gradient: one partial per slice
-    sg = _desc(8, 3, 256, 256, 64, 3, 3, 2, 1, 1)
+    # strided few-channel kernel gradient: CUDA-core kernel (fp32 math) one partial per slice; tensor-core kernel one [128][32] partial per CTA
+    sg = _desc(8, 3, 256, 256, 64, 3, 3, 2, 1, 1, math=lib.MATH_FP32)
     assert ws(lib.OP_KERNELS_GRADIENT, sg) % (64 * 27 * 4) == 0 and ws(lib.OP_KERNELS_GRADIENT, sg) >= 64 * 27 * 4
+    sg = _desc(8, 3, 256, 256, 64, 3, 3, 2, 1, 1)
+    assert ws(lib.OP_KERNELS_GRADIENT, sg) == 148 * 128 * 32 * 4
+    d1 = _desc(8, 6, 259, 259, 64, 4, 4, 2, 0, 0)
+    assert ws(lib.OP_KERNELS_GRADIENT, d1) == 148 * 128 * 96 * 4
 
 
 def test_workspace_bytes_is_what_the_launcher_demands_for_odd_filter_counts(L):

@@ -119,6 +119,11 @@ TC_CASES = [
     # channel-split forward / input gradient (few tiles, many channels: batch-1 style transfer on the deep layers)
     (0, 1, 256, 32, 32, 128, 3, 3, 1, 1, 1),   # 8 tiles x 4 channel splits (forward), 16 tiles x 2 splits (input gradient)
     (0, 1, 160, 32, 64, 96, 3, 3, 1, 1, 1),    # 5 channel blocks: uneven split 3 + 2
+    # few-channel kernel gradient as an SS-form tcgen05 GEMM with gathered im2col rows (TF32, >= 16K output pixels, C*R*S <= 96)
+    (0, 8, 3, 128, 128, 24, 3, 3, 2, 1, 1),    # pix2pix enc1 / DCGAN D conv1 geometry: 3 channels, 3x3, stride 2 (27 of 32 rows live)
+    (0, 4, 6, 131, 131, 40, 4, 4, 2, 0, 0),    # PatchGAN d1 geometry: 6 channels, 4x4, stride 2, odd input width (x not TMA-addressable), 96 rows
+    (0, 2, 5, 100, 134, 136, 3, 3, 1, 0, 0),   # stride 1, 5 channels (48 rows, 45 live), two filter tiles (the second ragged), ragged last segment
+    (0, 2, 2, 90, 100, 16, 5, 5, 3, 2, 2),     # stride 3, 5x5, padding 2: 50 rows in 64
     # odd filter / channel counts on the halo-tile path: the repacked filters are only a multiple of 128 bytes
     (0, 2, 16, 32, 32, 9, 3, 3, 1, 1, 1),      # 9 filters (forward repack 9*9*32*4 bytes), 9-row input-gradient tiles
     (0, 2, 32, 32, 32, 21, 1, 1, 1, 0, 0),     # 1x1 conv to 21 classes
@@ -376,7 +381,8 @@ FULL_SIZE = [  # (name, N, C, H, W, K, F, stride, pad): BASELINE-size layers of 
     ("pix2pix_patchgan_d4", 8, 256, 34, 34, 512, 4, 1, 0),    # 31x31 output maps: kernel gradient through the pitched copy of dy
     ("pix2pix_unet_dec2", 8, 1024, 4, 4, 512, 3, 1, 1),       # weight-bound: narrowed filter tile + channel splits
     ("pix2pix_last", 8, 128, 256, 256, 3, 3, 1, 1),           # few-filter layer (roles exchanged)
-    ("pix2pix_enc1", 8, 3, 256, 256, 64, 3, 2, 1),            # strided few-channel kernel gradient
+    ("pix2pix_enc1", 8, 3, 256, 256, 64, 3, 2, 1),            # strided few-channel kernel gradient (SS-form tcgen05 GEMM, gathered im2col rows)
+    ("pix2pix_patchgan_d1", 8, 6, 259, 259, 64, 4, 2, 0),     # the same with 96 im2col rows on the 259 x 259 padded pair
 ]
 
 
