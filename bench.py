@@ -204,7 +204,7 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(batch, gpus):
@@ -503,7 +503,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_run(2, 1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -730,7 +730,21 @@ def neighbour_pass(batch, iters=20):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else printed during the run (NCCL's version banner,
+    library warnings) was redirected to stderr in main()."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n"); out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)       # fd 1 -> stderr for native libraries and child processes
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

@@ -163,6 +163,29 @@ NB200_API int nb200_conv2d_forward_prepared(const nb200_conv_desc* d, const floa
 NB200_API int nb200_conv2d_input_gradient_prepared(const nb200_conv_desc* d, const float* dy, const float* w, float* dx,
                                                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- plans: one problem, fixed buffers, ONE launch call per run --------------------------------------------------------
+ * The reference-shaped entry points above re-derive everything on every call, as the reference interface demands
+ * (descriptor validation, kernel choice, cuTensorMapEncodeTiled of 2 tensor maps, the filter repack launch; the
+ * reference's cuDNN path did the same with descriptors + algorithm search, TensorOpGpu.cpp:629-668). A PLAN binds one
+ * (op, descriptor) to fixed device buffers and records the op's kernel launches -- tensor maps, grids, workspace layout
+ * baked in -- as an instantiated CUDA graph; nb200_conv2d_plan_run replays it on any stream with no host-side work
+ * beyond one cudaGraphLaunch. Results are bit-identical to the plain call (same kernels, same order).
+ *   in / out by op:  FORWARD          a = x,  b = w,  out = y   (+ bias, act, alpha)
+ *                    INPUT_GRADIENT   a = dy, b = w,  out = dx
+ *                    KERNELS_GRADIENT a = x,  b = dy, out = dw  (+ db in `bias`, may be NULL)
+ * filters_constant != 0 (FORWARD / INPUT_GRADIENT): w is repacked ONCE at plan creation (nb200_conv2d_prepare_filters)
+ * and runs skip the repack launch -- inference, style transfer against frozen VGG weights; w must then stay unchanged.
+ * The workspace (nb200_conv2d_workspace_bytes) is owned by the caller, dedicated to the plan and must outlive it.
+ * A plan belongs to the device that was current when it was created. */
+typedef struct nb200_conv_plan nb200_conv_plan;
+NB200_API int nb200_conv2d_plan_create(int32_t op, const nb200_conv_desc* d, const float* a, const float* b, float* out,
+                                       float* bias, int32_t act, float alpha, int32_t filters_constant,
+                                       void* workspace, size_t workspace_bytes, nb200_conv_plan** plan);
+NB200_API int nb200_conv2d_plan_run(const nb200_conv_plan* plan, void* stream);
+/* Number of kernel nodes the plan replays (for reports). */
+NB200_API int32_t nb200_conv2d_plan_kernels(const nb200_conv_plan* plan);
+NB200_API void nb200_conv2d_plan_destroy(nb200_conv_plan* plan);
+
 /* ---- spatial resamplers on either side of the convolutions; HBM-bound, bit-exact vs the reference ----
  * EPoolingMode, Neuro/include/Types.h:56-60 */
 enum { NB200_POOL_MAX = 0, NB200_POOL_AVG = 1 };

@@ -477,6 +477,101 @@ extern "C"
         return nb200_conv2d_input_gradient(d, dy, w, dx, workspace, workspace_bytes, stream);
     }
 
+    // ---- plans: the op's launches recorded once as an instantiated CUDA graph ----
+    struct nb200_conv_plan
+    {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        int device = -1;
+        int kernels = 0;
+    };
+
+    int nb200_conv2d_plan_create(int32_t op, const nb200_conv_desc* d, const float* a, const float* b, float* out, float* bias, int32_t act,
+                                 float alpha, int32_t filters_constant, void* workspace, size_t workspace_bytes, nb200_conv_plan** plan)
+    {
+        if (!plan)
+            return fail(NB200_E_INVALID, "null plan pointer");
+        *plan = nullptr;
+        if (op < NB200_OP_FORWARD || op > NB200_OP_KERNELS_GRADIENT)
+            return fail(NB200_E_INVALID, "unknown op %d", op);
+        int rc = validate(d, op);
+        if (rc) return rc;
+        if ((rc = require_device())) return rc;
+        if (filters_constant && op == NB200_OP_KERNELS_GRADIENT)
+            return fail(NB200_E_INVALID, "filters_constant applies to the forward and input-gradient ops");
+        cudaStream_t cs = nullptr;
+        NB200_CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{cs};
+        if (filters_constant)
+        {
+            // outside the recording: the repacked filters are part of the plan's state, not of every run
+            if ((rc = nb200_conv2d_prepare_filters(op, d, b, workspace, workspace_bytes, cs))) return rc;
+            NB200_CUDA_TRY(cudaStreamSynchronize(cs));
+        }
+        // warm the one-time per-device state (shared-memory opt-ins, driver entry points) outside the capture: those calls are
+        // not capturable. The result of this run is simply overwritten by the first replay.
+        auto issue = [&]() -> int {
+            switch (op)
+            {
+            case NB200_OP_FORWARD:
+                return filters_constant ? nb200_conv2d_forward_prepared(d, a, b, bias, act, alpha, out, workspace, workspace_bytes, cs)
+                                        : nb200_conv2d_forward(d, a, b, bias, act, alpha, out, workspace, workspace_bytes, cs);
+            case NB200_OP_INPUT_GRADIENT:
+                return filters_constant ? nb200_conv2d_input_gradient_prepared(d, a, b, out, workspace, workspace_bytes, cs)
+                                        : nb200_conv2d_input_gradient(d, a, b, out, workspace, workspace_bytes, cs);
+            default:
+                return nb200_conv2d_kernels_gradient(d, a, b, out, bias, workspace, workspace_bytes, cs);
+            }
+        };
+        if ((rc = issue())) return rc;
+        NB200_CUDA_TRY(cudaStreamSynchronize(cs));
+        nb200_conv_plan* p = new nb200_conv_plan();
+        NB200_CUDA_TRY(cudaGetDevice(&p->device));
+        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) { delete p; return fail(NB200_E_CUDA, "cudaStreamBeginCapture failed: %s", cudaGetErrorString(e)); }
+        rc = issue();
+        e = cudaStreamEndCapture(cs, &p->graph);
+        if (rc || e != cudaSuccess || !p->graph)
+        {
+            if (p->graph) cudaGraphDestroy(p->graph);
+            delete p;
+            cudaGetLastError();
+            return rc ? rc : fail(NB200_E_CUDA, "recording the plan failed: %s", cudaGetErrorString(e));
+        }
+        size_t nodes = 0;
+        cudaGraphGetNodes(p->graph, nullptr, &nodes);
+        p->kernels = (int)nodes;
+        e = cudaGraphInstantiate(&p->exec, p->graph, 0);
+        if (e != cudaSuccess)
+        {
+            cudaGraphDestroy(p->graph);
+            delete p;
+            return fail(NB200_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        }
+        *plan = p;
+        return NB200_OK;
+    }
+
+    int nb200_conv2d_plan_run(const nb200_conv_plan* plan, void* stream)
+    {
+        if (!plan || !plan->exec)
+            return fail(NB200_E_INVALID, "null or empty plan");
+        NB200_CUDA_TRY(cudaGraphLaunch(plan->exec, (cudaStream_t)stream));
+        count_launch(plan->kernels);
+        return NB200_OK;
+    }
+
+    int32_t nb200_conv2d_plan_kernels(const nb200_conv_plan* plan) { return plan ? plan->kernels : 0; }
+
+    void nb200_conv2d_plan_destroy(nb200_conv_plan* plan)
+    {
+        if (!plan)
+            return;
+        if (plan->exec) cudaGraphExecDestroy(plan->exec);
+        if (plan->graph) cudaGraphDestroy(plan->graph);
+        delete plan;
+    }
+
     int nb200_adam_step(float* param, const float* grad, float* m, float* v, size_t count, float grad_scale, float lr, float beta1,
                         float beta2, float epsilon, void* stream)
     {

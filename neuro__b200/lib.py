@@ -23,6 +23,7 @@ EXPORTS = [
     "nb200_conv2d_bias_activation_gradient_workspace_bytes", "nb200_conv2d_bias_activation_gradient",
     "nb200_conv2d_prepare_filters", "nb200_conv2d_forward_prepared", "nb200_conv2d_input_gradient_prepared",
     "nb200_pool2d", "nb200_pool2d_gradient", "nb200_upsample2d", "nb200_upsample2d_gradient", "nb200_constant_pad2d",
+    "nb200_conv2d_plan_create", "nb200_conv2d_plan_run", "nb200_conv2d_plan_kernels", "nb200_conv2d_plan_destroy",
     "nb200_bias_activation", "nb200_pool2d_gradient_activation_supported", "nb200_pool2d_gradient_activation_workspace_bytes",
     "nb200_pool2d_gradient_activation", "nb200_batch_norm_groups", "nb200_batch_norm_workspace_bytes", "nb200_batch_norm", "nb200_batch_norm_train",
     "nb200_batch_norm_gradient", "nb200_batch_norm_moments", "nb200_batch_norm_train_from_moments",
@@ -101,6 +102,10 @@ def load():
     L.nb200_conv2d_bias_activation_gradient_workspace_bytes.argtypes = [dp]
     L.nb200_conv2d_bias_activation_gradient_workspace_bytes.restype = c_sz
     L.nb200_conv2d_bias_activation_gradient.argtypes = [dp, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]
+    L.nb200_conv2d_plan_create.argtypes = [c_i, dp, c_p, c_p, c_p, c_p, c_i, c_f, c_i, c_p, c_sz, ctypes.POINTER(c_p)]
+    L.nb200_conv2d_plan_run.argtypes = [c_p, c_p]
+    L.nb200_conv2d_plan_kernels.argtypes = [c_p]; L.nb200_conv2d_plan_kernels.restype = c_i
+    L.nb200_conv2d_plan_destroy.argtypes = [c_p]; L.nb200_conv2d_plan_destroy.restype = None
     L.nb200_bias_activation.argtypes = [dp, c_p, c_p, c_i, c_f, c_p, c_p]
     L.nb200_conv2d_prepare_filters.argtypes = [c_i, dp, c_p, c_p, c_sz, c_p]
     L.nb200_conv2d_forward_prepared.argtypes = L.nb200_conv2d_forward.argtypes

@@ -73,6 +73,31 @@ class PreparedKernels:
         return (ctypes.c_void_p(self.ws.data_ptr()) if self.ws is not None else None), self.nbytes
 
 
+class ConvPlan:
+    """nb200_conv2d_plan_*: one (op, descriptor) bound to fixed device tensors, its launches recorded once; run() is one
+    cudaGraphLaunch with no host-side encode / repack. Owns its workspace; keeps the tensors alive."""
+
+    def __init__(self, L, op, d, a, b, out, bias=None, act=lib.ACT_IDENTITY, alpha=0.0, filters_constant=False):
+        self._L, self.tensors = L, (a, b, out, bias)
+        need = L.nb200_conv2d_workspace_bytes(op, ctypes.byref(d))
+        self.ws = torch.empty(max(need, 16), dtype=torch.uint8, device=a.device)
+        self.handle = ctypes.c_void_p()
+        check(L.nb200_conv2d_plan_create(op, ctypes.byref(d), _ptr(a), _ptr(b), _ptr(out), _ptr(bias), act, alpha, 1 if filters_constant else 0,
+                                         ctypes.c_void_p(self.ws.data_ptr()), need, ctypes.byref(self.handle)))
+
+    def run(self):
+        check(self._L.nb200_conv2d_plan_run(self.handle, _stream()))
+
+    @property
+    def kernels(self):
+        return self._L.nb200_conv2d_plan_kernels(self.handle)
+
+    def __del__(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self._L.nb200_conv2d_plan_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+
 class TensorOpB200:
     """Stateless apart from a grow-only device workspace per instance (reference: pooled workspace,
     TensorOpGpu.cpp:648)."""
@@ -114,6 +139,20 @@ class TensorOpB200:
         p, n = h.ptr()
         check(self._L.nb200_conv2d_prepare_filters(op, ctypes.byref(d), _ptr(kernels), p, n, _stream()))
         return h
+
+    # -- plans (include/neuro_b200.h: nb200_conv2d_plan_create)
+    def PlanConv2DBiasActivation(self, input, kernels, stride, paddingX, paddingY, bias, activation, activationAlpha, output, dataFormat=NCHW,
+                                 filtersConstant=False):
+        d = self._desc(dataFormat, input, kernels, output, stride, paddingX, paddingY)
+        return ConvPlan(self._L, lib.OP_FORWARD, d, input, kernels, output, bias, activation, activationAlpha, filtersConstant)
+
+    def PlanConv2DInputGradient(self, gradient, kernels, stride, paddingX, paddingY, dataFormat, inputGradient, filtersConstant=False):
+        d = self._desc(dataFormat, inputGradient, kernels, gradient, stride, paddingX, paddingY)
+        return ConvPlan(self._L, lib.OP_INPUT_GRADIENT, d, gradient, kernels, inputGradient, filters_constant=filtersConstant)
+
+    def PlanConv2DKernelsGradient(self, input, gradient, stride, paddingX, paddingY, dataFormat, kernelsGradient, biasGradient=None):
+        d = self._desc(dataFormat, input, kernelsGradient, gradient, stride, paddingX, paddingY)
+        return ConvPlan(self._L, lib.OP_KERNELS_GRADIENT, d, input, gradient, kernelsGradient, biasGradient)
 
     # -- the op interface (TensorOpCpu.h:46-50)
     def Conv2D(self, input, kernels, stride, paddingX, paddingY, dataFormat, output, prepared=None):

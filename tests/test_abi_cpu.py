@@ -269,3 +269,20 @@ def test_batch_norm_entry_points_are_host_validated(L):
         assert L.nb200_batch_norm_train(ctypes.byref(d), p, p, p, 0.9, 1e-3, None, None, p, p, p, p, 1 << 20, None) == -2
         assert L.nb200_batch_norm_gradient(ctypes.byref(d), p, p, p, p, p, p, p, p, p, 1 << 20, None) == -2
         assert L.nb200_batch_norm(ctypes.byref(d), p, p, p, 1e-3, p, p, p, None) == -2
+
+
+def test_plan_entry_points_are_host_validated(L):
+    """nb200_conv2d_plan_create validates like the plain calls and needs a device (no CPU fallback); NULL plans are harmless."""
+    d = lib.ConvDesc(1, 2, 6, 6, 1, 3, 3, 4, 4, 1, 0, 0, lib.NCHW, lib.MATH_FP32)
+    bad = lib.ConvDesc(1, 2, 6, 6, 1, 3, 3, 5, 4, 1, 0, 0, lib.NCHW, lib.MATH_FP32)
+    p = ctypes.c_void_p(16)
+    h = ctypes.c_void_p()
+    assert L.nb200_conv2d_plan_create(lib.OP_FORWARD, ctypes.byref(bad), p, p, p, None, 0, 0.0, 0, None, 0, ctypes.byref(h)) == -1 and not h.value
+    assert L.nb200_conv2d_plan_create(7, ctypes.byref(d), p, p, p, None, 0, 0.0, 0, None, 0, ctypes.byref(h)) == -1
+    assert L.nb200_conv2d_plan_create(lib.OP_FORWARD, ctypes.byref(d), p, p, p, None, 0, 0.0, 0, None, 0, None) == -1
+    assert L.nb200_conv2d_plan_run(None, None) == -1 and L.nb200_conv2d_plan_kernels(None) == 0
+    L.nb200_conv2d_plan_destroy(None)
+    import torch
+    if not torch.cuda.is_available():
+        assert L.nb200_conv2d_plan_create(lib.OP_FORWARD, ctypes.byref(d), p, p, p, None, 0, 0.0, 0, None, 0, ctypes.byref(h)) == -2
+        assert L.nb200_conv2d_plan_create(lib.OP_KERNELS_GRADIENT, ctypes.byref(d), p, p, p, None, 0, 0.0, 1, None, 0, ctypes.byref(h)) in (-1, -2)

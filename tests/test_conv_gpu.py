@@ -465,3 +465,41 @@ def test_full_layer_element_for_element_with_the_compiled_reference():
         assert max_norm_err(y, yr) <= tol and max_norm_err(dx, dxr) <= tol
         # the reference's fp32 running sum over 1024 pixels is itself ~1e-6 off; the 3xTF32 bound still holds against it
         assert max_norm_err(dw, dwr) <= tol
+
+
+PLAN_CASES = [(8, 64, 32, 32, 64, 3, 1, 1), (4, 64, 32, 32, 128, 3, 2, 1), (8, 128, 8, 8, 256, 4, 2, 1), (2, 3, 64, 64, 64, 3, 1, 1), (2, 256, 4, 4, 128, 3, 1, 1)]
+
+
+@pytest.mark.parametrize("cfg", PLAN_CASES, ids=["-".join(map(str, c)) for c in PLAN_CASES])
+def test_plans_replay_the_plain_calls(cfg):
+    """nb200_conv2d_plan_*: the op's launches recorded once (tensor maps, grids, workspace layout baked in) and replayed by one
+    cudaGraphLaunch -- same kernels in the same order, so bit-identical to the reference-shaped calls; the plan reads the LIVE
+    buffers (new inputs -> new outputs), and filters_constant skips the repack launch."""
+    N, C, H, W, K, F, st, p = cfg
+    x, w, dy = make_inputs(lib.NCHW, N, C, H, W, K, F, F, st, p, p, glorot=True)
+    b = synth.uniform(synth.SEED_BIAS, (K,))
+    op = TensorOpB200(lib.MATH_TF32)
+    xd, wd, bd, dyd = dev(x), dev(w), dev(b), dev(dy)
+    y0 = torch.empty(dy.shape, device="cuda"); dx0 = torch.empty(x.shape, device="cuda"); dw0 = torch.empty(w.shape, device="cuda"); db0 = torch.empty(K, device="cuda")
+    op.Conv2DBiasActivation(xd, wd, st, p, p, bd, lib.ACT_RELU, 0.0, y0)
+    op.Conv2DInputGradient(dyd, wd, st, p, p, lib.NCHW, dx0)
+    op.Conv2DKernelsGradient(xd, dyd, st, p, p, lib.NCHW, dw0, db0)
+    y1 = torch.full(dy.shape, float("nan"), device="cuda"); dx1 = torch.full(x.shape, float("nan"), device="cuda")
+    dw1 = torch.full(w.shape, float("nan"), device="cuda"); db1 = torch.full((K,), float("nan"), device="cuda")
+    pf = op.PlanConv2DBiasActivation(xd, wd, st, p, p, bd, lib.ACT_RELU, 0.0, y1, filtersConstant=True)
+    pg = op.PlanConv2DInputGradient(dyd, wd, st, p, p, lib.NCHW, dx1)
+    pw = op.PlanConv2DKernelsGradient(xd, dyd, st, p, p, lib.NCHW, dw1, db1)
+    L = lib.load()
+    for _ in range(2):
+        for t in (y1, dx1, dw1, db1):
+            t.fill_(float("nan"))
+        n0 = L.nb200_kernel_launches()
+        pf.run(); pg.run(); pw.run()
+        assert L.nb200_kernel_launches() - n0 == pf.kernels + pg.kernels + pw.kernels
+        assert torch.equal(y1, y0) and torch.equal(dx1, dx0) and torch.equal(dw1, dw0) and torch.equal(db1, db0)
+    assert pf.kernels <= pg.kernels      # constant filters: no repack node in the forward plan
+    # live buffers: scale the input, the replayed forward follows
+    xd.mul_(0.5)
+    op.Conv2DBiasActivation(xd, wd, st, p, p, bd, lib.ACT_RELU, 0.0, y0)
+    pf.run()
+    assert torch.equal(y1, y0)
