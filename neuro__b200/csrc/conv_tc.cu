@@ -2618,6 +2618,10 @@ namespace nb200
         // tc_fprop_kernel<BN, true>).
         constexpr int kWgX3Segment = 8;
 
+        // (A TF32 variant that wrote the A tiles straight into shared memory as swizzled K-major tiles -- SS-form MMA, no transposing
+        // scratch, no TMEM store -- was parity-clean and SLOWER: 128 -> 128 @16x16, batch 128: 0.138 -> 0.200 ms; 256 -> 512 @31x31:
+        // 0.257 -> 0.379 ms. An M128 x N128 x K8 SS MMA reads 8 KB of operands from shared memory per 64 cycles = the whole 128 B/clk
+        // of the SM while the converters' stores and the TMA writes want it too; the TS form keeps A off that path.)
         template <int BN, bool X3>
         __global__ void __launch_bounds__(kThreads, 1)
         tc_wgrad_gather_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ WgatherParams p, const float* __restrict__ x,
@@ -2630,11 +2634,8 @@ namespace nb200
 
             extern __shared__ uint8_t smemRaw[];
             uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
-            // TF32 mode: the A tiles live in shared memory (SS-form MMA): [kWgAStages][128 channel rows][32 pixels], SWIZZLE_128B.
-            // 3xTF32 mode: A tiles in tensor memory (TS form), built through a per-warp transposing scratch [8 warps][32][33].
-            uint8_t* aRing = smem + p.stages * kBBytes;
-            float* scratch = (float*)aRing;
-            uint64_t* bars = (uint64_t*)(aRing + (X3 ? 8 * kWgScratchFloats * 4 : kWgAStages * 16384));
+            float* scratch = (float*)(smem + p.stages * kBBytes);              // [8 warps][32][33]
+            uint64_t* bars = (uint64_t*)(scratch + 8 * kWgScratchFloats);
             uint64_t* full = bars;
             uint64_t* empty = full + 8;
             uint64_t* aFull = empty + 8;
@@ -2701,7 +2702,6 @@ namespace nb200
             {
                 constexpr uint32_t idesc = ptx::idesc_tf32(128, BN, 0, 0);
                 const uint64_t descB0 = ptx::smem_desc_kmajor(ptx::smem_u32(smem), 8 * p.rowBytes, p.layoutType);
-                const uint64_t descA0 = ptx::smem_desc_sw128(ptx::smem_u32(aRing), 16, 1024);
                 const uint32_t subTile = BN * p.rowBytes;   // bytes of one image's sub-tile
                 int st = 0, as = 0;
                 uint32_t ph = 0, aph = 0;
@@ -2728,10 +2728,7 @@ namespace nb200
                                 // reduction elements kk*8 .. kk*8+7: sub-tile (kk*8)/PXI, byte offset ((kk*8)%PXI)*4 inside the row
                                 const uint32_t off = stageOff + ((kk * 8) / p.PXI) * subTile + (((kk * 8) % p.PXI) << 2);
                                 const uint32_t accumulate = X3 ? ((it % kWgX3Segment) | kk) != 0 : (it | kk) != 0;
-                                if (!X3)
-                                    ptx::mma_tf32_ss(tmemAcc + tp * BN, descA0 + (uint64_t)((as * 16384) >> 4) + kk * 2, descB0 + (uint64_t)(off >> 4), idesc, accumulate);
-                                else
-                                    ptx::mma_tf32_ts(tmemAcc + tp * BN, ta + kk * 8, descB0 + (uint64_t)(off >> 4), idesc, accumulate);          // hi * hi
+                                ptx::mma_tf32_ts(tmemAcc + tp * BN, ta + kk * 8, descB0 + (uint64_t)(off >> 4), idesc, accumulate);          // hi * hi
                                 if (X3)
                                 {
                                     ptx::mma_tf32_ts(tmemAcc, ta + kk * 8, descB0 + (uint64_t)((off + kBTile) >> 4), idesc, 1);              // hi * lo
@@ -2849,27 +2846,6 @@ namespace nb200
                     const int iy = oh * p.stride - p.padY + r, ix = ow * p.stride - p.padX + s;
                     const bool ok = img < p.N && hw < hwTotal && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
                     const float* src = x + (img * p.C + cw0) * plane + (long long)iy * p.W + ix;
-                    if constexpr (!X3)
-                    {
-                        // SS form: lane = pixel writes row = channel of the swizzled K-major tile directly (no transpose, no TMEM store):
-                        // element (channel row rr, pixel lane) sits in 16-byte chunk (lane / 4) ^ (rr % 8) of its 128-byte row
-                        uint32_t vv[32];
-#pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            vv[c] = ptx::tf32_round_bits(__float_as_uint((ok && cw0 + c < p.C) ? __ldg(src + c * plane) : 0.f));
-                        const int asS = (int)(j & (kWgAStages - 1));
-                        ptx::mbar_wait(&aEmpty[asS], ((uint32_t)(j / kWgAStages) & 1) ^ 1);
-                        const uint32_t tile = ptx::smem_u32(aRing) + (uint32_t)asS * 16384u + (uint32_t)(q * 32) * 128u + (uint32_t)(lane & 3) * 4u;
-                        const uint32_t chunk = (uint32_t)(lane >> 2);
-#pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            ptx::sts_b32(tile + (uint32_t)c * 128u + ((chunk ^ (uint32_t)(c & 7)) << 4), vv[c]);   // (q*32 + c) % 8 == c % 8
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the MMA's async proxy
-                        __syncwarp();
-                        if (lane == 0)
-                            ptx::mbar_arrive(&aFull[asS]);
-                        continue;
-                    }
 #pragma unroll
                     for (int c = 0; c < 32; ++c)
                     {
@@ -4280,9 +4256,8 @@ namespace nb200
                 return pl;
             pl.BN = d.K > 64 ? 128 : 64;
             const int ntaps = d.R * d.S;
-            pl.tapsPerGroup = (x3 ? 384 : 512) / pl.BN; // accumulator columns / BN (3xTF32 keeps its A ring in tensor memory)
+            pl.tapsPerGroup = 384 / pl.BN; // accumulator columns (512 - 128 for the A ring) / BN
             if (pl.tapsPerGroup > ntaps) pl.tapsPerGroup = ntaps;
-            pl.tapsPerGroup = ceil_div(ntaps, ceil_div(ntaps, pl.tapsPerGroup)); // same number of groups, evenly filled (9 taps: 3 + 3 + 3, not 4 + 4 + 1)
             if (x3) pl.tapsPerGroup = 1; // one accumulator per CTA: its running sums live in registers between segments
             pl.groups = ceil_div(ntaps, pl.tapsPerGroup);
             pl.tilesC = ceil_div(d.C, 128);
@@ -4296,7 +4271,7 @@ namespace nb200
             pl.chunksPerSplit = (pl.chunks + splits - 1) / splits;
             pl.splits = (int)((pl.chunks + pl.chunksPerSplit - 1) / pl.chunksPerSplit);
             pl.stages = x3 ? 5 : 6;     // 3xTF32 stages carry a hi and a lo tile
-            pl.smemBytes = 1024 + 512 + (size_t)pl.stages * pl.BN * 128 * (x3 ? 2 : 1) + (x3 ? 8 * kWgScratchFloats * sizeof(float) : (size_t)kWgAStages * 16384);
+            pl.smemBytes = 1024 + 512 + (size_t)pl.stages * pl.BN * 128 * (x3 ? 2 : 1) + 8 * kWgScratchFloats * sizeof(float);
             pl.partialBytes = ((size_t)pl.splits * ntaps * d.K * d.C * sizeof(float) + 255) & ~(size_t)255;
             pl.wsBytes = pl.partialBytes + (pl.hwPad != hw ? (size_t)d.N * d.K * pl.hwPad * sizeof(float) : 0);
             return pl;
