@@ -97,8 +97,21 @@ NB200_API int32_t nb200_conv_transpose_out_size(int32_t in, int32_t filter, int3
 /* Bytes of device scratch the op may use for this problem (0 is a valid answer). */
 NB200_API size_t nb200_conv2d_workspace_bytes(int32_t op, const nb200_conv_desc* d);
 
-/* Name of the kernel family the dispatcher picks for this problem ("tcgen05_fprop", "direct_fprop", ...);
- * static storage. For reports and tests. */
+/* Name of the kernel family the dispatcher picks for this problem; static storage. This is the advertised way to find out
+ * whether a problem runs on the tensor cores ("tcgen05_*") or on a CUDA-core family -- nothing degrades silently:
+ *
+ *   math \ layout, shape        NCHW, C and K > 4                NCHW, C <= 4 or K <= 4 (HBM-bound)        NHWC
+ *   NB200_MATH_TF32             tcgen05_{fprop,dgrad,wgrad}      smallc_* / smallk_* (fp32 FMA) forward    tcgen05_*_nhwc (the NCHW
+ *                               tcgen05_rowtap_*, _rowfold_wgrad and input gradient; kernel gradient:    kernels between two layout
+ *                               tcgen05_gather_* (strides,       tcgen05_smallc_wgrad,                    passes), else direct_*
+ *                               small / odd maps)                tcgen05_smallc_gather_wgrad (strided)
+ *   NB200_MATH_3XTF32           tcgen05_{fprop,dgrad},           as above (fp32 FMA kernels serve every   as above
+ *                               tcgen05_gather_{fprop,dgrad,     math mode; small strided kernel
+ *                               wgrad}                           gradients: strided_smallc_wgrad)
+ *   NB200_MATH_FP32             direct_* (fp32 FMA)              smallc_* / smallk_* / strided_*          direct_*
+ *
+ * Grid-size heuristics assume the 148 SMs of a B200 (workspace sizes must be computable without a device); persistent
+ * grids query the device's SM count at launch. */
 NB200_API const char* nb200_conv2d_kernel_name(int32_t op, const nb200_conv_desc* d);
 
 /* y = act(conv(x, w) + bias).
@@ -116,9 +129,10 @@ NB200_API int nb200_conv2d_forward(const nb200_conv_desc* d, const float* x, con
 NB200_API int nb200_conv2d_input_gradient(const nb200_conv_desc* d, const float* dy, const float* w,
                                           float* dx, void* workspace, size_t workspace_bytes, void* stream);
 
-/* dw = conv_kernels_gradient(x, dy); optionally db[k] = sum_{n,ho,wo} dy (bias gradient folded into
- * the same pass over dy). Replaces TensorOpCpu::Conv2DKernelsGradient (TensorOpCpu.h:50,
- * TensorOpCpu.cpp:1129); db != NULL additionally replaces Conv2DBiasGradient (TensorOpCpu.h:48). */
+/* dw = conv_kernels_gradient(x, dy); optionally db[k] = sum_{n,ho,wo} dy in the same CALL (a separate pass over dy
+ * inside it: use nb200_conv2d_bias_activation_gradient / nb200_pool2d_gradient_activation to get db for free from the pass
+ * that produces dy). Replaces TensorOpCpu::Conv2DKernelsGradient (TensorOpCpu.h:50, TensorOpCpu.cpp:1129); db != NULL
+ * additionally replaces Conv2DBiasGradient (TensorOpCpu.h:48). */
 NB200_API int nb200_conv2d_kernels_gradient(const nb200_conv_desc* d, const float* x, const float* dy,
                                             float* dw, float* db, void* workspace, size_t workspace_bytes,
                                             void* stream);

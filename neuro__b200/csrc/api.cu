@@ -198,6 +198,50 @@ namespace nb200
                 return tc_kernels_gradient_supported(d) ? kTc : kDirect;
             }
         }
+
+        // ---- NHWC on the tensor cores: the NCHW kernels between two layout passes ----
+        // (the reference's GPU path ignored dataFormat in the forward op and fell back to the CPU for NHWC gradients,
+        // TensorOpGpu.cpp:629-845; here an NHWC problem whose NCHW twin has a tcgen05 kernel runs that kernel on NCHW copies)
+        nb200_conv_desc nchw_twin(const nb200_conv_desc& d)
+        {
+            nb200_conv_desc t = d;
+            t.fmt = NB200_NCHW;
+            return t;
+        }
+
+        bool nhwc_via_layout(int op, const nb200_conv_desc& d)
+        {
+            static const char* env = getenv("NB200_NHWC_TC"); // 0 disables (profiling)
+            if (d.fmt != NB200_NHWC || d.math == NB200_MATH_FP32 || (env && env[0] == '0'))
+                return false;
+            const Family f = pick(op, nchw_twin(d));
+            return f == kTc || f == kGather;
+        }
+
+        struct NhwcLayout { size_t xOff, yOff, total; };
+        NhwcLayout nhwc_layout(int op, const nb200_conv_desc& d)
+        {
+            const nb200_conv_desc t = nchw_twin(d);
+            const size_t inner = pick(op, t) == kTc ? tc_workspace_bytes(op, t)
+                               : op == NB200_OP_KERNELS_GRADIENT ? tc_gather_kernels_gradient_workspace(t) : tc_gather_workspace_bytes(op, t);
+            NhwcLayout l;
+            l.xOff = align256(inner);
+            l.yOff = l.xOff + align256((size_t)d.N * d.C * d.H * d.W * sizeof(float));
+            l.total = l.yOff + align256((size_t)d.N * d.K * d.Ho * d.Wo * sizeof(float));
+            return l;
+        }
+
+        const char* nhwc_name(const char* twin)
+        {
+            static const char* const names[][2] = {
+                {"tcgen05_fprop", "tcgen05_fprop_nhwc"}, {"tcgen05_rowtap_fprop", "tcgen05_rowtap_fprop_nhwc"}, {"tcgen05_gather_fprop", "tcgen05_gather_fprop_nhwc"},
+                {"tcgen05_dgrad", "tcgen05_dgrad_nhwc"}, {"tcgen05_rowtap_dgrad", "tcgen05_rowtap_dgrad_nhwc"}, {"tcgen05_gather_dgrad", "tcgen05_gather_dgrad_nhwc"},
+                {"tcgen05_wgrad", "tcgen05_wgrad_nhwc"}, {"tcgen05_rowfold_wgrad", "tcgen05_rowfold_wgrad_nhwc"}, {"tcgen05_gather_wgrad", "tcgen05_gather_wgrad_nhwc"}};
+            for (const auto& n : names)
+                if (!strcmp(n[0], twin))
+                    return n[1];
+            return "tcgen05_nhwc";
+        }
     }
 }
 
@@ -246,6 +290,8 @@ extern "C"
     {
         if (!d || validate(d, -1) != NB200_OK)
             return 0;
+        if (nhwc_via_layout(op, *d))
+            return nhwc_layout(op, *d).total;
         const Family f = pick(op, *d);
         if (f == kTc)
             return tc_workspace_bytes(op, *d);
@@ -266,6 +312,11 @@ extern "C"
     {
         if (!d || validate(d, -1) != NB200_OK)
             return "invalid";
+        if (nhwc_via_layout(op, *d))
+        {
+            const nb200_conv_desc t = nchw_twin(*d);
+            return nhwc_name(nb200_conv2d_kernel_name(op, &t));
+        }
         const Family f = pick(op, *d);
         if (f == kSmallCGather)
             return "tcgen05_smallc_gather_wgrad";
@@ -299,6 +350,17 @@ extern "C"
             return fail(NB200_E_INVALID, "null tensor pointer");
         if ((rc = require_device())) return rc;
         cudaStream_t st = (cudaStream_t)stream;
+        if (nhwc_via_layout(NB200_OP_FORWARD, *d))
+        {
+            const NhwcLayout l = nhwc_layout(NB200_OP_FORWARD, *d);
+            if (!workspace || workspace_bytes < l.total)
+                return fail(NB200_E_WORKSPACE, "NHWC conv needs %zu workspace bytes, got %zu", l.total, workspace_bytes);
+            const nb200_conv_desc t = nchw_twin(*d);
+            float* xs = (float*)((uint8_t*)workspace + l.xOff); float* ys = (float*)((uint8_t*)workspace + l.yOff);
+            if (g_tcFilterMode != kFiltersOnly && (rc = layout_transpose(x, xs, d->N, d->C, d->H * d->W, true, st))) return rc;
+            if ((rc = nb200_conv2d_forward(&t, xs, w, bias, act, alpha, ys, workspace, l.xOff, stream))) return rc;
+            return g_tcFilterMode == kFiltersOnly ? NB200_OK : layout_transpose(ys, y, d->N, d->K, d->Ho * d->Wo, false, st);
+        }
         const Family f = pick(NB200_OP_FORWARD, *d);
         if (f == kTc)
             return tc_forward(*d, x, w, bias, act, alpha, y, workspace, workspace_bytes, st);
@@ -322,6 +384,17 @@ extern "C"
             return fail(NB200_E_INVALID, "null tensor pointer");
         if ((rc = require_device())) return rc;
         cudaStream_t st = (cudaStream_t)stream;
+        if (nhwc_via_layout(NB200_OP_INPUT_GRADIENT, *d))
+        {
+            const NhwcLayout l = nhwc_layout(NB200_OP_INPUT_GRADIENT, *d);
+            if (!workspace || workspace_bytes < l.total)
+                return fail(NB200_E_WORKSPACE, "NHWC conv needs %zu workspace bytes, got %zu", l.total, workspace_bytes);
+            const nb200_conv_desc t = nchw_twin(*d);
+            float* xs = (float*)((uint8_t*)workspace + l.xOff); float* ys = (float*)((uint8_t*)workspace + l.yOff);
+            if (g_tcFilterMode != kFiltersOnly && (rc = layout_transpose(dy, ys, d->N, d->K, d->Ho * d->Wo, true, st))) return rc;
+            if ((rc = nb200_conv2d_input_gradient(&t, ys, w, xs, workspace, l.xOff, stream))) return rc;
+            return g_tcFilterMode == kFiltersOnly ? NB200_OK : layout_transpose(xs, dx, d->N, d->C, d->H * d->W, false, st);
+        }
         const Family f = pick(NB200_OP_INPUT_GRADIENT, *d);
         if (f == kTc)
             return tc_input_gradient(*d, dy, w, dx, workspace, workspace_bytes, st);
@@ -349,6 +422,17 @@ extern "C"
         if (!dw || ((!x || !dy) && (long long)d->N * d->Ho * d->Wo > 0))
             return fail(NB200_E_INVALID, "null tensor pointer");
         if ((rc = require_device())) return rc;
+        if (nhwc_via_layout(NB200_OP_KERNELS_GRADIENT, *d))
+        {
+            const NhwcLayout l = nhwc_layout(NB200_OP_KERNELS_GRADIENT, *d);
+            if (!workspace || workspace_bytes < l.total)
+                return fail(NB200_E_WORKSPACE, "NHWC conv needs %zu workspace bytes, got %zu", l.total, workspace_bytes);
+            const nb200_conv_desc t = nchw_twin(*d);
+            float* xs = (float*)((uint8_t*)workspace + l.xOff); float* ys = (float*)((uint8_t*)workspace + l.yOff);
+            if ((rc = layout_transpose(x, xs, d->N, d->C, d->H * d->W, true, st))) return rc;
+            if ((rc = layout_transpose(dy, ys, d->N, d->K, d->Ho * d->Wo, true, st))) return rc;
+            return nb200_conv2d_kernels_gradient(&t, xs, ys, dw, nullptr, workspace, l.xOff, stream);   // kernels are KCRS in both formats; db was taken above
+        }
         const Family f = pick(NB200_OP_KERNELS_GRADIENT, *d);
         if (f == kTc)
             return tc_kernels_gradient(*d, x, dy, dw, workspace, workspace_bytes, st);
@@ -449,6 +533,15 @@ extern "C"
         if (!w)
             return fail(NB200_E_INVALID, "null tensor pointer");
         if ((rc = require_device())) return rc;
+        if (nhwc_via_layout(op, *d))
+        {
+            // the NCHW twin's repacked filters live at the head of the same workspace the *_prepared call will be given
+            const NhwcLayout l = nhwc_layout(op, *d);
+            if (!workspace || workspace_bytes < l.total)
+                return fail(NB200_E_WORKSPACE, "NHWC conv needs %zu workspace bytes, got %zu", l.total, workspace_bytes);
+            const nb200_conv_desc t = nchw_twin(*d);
+            return nb200_conv2d_prepare_filters(op, &t, w, workspace, l.xOff, stream);
+        }
         const Family f = pick(op, *d);
         if (f != kTc && f != kGather && f != kSmallK)
             return NB200_OK; // these kernels read w as it is

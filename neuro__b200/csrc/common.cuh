@@ -165,6 +165,9 @@ namespace nb200
     int tc_gather_kernels_gradient(const nb200_conv_desc& d, const float* x, const float* dy, float* dw, void* ws, size_t wsBytes,
                                    cudaStream_t st);
 
+    // resample.cu: NHWC <-> NCHW layout pass (per image [HW][C] <-> [C][HW])
+    int layout_transpose(const float* src, float* dst, int N, int C, int HW, bool toNchw, cudaStream_t st);
+
     // elementwise.cu
     int bias_gradient(const nb200_conv_desc& d, const float* dy, float* db, cudaStream_t st);
     // dz = act'(y) * dy and (optionally) db = sum over N,H,W of dz, one pass over HBM

@@ -314,6 +314,35 @@ namespace nb200
         }
 
         // 2x2 stride-2 unpadded NCHW pooling on rows of whole float4 pairs; every pointer that is passed must be 16-byte aligned
+        // Layout pass between the reference's two data formats: per image, dst[c][p] = src[p][c] (toNchw) or dst[p][c] = src[c][p],
+        // p = h*W + w; 32 x 32 tiles through padded shared memory, both sides coalesced. Bound: HBM, 8 bytes per element.
+        __global__ void __launch_bounds__(256)
+        layout_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols)
+        {
+            ptx::pdl_launch_dependents(); // programmatic dependent launch, see common.cuh
+            ptx::pdl_wait();
+            // src is [rows][cols] per image, dst [cols][rows]
+            __shared__ float tile[32][33];
+            const long long img = (long long)blockIdx.z * rows * cols;
+            const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+            const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8)
+            {
+                const int r = r0 + ty + i, c = c0 + tx;
+                if (r < rows && c < cols)
+                    tile[ty + i][tx] = __ldg(src + img + (long long)r * cols + c);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 32; i += 8)
+            {
+                const int c = c0 + ty + i, r = r0 + tx;
+                if (r < rows && c < cols)
+                    dst[img + (long long)c * rows + r] = tile[tx][ty + i];
+            }
+        }
+
         bool pool2x2_fast(const nb200_pool_desc& d, const void* a, const void* b, const void* c, const void* e)
         {
             return d.fmt == NB200_NCHW && d.filter == 2 && d.stride == 2 && d.padX == 0 && d.padY == 0 && d.H % 2 == 0 && d.W % 8 == 0 &&
@@ -368,6 +397,23 @@ namespace nb200
 }
 
 using namespace nb200;
+
+namespace nb200
+{
+    // NHWC (N, H*W, C) <-> NCHW (N, C, H*W): the tensor-core kernels are NCHW; NHWC problems run them between two layout passes
+    int layout_transpose(const float* src, float* dst, int N, int C, int HW, bool toNchw, cudaStream_t st)
+    {
+        if ((long long)N * C * HW == 0)
+            return NB200_OK;
+        if (N > 65535 || (C + 31) / 32 > 65535 || (HW + 31) / 32 > 65535)
+            return fail(NB200_E_UNSUPPORTED, "layout pass: extent too large for one grid");
+        const int rows = toNchw ? HW : C, cols = toNchw ? C : HW;
+        const dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32), (unsigned)N);
+        NB200_CUDA_TRY(launch_kernel(layout_transpose_kernel, grid, dim3(256), 0, st, src, dst, rows, cols));
+        count_launch();
+        return NB200_OK;
+    }
+}
 
 extern "C"
 {

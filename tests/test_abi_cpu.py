@@ -159,9 +159,16 @@ def test_kernel_dispatch_is_host_logic(L):
     for shape in [(128, 64, 32, 32, 128, 3, 3, 2, 1, 1), (128, 128, 8, 8, 256, 4, 4, 2, 1, 1), (8, 256, 34, 34, 512, 4, 4, 1, 0, 0), (8, 512, 512 // 16, 512 // 16, 512, 3, 3, 1, 1, 1)]:
         n3 = names(_desc(*shape, math=lib.MATH_3XTF32))
         assert all(n.startswith("tcgen05_") for n in n3), (shape, n3)
-    # fp32 math and NHWC never touch the tensor-core families
+    # fp32 math never touches the tensor-core families; NHWC runs the NCHW tensor-core kernels between two layout passes
     assert all(n.startswith("direct_") for n in names(_desc(8, 64, 64, 64, 64, 3, 3, 1, 1, 1, math=lib.MATH_FP32)))
-    assert all(n.startswith("direct_") for n in names(_desc(8, 64, 64, 64, 64, 3, 3, 1, 1, 1, fmt=lib.NHWC)))
+    assert names(_desc(8, 64, 64, 64, 64, 3, 3, 1, 1, 1, fmt=lib.NHWC)) == ["tcgen05_rowtap_fprop_nhwc", "tcgen05_rowtap_dgrad_nhwc", "tcgen05_rowfold_wgrad_nhwc"]
+    assert names(_desc(8, 64, 32, 32, 128, 3, 3, 2, 1, 1, fmt=lib.NHWC, math=lib.MATH_3XTF32)) == ["tcgen05_gather_fprop_nhwc", "tcgen05_gather_dgrad_nhwc", "tcgen05_gather_wgrad_nhwc"]
+    assert all(n.startswith("direct_") for n in names(_desc(8, 64, 64, 64, 64, 3, 3, 1, 1, 1, fmt=lib.NHWC, math=lib.MATH_FP32)))
+    assert all(n.startswith("direct_") for n in names(_desc(2, 3, 64, 64, 16, 3, 3, 1, 1, 1, fmt=lib.NHWC)))       # first layers stay on the fp32 path
+    # ... and its workspace holds the NCHW copies of both activation tensors behind the twin's own workspace
+    nh = _desc(8, 64, 64, 64, 64, 3, 3, 1, 1, 1, fmt=lib.NHWC); nc = _desc(8, 64, 64, 64, 64, 3, 3, 1, 1, 1)
+    L.nb200_conv2d_workspace_bytes.restype = ctypes.c_size_t
+    assert L.nb200_conv2d_workspace_bytes(lib.OP_FORWARD, ctypes.byref(nh)) >= L.nb200_conv2d_workspace_bytes(lib.OP_FORWARD, ctypes.byref(nc)) + 2 * 8 * 64 * 64 * 64 * 4
 
 
 def test_workspace_sizes_cover_every_kernel_of_an_op(L):

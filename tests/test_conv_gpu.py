@@ -60,7 +60,9 @@ TC_CASES = [
     (0, 1, 64, 32, 32, 64, 1, 1, 1, 0, 0),     # 1x1
     (0, 4, 64, 32, 32, 128, 3, 3, 2, 1, 1),    # DCGAN D stride 2
     (0, 4, 128, 16, 16, 64, 4, 4, 2, 1, 1),    # DCGAN G deconv geometry (4x4 s2 p1)
-    (1, 2, 64, 32, 32, 64, 3, 3, 1, 1, 1),     # NHWC twin
+    (1, 2, 64, 32, 32, 64, 3, 3, 1, 1, 1),     # NHWC twin: the NCHW tensor-core kernels between two layout passes
+    (1, 4, 64, 16, 16, 128, 3, 3, 2, 1, 1),    # NHWC, strided (gathered kernels underneath), channel / pixel counts not multiples of 32 in the layout pass tiles
+    (1, 2, 40, 20, 24, 72, 3, 3, 1, 1, 1),     # NHWC, ragged channels and filters
     (0, 1, 64, 30, 30, 64, 3, 3, 1, 1, 1),     # W % 4 != 0 -> TMA stride rule fails, must fall back
     (0, 2, 3, 64, 64, 64, 3, 3, 1, 1, 1),      # first-layer (small-channel) kernels: VGG block1_conv1 geometry
     (0, 4, 1, 28, 28, 16, 3, 3, 1, 1, 1),      # conv autoencoder enc conv1 (config 1)
@@ -503,3 +505,24 @@ def test_plans_replay_the_plain_calls(cfg):
     op.Conv2DBiasActivation(xd, wd, st, p, p, bd, lib.ACT_RELU, 0.0, y0)
     pf.run()
     assert torch.equal(y1, y0)
+
+
+def test_nhwc_prepared_filters_and_plan():
+    """NHWC through the layout passes with constant filters: prepare once, run prepared / as a plan -- same results as the plain NHWC call."""
+    N, C, H, W, K, F, st, p = 2, 64, 32, 32, 96, 3, 1, 1
+    x, w, dy = make_inputs(lib.NHWC, N, C, H, W, K, F, F, st, p, p, glorot=True)
+    op = TensorOpB200(lib.MATH_TF32)
+    xd, wd, dyd = dev(x), dev(w), dev(dy)
+    assert op.kernel_name(lib.OP_FORWARD, lib.ConvDesc(N, C, H, W, K, F, F, H, W, st, p, p, lib.NHWC, lib.MATH_TF32)).endswith("_nhwc")
+    y0 = torch.empty(dy.shape, device="cuda"); dx0 = torch.empty(x.shape, device="cuda")
+    op.Conv2D(xd, wd, st, p, p, lib.NHWC, y0); op.Conv2DInputGradient(dyd, wd, st, p, p, lib.NHWC, dx0)
+    assert max_norm_err(y0, O.conv2d(x, w, st, p, p, lib.NHWC)) <= TOL[lib.MATH_TF32]
+    hf = op.PrepareKernels(lib.OP_FORWARD, xd, wd, y0, st, p, p, lib.NHWC)
+    hg = op.PrepareKernels(lib.OP_INPUT_GRADIENT, dx0, wd, dyd, st, p, p, lib.NHWC)
+    y1 = torch.full(dy.shape, float("nan"), device="cuda"); dx1 = torch.full(x.shape, float("nan"), device="cuda")
+    op.Conv2D(xd, wd, st, p, p, lib.NHWC, y1, prepared=hf); op.Conv2DInputGradient(dyd, wd, st, p, p, lib.NHWC, dx1, prepared=hg)
+    assert torch.equal(y1, y0) and torch.equal(dx1, dx0)
+    y2 = torch.full(dy.shape, float("nan"), device="cuda")
+    plan = op.PlanConv2DBiasActivation(xd, wd, st, p, p, None, lib.ACT_IDENTITY, 0.0, y2, dataFormat=lib.NHWC, filtersConstant=True)
+    plan.run()
+    assert torch.equal(y2, y0)
