@@ -37,6 +37,7 @@ namespace NeuroB200
     enum EDataFormat { NCHW = NB200_NCHW, NHWC = NB200_NHWC };               // Types.h:94-98
     enum EPoolingMode { MaxPool = NB200_POOL_MAX, AvgPool = NB200_POOL_AVG };  // Types.h:56-60
     enum EActivation { _Identity, _Sigmoid, _ReLU, _TanH, _ELU, _LeakyReLU, _Softmax }; // Types.h:83-92
+    enum EBatchNormMode { PerActivation = NB200_BN_PER_ACTIVATION, Spatial = NB200_BN_SPATIAL, Instance = NB200_BN_INSTANCE }; // Types.h:70-75
 
     inline void CudaCheck(cudaError_t e, const char* what)
     {
@@ -101,6 +102,10 @@ namespace NeuroB200
         virtual void UpSample2D(const Tensor&, uint32_t, Tensor&) const { throw std::runtime_error("UpSample2D: not implemented by this backend"); }
         virtual void UpSample2DGradient(const Tensor&, uint32_t, Tensor&) const { throw std::runtime_error("UpSample2DGradient: not implemented by this backend"); }
         virtual void ConstantPad2D(const Tensor&, uint32_t, uint32_t, uint32_t, uint32_t, float, Tensor&) const { throw std::runtime_error("ConstantPad2D: not implemented by this backend"); }
+        // batch normalisation (TensorOpCpu.h:55-57); gamma / beta / statistics hold one value per normalisation group
+        virtual void BatchNormalization(const Tensor&, EBatchNormMode, const Tensor&, const Tensor&, float, const Tensor*, const Tensor*, Tensor&) const { throw std::runtime_error("BatchNormalization: not implemented by this backend"); }
+        virtual void BatchNormalizationTrain(const Tensor&, EBatchNormMode, const Tensor&, const Tensor&, float, float, Tensor*, Tensor*, Tensor&, Tensor&, Tensor&) const { throw std::runtime_error("BatchNormalizationTrain: not implemented by this backend"); }
+        virtual void BatchNormalizationGradient(const Tensor&, EBatchNormMode, const Tensor&, float, const Tensor&, const Tensor&, const Tensor&, Tensor&, Tensor&, bool, Tensor&) const { throw std::runtime_error("BatchNormalizationGradient: not implemented by this backend"); }
         virtual void AdamStep(Tensor& parameter, const Tensor& gradient, Tensor& mGrad, Tensor& vGrad, float lr, float beta1, float beta2, float epsilon) const = 0;
         virtual void SgdStep(Tensor& parameter, const Tensor& gradient, float lr) const = 0;
     };
@@ -268,6 +273,19 @@ namespace NeuroB200
         void Conv2DKernelsGradient(const Tensor& input, const Tensor& gradient, uint32_t stride, uint32_t padding, EDataFormat fmt, Tensor& kernelsGradient) const
         {
             Op()->Conv2DKernelsGradient(input, gradient, stride, padding, padding, fmt, kernelsGradient);
+        }
+        // ---- batch normalisation wrappers (Tensor.cpp: BatchNormalization / BatchNormalizationTrain / BatchNormalizationGradient) ----
+        void BatchNormalization(const Tensor& gamma, const Tensor& beta, float epsilon, const Tensor* runningMean, const Tensor* runningVar, Tensor& result, EBatchNormMode mode = Spatial) const
+        {
+            Op()->BatchNormalization(*this, mode, gamma, beta, epsilon, runningMean, runningVar, result);
+        }
+        void BatchNormalizationTrain(const Tensor& gamma, const Tensor& beta, float momentum, float epsilon, Tensor* runningMean, Tensor* runningVar, Tensor& saveMean, Tensor& saveInvVariance, Tensor& result, EBatchNormMode mode = Spatial) const
+        {
+            Op()->BatchNormalizationTrain(*this, mode, gamma, beta, momentum, epsilon, runningMean, runningVar, saveMean, saveInvVariance, result);
+        }
+        void BatchNormalizationGradient(const Tensor& input, const Tensor& gamma, float epsilon, const Tensor& outputGradient, const Tensor& savedMean, const Tensor& savedInvVariance, Tensor& gammaGradient, Tensor& betaGradient, bool trainable, Tensor& inputGradient, EBatchNormMode mode = Spatial) const
+        {
+            Op()->BatchNormalizationGradient(input, mode, gamma, epsilon, outputGradient, savedMean, savedInvVariance, gammaGradient, betaGradient, trainable, inputGradient);
         }
         // ---- resampler wrappers (Tensor.cpp:1833-1876, 1500-1512): shape checks + dispatch ----
         static Shape GetPooling2DOutputShape(const Shape& in, uint32_t kernelWidth, uint32_t kernelHeight, uint32_t stride, uint32_t paddingX, uint32_t paddingY, EDataFormat fmt)

@@ -103,6 +103,49 @@ namespace NeuroB200
                                             output.GetDevicePtr(), m_Stream));
         }
 
+        // TensorOpCpu.h:55-57 -> nb200_batch_norm*; statistics / gamma / beta are flat G-element tensors (Spatial: G = depth)
+        void BatchNormalization(const Tensor& input, EBatchNormMode mode, const Tensor& gamma, const Tensor& beta, float epsilon, const Tensor* runningMean, const Tensor* runningVar, Tensor& output) const override
+        {
+            if (!runningMean || !runningVar) throw std::runtime_error("BatchNormalization: running statistics required");
+            input.CopyToDevice(); gamma.CopyToDevice(); beta.CopyToDevice(); runningMean->CopyToDevice(); runningVar->CopyToDevice(); output.OverrideDevice();
+            const nb200_bn_desc d = DescribeBn(input, mode);
+            Nb200Check(nb200_batch_norm(&d, input.GetDevicePtr(), gamma.GetDevicePtr(), beta.GetDevicePtr(), epsilon, runningMean->GetDevicePtr(), runningVar->GetDevicePtr(), output.GetDevicePtr(), m_Stream));
+        }
+
+        void BatchNormalizationTrain(const Tensor& input, EBatchNormMode mode, const Tensor& gamma, const Tensor& beta, float momentum, float epsilon, Tensor* runningMean, Tensor* runningVar, Tensor& saveMean, Tensor& saveInvVariance, Tensor& output) const override
+        {
+            input.CopyToDevice(); gamma.CopyToDevice(); beta.CopyToDevice(); output.OverrideDevice(); saveMean.OverrideDevice(); saveInvVariance.OverrideDevice();
+            if (runningMean) runningMean->CopyToDevice();
+            if (runningVar) runningVar->CopyToDevice();
+            const nb200_bn_desc d = DescribeBn(input, mode);
+            const size_t bytes = nb200_batch_norm_workspace_bytes(&d);
+            Nb200Check(nb200_batch_norm_train(&d, input.GetDevicePtr(), gamma.GetDevicePtr(), beta.GetDevicePtr(), momentum, epsilon, runningMean ? runningMean->GetDevicePtr() : nullptr,
+                                              runningVar ? runningVar->GetDevicePtr() : nullptr, saveMean.GetDevicePtr(), saveInvVariance.GetDevicePtr(), output.GetDevicePtr(),
+                                              bytes ? Grow(bytes) : nullptr, bytes, m_Stream));
+        }
+
+        void BatchNormalizationGradient(const Tensor& input, EBatchNormMode mode, const Tensor& gamma, float /*epsilon*/, const Tensor& outputGradient, const Tensor& savedMean, const Tensor& savedInvVariance, Tensor& gammaGradient, Tensor& betaGradient, bool /*trainable*/, Tensor& inputGradient) const override
+        {
+            input.CopyToDevice(); gamma.CopyToDevice(); outputGradient.CopyToDevice(); savedMean.CopyToDevice(); savedInvVariance.CopyToDevice();
+            gammaGradient.OverrideDevice(); betaGradient.OverrideDevice(); inputGradient.OverrideDevice();
+            const nb200_bn_desc d = DescribeBn(input, mode);
+            const size_t bytes = nb200_batch_norm_workspace_bytes(&d);
+            Nb200Check(nb200_batch_norm_gradient(&d, input.GetDevicePtr(), gamma.GetDevicePtr(), outputGradient.GetDevicePtr(), savedMean.GetDevicePtr(), savedInvVariance.GetDevicePtr(),
+                                                 gammaGradient.GetDevicePtr(), betaGradient.GetDevicePtr(), inputGradient.GetDevicePtr(), bytes ? Grow(bytes) : nullptr, bytes, m_Stream));
+        }
+
+        // backward of "fused conv layer -> 2x2 max pooling" in one pass (include/neuro_b200.h: nb200_pool2d_gradient_activation); false = geometry not covered, caller issues the two ops
+        bool Pool2DGradientActivation(const Tensor& output, const Tensor& input, const Tensor& outputGradient, uint32_t filterSize, uint32_t stride, EPoolingMode type, uint32_t padding, EActivation activation, float alpha, Tensor& activationInputGradient, Tensor& biasGradient) const
+        {
+            const nb200_pool_desc d = DescribePool(input, output, filterSize, stride, type, padding, padding, NCHW);
+            if (!nb200_pool2d_gradient_activation_supported(&d)) return false;
+            output.CopyToDevice(); input.CopyToDevice(); outputGradient.CopyToDevice(); activationInputGradient.OverrideDevice(); biasGradient.OverrideDevice();
+            const size_t bytes = nb200_pool2d_gradient_activation_workspace_bytes(&d);
+            Nb200Check(nb200_pool2d_gradient_activation(&d, (int)activation, alpha, output.GetDevicePtr(), input.GetDevicePtr(), outputGradient.GetDevicePtr(), activationInputGradient.GetDevicePtr(),
+                                                        biasGradient.GetDevicePtr(), bytes ? Grow(bytes) : nullptr, bytes, m_Stream));
+            return true;
+        }
+
         void AdamStep(Tensor& parameter, const Tensor& gradient, Tensor& mGrad, Tensor& vGrad, float lr, float beta1, float beta2, float epsilon) const override
         {
             parameter.CopyToDevice(); gradient.CopyToDevice(); mGrad.CopyToDevice(); vGrad.CopyToDevice();
@@ -133,6 +176,12 @@ namespace NeuroB200
             const nb200_conv_desc d = Describe(input, kernels, output, stride, paddingX, paddingY, fmt);
             size_t ws = 0; void* w = Workspace(NB200_OP_FORWARD, d, ws);
             Nb200Check(nb200_conv2d_forward(&d, input.GetDevicePtr(), kernels.GetDevicePtr(), bias ? bias->GetDevicePtr() : nullptr, (int)act, alpha, output.GetDevicePtr(), w, ws, m_Stream));
+        }
+        static nb200_bn_desc DescribeBn(const Tensor& x, EBatchNormMode mode)
+        {
+            nb200_bn_desc d{};
+            d.N = x.Batch(); d.C = x.Depth(); d.H = x.Height(); d.W = x.Width(); d.mode = (int)mode;
+            return d;
         }
         static nb200_pool_desc DescribePool(const Tensor& x, const Tensor& y, uint32_t filterSize, uint32_t stride, EPoolingMode type, uint32_t paddingX, uint32_t paddingY, EDataFormat fmt)
         {

@@ -26,6 +26,9 @@ extern "C"
     void oracle_upsample2d(int, int, int, int, const float*, float*);
     void oracle_upsample2d_gradient(int, int, int, int, const float*, float*);
     void oracle_constant_pad2d(int, int, int, int, int, int, int, float, const float*, float*);
+    void oracle_batch_norm_train(int, int, int, const float*, const float*, const float*, float, float, float*, float*, float*, float*, float*);
+    void oracle_batch_norm(int, int, int, const float*, const float*, const float*, float, const float*, const float*, float*);
+    void oracle_batch_norm_gradient(int, int, int, const float*, const float*, const float*, const float*, const float*, float*, float*, float*);
     void oracle_adam_step(float*, const float*, float*, float*, size_t, float, float, float, float);
     void oracle_sgd_step(float*, const float*, size_t, float);
 }
@@ -77,6 +80,23 @@ public:
     void AdamStep(Tensor& p, const Tensor& g, Tensor& m, Tensor& v, float lr, float b1, float b2, float eps) const override
     { oracle_adam_step(p.Values(), g.Values(), m.Values(), v.Values(), p.Length(), lr, b1, b2, eps); }
     void SgdStep(Tensor& p, const Tensor& g, float lr) const override { oracle_sgd_step(p.Values(), g.Values(), p.Length(), lr); }
+    // Spatial mode only (what the conv stacks use): (Nn, G, S) = (N, C, H*W)
+    void BatchNormalizationTrain(const Tensor& x, EBatchNormMode, const Tensor& gamma, const Tensor& beta, float momentum, float eps, Tensor* rm, Tensor* rv, Tensor& sm, Tensor& sv, Tensor& y) const override
+    {
+        y.OverrideHost(); sm.OverrideHost(); sv.OverrideHost();
+        oracle_batch_norm_train(x.Batch(), x.Depth(), x.Height() * x.Width(), x.Values(), gamma.Values(), beta.Values(), momentum, eps, rm ? rm->Values() : nullptr, rv ? rv->Values() : nullptr,
+                                sm.Values(), sv.Values(), y.Values());
+    }
+    void BatchNormalization(const Tensor& x, EBatchNormMode, const Tensor& gamma, const Tensor& beta, float eps, const Tensor* rm, const Tensor* rv, Tensor& y) const override
+    {
+        y.OverrideHost();
+        oracle_batch_norm(x.Batch(), x.Depth(), x.Height() * x.Width(), x.Values(), gamma.Values(), beta.Values(), eps, rm->Values(), rv->Values(), y.Values());
+    }
+    void BatchNormalizationGradient(const Tensor& x, EBatchNormMode, const Tensor& gamma, float, const Tensor& g, const Tensor& sm, const Tensor& sv, Tensor& dgamma, Tensor& dbeta, bool, Tensor& dx) const override
+    {
+        dgamma.OverrideHost(); dbeta.OverrideHost(); dx.OverrideHost();
+        oracle_batch_norm_gradient(x.Batch(), x.Depth(), x.Height() * x.Width(), x.Values(), gamma.Values(), g.Values(), sm.Values(), sv.Values(), dgamma.Values(), dbeta.Values(), dx.Values());
+    }
 };
 
 static int g_Failed = 0, g_Run = 0;
@@ -215,6 +235,32 @@ TEST_METHOD(UpSample2D_2)
     Tensor r = t1.UpSample2D(2);
     Tensor correct({ 0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3, 4, 4, 5, 5, 4, 4, 5, 5, 6, 6, 7, 7, 6, 6, 7, 7 }, Shape(4, 4, 1, 2));
     IsTrue(r.Equals(correct, 0.f));
+}
+
+TEST_METHOD(BatchNormalization_Spatial_CompareWithCpuResult) // TensorOpGpuTests.cpp:1767-1873: Shape(3,4,5,6), momentum 0.9, epsilon 0.001
+{
+    for (const Shape& shape : { Shape(3, 4, 5, 6), Shape(16, 16, 24, 8) })
+    {
+        Tensor x(shape); x.FillWithRand(31); Tensor g(shape); g.FillWithRand(32);
+        Tensor gamma(Shape(1, 1, shape.Depth())); gamma.FillWithRand(33); Tensor beta(Shape(1, 1, shape.Depth())); beta.FillWithRand(34);
+        Tensor out[2], sm[2], sv[2], rm[2], rv[2], dx[2], dg[2], db[2], inf[2];
+        int i = 0;
+        for (EOpMode mode : { CPU, B200 })
+        {
+            Tensor::SetForcedOpMode(mode);
+            out[i] = Tensor(shape); sm[i] = Tensor(gamma.GetShape()); sv[i] = Tensor(gamma.GetShape()); dx[i] = Tensor(shape); dg[i] = Tensor(gamma.GetShape()); db[i] = Tensor(gamma.GetShape());
+            rm[i] = Tensor(gamma.GetShape()); rm[i].FillWithRand(35); rv[i] = Tensor(gamma.GetShape()); rv[i].FillWithRand(36, 0.1f, 1.f); inf[i] = Tensor(shape);
+            x.BatchNormalizationTrain(gamma, beta, 0.9f, 0.001f, &rm[i], &rv[i], sm[i], sv[i], out[i]);
+            g.BatchNormalizationGradient(x, gamma, 0.001f, g, sm[0], sv[0], dg[i], db[i], true, dx[i]);     // both from the CPU statistics: only this op differs
+            x.BatchNormalization(gamma, beta, 0.001f, &rm[i], &rv[i], inf[i]);
+            ++i;
+        }
+        // reordered fp32 sums: tolerance, not equality (tests/test_batchnorm_gpu.py states the bound: 2e-5 max-normalised)
+        IsTrue(out[1].MaxNormalisedError(out[0]) <= 2e-5f); IsTrue(sm[1].MaxNormalisedError(sm[0]) <= 2e-5f); IsTrue(sv[1].MaxNormalisedError(sv[0]) <= 2e-5f);
+        IsTrue(rm[1].MaxNormalisedError(rm[0]) <= 2e-5f); IsTrue(rv[1].MaxNormalisedError(rv[0]) <= 2e-5f);
+        IsTrue(dx[1].MaxNormalisedError(dx[0]) <= 2e-5f); IsTrue(dg[1].MaxNormalisedError(dg[0]) <= 2e-5f); IsTrue(db[1].MaxNormalisedError(db[0]) <= 2e-5f);
+        IsTrue(inf[1].MaxNormalisedError(inf[0]) <= 2e-5f);
+    }
 }
 
 TEST_METHOD(Resamplers_CompareWithCpuResult)
