@@ -294,8 +294,10 @@ def run_ours(args):
     barrier()
 
     op = TimedOp(TensorOpB200(lib.MATH_TF32))
+    # use_graph: forward + backward + exchange replayed as ONE CUDA graph (the trainer's public switch; bit-identical to the eager step,
+    # tests/test_fit_gpu.py, tests/test_fit_nccl_gpu.py) for the headline and e2e passes; the instrumented pass issues call by call
     tr = ConvStackTrainer(op, (3, 512, 512), vgg_layers("vgg16"), dev, optimizer="adam", lr=1e-5, seed=synth.SEED_MODEL,
-                          world_size=world, rank=rank, input_gradient=True, use_graph=False)
+                          world_size=world, rank=rank, input_gradient=True, use_graph=not args.no_graph)
     gen = torch.Generator(device=dev); gen.manual_seed(1000 + rank)       # a different data shard per rank
     x_dev = torch.rand(B, 3, 512, 512, device=dev, generator=gen) * 2 - 1   # U(-1,1) (Tensor::FillWithRand default)
     t_dev = torch.rand(B, *tr.out_shape, device=dev, generator=gen)
@@ -333,7 +335,8 @@ def run_ours(args):
         tr.run_step(global_batch)
     t1.record()
     barrier()
-    launches = (L.nb200_kernel_launches() - launches0) // rounds     # per block of --steps steps
+    # the library counts the kernels it launches; a replayed graph launches tr.graph_kernel_launches of them per step on top
+    launches = (L.nb200_kernel_launches() - launches0 + (timed_steps * tr.graph_kernel_launches if tr.use_graph else 0)) // rounds   # per block of --steps steps
     ms = t0.elapsed_time(t1) / timed_steps
     if world > 1:
         tmax = torch.tensor([ms], device=dev); dist.all_reduce(tmax, op=dist.ReduceOp.MAX); ms = float(tmax.item())
@@ -341,11 +344,13 @@ def run_ours(args):
     # records per step cost ~1 %, which is why the headline pass above runs without them)
     op.events = []
     op_steps = max(3, min(args.steps, 20))
+    graph_mode, tr.use_graph = tr.use_graph, False
     barrier()
     for _ in range(op_steps):
         tr.run_step(global_batch)
     barrier()
     events, op.events = op.events, None
+    tr.use_graph = graph_mode
     if sampler:
         sampler.stop()
     fam_ms = {0: 0.0, 1: 0.0, 2: 0.0}
@@ -475,7 +480,7 @@ def run_ours(args):
                          "share_of_step": dom_ms / total_ms if total_ms else None},
             "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": img_host.numel() * 4,
                     "d2h_bytes_per_step": grad_host[0].numel() * 4, "ms_per_step": e2e_ms, "steps": e2e_steps},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "step_issue": "cuda_graph" if tr.use_graph else "eager",
             "exchange": {"buckets": len(tr.buckets), "bucket_bytes": [4 * (hi - lo) for lo, hi, _ in tr.buckets],
                          "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")} if world > 1 else None,
             "clocks": clocks,
@@ -753,6 +758,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs and the neighbour-kernel passes")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step call by call instead of replaying it as one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

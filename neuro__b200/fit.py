@@ -90,6 +90,7 @@ class ConvStackTrainer:
         self.iteration = 0
         self._plan_n = None
         self._graph = None
+        self.graph_kernel_launches = 0
         C, H, W = in_shape
         self.in_shape = in_shape
         # one flat buffer for all parameters / gradients / Adam moments; per-layer views into it
@@ -336,9 +337,12 @@ class ConvStackTrainer:
                 self._fwd_bwd(global_batch)
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
+        counter = lib.load().nb200_kernel_launches
+        n0 = counter()
         with torch.cuda.graph(g):
             self._fwd_bwd(global_batch)
         self._graph = g
+        self.graph_kernel_launches = int(counter() - n0)   # library kernels one replay launches (bookkeeping for benchmarks)
         # batch-norm running statistics advanced during warm-up / capture are part of the model state; parameters are not touched
         self.params.copy_(params); self.m.copy_(m); self.v.copy_(v); self.iteration = it
 
