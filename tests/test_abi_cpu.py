@@ -293,3 +293,25 @@ def test_plan_entry_points_are_host_validated(L):
     if not torch.cuda.is_available():
         assert L.nb200_conv2d_plan_create(lib.OP_FORWARD, ctypes.byref(d), p, p, p, None, 0, 0.0, 0, None, 0, ctypes.byref(h)) == -2
         assert L.nb200_conv2d_plan_create(lib.OP_KERNELS_GRADIENT, ctypes.byref(d), p, p, p, None, 0, 0.0, 1, None, 0, ctypes.byref(h)) in (-1, -2)
+
+
+def test_bench_flop_tables_are_consistent():
+    """bench.py counts 2*N*K*Ho*Wo*C*R*S per conv op; its layer table, the trainer's VGG16 stack and the per-image total
+    (160.4 GFLOP per op at 512x512) must agree, and the gradient buckets must tile the flat buffer from the end."""
+    import torch
+    import bench
+    from neuro__b200.fit import ConvLayerSpec, ConvStackTrainer
+    from tests.oracle_op import OracleOp
+    assert abs(bench.SAMPLE_FLOPS_PER_OP / 1e9 - 160.4) < 0.1
+    assert abs(bench.vgg_flops_per_image("vgg16", 512) - bench.SAMPLE_FLOPS_PER_OP) < 1.0
+    assert abs(bench.stack_flops((3, 512, 512), bench.vgg_layers("vgg16")) - bench.SAMPLE_FLOPS_PER_OP) < 1.0
+    assert bench.vgg_flops_per_image("vgg19", 512) > bench.SAMPLE_FLOPS_PER_OP
+    layers = bench.vgg_layers("vgg16")
+    assert sum(isinstance(l, ConvLayerSpec) for l in layers) == 13 and len(layers) == 18
+    tr = ConvStackTrainer(OracleOp(), (3, 32, 32), layers, torch.device("cpu"), bucket_bytes=24 << 20)
+    assert tr.out_shape == (512, 1, 1) and tr.params.numel() == 14710464 + 4224       # VGG16 conv kernels + biases
+    assert [b[1] - b[0] for b in tr.buckets] == [7079424, 6489856, 1145408]           # 28.3 + 26.0 + 4.6 MB, filled from the end
+    assert tr.buckets[0][1] == tr.grads.numel() and tr.buckets[-1][0] == 0
+    for name, (in_shape, stack, batch) in bench.model_stacks().items():
+        t = ConvStackTrainer(OracleOp(), in_shape, stack, torch.device("cpu"))
+        assert all(v > 0 for v in t.out_shape) and bench.stack_flops(in_shape, stack) > 0, name
