@@ -159,7 +159,27 @@ class ConvStackTrainer:
                 self.buckets.append((acc_lo, hi, i)); hi = acc_lo; first = None
         if first is not None and hi > acc_lo:
             self.buckets.append((acc_lo, hi, first))
-        self.first_param_layer = min((i for i, v in enumerate(self.views) if v is not None), default=0)
+        # The bucket that ends the backward pass cannot start before the FIRST layer's kernel gradient and the optimiser waits for it:
+        # its all-reduce is the exposed tail of the exchange. Keep that one small (<= tail_bytes): split the leading layers off so
+        # that everything else is already in flight underneath the first layers' (largest-activation, slowest) backward kernels.
+        tail_bytes = 1 << 20
+        lo, hi, _ = self.buckets[-1] if self.buckets else (0, 0, 0)
+        if (hi - lo) * 4 > tail_bytes:
+            cut = None
+            for i, v in enumerate(self.views):
+                if v is None:
+                    continue
+                if v["lo"] >= hi or (v["hi"] - lo) * 4 > tail_bytes:
+                    break
+                cut = (v["hi"], i)
+            if cut is not None and cut[0] < hi:
+                nxt = min(i for i, v in enumerate(self.views) if v is not None and v["lo"] >= cut[0])
+                self.buckets[-1] = (cut[0], hi, nxt)
+                self.buckets.append((lo, cut[0], self.first_param_layer_index()))
+        self.first_param_layer = self.first_param_layer_index()
+
+    def first_param_layer_index(self):
+        return min((i for i, v in enumerate(self.views) if v is not None), default=0)
 
     # ---- static buffers for one shard shape
     def _plan(self, n):

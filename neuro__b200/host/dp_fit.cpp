@@ -167,6 +167,28 @@ struct Replica
             if ((hi - lo) * 4 >= bucketBytes) { buckets.push_back({lo, hi, i, nullptr}); hi = lo; first = -1; }
         }
         if (first >= 0 && hi > lo) buckets.push_back({lo, hi, first, nullptr});
+        // keep the bucket that ends the backward pass small (<= 1 MB): its all-reduce is the exposed tail of the exchange (see fit.py)
+        if (!buckets.empty() && (buckets.back().hi - buckets.back().lo) * 4 > (1u << 20))
+        {
+            const size_t blo = buckets.back().lo, bhi = buckets.back().hi;
+            size_t cut = 0; int next = -1;
+            for (size_t i = 0; i < layers.size(); ++i)
+            {
+                if (layers[i].s.pool) continue;
+                const size_t end = layers[i].bOff + layers[i].K;
+                if (layers[i].wOff >= bhi || (end - blo) * 4 > (1u << 20)) break;
+                cut = end;
+            }
+            if (cut > blo && cut < bhi)
+            {
+                for (size_t i = 0; i < layers.size(); ++i)
+                    if (!layers[i].s.pool && layers[i].wOff >= cut) { next = (int)i; break; }
+                int firstLayer = 0;
+                for (size_t i = 0; i < layers.size(); ++i) if (!layers[i].s.pool) { firstLayer = (int)i; break; }
+                buckets.back() = {cut, bhi, next, nullptr};
+                buckets.push_back({blo, cut, firstLayer, nullptr});
+            }
+        }
         for (Bucket& b : buckets) CK(cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming));
     }
 

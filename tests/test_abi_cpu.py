@@ -310,7 +310,8 @@ def test_bench_flop_tables_are_consistent():
     assert sum(isinstance(l, ConvLayerSpec) for l in layers) == 13 and len(layers) == 18
     tr = ConvStackTrainer(OracleOp(), (3, 32, 32), layers, torch.device("cpu"), bucket_bytes=24 << 20)
     assert tr.out_shape == (512, 1, 1) and tr.params.numel() == 14710464 + 4224       # VGG16 conv kernels + biases
-    assert [b[1] - b[0] for b in tr.buckets] == [7079424, 6489856, 1145408]           # 28.3 + 26.0 + 4.6 MB, filled from the end
+    assert [b[1] - b[0] for b in tr.buckets] == [7079424, 6489856, 885248, 260160]    # 28.3 + 26.0 + 3.5 MB filled from the end + a 1.0 MB tail (blocks 1-2)
+    assert [b[2] for b in tr.buckets] == [14, 8, 6, 0]                                  # the layer whose kernel gradient completes each bucket
     assert tr.buckets[0][1] == tr.grads.numel() and tr.buckets[-1][0] == 0
     for name, (in_shape, stack, batch) in bench.model_stacks().items():
         t = ConvStackTrainer(OracleOp(), in_shape, stack, torch.device("cpu"))
