@@ -126,6 +126,7 @@ TC_CASES = [
     (0, 4, 6, 131, 131, 40, 4, 4, 2, 0, 0),    # PatchGAN d1 geometry: 6 channels, 4x4, stride 2, odd input width (x not TMA-addressable), 96 rows
     (0, 2, 5, 100, 134, 136, 3, 3, 1, 0, 0),   # stride 1, 5 channels (48 rows, 45 live), two filter tiles (the second ragged), ragged last segment
     (0, 2, 2, 90, 100, 16, 5, 5, 3, 2, 2),     # stride 3, 5x5, padding 2: 50 rows in 64
+    (0, 128, 3, 32, 32, 64, 3, 3, 2, 1, 1),    # DCGAN D conv1 at its BASELINE size: 16-column output rows, half of every 32-pixel dy box is TMA zero fill
     # odd filter / channel counts on the halo-tile path: the repacked filters are only a multiple of 128 bytes
     (0, 2, 16, 32, 32, 9, 3, 3, 1, 1, 1),      # 9 filters (forward repack 9*9*32*4 bytes), 9-row input-gradient tiles
     (0, 2, 32, 32, 32, 21, 1, 1, 1, 0, 0),     # 1x1 conv to 21 classes
